@@ -1,0 +1,185 @@
+/*
+ * msckf_b200.h -- C ABI of the B200-native (sm_100a, FP64) batched MSCKF measurement-update hot path.
+ *
+ * The reference (ValerioSpagnoli/Monocular-Visual-Inertial-MSCKF) is pure Python and has no FFI/plugin layer
+ * (SURVEY.md section 8b); its boundary for this path is the method set of class MSCKF in src/msckf/MSCKF.py.
+ * Each entry point below names the reference method(s) it replaces (file:line relative to the reference root).
+ * The reference-side binding a maintainer would add (a ctypes stub) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the function name ends in _host.  FP64 everywhere.
+ *   - Batch-major struct-of-arrays: B independent filters, each with capacity F features, M observations per
+ *     feature, N camera poses in the sliding window.  Filter b uses n_cams[b] <= N poses; its error-state
+ *     dimension is d_b = 15 + 6 n_cams[b] in the reference's order [dtheta, dbg, dv, dba, dp | (dtheta, dp) per
+ *     camera] (MSCKF.py:171, 258-262).  P is [B][ldp][ldp] row-major, ldp >= 15 + 6 N.
+ *   - No hidden allocations: the caller passes a workspace obtained from the matching *_workspace_bytes query.
+ *   - Every function returns 0 on success, a negative MSCKF_E* code on bad arguments, or a positive cudaError_t
+ *     if a launch failed.  Nothing throws.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - Error behaviour mirrors the reference: a filter whose features are all rejected (or that has none) is left
+ *     untouched and reports n_accepted = 0 (MSCKF.py:584-585); no exception is raised for degenerate geometry.
+ */
+#ifndef MSCKF_B200_H
+#define MSCKF_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSCKF_B200_ABI_VERSION 1
+
+/* error codes (negative); positive return values are cudaError_t */
+#define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
+#define MSCKF_ECAPACITY (-2)   /* a dimension exceeds what this build's kernels support */
+#define MSCKF_EWORKSPACE (-3)  /* workspace too small */
+
+/* feat_status codes written per feature (rows 3 and 8 of SURVEY.md section 8a) */
+#define MSCKF_FEAT_SKIPPED 0       /* not selected: neither lost nor enough parallax (MSCKF.py:479), or empty slot */
+#define MSCKF_FEAT_ACCEPTED 1      /* valid and passed the chi-square gate: its rows entered the stacked update */
+#define MSCKF_FEAT_GATED_OUT 2     /* valid but rejected by gating_test (MSCKF.py:577-579) */
+#define MSCKF_FEAT_LOST_DISCARD 3  /* lost before it was tracked long enough (MSCKF.py:467-469) */
+#define MSCKF_FEAT_LOST_FLAG 0x10  /* OR-ed in when the feature is in the reference's `lost_features` dict */
+
+/* how the surviving rows are compressed before the Kalman update (row 9) */
+#define MSCKF_COMPRESS_QR 0    /* Householder TSQR of the stacked rows: T_H = R, r_n = Q^T r (MSCKF.py:594-598) */
+#define MSCKF_COMPRESS_GRAM 1  /* information form: G = H^T H, g = H^T r, solved through (sigma^2 I + G P)^-1 */
+
+typedef struct msckf_dims {
+    int B;    /* filters in the batch */
+    int F;    /* feature capacity per filter */
+    int M;    /* observation capacity per feature */
+    int N;    /* camera-pose capacity per filter */
+    int ldp;  /* row stride (in doubles) of each P matrix, >= 15 + 6 N */
+} msckf_dims;
+
+typedef struct msckf_update_params {
+    double K[9];             /* pinhole intrinsics, row-major (MSCKFParameters.K, MSCKF.py:21-23) */
+    double Kinv[9];          /* inverse of K as the host computes it (the reference calls np.linalg.inv(K)) */
+    int width, height;       /* image bounds test of Camera.project_point (Camera.py:18-26) */
+    double sigma_image;      /* MSCKF.py:92 */
+    double gravity[3];       /* W_gravity, MSCKF.py:32 */
+    int min_lost;            /* min_number_of_frames_to_be_lost (clamped >= 1, MSCKF.py:119) */
+    int min_tracked;         /* min_number_of_frames_to_be_tracked (clamped >= 2, MSCKF.py:120) */
+    int use_parallax;        /* MSCKF.py:114 */
+    double min_parallax_deg; /* MSCKF.py:115 */
+    int compress_mode;       /* MSCKF_COMPRESS_* */
+} msckf_update_params;
+
+/* imu_state: [B][21] = R_W_I (9, row-major), t (3), v (3), b_g (3), b_a (3)       (IMU.py:13-41)
+ * imu_null:  [B][15] = R_null (9), t_null (3), v_null (3)                          (IMU.py:38-39)
+ * cam_R:     [B][N][9] row-major R_W_C, cam_t: [B][N][3]; a camera's null pose is its pose (Camera.py:11)       */
+#define MSCKF_IMU_STATE_DOUBLES 21
+#define MSCKF_IMU_NULL_DOUBLES 15
+
+int msckf_abi_version(void);
+
+/* Largest supported capacities of this build (queried by the host wrappers and the tests). */
+int msckf_max_obs_per_feature(void);
+int msckf_max_cameras(int compress_mode);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * msckf_update_batched  <->  MSCKF.get_valid_features (MSCKF.py:458-495) + MSCKF.update (570-609)
+ *                            + MSCKF.correct (611-661), for B filters at once.
+ *
+ * Inputs per filter b / feature j / observation i:
+ *   feat_len[B][F]            number of observations of the track (0 = empty slot)
+ *   obs_uv[B][F][M][2]        keypoints in pixels (Feature.keypoints)
+ *   obs_dir[B][F][M][3]       world ray directions frozen at capture (Line.direction, MSCKF.py:403-410)
+ *   obs_conf[B][F][M]         Line.confidence (detector score)
+ *   obs_slot[B][F][M]         position of the observing camera in the window (MSCKF.py:539); Line.base is that
+ *                             camera's LIVE position (aliasing, MSCKF.py:305,410), so it is read from cam_t
+ *   idp_anchor_slot[B][F]     window slot whose position InverseDepthPoint.base aliases, or -1: use idp_base
+ *   idp_base[B][F][3]         explicit base (anchor camera already deleted)
+ *   idp_m[B][F][3], idp_rho[B][F]   inverse-depth parameters; re-triangulated IN PLACE (MSCKF.py:485-488)
+ *   lost_cnt, tracked_cnt[B][F]     Feature.lost_for_n_frames / tracked_for_n_frames
+ *   chi2_table[chi2_len]      chi2.ppf(0.95, k), k = 0..chi2_len-1 (entry 0 must be NaN), chi2_len >= 2 M + 1
+ * In/out: P, imu_state, cam_R, cam_t.   n_cams[B] is read only.
+ * Outputs:
+ *   feat_status[B][F]         MSCKF_FEAT_* | MSCKF_FEAT_LOST_FLAG
+ *   gamma[B][F], dof[B][F]    Mahalanobis distance and degrees of freedom of each valid feature (NaN / 0 else)
+ *   delta_x[B][ldp]           the correction that was applied (zeros when nothing was accepted)
+ *   n_accepted[B], n_rejected[B]   features stacked / gated out (the reference's discard counter, MSCKF.py:578)
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t msckf_update_workspace_bytes(const msckf_dims* dims, int compress_mode);
+
+int msckf_update_batched(const msckf_dims* dims, const msckf_update_params* params,
+                         const double* chi2_table, int chi2_len,
+                         double* P, double* imu_state, double* cam_R, double* cam_t, const int* n_cams,
+                         const int* feat_len, const double* obs_uv, const double* obs_dir, const double* obs_conf,
+                         const int* obs_slot, const double* idp_base, const int* idp_anchor_slot,
+                         double* idp_m, double* idp_rho, const int* lost_cnt, const int* tracked_cnt,
+                         unsigned char* feat_status, double* gamma, int* dof, double* delta_x,
+                         int* n_accepted, int* n_rejected,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fine-grained stages of the same call (function-level parity tests; same argument meaning as above).
+ *
+ * msckf_front_batched      <-> get_valid_features + compute_residual_and_jacobians (MSCKF.py:497-552)
+ *                              + project_on_nullspace (554-559) + gating_test (561-568), per feature.
+ *   Also leaves the per-feature factors (A blocks, range basis Q1 of H_f, residual) in the workspace for the
+ *   compression stage, and can export basis-invariant per-feature quantities for tests:
+ *   HtH_diag[B][F][M][36] = A_i^T A_i, and W[B][F][3][6 M] = Q1^T H_x by observation (any may be NULL).
+ * msckf_compress_batched   <-> the vstack + np.linalg.qr block of update (MSCKF.py:587-602):
+ *   T_H[B][6N][6N] (upper triangular over the camera columns; the 15 IMU columns of H are identically zero) and
+ *   r_n[B][6N].  Must follow msckf_front_batched on the same workspace.
+ * msckf_apply_update_batched <-> S, K, delta_x (MSCKF.py:604-607) + correct (611-661).
+ * ------------------------------------------------------------------------------------------------------------- */
+int msckf_front_batched(const msckf_dims* dims, const msckf_update_params* params,
+                        const double* chi2_table, int chi2_len,
+                        const double* P, const double* cam_R, const double* cam_t, const int* n_cams,
+                        const int* feat_len, const double* obs_uv, const double* obs_dir, const double* obs_conf,
+                        const int* obs_slot, const double* idp_base, const int* idp_anchor_slot,
+                        double* idp_m, double* idp_rho, const int* lost_cnt, const int* tracked_cnt,
+                        unsigned char* feat_status, double* gamma, int* dof,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+int msckf_compress_batched(const msckf_dims* dims, const msckf_update_params* params,
+                           const int* n_cams, const int* feat_len, const int* obs_slot,
+                           const unsigned char* feat_status, double* T_H, double* r_n,
+                           int* n_accepted, int* n_rejected,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+int msckf_apply_update_batched(const msckf_dims* dims, const msckf_update_params* params,
+                               double* P, double* imu_state, double* cam_R, double* cam_t, const int* n_cams,
+                               const double* T_H, const double* r_n, const int* n_accepted, double* delta_x,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * msckf_propagate_batched  <->  MSCKF.process_imu (MSCKF.py:160-248) + IMU.integrate (IMU.py:78-100), applied
+ * n_samples times per filter in one launch (the samples between two camera frames).
+ *
+ *   imu_samples[B][n_samples][7]  timestamp, angular velocity (3), linear acceleration (3)  (IMUMeasurement)
+ *   imu_time[B]                   in/out: IMU.timestamp
+ *   Qc_diag[B][4]                 sigma_g^2, sigma_bg^2, sigma_a^2, sigma_ba^2 (MSCKF.py:99-103)
+ *   gravity[3]                    host pointer
+ * In/out: imu_state, imu_null (null state <- state after every sample, MSCKF.py:247-248), P rows/cols 0:15.
+ * ------------------------------------------------------------------------------------------------------------- */
+int msckf_propagate_batched(const msckf_dims* dims, int n_samples, const double* imu_samples, double* imu_time,
+                            const double* Qc_diag, const double* gravity_host,
+                            double* imu_state, double* imu_null, double* P, const int* n_cams, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Next rows (window surgery kept on the device so P never leaves HBM between calls):
+ * msckf_augment_batched  <-> MSCKF.state_augmentation (MSCKF.py:250-265): appends camera pose slot n_cams[b]
+ *   (T_W_C = T_W_I * T_I_C), P <- [I; J] P [I; J]^T symmetrised, n_cams[b] += 1.   T_I_C: host R (9) + t (3).
+ * msckf_remove_cameras_batched <-> MSCKF.remove_cameras (MSCKF.py:751-758): deletes the poses flagged in
+ *   remove_mask[B][N] (and their covariance rows/columns), compacting slots; n_cams updated.
+ * ------------------------------------------------------------------------------------------------------------- */
+int msckf_augment_batched(const msckf_dims* dims, const double* T_I_C_host, const double* imu_state,
+                          double* cam_R, double* cam_t, double* P, int* n_cams, const unsigned char* active,
+                          void* stream);
+
+size_t msckf_remove_workspace_bytes(const msckf_dims* dims);
+int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* remove_mask,
+                                 double* cam_R, double* cam_t, double* P, int* n_cams,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels launched by this library since load (the benchmark reports it as gpu_launches). */
+long long msckf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCKF_B200_H */

@@ -1,0 +1,11 @@
+"""B200-native (sm_100a, FP64) batched MSCKF measurement-update hot path.
+
+Host side of the drop-in for the reference's `MSCKF.update` / `process_imu` path
+(ValerioSpagnoli/Monocular-Visual-Inertial-MSCKF, src/msckf/MSCKF.py).  The compute lives in hand-written CUDA kernels
+behind the C ABI of include/msckf_b200.h (csrc/libmsckf_b200.so, built in-tree by `make` / __graft_entry__.build()).
+There is no CPU fallback: every compute entry point raises if the library or a CUDA device is missing.
+"""
+from ._lib import LibraryNotBuilt, lib_path, load_library  # noqa: F401
+from .batched import BatchedMSCKF, UpdateParams, pack_cases  # noqa: F401
+
+__all__ = ["BatchedMSCKF", "UpdateParams", "pack_cases", "load_library", "lib_path", "LibraryNotBuilt"]

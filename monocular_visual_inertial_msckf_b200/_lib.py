@@ -1,0 +1,90 @@
+"""ctypes binding of csrc/libmsckf_b200.so (C ABI: include/msckf_b200.h).  Fails loudly when the library is missing."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+COMPRESS_QR = 0
+COMPRESS_GRAM = 1
+
+FEAT_SKIPPED, FEAT_ACCEPTED, FEAT_GATED_OUT, FEAT_LOST_DISCARD, FEAT_LOST_FLAG = 0, 1, 2, 3, 0x10
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+class Dims(C.Structure):
+    _fields_ = [("B", C.c_int), ("F", C.c_int), ("M", C.c_int), ("N", C.c_int), ("ldp", C.c_int)]
+
+
+class Params(C.Structure):
+    _fields_ = [("K", C.c_double * 9), ("Kinv", C.c_double * 9), ("width", C.c_int), ("height", C.c_int),
+                ("sigma_image", C.c_double), ("gravity", C.c_double * 3), ("min_lost", C.c_int),
+                ("min_tracked", C.c_int), ("use_parallax", C.c_int), ("min_parallax_deg", C.c_double),
+                ("compress_mode", C.c_int)]
+
+
+# every symbol include/msckf_b200.h declares
+EXPORTS = [
+    "msckf_abi_version", "msckf_max_obs_per_feature", "msckf_max_cameras", "msckf_update_workspace_bytes",
+    "msckf_update_batched", "msckf_front_batched", "msckf_compress_batched", "msckf_apply_update_batched",
+    "msckf_propagate_batched", "msckf_augment_batched", "msckf_remove_workspace_bytes",
+    "msckf_remove_cameras_batched", "msckf_launch_count",
+]
+
+
+def lib_path():
+    return os.path.join(_HERE, "csrc", "libmsckf_b200.so")
+
+
+def load_library():
+    """Load the CUDA library (once).  Raises LibraryNotBuilt -- there is no CPU fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise LibraryNotBuilt(f"{path} is missing: run `make` (or __graft_entry__.build()) at the repo root. "
+                              "This package has no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, dp, ip, u8 = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    pd, pp = C.POINTER(Dims), C.POINTER(Params)
+    lib.msckf_abi_version.restype = C.c_int
+    lib.msckf_max_obs_per_feature.restype = C.c_int
+    lib.msckf_max_cameras.restype = C.c_int
+    lib.msckf_max_cameras.argtypes = [C.c_int]
+    lib.msckf_launch_count.restype = C.c_longlong
+    lib.msckf_update_workspace_bytes.restype = C.c_size_t
+    lib.msckf_update_workspace_bytes.argtypes = [pd, C.c_int]
+    lib.msckf_remove_workspace_bytes.restype = C.c_size_t
+    lib.msckf_remove_workspace_bytes.argtypes = [pd]
+    front_tail = [dp, dp, ip,                      # cam_R cam_t n_cams
+                  ip, dp, dp, dp, ip, dp, ip, dp, dp, ip, ip,   # feat_len .. tracked_cnt
+                  u8, dp, ip]                      # feat_status gamma dof
+    lib.msckf_front_batched.restype = C.c_int
+    lib.msckf_front_batched.argtypes = [pd, pp, dp, C.c_int, dp] + front_tail + [vp, C.c_size_t, vp]
+    lib.msckf_update_batched.restype = C.c_int
+    lib.msckf_update_batched.argtypes = ([pd, pp, dp, C.c_int, dp, dp] + front_tail +
+                                         [dp, ip, ip, vp, C.c_size_t, vp])
+    lib.msckf_compress_batched.restype = C.c_int
+    lib.msckf_compress_batched.argtypes = [pd, pp, ip, ip, ip, u8, dp, dp, ip, ip, vp, C.c_size_t, vp]
+    lib.msckf_apply_update_batched.restype = C.c_int
+    lib.msckf_apply_update_batched.argtypes = [pd, pp, dp, dp, dp, dp, ip, dp, dp, ip, dp, vp, C.c_size_t, vp]
+    lib.msckf_propagate_batched.restype = C.c_int
+    lib.msckf_propagate_batched.argtypes = [pd, C.c_int, dp, dp, dp, C.POINTER(C.c_double), dp, dp, dp, ip, vp]
+    lib.msckf_augment_batched.restype = C.c_int
+    lib.msckf_augment_batched.argtypes = [pd, C.POINTER(C.c_double), dp, dp, dp, dp, ip, u8, vp]
+    lib.msckf_remove_cameras_batched.restype = C.c_int
+    lib.msckf_remove_cameras_batched.argtypes = [pd, u8, dp, dp, dp, ip, vp, C.c_size_t, vp]
+    if lib.msckf_abi_version() != 1:
+        raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
+    _LIB = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        kind = {-1: "invalid argument", -2: "capacity exceeded", -3: "workspace too small"}.get(rc, f"CUDA error {rc}")
+        raise RuntimeError(f"{what} failed: {kind}")

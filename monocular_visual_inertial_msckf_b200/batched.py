@@ -1,0 +1,267 @@
+"""Device-resident batch of independent MSCKF filters: the host-side owner of the HBM state the CUDA kernels work on.
+
+Mirrors, for B filters at once, the calls the reference makes on one `MSCKF` object (reference src/msckf/MSCKF.py):
+    propagate()       <-> process_imu            (MSCKF.py:160-248)   n samples per launch
+    augment()         <-> state_augmentation     (MSCKF.py:250-265)
+    update()          <-> get_valid_features + update + correct   (MSCKF.py:458-495, 570-661)
+    remove_cameras()  <-> remove_cameras (covariance/pose part)   (MSCKF.py:751-758)
+PyTorch is used for device memory and streams only; all arithmetic happens in csrc/*.cu through include/msckf_b200.h.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _chi2_table(n):
+    from scipy.stats import chi2
+    with np.errstate(all="ignore"):
+        t = np.array([chi2.ppf(0.95, k) for k in range(n)], float)
+    t[0] = np.nan     # chi2.ppf(0.95, 0) is NaN: a feature with an empty null space is rejected (MSCKF.py:566-568)
+    return t
+
+
+@dataclass
+class UpdateParams:
+    """The MSCKFParameters fields the hot path reads (reference MSCKF.py:14-46) plus the compression mode."""
+    K: np.ndarray = field(default_factory=lambda: np.array([[320.0, 0, 320], [0, 320.0, 240], [0, 0, 1]]))
+    width: int = 640
+    height: int = 480
+    sigma_image: float = 0.1
+    gravity: np.ndarray = field(default_factory=lambda: np.array([0.0, 0.0, -9.81]))
+    min_lost: int = 2
+    min_tracked: int = 4
+    use_parallax: bool = True
+    min_parallax: float = 45.0
+    compress_mode: int = _lib.COMPRESS_QR
+
+    def to_c(self):
+        p = _lib.Params()
+        K = np.asarray(self.K, float)
+        Kinv = np.linalg.inv(K)
+        for i in range(9):
+            p.K[i] = float(K.flat[i])
+            p.Kinv[i] = float(Kinv.flat[i])
+        p.width, p.height = int(self.width), int(self.height)
+        p.sigma_image = float(self.sigma_image)
+        for i in range(3):
+            p.gravity[i] = float(self.gravity[i])
+        p.min_lost = max(int(self.min_lost), 1)            # clamps of MSCKF.__init__, MSCKF.py:119-120
+        p.min_tracked = max(int(self.min_tracked), 2)
+        p.use_parallax = int(bool(self.use_parallax))
+        p.min_parallax_deg = float(self.min_parallax)
+        p.compress_mode = int(self.compress_mode)
+        return p
+
+    @staticmethod
+    def from_case(c, compress_mode=_lib.COMPRESS_QR):
+        return UpdateParams(K=np.array(c["K"], float), width=int(c["width"]), height=int(c["height"]),
+                            sigma_image=float(c["sigma"]), gravity=np.array(c["gravity"], float),
+                            min_lost=int(c["min_lost"]), min_tracked=int(c["min_tracked"]),
+                            use_parallax=bool(c["use_parallax"]), min_parallax=float(c["min_parallax"]),
+                            compress_mode=compress_mode)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class BatchedMSCKF:
+    """B filters x F feature slots x M observations x N window poses, all state resident in HBM (FP64)."""
+
+    def __init__(self, B, F, M, N, params: UpdateParams, device="cuda", ldp=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedMSCKF needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load_library()
+        self.B, self.F, self.M, self.N = int(B), int(F), int(M), int(N)
+        self.ldp = int(ldp) if ldp is not None else 15 + 6 * self.N
+        self.params = params
+        self.device = torch.device(device)
+        self.dims = _lib.Dims(self.B, self.F, self.M, self.N, self.ldp)
+        self.cpar = params.to_c()
+        if self.M > self.lib.msckf_max_obs_per_feature() or self.N > self.lib.msckf_max_cameras(params.compress_mode):
+            raise ValueError(f"capacity exceeded: M={self.M} (max {self.lib.msckf_max_obs_per_feature()}), "
+                             f"N={self.N} (max {self.lib.msckf_max_cameras(params.compress_mode)} in this mode)")
+        dv, f64, i32 = self.device, torch.float64, torch.int32
+        z = lambda *s, dtype=f64: torch.zeros(*s, dtype=dtype, device=dv)  # noqa: E731
+        # filter state
+        self.P = z(B, self.ldp, self.ldp)
+        self.imu_state = z(B, 21)
+        self.imu_state[:, [0, 4, 8]] = 1.0
+        self.imu_null = z(B, 15)
+        self.imu_null[:, [0, 4, 8]] = 1.0
+        self.imu_time = z(B)
+        self.cam_R = z(B, N, 9)
+        self.cam_t = z(B, N, 3)
+        self.n_cams = z(B, dtype=i32)
+        # tracks
+        self.feat_len = z(B, F, dtype=i32)
+        self.obs_uv = z(B, F, M, 2)
+        self.obs_dir = z(B, F, M, 3)
+        self.obs_conf = z(B, F, M)
+        self.obs_slot = z(B, F, M, dtype=i32)
+        self.idp_base = z(B, F, 3)
+        self.idp_anchor_slot = torch.full((B, F), -1, dtype=i32, device=dv)
+        self.idp_m = z(B, F, 3)
+        self.idp_rho = z(B, F)
+        self.lost_cnt = z(B, F, dtype=i32)
+        self.tracked_cnt = z(B, F, dtype=i32)
+        # outputs
+        self.feat_status = z(B, F, dtype=torch.uint8)
+        self.gamma = z(B, F)
+        self.dof = z(B, F, dtype=i32)
+        self.delta_x = z(B, self.ldp)
+        self.n_accepted = z(B, dtype=i32)
+        self.n_rejected = z(B, dtype=i32)
+        self.T_H = None
+        self.r_n = None
+        self.chi2_len = 2 * self.M + 3
+        self.chi2 = torch.from_numpy(_chi2_table(self.chi2_len)).to(dv)
+        nbytes = self.lib.msckf_update_workspace_bytes(C.byref(self.dims), params.compress_mode)
+        if nbytes == 0:
+            raise ValueError("unsupported dimensions")
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dv)
+        self._remove_ws = None
+        self.Qc_diag = z(B, 4)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _front_tail(self):
+        return [_ptr(self.cam_R), _ptr(self.cam_t), _ptr(self.n_cams), _ptr(self.feat_len), _ptr(self.obs_uv),
+                _ptr(self.obs_dir), _ptr(self.obs_conf), _ptr(self.obs_slot), _ptr(self.idp_base),
+                _ptr(self.idp_anchor_slot), _ptr(self.idp_m), _ptr(self.idp_rho), _ptr(self.lost_cnt),
+                _ptr(self.tracked_cnt), _ptr(self.feat_status), _ptr(self.gamma), _ptr(self.dof)]
+
+    def update(self):
+        """get_valid_features + update + correct for every filter (one C-ABI call, three kernels)."""
+        rc = self.lib.msckf_update_batched(C.byref(self.dims), C.byref(self.cpar), _ptr(self.chi2), self.chi2_len,
+                                           _ptr(self.P), _ptr(self.imu_state), *self._front_tail(),
+                                           _ptr(self.delta_x), _ptr(self.n_accepted), _ptr(self.n_rejected),
+                                           _ptr(self.workspace), self.workspace.numel(), self._stream())
+        _lib.check(rc, "msckf_update_batched")
+
+    def front(self):
+        rc = self.lib.msckf_front_batched(C.byref(self.dims), C.byref(self.cpar), _ptr(self.chi2), self.chi2_len,
+                                          _ptr(self.P), *self._front_tail(), _ptr(self.workspace),
+                                          self.workspace.numel(), self._stream())
+        _lib.check(rc, "msckf_front_batched")
+
+    def compress(self):
+        c = 6 * self.N
+        if self.T_H is None:
+            self.T_H = torch.zeros(self.B, c, c, dtype=torch.float64, device=self.device)
+            self.r_n = torch.zeros(self.B, c, dtype=torch.float64, device=self.device)
+        rc = self.lib.msckf_compress_batched(C.byref(self.dims), C.byref(self.cpar), _ptr(self.n_cams),
+                                             _ptr(self.feat_len), _ptr(self.obs_slot), _ptr(self.feat_status),
+                                             _ptr(self.T_H), _ptr(self.r_n), _ptr(self.n_accepted),
+                                             _ptr(self.n_rejected), _ptr(self.workspace), self.workspace.numel(),
+                                             self._stream())
+        _lib.check(rc, "msckf_compress_batched")
+        return self.T_H, self.r_n
+
+    def apply_update(self):
+        rc = self.lib.msckf_apply_update_batched(C.byref(self.dims), C.byref(self.cpar), _ptr(self.P),
+                                                 _ptr(self.imu_state), _ptr(self.cam_R), _ptr(self.cam_t),
+                                                 _ptr(self.n_cams), _ptr(self.T_H), _ptr(self.r_n),
+                                                 _ptr(self.n_accepted), _ptr(self.delta_x), _ptr(self.workspace),
+                                                 self.workspace.numel(), self._stream())
+        _lib.check(rc, "msckf_apply_update_batched")
+
+    def propagate(self, samples, use_null_state=False):
+        """samples: [B, n, 7] device tensor (timestamp, omega, acc).  With use_null_state=False the null state is the
+        state on entry -- the aliasing the reference exhibits after its first process_imu call (MSCKF.py:247-248)."""
+        assert samples.shape[0] == self.B and samples.shape[2] == 7 and samples.dtype == torch.float64
+        samples = samples.contiguous()
+        g = (C.c_double * 3)(*[float(x) for x in self.params.gravity])
+        rc = self.lib.msckf_propagate_batched(C.byref(self.dims), int(samples.shape[1]), _ptr(samples),
+                                              _ptr(self.imu_time), _ptr(self.Qc_diag), g, _ptr(self.imu_state),
+                                              _ptr(self.imu_null) if use_null_state else C.c_void_p(0),
+                                              _ptr(self.P), _ptr(self.n_cams), self._stream())
+        _lib.check(rc, "msckf_propagate_batched")
+
+    def augment(self, R_I_C, t_I_C, active=None):
+        T = (C.c_double * 12)(*[float(x) for x in np.asarray(R_I_C, float).flatten()],
+                              *[float(x) for x in np.asarray(t_I_C, float).flatten()])
+        rc = self.lib.msckf_augment_batched(C.byref(self.dims), T, _ptr(self.imu_state), _ptr(self.cam_R),
+                                            _ptr(self.cam_t), _ptr(self.P), _ptr(self.n_cams), _ptr(active),
+                                            self._stream())
+        _lib.check(rc, "msckf_augment_batched")
+
+    def remove_cameras(self, mask):
+        """mask: [B, N] uint8 device tensor, 1 = delete that window slot."""
+        if self._remove_ws is None:
+            n = self.lib.msckf_remove_workspace_bytes(C.byref(self.dims))
+            self._remove_ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+        rc = self.lib.msckf_remove_cameras_batched(C.byref(self.dims), _ptr(mask), _ptr(self.cam_R),
+                                                   _ptr(self.cam_t), _ptr(self.P), _ptr(self.n_cams),
+                                                   _ptr(self._remove_ws), self._remove_ws.numel(), self._stream())
+        _lib.check(rc, "msckf_remove_cameras_batched")
+
+    # ------------------------------------------------------------------------------------------------------------
+    def load_cases(self, cases):
+        """Fill filter b from packed case dict cases[b] (the layout of tests/golden and tools/make_golden.py)."""
+        assert len(cases) == self.B
+        h = pack_cases(cases, self.F, self.M, self.N, self.ldp)
+        for k, v in h.items():
+            getattr(self, k).copy_(torch.from_numpy(v))
+
+    def case_outputs(self, b, case):
+        """Outputs of filter b in the golden `out_*` vocabulary (numpy, trimmed to the case's true sizes)."""
+        F = len(case["feat_len"])
+        n = int(case["n_cams"])
+        d = 15 + 6 * n
+        st = self.feat_status[b, :F].cpu().numpy()
+        code = st & 0xF
+        imu = self.imu_state[b].cpu().numpy()
+        return dict(
+            out_valid=(code == _lib.FEAT_ACCEPTED) | (code == _lib.FEAT_GATED_OUT),
+            out_lost=(st & _lib.FEAT_LOST_FLAG) != 0,
+            out_gate=code == _lib.FEAT_ACCEPTED,
+            out_gamma=self.gamma[b, :F].cpu().numpy(), out_dof=self.dof[b, :F].cpu().numpy(),
+            out_idp_m=self.idp_m[b, :F].cpu().numpy(), out_idp_rho=self.idp_rho[b, :F].cpu().numpy(),
+            out_delta_x=self.delta_x[b, :d].cpu().numpy(), out_P=self.P[b, :d, :d].cpu().numpy(),
+            out_cam_R=self.cam_R[b, :n].cpu().numpy().reshape(n, 3, 3), out_cam_t=self.cam_t[b, :n].cpu().numpy(),
+            out_imu_R=imu[:9].reshape(3, 3), out_imu_t=imu[9:12], out_imu_v=imu[12:15], out_imu_bg=imu[15:18],
+            out_imu_ba=imu[18:21], out_n_rejected=int(self.n_rejected[b]), out_n_accepted=int(self.n_accepted[b]),
+            out_updated=int(self.n_accepted[b]) > 0)
+
+
+def pack_cases(cases, F, M, N, ldp):
+    """numpy [B, ...] arrays in the C-ABI layout from a list of single-filter case dicts (padding with empty slots)."""
+    B = len(cases)
+    h = dict(
+        P=np.zeros((B, ldp, ldp)), imu_state=np.zeros((B, 21)), cam_R=np.zeros((B, N, 9)), cam_t=np.zeros((B, N, 3)),
+        n_cams=np.zeros(B, np.int32), feat_len=np.zeros((B, F), np.int32), obs_uv=np.zeros((B, F, M, 2)),
+        obs_dir=np.zeros((B, F, M, 3)), obs_conf=np.zeros((B, F, M)), obs_slot=np.zeros((B, F, M), np.int32),
+        idp_base=np.zeros((B, F, 3)), idp_anchor_slot=-np.ones((B, F), np.int32), idp_m=np.zeros((B, F, 3)),
+        idp_rho=np.zeros((B, F)), lost_cnt=np.zeros((B, F), np.int32), tracked_cnt=np.zeros((B, F), np.int32))
+    for b, c in enumerate(cases):
+        n = int(c["n_cams"])
+        d = 15 + 6 * n
+        f = len(c["feat_len"])
+        m = c["obs_uv"].shape[1] if f else 0
+        assert n <= N and f <= F and m <= M and d <= ldp, (n, f, m, d)
+        h["P"][b, :d, :d] = c["P"]
+        h["imu_state"][b] = np.concatenate([np.asarray(c["imu_R"], float).flatten(), c["imu_t"], c["imu_v"],
+                                            c["imu_bg"], c["imu_ba"]])
+        h["cam_R"][b, :n] = np.asarray(c["cam_R"], float).reshape(n, 9)
+        h["cam_t"][b, :n] = c["cam_t"]
+        h["n_cams"][b] = n
+        if f:
+            h["feat_len"][b, :f] = c["feat_len"]
+            h["obs_uv"][b, :f, :m] = c["obs_uv"]
+            h["obs_dir"][b, :f, :m] = c["obs_dir"]
+            h["obs_conf"][b, :f, :m] = c["obs_conf"]
+            h["obs_slot"][b, :f, :m] = np.maximum(c["obs_slot"], 0)
+            h["idp_base"][b, :f] = c["idp_base"]
+            h["idp_anchor_slot"][b, :f] = c["idp_anchor_slot"]
+            h["idp_m"][b, :f] = c["idp_m"]
+            h["idp_rho"][b, :f] = c["idp_rho"]
+            h["lost_cnt"][b, :f] = c["lost_cnt"]
+            h["tracked_cnt"][b, :f] = c["tracked_cnt"]
+    return h

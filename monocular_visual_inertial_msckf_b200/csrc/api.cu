@@ -1,0 +1,189 @@
+// C-ABI entry points of libmsckf_b200.so (declared in include/msckf_b200.h).  Argument checking + workspace carve-up +
+// kernel launches on the caller's stream; no allocation, no synchronisation, no torch types.
+#include <atomic>
+#include "msckf_common.cuh"
+
+static std::atomic<long long> g_launches{0};
+void msckf_count_launch(int n) { g_launches += n; }
+int tsqr_max_cams();
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+WsLayout msckf_ws_layout(const msckf_dims& d, int mode) {
+    WsLayout w{};
+    const size_t BF = (size_t)d.B * d.F, ccap = 6 * (size_t)d.N;
+    size_t off = 0;
+    w.fac_A = off;    off = align256(off + BF * d.M * 12 * sizeof(double));
+    w.fac_Q = off;    off = align256(off + BF * d.M * 6 * sizeof(double));
+    w.fac_rt = off;   off = align256(off + BF * d.M * 2 * sizeof(double));
+    w.fac_rank = off; off = align256(off + BF * sizeof(int));
+    w.T_H = off;      off = align256(off + (size_t)d.B * ccap * ccap * sizeof(double));
+    w.r_n = off;      off = align256(off + (size_t)d.B * ccap * sizeof(double));
+    w.nacc = off;     off = align256(off + (size_t)d.B * sizeof(int));
+    w.nrej = off;     off = align256(off + (size_t)d.B * sizeof(int));
+    w.n_update_ctas = apply_num_ctas(d);
+    w.scratch_per_cta = align256(apply_scratch_doubles(d) * sizeof(double));
+    w.scratch = off;  off = align256(off + (size_t)w.n_update_ctas * w.scratch_per_cta);
+    w.total = off;
+    (void)mode;
+    return w;
+}
+
+static int check_dims(const msckf_dims* d) {
+    if (!d) return MSCKF_EINVAL;
+    if (d->B <= 0 || d->F < 0 || d->M <= 0 || d->N <= 0 || d->ldp < 15 + 6 * d->N) return MSCKF_EINVAL;
+    if (d->B > 65535 || d->M > MSCKF_MAX_OBS || d->N > MSCKF_MAX_CAMS) return MSCKF_ECAPACITY;
+    return 0;
+}
+
+extern "C" {
+
+int msckf_abi_version(void) { return MSCKF_B200_ABI_VERSION; }
+int msckf_max_obs_per_feature(void) { return MSCKF_MAX_OBS; }
+int msckf_max_cameras(int mode) { return mode == MSCKF_COMPRESS_QR ? tsqr_max_cams() : MSCKF_MAX_CAMS; }
+long long msckf_launch_count(void) { return g_launches.load(); }
+
+size_t msckf_update_workspace_bytes(const msckf_dims* dims, int mode) {
+    if (check_dims(dims) != 0) return 0;
+    return msckf_ws_layout(*dims, mode).total;
+}
+
+static FrontArgs make_front(const msckf_dims* dims, const msckf_update_params* params, const double* chi2_table,
+                            int chi2_len, const double* P, const double* cam_R, const double* cam_t, const int* n_cams,
+                            const int* feat_len, const double* obs_uv, const double* obs_dir, const double* obs_conf,
+                            const int* obs_slot, const double* idp_base, const int* idp_anchor_slot, double* idp_m,
+                            double* idp_rho, const int* lost_cnt, const int* tracked_cnt, unsigned char* feat_status,
+                            double* gamma, int* dof, char* ws, const WsLayout& w) {
+    FrontArgs a{};
+    a.dims = *dims; a.par = *params; a.chi2_table = chi2_table; a.chi2_len = chi2_len;
+    a.P = P; a.cam_R = cam_R; a.cam_t = cam_t; a.n_cams = n_cams; a.feat_len = feat_len;
+    a.obs_uv = obs_uv; a.obs_dir = obs_dir; a.obs_conf = obs_conf; a.obs_slot = obs_slot;
+    a.idp_base = idp_base; a.idp_anchor_slot = idp_anchor_slot; a.idp_m = idp_m; a.idp_rho = idp_rho;
+    a.lost_cnt = lost_cnt; a.tracked_cnt = tracked_cnt; a.feat_status = feat_status; a.gamma = gamma; a.dof = dof;
+    a.fac_A = (double*)(ws + w.fac_A); a.fac_Q = (double*)(ws + w.fac_Q); a.fac_rt = (double*)(ws + w.fac_rt);
+    a.fac_rank = (int*)(ws + w.fac_rank);
+    return a;
+}
+
+int msckf_front_batched(const msckf_dims* dims, const msckf_update_params* params, const double* chi2_table,
+                        int chi2_len, const double* P, const double* cam_R, const double* cam_t, const int* n_cams,
+                        const int* feat_len, const double* obs_uv, const double* obs_dir, const double* obs_conf,
+                        const int* obs_slot, const double* idp_base, const int* idp_anchor_slot, double* idp_m,
+                        double* idp_rho, const int* lost_cnt, const int* tracked_cnt, unsigned char* feat_status,
+                        double* gamma, int* dof, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!params || !chi2_table || !P || !cam_R || !cam_t || !n_cams || !feat_len || !obs_uv || !obs_dir || !obs_conf ||
+        !obs_slot || !idp_base || !idp_anchor_slot || !idp_m || !idp_rho || !lost_cnt || !tracked_cnt || !feat_status ||
+        !gamma || !dof || !workspace)
+        return MSCKF_EINVAL;
+    if (chi2_len < 2 * dims->M + 1) return MSCKF_EINVAL;
+    if (dims->F == 0) return 0;
+    const WsLayout w = msckf_ws_layout(*dims, params->compress_mode);
+    if (workspace_bytes < w.total) return MSCKF_EWORKSPACE;
+    FrontArgs a = make_front(dims, params, chi2_table, chi2_len, P, cam_R, cam_t, n_cams, feat_len, obs_uv, obs_dir,
+                             obs_conf, obs_slot, idp_base, idp_anchor_slot, idp_m, idp_rho, lost_cnt, tracked_cnt,
+                             feat_status, gamma, dof, (char*)workspace, w);
+    return (int)launch_front(a, (cudaStream_t)stream);
+}
+
+int msckf_compress_batched(const msckf_dims* dims, const msckf_update_params* params, const int* n_cams,
+                           const int* feat_len, const int* obs_slot, const unsigned char* feat_status, double* T_H,
+                           double* r_n, int* n_accepted, int* n_rejected, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!params || !n_cams || !feat_len || !obs_slot || !feat_status || !T_H || !r_n || !n_accepted || !n_rejected ||
+        !workspace)
+        return MSCKF_EINVAL;
+    if (dims->N > msckf_max_cameras(params->compress_mode)) return MSCKF_ECAPACITY;
+    const WsLayout w = msckf_ws_layout(*dims, params->compress_mode);
+    if (workspace_bytes < w.total) return MSCKF_EWORKSPACE;
+    char* ws = (char*)workspace;
+    CompressArgs c{};
+    c.dims = *dims; c.mode = params->compress_mode; c.n_cams = n_cams; c.feat_len = feat_len; c.obs_slot = obs_slot;
+    c.feat_status = feat_status; c.fac_A = (double*)(ws + w.fac_A); c.fac_Q = (double*)(ws + w.fac_Q);
+    c.fac_rt = (double*)(ws + w.fac_rt); c.T_H = T_H; c.r_n = r_n; c.n_accepted = n_accepted; c.n_rejected = n_rejected;
+    if (params->compress_mode == MSCKF_COMPRESS_QR) return (int)launch_compress_qr(c, (cudaStream_t)stream);
+    return (int)launch_compress_gram(c, (cudaStream_t)stream);
+}
+
+int msckf_apply_update_batched(const msckf_dims* dims, const msckf_update_params* params, double* P, double* imu_state,
+                               double* cam_R, double* cam_t, const int* n_cams, const double* T_H, const double* r_n,
+                               const int* n_accepted, double* delta_x, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!params || !P || !imu_state || !cam_R || !cam_t || !n_cams || !T_H || !r_n || !n_accepted || !delta_x || !workspace)
+        return MSCKF_EINVAL;
+    const WsLayout w = msckf_ws_layout(*dims, params->compress_mode);
+    if (workspace_bytes < w.total) return MSCKF_EWORKSPACE;
+    ApplyArgs a{};
+    a.dims = *dims; a.sigma = params->sigma_image; a.P = P; a.imu_state = imu_state; a.cam_R = cam_R; a.cam_t = cam_t;
+    a.n_cams = n_cams; a.T_H = T_H; a.r_n = r_n; a.n_accepted = n_accepted; a.delta_x = delta_x;
+    a.scratch = (double*)((char*)workspace + w.scratch);
+    a.scratch_per_cta = w.scratch_per_cta / sizeof(double);
+    return (int)launch_apply(a, w.n_update_ctas, (cudaStream_t)stream);
+}
+
+int msckf_update_batched(const msckf_dims* dims, const msckf_update_params* params, const double* chi2_table,
+                         int chi2_len, double* P, double* imu_state, double* cam_R, double* cam_t, const int* n_cams,
+                         const int* feat_len, const double* obs_uv, const double* obs_dir, const double* obs_conf,
+                         const int* obs_slot, const double* idp_base, const int* idp_anchor_slot, double* idp_m,
+                         double* idp_rho, const int* lost_cnt, const int* tracked_cnt, unsigned char* feat_status,
+                         double* gamma, int* dof, double* delta_x, int* n_accepted, int* n_rejected, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    int rc = msckf_front_batched(dims, params, chi2_table, chi2_len, P, cam_R, cam_t, n_cams, feat_len, obs_uv, obs_dir,
+                                 obs_conf, obs_slot, idp_base, idp_anchor_slot, idp_m, idp_rho, lost_cnt, tracked_cnt,
+                                 feat_status, gamma, dof, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    if (!imu_state || !delta_x || !n_accepted || !n_rejected) return MSCKF_EINVAL;
+    const WsLayout w = msckf_ws_layout(*dims, params->compress_mode);
+    char* ws = (char*)workspace;
+    double* T_H = (double*)(ws + w.T_H);
+    double* r_n = (double*)(ws + w.r_n);
+    rc = msckf_compress_batched(dims, params, n_cams, feat_len, obs_slot, feat_status, T_H, r_n, n_accepted, n_rejected,
+                                workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return msckf_apply_update_batched(dims, params, P, imu_state, cam_R, cam_t, n_cams, T_H, r_n, n_accepted, delta_x,
+                                      workspace, workspace_bytes, stream);
+}
+
+int msckf_propagate_batched(const msckf_dims* dims, int n_samples, const double* imu_samples, double* imu_time,
+                            const double* Qc_diag, const double* gravity_host, double* imu_state, double* imu_null,
+                            double* P, const int* n_cams, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (n_samples < 0 || !imu_samples || !imu_time || !Qc_diag || !gravity_host || !imu_state || !P || !n_cams)
+        return MSCKF_EINVAL;
+    if (n_samples == 0) return 0;
+    return (int)launch_propagate(*dims, n_samples, imu_samples, imu_time, Qc_diag, gravity_host, imu_state, imu_null, P,
+                                 n_cams, (cudaStream_t)stream);
+}
+
+int msckf_augment_batched(const msckf_dims* dims, const double* T_I_C_host, const double* imu_state, double* cam_R,
+                          double* cam_t, double* P, int* n_cams, const unsigned char* active, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!T_I_C_host || !imu_state || !cam_R || !cam_t || !P || !n_cams) return MSCKF_EINVAL;
+    if (15 + 6 * dims->N > 512) return MSCKF_ECAPACITY;
+    return (int)launch_augment(*dims, T_I_C_host, imu_state, cam_R, cam_t, P, n_cams, active, (cudaStream_t)stream);
+}
+
+size_t msckf_remove_workspace_bytes(const msckf_dims* dims) {
+    if (check_dims(dims) != 0) return 0;
+    const int ctas = dims->B < 148 * 4 ? dims->B : 148 * 4;
+    return (size_t)ctas * dims->ldp * dims->ldp * sizeof(double);
+}
+
+int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* remove_mask, double* cam_R, double* cam_t,
+                                 double* P, int* n_cams, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!remove_mask || !cam_R || !cam_t || !P || !n_cams || !workspace) return MSCKF_EINVAL;
+    if (dims->N > 128) return MSCKF_ECAPACITY;
+    if (workspace_bytes < msckf_remove_workspace_bytes(dims)) return MSCKF_EWORKSPACE;
+    return (int)launch_remove(*dims, remove_mask, cam_R, cam_t, P, n_cams, (double*)workspace, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the ctypes binding) against the golden vectors captured
+from the unmodified reference and against the NumPy oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): state and covariance within 1e-9 relative (relative to the scale of the
+quantity: max|a-b| / max|b|) in FP64; gating decisions identical away from the threshold (|gamma/chi2 - 1| > 1e-6).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import compare_update_outputs, rel_err
+from oracle import msckf_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+from monocular_visual_inertial_msckf_b200 import BatchedMSCKF, UpdateParams, _lib  # noqa: E402
+
+CHI = o.chi2_table(512)
+
+
+def _load(golden_dir, name):
+    return o.load_cases(os.path.join(golden_dir, name))
+
+
+def _batch_from_cases(cases, mode=_lib.COMPRESS_QR, pad_F=0, pad_M=0, pad_N=0):
+    F = max(len(c["feat_len"]) for c in cases) + pad_F
+    M = max(c["obs_uv"].shape[1] for c in cases) + pad_M
+    N = max(int(c["n_cams"]) for c in cases) + pad_N
+    flt = BatchedMSCKF(len(cases), F, M, N, UpdateParams.from_case(cases[0], mode))
+    flt.load_cases(cases)
+    return flt
+
+
+def _summarise(all_errs):
+    keys = sorted({k for e in all_errs for k in e})
+    return {k: max(e.get(k, 0) for e in all_errs) for k in keys}
+
+
+@pytest.mark.parametrize("name", ["small_updates.npz", "mid_48x10_updates.npz", "baseline_256x30_updates.npz"])
+def test_update_vs_golden(golden_dir, name):
+    cases, _ = _load(golden_dir, name)
+    flt = _batch_from_cases(cases)
+    flt.update()
+    torch.cuda.synchronize()
+    errs = []
+    for b, c in enumerate(cases):
+        out = flt.case_outputs(b, c)
+        errs.append(compare_update_outputs(out, c, CHI, label=f"{name}#{c['call_index']}"))
+    print(name, _summarise(errs))
+
+
+def test_front_stage_vs_golden(golden_dir):
+    """rows 3-8 alone: selection, triangulation, gamma/dof/gate per feature, state untouched."""
+    cases, _ = _load(golden_dir, "small_updates.npz")
+    flt = _batch_from_cases(cases, pad_F=3, pad_M=2, pad_N=1)
+    P0 = flt.P.clone()
+    flt.front()
+    torch.cuda.synchronize()
+    assert torch.equal(P0, flt.P)
+    n_checked = 0
+    for b, c in enumerate(cases):
+        out = flt.case_outputs(b, c)
+        v = c["out_valid"]
+        assert (out["out_valid"] == v).all() and (out["out_lost"] == c["out_lost"]).all()
+        assert (out["out_dof"][v] == c["out_dof"][v]).all()
+        assert rel_err(out["out_idp_m"], c["out_idp_m"]) < 1e-12 and rel_err(out["out_idp_rho"], c["out_idp_rho"]) < 1e-12
+        if v.any():
+            g = c["out_gamma"][v]
+            assert np.max(np.abs(out["out_gamma"][v] - g) / np.maximum(np.abs(g), 1e-3)) < 1e-7
+            n_checked += int(v.sum())
+        F = len(v)
+        assert (flt.feat_status[b, F:] == 0).all()           # padded slots are skipped
+    assert n_checked > 1000
+
+
+def test_compress_invariants_vs_oracle(golden_dir):
+    """row 9: T_H^T T_H = sum_j H_o^T H_o and T_H^T r_n = sum_j H_o^T r_o (the basis-invariant content of the QR)."""
+    cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
+    flt = _batch_from_cases(cases)
+    flt.front()
+    T_H, r_n = flt.compress()
+    torch.cuda.synchronize()
+    for b, c in enumerate(cases):
+        ref = o.update_case(c, return_intermediates=True)
+        n = int(c["n_cams"])
+        cc = 6 * n
+        acc = [i for i, j in enumerate(np.nonzero(ref["out_valid"])[0]) if ref["out_gate"][j]]
+        G = sum(ref["inter"]["HtH"][i] for i in acc)[15:, 15:]
+        g = sum(ref["inter"]["Htr"][i] for i in acc)[15:]
+        T = T_H[b, :cc, :cc].cpu().numpy()
+        rn = r_n[b, :cc].cpu().numpy()
+        assert np.allclose(np.tril(T, -1), 0.0)
+        assert rel_err(T.T @ T, G) < 1e-11
+        assert rel_err(T.T @ rn, g) < 1e-10
+        assert int(flt.n_accepted[b]) == len(acc)
+        assert (T_H[b, cc:, :] == 0).all() and (T_H[b, :, cc:] == 0).all()
+
+
+def test_update_matches_oracle_on_perturbed_inputs(golden_dir):
+    """Same seeded perturbation handed to the oracle and to the GPU (inputs the reference run never saw)."""
+    cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
+    rng = np.random.default_rng(7)
+    pert = []
+    for c in cases:
+        c = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in c.items()}
+        c["obs_uv"] = c["obs_uv"] + 0.3 * rng.standard_normal(c["obs_uv"].shape)
+        bad = rng.random(c["obs_uv"].shape[:2]) < 0.03
+        c["obs_uv"][bad] += 80.0 * rng.standard_normal((int(bad.sum()), 2))
+        c["cam_t"] = c["cam_t"] + 1e-3 * rng.standard_normal(c["cam_t"].shape)
+        ref = o.update_case(c)
+        c.update(ref)
+        c["out_n_rejected"] = ref["out_n_rejected"]
+        pert.append(c)
+    flt = _batch_from_cases(pert)
+    flt.update()
+    torch.cuda.synchronize()
+    n_rej = 0
+    for b, c in enumerate(pert):
+        compare_update_outputs(flt.case_outputs(b, c), c, CHI, label=f"perturbed#{b}")
+        n_rej += c["out_n_rejected"]
+    assert n_rej > 0
+
+
+def test_edge_cases(golden_dir):
+    cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
+    base = cases[0]
+
+    def clone():
+        return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in base.items()}
+
+    # (a) every track cut to one observation: dof 0 -> all rejected, state untouched (MSCKF.py:566-585)
+    a = clone()
+    a["feat_len"][:] = 1
+    a["lost_cnt"][:] = 5
+    a["tracked_cnt"][:] = 10
+    # (b) nothing selected: no lost tracks and parallax threshold unreachable
+    b_ = clone()
+    b_["lost_cnt"][:] = 0
+    b_["min_parallax"] = 1e9
+    # (c) lost before tracked long enough: discarded, flagged lost, no update
+    c_ = clone()
+    c_["lost_cnt"][:] = 5
+    c_["tracked_cnt"][:] = 1
+    # (d) two observations from the same pose (parallel rays, rank-deficient H_f -> larger null space)
+    d_ = clone()
+    d_["feat_len"][:] = 2
+    d_["obs_slot"][:, 1] = d_["obs_slot"][:, 0]
+    d_["obs_uv"][:, 1] = d_["obs_uv"][:, 0]
+    d_["obs_dir"][:, 1] = d_["obs_dir"][:, 0]
+    d_["lost_cnt"][:] = 5
+    d_["tracked_cnt"][:] = 10
+    # (e) empty filter (no features at all)
+    e_ = clone()
+    e_["feat_len"][:] = 0
+    batch = []
+    for c in (a, b_, c_, d_, e_):
+        # the per-case params differ (min_parallax): run them as separate single-filter batches
+        ref = o.update_case(c) if c["feat_len"].max() > 0 else None
+        flt = _batch_from_cases([c])
+        flt.update()
+        torch.cuda.synchronize()
+        out = flt.case_outputs(0, c)
+        batch.append((c, ref, out))
+    (a, ra, oa), (b_, rb, ob), (c_, rc, oc), (d_, rd, od), (e_, _, oe) = batch
+    assert oa["out_valid"].all() and not oa["out_gate"].any() and oa["out_n_rejected"] == len(a["feat_len"])
+    assert rel_err(oa["out_P"], a["P"]) == 0.0 and (oa["out_delta_x"] == 0).all()
+    assert not ob["out_valid"].any() and not ob["out_updated"] and rel_err(ob["out_P"], b_["P"]) == 0.0
+    assert not oc["out_valid"].any() and oc["out_lost"].all() and rel_err(oc["out_P"], c_["P"]) == 0.0
+    assert (od["out_dof"] == rd["out_dof"]).all() and (rd["out_dof"][rd["out_valid"]] == 2).all()
+    compare_update_outputs(od, rd, CHI, label="rank-deficient")
+    assert not oe["out_valid"].any() and not oe["out_updated"]
+
+
+@pytest.mark.parametrize("name", ["small_propagate.npz", "baseline_256x30_propagate.npz"])
+def test_propagate_vs_golden(golden_dir, name):
+    cases, _ = _load(golden_dir, name)
+    B = len(cases)
+    N = max((c["P"].shape[0] - 15) // 6 for c in cases)
+    N = max(N, 1)
+    flt = BatchedMSCKF(B, 1, 2, N, UpdateParams(gravity=np.array(cases[0]["gravity"], float)))
+    samples = torch.zeros(B, 1, 7, dtype=torch.float64, device="cuda")
+    for b, c in enumerate(cases):
+        d = c["P"].shape[0]
+        flt.P[b, :d, :d] = torch.from_numpy(c["P"])
+        flt.n_cams[b] = (d - 15) // 6
+        flt.imu_state[b] = torch.from_numpy(np.concatenate([c["imu_R"].flatten(), c["imu_t"], c["imu_v"], c["imu_bg"], c["imu_ba"]]))
+        flt.imu_null[b] = torch.from_numpy(np.concatenate([c["null_R"].flatten(), c["null_t"], c["null_v"]]))
+        flt.imu_time[b] = float(c["timestamp"])
+        flt.Qc_diag[b] = torch.from_numpy(np.asarray(c["Qc_diag"])[[0, 3, 6, 9]].copy())
+        samples[b, 0] = torch.from_numpy(np.asarray(c["sample"], float))
+    flt.propagate(samples, use_null_state=True)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for b, c in enumerate(cases):
+        d = c["P"].shape[0]
+        st = flt.imu_state[b].cpu().numpy()
+        e = max(rel_err(st[:9].reshape(3, 3), c["out_imu_R"]), rel_err(st[9:12], c["out_imu_t"]),
+                rel_err(st[12:15], c["out_imu_v"]), rel_err(flt.P[b, :d, :d].cpu().numpy(), c["out_P"]))
+        worst = max(worst, e)
+        assert e < 1e-12, (name, c["call_index"], e)
+        assert np.array_equal(flt.imu_null[b].cpu().numpy(), st[:15])      # null state <- state (MSCKF.py:247-248)
+    print(name, "worst rel err", worst)
+
+
+def test_propagate_fused_samples_match_sequential_oracle(golden_dir):
+    """n samples in one launch == n reference process_imu calls (null state aliasing included)."""
+    cases, _ = _load(golden_dir, "mid_48x10_propagate.npz")
+    c0 = cases[0]
+    d = c0["P"].shape[0]
+    n = len(cases)
+    assert all(cases[i + 1]["call_index"] == cases[i]["call_index"] + 1 for i in range(n - 1))
+    flt = BatchedMSCKF(2, 1, 2, (d - 15) // 6, UpdateParams(gravity=np.array(c0["gravity"], float)))
+    samples = torch.zeros(2, n, 7, dtype=torch.float64, device="cuda")
+    for b in range(2):
+        flt.P[b, :d, :d] = torch.from_numpy(c0["P"])
+        flt.n_cams[b] = (d - 15) // 6
+        flt.imu_state[b] = torch.from_numpy(np.concatenate([c0["imu_R"].flatten(), c0["imu_t"], c0["imu_v"], c0["imu_bg"], c0["imu_ba"]]))
+        flt.imu_null[b] = torch.from_numpy(np.concatenate([c0["null_R"].flatten(), c0["null_t"], c0["null_v"]]))
+        flt.imu_time[b] = float(c0["timestamp"])
+        flt.Qc_diag[b] = torch.from_numpy(np.asarray(c0["Qc_diag"])[[0, 3, 6, 9]].copy())
+        for i in range(n):
+            samples[b, i] = torch.from_numpy(np.asarray(cases[i]["sample"], float))
+    flt.propagate(samples, use_null_state=True)
+    torch.cuda.synchronize()
+    last = cases[-1]          # consecutive reference calls: the golden output of the last one is the chained result
+    for b in range(2):
+        st = flt.imu_state[b].cpu().numpy()
+        assert rel_err(flt.P[b, :d, :d].cpu().numpy(), last["out_P"]) < 1e-12
+        assert rel_err(st[:9].reshape(3, 3), last["out_imu_R"]) < 1e-13
+        assert rel_err(st[9:12], last["out_imu_t"]) < 1e-13 and rel_err(st[12:15], last["out_imu_v"]) < 1e-13
+
+
+def test_window_surgery_vs_oracle(golden_dir):
+    """next rows: state_augmentation and remove_cameras on device against the oracle restatement."""
+    cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
+    c = cases[0]
+    n = int(c["n_cams"])
+    flt = _batch_from_cases([c, c], pad_N=2)
+    R_I_C = np.array([[0.0, 0, 1], [-1, 0, 0], [0, -1, 0]])
+    t_I_C = np.array([0.05, -0.02, 0.01])
+    flt.augment(R_I_C, t_I_C)
+    torch.cuda.synchronize()
+    P_ref = o.augment_covariance(np.array(c["P"], float), R_I_C, t_I_C, np.array(c["imu_R"], float))
+    d1 = P_ref.shape[0]
+    assert int(flt.n_cams[0]) == n + 1
+    assert rel_err(flt.P[0, :d1, :d1].cpu().numpy(), P_ref) < 1e-13
+    Rc = np.array(c["imu_R"]) @ R_I_C
+    tc = np.array(c["imu_R"]) @ t_I_C + np.array(c["imu_t"])
+    assert rel_err(flt.cam_R[0, n].cpu().numpy().reshape(3, 3), Rc) < 1e-15
+    assert rel_err(flt.cam_t[0, n].cpu().numpy(), tc) < 1e-15
+    mask = torch.zeros(2, flt.N, dtype=torch.uint8, device="cuda")
+    mask[:, 1] = 1
+    mask[:, 4] = 1
+    flt.remove_cameras(mask)
+    torch.cuda.synchronize()
+    P2 = o.remove_camera_covariance(o.remove_camera_covariance(P_ref, 4), 1)
+    d2 = P2.shape[0]
+    assert int(flt.n_cams[1]) == n - 1
+    assert np.array_equal(flt.P[1, :d2, :d2].cpu().numpy(), flt.P[0, :d2, :d2].cpu().numpy())
+    assert rel_err(flt.P[0, :d2, :d2].cpu().numpy(), P2) < 1e-13
+    keep = [s for s in range(n + 1) if s not in (1, 4)]
+    cam_t_ref = np.concatenate([np.asarray(c["cam_t"]), tc[None]])[keep]
+    assert rel_err(flt.cam_t[0, :len(keep)].cpu().numpy(), cam_t_ref) < 1e-15
+
+
+def test_full_size_properties(golden_dir):
+    """BASELINE shape (256 features x 30 poses) replicated over a batch with per-filter pixel noise: size-independent
+    properties -- P+ symmetric, trace reduced, invariance to the order of the features, determinism."""
+    cases, _ = _load(golden_dir, "baseline_256x30_updates.npz")
+    base = cases[0]
+    rng = np.random.default_rng(11)
+    B = 24
+    batch = []
+    for b in range(B):
+        c = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in base.items()}
+        if b >= 2:
+            c["obs_uv"] = c["obs_uv"] + 0.1 * rng.standard_normal(c["obs_uv"].shape)
+        batch.append(c)
+    # filter 1 = filter 0 with its features permuted
+    perm = rng.permutation(len(base["feat_len"]))
+    for k in ("feat_len", "obs_uv", "obs_dir", "obs_conf", "obs_slot", "idp_base", "idp_anchor_slot", "idp_m", "idp_rho",
+              "lost_cnt", "tracked_cnt"):
+        batch[1][k] = batch[1][k][perm]
+    flt = _batch_from_cases(batch)
+    flt.update()
+    torch.cuda.synchronize()
+    P = flt.P.cpu().numpy()
+    d = base["P"].shape[0]
+    assert np.array_equal(P, np.transpose(P, (0, 2, 1)))                       # exactly symmetric after (P+P^T)/2
+    for b in range(B):
+        assert np.trace(P[b, :d, :d]) < np.trace(base["P"])                     # information was added
+        assert np.linalg.eigvalsh(P[b, :d, :d]).min() > -1e-12 * np.abs(P[b]).max()
+    compare_update_outputs(flt.case_outputs(0, base), base, CHI, label="baseline#0 in batch")
+    assert rel_err(P[1], P[0]) < 1e-11                                          # feature order only changes rounding
+    assert rel_err(flt.delta_x[1].cpu().numpy(), flt.delta_x[0].cpu().numpy()) < 1e-9
+    assert (flt.feat_status[1].cpu().numpy() == flt.feat_status[0].cpu().numpy()[perm]).all()
+    # determinism: a second run on identical inputs is bit-identical
+    flt2 = _batch_from_cases(batch)
+    flt2.update()
+    torch.cuda.synchronize()
+    assert torch.equal(flt2.P, flt.P) and torch.equal(flt2.delta_x, flt.delta_x)

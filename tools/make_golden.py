@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference (imported from
+/root/reference through tools/ref_shim.py) on this repo's synthetic streams.
+
+Run HERE (CPU container; the GPU box has no /root/reference):   python tools/make_golden.py [--only NAME]
+
+For every reference `get_valid_features` + `update` pair (the unit the C-ABI call msckf_update_batched replaces,
+reference src/msckf/MSCKF.py:450-456, 733-735) an "update case" is captured: the packed inputs exactly as the
+reference's objects held them on entry, and everything the call produced (validity/lost flags, re-triangulated
+inverse-depth parameters, per-feature gamma/dof/gate decision, delta_x, P+, corrected IMU state and camera poses).
+For `process_imu` (MSCKF.py:160-248) "propagate cases" hold (state, null state, P, sample) -> (state, P).
+Trajectory fixtures hold the per-frame state of a whole run.
+
+The captures are taken by wrapping bound methods on the reference instance; the reference source is not modified.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+from scipy.stats import chi2
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+from monocular_visual_inertial_msckf_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pack_update_inputs(ns, f, features):
+    """Pack the reference's objects into the SoA layout of include/msckf_b200.h (one filter)."""
+    cams = list(f.state.cameras.items())
+    cam_ids = [k for k, _ in cams]
+    N = len(cams)
+    F = len(features)
+    M = max([len(ft.keypoints) for ft in features.values()] + [1])
+    c = dict(
+        K=np.array(f.K, float), Kinv=np.linalg.inv(f.K), width=f.width, height=f.height, sigma=f.sigma_image,
+        gravity=np.array(f.state.imu.W_gravity, float), min_lost=f.min_number_of_frames_to_be_lost,
+        min_tracked=f.min_number_of_frames_to_be_tracked, use_parallax=int(f.use_parallax),
+        min_parallax=float(f.min_parallax), n_cams=N,
+        cam_R=np.stack([cam.T_W_Ci.R for _, cam in cams]).astype(float) if N else np.zeros((0, 3, 3)),
+        cam_t=np.stack([cam.T_W_Ci.t for _, cam in cams]).astype(float) if N else np.zeros((0, 3)),
+        imu_R=np.array(f.state.imu.T_W_Ii.R, float), imu_t=np.array(f.state.imu.T_W_Ii.t, float),
+        imu_v=np.array(f.state.imu.v_W_Ii, float), imu_bg=np.array(f.state.imu.gyroscope_bias, float),
+        imu_ba=np.array(f.state.imu.accelerometer_bias, float),
+        P=np.array(f.state.covariance, float),
+        feat_ids=np.array(list(features.keys()), np.int64),
+        feat_len=np.zeros(F, np.int32), obs_uv=np.zeros((F, M, 2)), obs_dir=np.zeros((F, M, 3)),
+        obs_conf=np.zeros((F, M)), obs_slot=-np.ones((F, M), np.int32),
+        idp_base=np.zeros((F, 3)), idp_anchor_slot=-np.ones(F, np.int32), idp_m=np.zeros((F, 3)),
+        idp_rho=np.zeros(F), lost_cnt=np.zeros(F, np.int32), tracked_cnt=np.zeros(F, np.int32),
+    )
+    for j, ft in enumerate(features.values()):
+        n = len(ft.keypoints)
+        c["feat_len"][j] = n
+        for i in range(n):
+            c["obs_uv"][j, i] = ft.keypoints[i]
+            c["obs_dir"][j, i] = ft.lines[i].direction
+            c["obs_conf"][j, i] = ft.lines[i].confidence
+            slot = cam_ids.index(ft.camera_indices[i])
+            c["obs_slot"][j, i] = slot
+            # Line.base is the camera's live position array (MSCKF.py:305,410)
+            assert ft.lines[i].base is f.state.cameras[ft.camera_indices[i]].T_W_Ci.t
+        idp = ft.inverse_depth_point
+        c["idp_base"][j] = idp.base
+        for s, (_, cam) in enumerate(cams):
+            if idp.base is cam.T_W_Ci.t:
+                c["idp_anchor_slot"][j] = s
+        c["idp_m"][j] = idp.m
+        c["idp_rho"][j] = idp.rho
+        c["lost_cnt"][j] = ft.lost_for_n_frames
+        c["tracked_cnt"][j] = ft.tracked_for_n_frames
+    return c
+
+
+class Capture:
+    def __init__(self, ns, f, keep_update=lambda i: True, keep_propagate=lambda i: False):
+        self.ns, self.f = ns, f
+        self.update_cases = []
+        self.propagate_cases = []
+        self.keep_update, self.keep_propagate = keep_update, keep_propagate
+        self.n_update_calls = 0
+        self.n_propagate_calls = 0
+        self._cur = None
+        self._orig_gvf = f.get_valid_features
+        self._orig_update = f.update
+        self._orig_gate = f.gating_test
+        self._orig_correct = f.correct
+        self._orig_process_imu = f.process_imu
+        f.get_valid_features = self.get_valid_features
+        f.update = self.update
+        f.gating_test = self.gating_test
+        f.correct = self.correct
+        f.process_imu = self.process_imu
+
+    # -- update path ---------------------------------------------------------------------------------------------
+    def get_valid_features(self, features):
+        f = self.f
+        idx = self.n_update_calls
+        self.n_update_calls += 1
+        keep = self.keep_update(idx)
+        if keep:
+            c = pack_update_inputs(self.ns, f, features)
+            c["call_index"] = idx
+        valid, lost = self._orig_gvf(features)
+        if keep:
+            keys = list(features.keys())
+            F = len(keys)
+            c["out_valid"] = np.array([k in valid for k in keys], bool)
+            c["out_lost"] = np.array([k in lost for k in keys], bool)
+            c["out_idp_m"] = np.stack([features[k].inverse_depth_point.m for k in keys]) if F else np.zeros((0, 3))
+            c["out_idp_rho"] = np.array([features[k].inverse_depth_point.rho for k in keys], float)
+            c["out_gamma"] = np.full(F, np.nan)
+            c["out_dof"] = np.zeros(F, np.int32)
+            c["out_gate"] = np.zeros(F, bool)
+            c["out_delta_x"] = np.zeros(f.state.covariance.shape[0])
+            c["out_updated"] = False
+            self._cur = c
+            self._valid_keys = [k for k in keys if k in valid]
+            self._gate_i = 0
+            self._keys = keys
+            self._n_rej0 = f.number_of_residuals_discarded_for_gasting_test
+            if len(valid) == 0:
+                self._finish()
+        return valid, lost
+
+    def gating_test(self, r, H):
+        ok = self._orig_gate(r, H)
+        c = self._cur
+        if c is not None:
+            f = self.f
+            S = H @ f.state.covariance @ H.T + f.sigma_image ** 2 * np.eye(H.shape[0])
+            gamma = float((r.T @ np.linalg.inv(S) @ r).flatten()[0]) if H.shape[0] > 0 else 0.0
+            j = self._keys.index(self._valid_keys[self._gate_i])
+            c["out_gamma"][j] = gamma
+            c["out_dof"][j] = r.shape[0]
+            c["out_gate"][j] = bool(ok)
+            self._gate_i += 1
+        return ok
+
+    def correct(self, K, T_H, R_n, delta_x):
+        if self._cur is not None:
+            self._cur["out_delta_x"] = np.array(delta_x, float).flatten()
+            self._cur["out_updated"] = True
+        return self._orig_correct(K, T_H, R_n, delta_x)
+
+    def update(self, features):
+        out = self._orig_update(features)
+        if self._cur is not None:
+            self._finish()
+        return out
+
+    def _finish(self):
+        f, c = self.f, self._cur
+        cams = list(f.state.cameras.values())
+        N = len(cams)
+        c["out_P"] = np.array(f.state.covariance, float)
+        c["out_cam_R"] = np.stack([cam.T_W_Ci.R for cam in cams]).astype(float) if N else np.zeros((0, 3, 3))
+        c["out_cam_t"] = np.stack([cam.T_W_Ci.t for cam in cams]).astype(float) if N else np.zeros((0, 3))
+        c["out_imu_R"] = np.array(f.state.imu.T_W_Ii.R, float)
+        c["out_imu_t"] = np.array(f.state.imu.T_W_Ii.t, float)
+        c["out_imu_v"] = np.array(f.state.imu.v_W_Ii, float)
+        c["out_imu_bg"] = np.array(f.state.imu.gyroscope_bias, float)
+        c["out_imu_ba"] = np.array(f.state.imu.accelerometer_bias, float)
+        c["out_n_rejected"] = f.number_of_residuals_discarded_for_gasting_test - self._n_rej0
+        self.update_cases.append(c)
+        self._cur = None
+
+    # -- propagation path ----------------------------------------------------------------------------------------
+    def process_imu(self, m):
+        f = self.f
+        idx = self.n_propagate_calls
+        self.n_propagate_calls += 1
+        keep = self.keep_propagate(idx)
+        if keep:
+            imu = f.state.imu
+            c = dict(call_index=idx, sample=np.concatenate([[m.timestamp], m.angular_velocity, m.linear_acceleration]),
+                     timestamp=imu.timestamp, gravity=np.array(imu.W_gravity, float),
+                     Qc_diag=np.diag(f.continuous_noise_covariance).copy(),
+                     imu_R=np.array(imu.T_W_Ii.R, float), imu_t=np.array(imu.T_W_Ii.t, float),
+                     imu_v=np.array(imu.v_W_Ii, float), imu_bg=np.array(imu.gyroscope_bias, float),
+                     imu_ba=np.array(imu.accelerometer_bias, float),
+                     null_R=np.array(imu.T_W_Ii_null.R, float), null_t=np.array(imu.T_W_Ii_null.t, float),
+                     null_v=np.array(imu.v_W_Ii_null, float), P=np.array(f.state.covariance, float))
+        out = self._orig_process_imu(m)
+        if keep:
+            imu = f.state.imu
+            c.update(out_imu_R=np.array(imu.T_W_Ii.R, float), out_imu_t=np.array(imu.T_W_Ii.t, float),
+                     out_imu_v=np.array(imu.v_W_Ii, float), out_P=np.array(f.state.covariance, float))
+            self.propagate_cases.append(c)
+        return out
+
+
+def make_params(ns, seq, **kw):
+    sa, sg, sba, sbg = synth.NOISE_LEVELS[seq.noise_level]
+    p = dict(K=seq.K, width=seq.width, height=seq.height, sigma_image=0.1, only_imu=False,
+             accelerometer_noise_density=sa, gyroscope_noise_density=sg, accelerometer_random_walk=sba,
+             gyroscope_random_walk=sbg, W_gravity=np.array([0, 0, -9.81]), number_of_extracted_features=300,
+             min_cosine_similarity=0.95, use_parallax=True, min_parallax=45, epipolar_rejection_threshold=0.005,
+             homography_rejection_threshold=5, min_number_of_frames_to_be_tracked=4,
+             min_number_of_frames_to_be_lost=2, max_number_of_camera_states=30)
+    p.update(kw)
+    return ns.MSCKFParameters(**p), p
+
+
+def run_reference(ns, seq, params, keep_update, keep_propagate, verbose=False):
+    f = ns.MSCKF(parameters=params, rr=None)
+    cap = Capture(ns, f, keep_update, keep_propagate)
+    image = np.zeros((seq.height, seq.width, 3), np.uint8)
+    frame_at = {fr.imu_index: fr for fr in seq.frames}
+    traj = []
+    t0 = time.time()
+    for i in range(len(seq.imu)):
+        row = seq.imu[i]
+        f.imu_callback(ns.IMUMeasurement(row[0], row[1:4].copy(), row[4:7].copy()))
+        fr = frame_at.get(i)
+        if fr is not None:
+            f.feature_callback(image, ns.CameraMeasurement(keypoints=fr.keypoints.copy(),
+                                                           descriptors=fr.descriptors.copy(),
+                                                           scores=fr.scores.copy()))
+            imu = f.state.imu
+            traj.append(np.concatenate([[row[0]], imu.T_W_Ii.R.flatten(), imu.T_W_Ii.t, imu.v_W_Ii,
+                                        imu.gyroscope_bias, imu.accelerometer_bias,
+                                        [len(f.state.cameras), len(f.features), f.state.covariance.shape[0],
+                                         f.number_of_residuals_discarded_for_gasting_test,
+                                         np.trace(f.state.covariance)]]))
+            if verbose:
+                print(f"  frame {len(traj):3d} cams {len(f.state.cameras):2d} feats {len(f.features):4d} "
+                      f"d {f.state.covariance.shape[0]:3d} updates {cap.n_update_calls:3d} "
+                      f"rej {f.number_of_residuals_discarded_for_gasting_test:4d} {time.time() - t0:6.1f}s",
+                      flush=True)
+    return f, cap, np.array(traj)
+
+
+def save_cases(path, cases, extra=None):
+    flat = {}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            flat[f"c{i}.{k}"] = np.asarray(v)
+    flat["n_cases"] = np.asarray(len(cases))
+    if extra:
+        flat.update(extra)
+    np.savez_compressed(path, **flat)
+    print(f"wrote {path}: {len(cases)} cases, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def seq_spec(**kw):
+    """The make_sequence kwargs are stored beside the fixture so tests can regenerate the identical stream."""
+    return {f"seq.{k}": np.asarray(v) for k, v in kw.items()}
+
+
+def fixture_small(ns):
+    """Natural-like workload: parallax/lost-driven updates, dropout, outliers, window 8; every update case kept."""
+    kw = dict(seed=42, n_frames=60, n_landmarks=40, noise_level="mid", p_drop=0.06, p_outlier=0.03, shuffle=True)
+    seq = synth.make_sequence(**kw)
+    fp = dict(min_parallax=2.0, max_number_of_camera_states=8, epipolar_rejection_threshold=1e9,
+              homography_rejection_threshold=1e9, min_number_of_frames_to_be_tracked=3)
+    params, pd = make_params(ns, seq, **fp)
+    f, cap, traj = run_reference(ns, seq, params, lambda i: True, lambda i: i < 40 or (200 <= i < 230), verbose=True)
+    extra = seq_spec(**kw)
+    extra.update({f"par.{k}": np.asarray(v) for k, v in fp.items()})
+    extra["traj"] = traj
+    save_cases(os.path.join(GOLDEN, "small_updates.npz"), cap.update_cases, extra)
+    save_cases(os.path.join(GOLDEN, "small_propagate.npz"), cap.propagate_cases, extra)
+
+
+def fixture_baseline(ns, n_landmarks=256, window=30, n_frames=36, name="baseline_256x30"):
+    """BASELINE.json configs[1] shape: every track updated every frame (min_parallax = 0), F = 256, M -> window."""
+    kw = dict(seed=42, n_frames=n_frames, n_landmarks=n_landmarks, noise_level="mid", p_outlier=0.02)
+    seq = synth.make_sequence(**kw)
+    fp = dict(min_parallax=0.0, max_number_of_camera_states=window, epipolar_rejection_threshold=1e9,
+              homography_rejection_threshold=1e9, min_number_of_frames_to_be_tracked=2)
+    params, pd = make_params(ns, seq, **fp)
+    # steady state: keep the last three update calls (d alternates 195 / 201) and 9 consecutive propagations
+    f, cap, traj = run_reference(ns, seq, params, lambda i: i >= KEEP_FROM[0], lambda i: i >= KEEP_FROM[1],
+                                 verbose=True)
+    extra = seq_spec(**kw)
+    extra.update({f"par.{k}": np.asarray(v) for k, v in fp.items()})
+    extra["traj"] = traj
+    save_cases(os.path.join(GOLDEN, f"{name}_updates.npz"), cap.update_cases[-3:], extra)
+    save_cases(os.path.join(GOLDEN, f"{name}_propagate.npz"), cap.propagate_cases[-9:][:3 if n_landmarks > 100 else 9], extra)
+
+
+KEEP_FROM = [0, 0]
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    ns = ref_shim.load_reference()
+    np.random.seed(42)
+    if args.only in (None, "small"):
+        fixture_small(ns)
+    if args.only in (None, "mid"):
+        # mid-size steady-state fixture (cheap to regenerate): F = 48, window 10
+        KEEP_FROM[:] = [18, 14 * 9]
+        fixture_baseline(ns, n_landmarks=48, window=10, n_frames=18, name="mid_48x10")
+    if args.only in (None, "baseline"):
+        KEEP_FROM[:] = [30, 34 * 9]
+        fixture_baseline(ns, n_landmarks=256, window=30, n_frames=38, name="baseline_256x30")
