@@ -1,0 +1,503 @@
+#!/usr/bin/env python
+"""Benchmark of the batched MSCKF filter-step (BASELINE.json metric: feature-updates/s and filter-steps/s, % roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--filters B] [--mode qr|gram] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[3] shape per GPU -- 4096 concurrent filters x 256 features x 30-pose
+window (d = 195), FP64, 9 IMU samples per camera frame.  Every filter starts from a steady-state snapshot (the window is
+full) taken from a real filter run at that shape (tests/golden/baseline_256x30_updates.npz: P, window poses and tracks as the
+reference held them), replicated over the batch with per-filter pixel noise and IMU-noise level (index mod 3).
+One step = one filter-step of every filter: restore the snapshot state (device copies, inside the timed region),
+9 fused IMU propagations, one update (selection, triangulation, Jacobians, nullspace, gating, compression, Joseph update,
+state correction).  Multi-GPU: filters are independent, each rank owns its own 4096 (weak scaling), no data-path
+collective; a final gather of the per-filter positions happens outside the timed region.
+
+`--impl reference` times the CPU path (the NumPy oracle, a line-by-line port of the reference's update; the reference
+itself is Python and is not present on the GPU box) on all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FIXTURE = os.path.join(ROOT, "tests", "golden", "baseline_256x30_updates.npz")
+N_IMU = 9
+FRAME_DT = 0.05
+NOISE = [(1e-3, 1e-4, 1e-4, 1e-5), (5e-3, 5e-4, 5e-4, 5e-5), (1e-2, 1e-3, 1e-3, 1e-4)]   # (sa, sg, sba, sbg) low/mid/high
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------------------
+def load_base_case():
+    z = np.load(FIXTURE)
+    n = int(z["n_cases"])
+    best = None
+    for i in range(n):
+        c = {k[len(f"c{i}."):]: (z[k].item() if z[k].ndim == 0 else z[k]) for k in z.files if k.startswith(f"c{i}.")}
+        if int(c["n_cams"]) == 30:
+            best = c
+    assert best is not None, "fixture holds no 30-pose case"
+    return best
+
+
+def filter_inputs(base, index):
+    """Per-filter variation of the snapshot: pixel noise on every observation + its IMU-noise level and samples."""
+    rng = np.random.default_rng(42 + index)
+    uv = base["obs_uv"] + 0.1 * rng.standard_normal(base["obs_uv"].shape)
+    sa, sg, sba, sbg = NOISE[index % 3]
+    dt = FRAME_DT / N_IMU
+    R = np.asarray(base["imu_R"], float)
+    t0 = 1.0
+    samples = np.zeros((N_IMU, 7))
+    samples[:, 0] = t0 + dt * np.arange(1, N_IMU + 1)
+    samples[:, 1:4] = 0.05 * np.sin(np.arange(N_IMU)[:, None] * 0.3 + np.arange(3)) + sg * rng.standard_normal((N_IMU, 3))
+    samples[:, 4:7] = (R.T @ np.array([0.0, 0.0, -9.81]))[None, :] + 0.2 * np.cos(np.arange(N_IMU)[:, None] * 0.2 + np.arange(3)) \
+        + sa * rng.standard_normal((N_IMU, 3))
+    qc = np.array([sg ** 2, sbg ** 2, sa ** 2, sba ** 2])
+    return uv, samples, qc, t0
+
+
+def algorithmic_bytes_per_filter_step(F, M, N, n):
+    """F (52 M + 104) + 2 d^2 8 + 2 (96 N + 168) + 2 15 d 8 + 56 n."""
+    d = 15 + 6 * N
+    return F * (52 * M + 104) + 2 * d * d * 8 + 2 * (96 * N + 168) + 2 * 15 * d * 8 + 56 * n
+
+
+def algorithmic_qr_flops_per_filter(rows, N):
+    """explicit QR of the stacked rows, 2 m c^2 - 2/3 c^3."""
+    c = 6 * N
+    return 2.0 * rows * c * c - (2.0 / 3.0) * c ** 3
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port on the host cores)
+# ----------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    index, n_steps = args
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    from oracle import msckf_oracle as o
+    base = load_base_case()
+    uv, samples, qc, t0 = filter_inputs(base, index)
+    c = dict(base)
+    c["obs_uv"] = uv
+    t_start = time.perf_counter()
+    nfeat = 0
+    for _ in range(n_steps):
+        st = dict(imu_R=c["imu_R"], imu_t=c["imu_t"], imu_v=c["imu_v"], imu_bg=c["imu_bg"], imu_ba=c["imu_ba"],
+                  null_R=c["imu_R"], null_t=c["imu_t"], null_v=c["imu_v"], P=c["P"], timestamp=t0,
+                  gravity=c["gravity"], Qc_diag=np.repeat(qc, 3))
+        for k in range(N_IMU):
+            st["sample"] = samples[k]
+            out = o.propagate_case(st)
+            st.update(imu_R=out["out_imu_R"], imu_t=out["out_imu_t"], imu_v=out["out_imu_v"], P=out["out_P"],
+                      null_R=out["out_imu_R"], null_t=out["out_imu_t"], null_v=out["out_imu_v"],
+                      timestamp=out["out_timestamp"])
+        cc = dict(c)
+        cc.update(P=st["P"], imu_R=st["imu_R"], imu_t=st["imu_t"], imu_v=st["imu_v"])
+        o.update_case(cc)
+        nfeat += len(c["feat_len"])
+    return time.perf_counter() - t_start, nfeat
+
+
+def run_cpu(n_workers, steps_per_worker):
+    """Each of n_workers processes (1 BLAS thread each) runs `steps_per_worker` filter-steps of its own filter."""
+    import multiprocessing as mp
+    for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(n_workers) as pool:
+        res = pool.map(_cpu_worker, [(i, steps_per_worker) for i in range(n_workers)])
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)          # exclude interpreter start-up / imports: the slowest worker's compute time
+    feats = sum(r[1] for r in res)
+    return dict(feature_updates_per_s=feats / busy, filter_steps_per_s=n_workers * steps_per_worker / busy,
+                wall_s=wall, busy_s=busy)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [ln.strip().split(", ") for ln in open(self.path) if ln.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for i, nme in enumerate(names):
+                    if any(len(r) >= 9 and r[5 + i].strip().lower() == "active" for r in rows):
+                        out["reasons"].append(nme)
+                out["samples"] = len(sm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from monocular_visual_inertial_msckf_b200 import BatchedMSCKF, UpdateParams, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    base = load_base_case()
+    B = args.filters
+    F = len(base["feat_len"])
+    M = base["obs_uv"].shape[1]
+    N = int(base["n_cams"])
+    mode = _lib.COMPRESS_QR if args.mode == "qr" else _lib.COMPRESS_GRAM
+    par = UpdateParams.from_case(base, mode)
+    flt = BatchedMSCKF(B, F, M, N, par, device=dev)
+
+    # ---- host-side inputs (pinned): what a caller hands over every step ----
+    t0h = time.time()
+    h_uv = torch.empty((B, F, M, 2), dtype=torch.float64).pin_memory()
+    h_samples = torch.empty((B, N_IMU, 7), dtype=torch.float64).pin_memory()
+    h_qc = torch.empty((B, 4), dtype=torch.float64)
+    uvn, smn, qcn = h_uv.numpy(), h_samples.numpy(), h_qc.numpy()
+    t_start = 1.0
+    for b in range(B):
+        uvn[b], smn[b], qcn[b], t_start = filter_inputs(base, rank * B + b)
+
+    def rep(x, dtype):
+        x = np.asarray(x)
+        return torch.from_numpy(np.broadcast_to(x, (B,) + x.shape).astype(dtype).copy()).pin_memory()
+
+    h_dir = rep(base["obs_dir"], np.float64)
+    h_conf = rep(base["obs_conf"], np.float64)
+    h_slot = rep(np.maximum(base["obs_slot"], 0), np.int32)
+    h_len = rep(base["feat_len"], np.int32)
+    h_lost = rep(base["lost_cnt"], np.int32)
+    h_trk = rep(base["tracked_cnt"], np.int32)
+    h_anchor = rep(base["idp_anchor_slot"], np.int32)
+    h_base = rep(base["idp_base"], np.float64)
+    h_m = rep(base["idp_m"], np.float64)
+    h_rho = rep(base["idp_rho"], np.float64)
+    step_inputs = [(flt.obs_uv, h_uv), (flt.obs_dir, h_dir), (flt.obs_conf, h_conf), (flt.obs_slot, h_slot),
+                   (flt.feat_len, h_len), (flt.lost_cnt, h_lost), (flt.tracked_cnt, h_trk),
+                   (flt.idp_anchor_slot, h_anchor), (flt.idp_base, h_base), (flt.idp_m, h_m), (flt.idp_rho, h_rho)]
+    h2d_bytes = sum(h.numel() * h.element_size() for _, h in step_inputs) + h_samples.numel() * 8
+    samples_dev = torch.empty((B, N_IMU, 7), dtype=torch.float64, device=dev)
+
+    # ---- resident snapshot state (restored at the start of every step) ----
+    d = 15 + 6 * N
+    P0 = torch.zeros_like(flt.P)
+    P0[:, :d, :d] = torch.from_numpy(np.asarray(base["P"], float)).to(dev)
+    imu0 = torch.from_numpy(np.concatenate([np.asarray(base["imu_R"], float).flatten(), base["imu_t"], base["imu_v"],
+                                            base["imu_bg"], base["imu_ba"]])).to(dev).repeat(B, 1)
+    camR0 = torch.from_numpy(np.asarray(base["cam_R"], float).reshape(N, 9)).to(dev).repeat(B, 1, 1)
+    camt0 = torch.from_numpy(np.asarray(base["cam_t"], float)).to(dev).repeat(B, 1, 1)
+    m0 = h_m.to(dev)
+    rho0 = h_rho.to(dev)
+    time0 = torch.full((B,), t_start, dtype=torch.float64, device=dev)
+    flt.n_cams.fill_(N)
+    flt.Qc_diag.copy_(h_qc)
+    for dst, src in step_inputs:
+        dst.copy_(src)
+    samples_dev.copy_(h_samples)
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0h
+
+    def restore():
+        flt.P.copy_(P0)
+        flt.imu_state.copy_(imu0)
+        flt.cam_R.copy_(camR0)
+        flt.cam_t.copy_(camt0)
+        flt.idp_m.copy_(m0)
+        flt.idp_rho.copy_(rho0)
+        flt.imu_time.copy_(time0)
+
+    def step_resident():
+        restore()
+        flt.propagate(samples_dev)
+        flt.update()
+
+    h_out_state = torch.empty((B, 21), dtype=torch.float64).pin_memory()
+    h_out_camt = torch.empty((B, N, 3), dtype=torch.float64).pin_memory()
+    h_out_status = torch.empty((B, F), dtype=torch.uint8).pin_memory()
+    h_out_nacc = torch.empty((B,), dtype=torch.int32).pin_memory()
+    d2h_bytes = sum(t.numel() * t.element_size() for t in (h_out_state, h_out_camt, h_out_status, h_out_nacc))
+
+    def step_e2e():
+        # the caller's host buffers -> device, the step, the result back to the host
+        for dst, src in step_inputs:
+            dst.copy_(src, non_blocking=True)
+        samples_dev.copy_(h_samples, non_blocking=True)
+        flt.P.copy_(P0)
+        flt.imu_state.copy_(imu0)
+        flt.cam_R.copy_(camR0)
+        flt.cam_t.copy_(camt0)
+        flt.imu_time.copy_(time0)
+        flt.propagate(samples_dev)
+        flt.update()
+        h_out_state.copy_(flt.imu_state, non_blocking=True)
+        h_out_camt.copy_(flt.cam_t, non_blocking=True)
+        h_out_status.copy_(flt.feat_status, non_blocking=True)
+        h_out_nacc.copy_(flt.n_accepted, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up, then the timed K steps ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = flt.lib.msckf_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = flt.lib.msckf_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    n_acc = int(flt.n_accepted.sum().item())
+    n_rej = int(flt.n_rejected.sum().item())
+    rows = 2 * int((flt.feat_len * ((flt.feat_status & 0xF) == 1)).sum().item())
+
+    # ---- per-kernel durations (CUDA events on the launching stream), one extra pass outside the timed region ----
+    def time_stage(fn, reps=3):
+        best = 1e30
+        for _ in range(reps):
+            restore()
+            flt.propagate(samples_dev)
+            prep()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    stage_ms = {}
+    prep = lambda: None  # noqa: E731
+    stage_ms["front"] = time_stage(flt.front)
+    prep = flt.front
+    stage_ms["compress"] = time_stage(flt.compress)
+    prep = lambda: (flt.front(), flt.compress())  # noqa: E731
+    stage_ms["apply"] = time_stage(flt.apply_update)
+    prep = lambda: None  # noqa: E731
+
+    def only_prop():
+        flt.propagate(samples_dev)
+    restore()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    only_prop()
+    e1.record()
+    torch.cuda.synchronize()
+    stage_ms["propagate"] = e0.elapsed_time(e1)
+
+    # ---- FP64 pipe peak (measured here: MEASURED_PEAKS.json has no FP64 figure) ----
+    import ctypes as C
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    flops = C.c_double(0)
+    fp64_peak = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        flt.lib.msckf_probe_fp64(148 * 8, 40000, C.c_void_p(sink.data_ptr()), C.byref(flops),
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        e1.record()
+        torch.cuda.synchronize()
+        fp64_peak = max(fp64_peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+
+    # ---- end to end: host buffers in, results out, copies inside the timed region ----
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e = timed(step_e2e, e2e_steps)
+
+    if world > 1:
+        # final gather of per-filter results (positions), outside the timed region
+        gathered = [torch.empty_like(flt.imu_state) for _ in range(world)] if rank == 0 else None
+        dist.gather(flt.imu_state, gathered, dst=0)
+        tot = torch.tensor([n_acc, n_rej, rows], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        n_acc, n_rej, rows = [int(x) for x in tot.tolist()]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    sec = ms_total * 1e-3
+    Btot = B * world
+    feats_per_step = Btot * F
+    value = feats_per_step * args.steps / sec
+    fsteps = Btot * args.steps / sec
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    step_bytes = algorithmic_bytes_per_filter_step(F, M, N, N_IMU) * B
+    rows_per_rank = rows / world
+    if args.mode == "qr":
+        dom_name, dom_ms = "tsqr_kernel", stage_ms["compress"]
+        dom_flops = algorithmic_qr_flops_per_filter(rows_per_rank / B, N) * B
+    else:
+        dom_name, dom_ms = "apply_kernel", stage_ms["apply"]
+        dom_flops = 8.0 * (15 + 6 * N) ** 3 * B
+    achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom_name)
+    except Exception:
+        pass
+    roofline = dict(bound="tensor", pipe="fp64 (DFMA/DMMA share one nominal peak on B200; tcgen05 has no f64 kind)",
+                    kernel=dom_name, achieved=achieved_tf, peak=fp64_peak, unit="TFLOP/s",
+                    frac=achieved_tf / fp64_peak if fp64_peak else None, traffic=traffic,
+                    peak_source="measured in this run by msckf_probe_fp64 (8 independent DFMA chains per thread)",
+                    kernel_ms=dom_ms, flops_per_launch=dom_flops, stage_ms=stage_ms,
+                    step_hbm=dict(bound="hbm", achieved=step_bytes / (sec / args.steps) / 1e9, peak=hbm_peak, unit="GB/s",
+                                  frac=step_bytes / (sec / args.steps) / 1e9 / hbm_peak, peak_source=hbm_src,
+                                  bytes_per_filter_step=algorithmic_bytes_per_filter_step(F, M, N, N_IMU)))
+
+    ncpu = os.cpu_count() or 1
+    cpu = dict(value=None)
+    if not args.no_cpu:
+        nw = min(ncpu, 64)
+        r = run_cpu(nw, 1)
+        cpu = dict(value=r["feature_updates_per_s"], unit="feature-updates/s", cores=nw, kind="port",
+                   filter_steps_per_s=r["filter_steps_per_s"],
+                   sample=f"{nw} filters x 1 filter-step (9 propagations + 256-feature update) of the same workload, "
+                          f"one single-threaded process per core, slowest worker {r['busy_s']:.1f} s")
+
+    e2e_sec = ms_e2e * 1e-3
+    line = dict(
+        metric="msckf_feature_updates_per_s", value=value, unit="feature-updates/s", n_gpus=world, steps=args.steps,
+        warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f64", data="synthetic",
+        filter_steps_per_s=fsteps,
+        config=dict(workload=f"BASELINE.json configs[3] shape: {B} filters/GPU x {F} features x {N}-pose window "
+                             f"(d={15 + 6 * N}), {N_IMU} IMU samples/frame, FP64; steady-state snapshot replicated with "
+                             f"per-filter pixel noise", filters_per_gpu=B, features=F, obs_per_feature=M, window=N,
+                    compress=args.mode, l2="inputs larger than L2 (%.1f GB touched per step)" % (
+                        (step_bytes + 2 * flt.P.numel() * 8) / 1e9),
+                    accepted_features=n_acc, gated_out=n_rej),
+        roofline=roofline, cpu_baseline=cpu,
+        e2e=dict(value=feats_per_step * e2e_steps / e2e_sec, unit="feature-updates/s", h2d_bytes_per_step=h2d_bytes * world,
+                 d2h_bytes_per_step=d2h_bytes * world, ms_per_step=ms_e2e / e2e_steps, steps=e2e_steps,
+                 filter_steps_per_s=Btot * e2e_steps / e2e_sec),
+        gpu_launches=int(launches), clocks=clocks, setup_s=setup_s)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncpu = os.cpu_count() or 1
+    nw = min(ncpu, 64)
+    for _ in range(0):
+        pass
+    t0 = time.perf_counter()
+    steps = max(1, min(args.steps, 3))
+    run_cpu(min(nw, 4), 1)                        # warm-up: imports, page cache
+    r = run_cpu(nw, steps)
+    base = load_base_case()
+    F, M, N = len(base["feat_len"]), base["obs_uv"].shape[1], int(base["n_cams"])
+    sample = (f"{nw} filters x {steps} filter-step(s) each (9 propagations + 256-feature update), one single-threaded "
+              f"process per core; NumPy port of the reference update (the Python reference is not on the GPU box)")
+    line = dict(impl="reference", metric="msckf_feature_updates_per_s", value=r["feature_updates_per_s"],
+                unit="feature-updates/s", n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=steps, warmup=1,
+                ms_per_step=r["busy_s"] * 1e3 / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", filter_steps_per_s=r["filter_steps_per_s"],
+                config=dict(workload=f"bounded sample of BASELINE.json configs[3] shape: {F} features x {N}-pose window, "
+                                     f"{N_IMU} IMU samples/frame, FP64", features=F, obs_per_feature=M, window=N),
+                cpu_baseline=dict(value=r["feature_updates_per_s"], unit="feature-updates/s", cores=nw, kind="port",
+                                  sample=sample),
+                e2e=dict(value=r["feature_updates_per_s"], unit="feature-updates/s", h2d_bytes_per_step=0,
+                         d2h_bytes_per_step=0),
+                gpu_launches=0, wall_s=time.perf_counter() - t0)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--filters", type=int, default=4096, help="filters per GPU")
+    ap.add_argument("--mode", default="qr", choices=["qr", "gram"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)

@@ -118,9 +118,8 @@ int msckf_update_batched(const msckf_dims* dims, const msckf_update_params* para
  *
  * msckf_front_batched      <-> get_valid_features + compute_residual_and_jacobians (MSCKF.py:497-552)
  *                              + project_on_nullspace (554-559) + gating_test (561-568), per feature.
- *   Also leaves the per-feature factors (A blocks, range basis Q1 of H_f, residual) in the workspace for the
- *   compression stage, and can export basis-invariant per-feature quantities for tests:
- *   HtH_diag[B][F][M][36] = A_i^T A_i, and W[B][F][3][6 M] = Q1^T H_x by observation (any may be NULL).
+ *   Also leaves the per-feature factors (A blocks, range basis Q1 of H_f, projected residual) in the workspace for
+ *   the compression stage.
  * msckf_compress_batched   <-> the vstack + np.linalg.qr block of update (MSCKF.py:587-602):
  *   T_H[B][6N][6N] (upper triangular over the camera columns; the 15 IMU columns of H are identically zero) and
  *   r_n[B][6N].  Must follow msckf_front_batched on the same workspace.
@@ -175,6 +174,10 @@ size_t msckf_remove_workspace_bytes(const msckf_dims* dims);
 int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* remove_mask,
                                  double* cam_R, double* cam_t, double* P, int* n_cams,
                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Diagnostic: launches n_ctas x 256 threads of 8 independent FP64 FMA chains of length iters (the measured FP64-pipe
+ * roofline denominator; MEASURED_PEAKS.json has no FP64 figure).  *flops_out_host receives the FLOP count. */
+int msckf_probe_fp64(int n_ctas, int iters, double* sink, double* flops_out_host, void* stream);
 
 /* Number of kernels launched by this library since load (the benchmark reports it as gpu_launches). */
 long long msckf_launch_count(void);

@@ -31,7 +31,7 @@ EXPORTS = [
     "msckf_abi_version", "msckf_max_obs_per_feature", "msckf_max_cameras", "msckf_update_workspace_bytes",
     "msckf_update_batched", "msckf_front_batched", "msckf_compress_batched", "msckf_apply_update_batched",
     "msckf_propagate_batched", "msckf_augment_batched", "msckf_remove_workspace_bytes",
-    "msckf_remove_cameras_batched", "msckf_launch_count",
+    "msckf_remove_cameras_batched", "msckf_launch_count", "msckf_probe_fp64",
 ]
 
 
@@ -78,6 +78,8 @@ def load_library():
     lib.msckf_augment_batched.argtypes = [pd, C.POINTER(C.c_double), dp, dp, dp, dp, ip, u8, vp]
     lib.msckf_remove_cameras_batched.restype = C.c_int
     lib.msckf_remove_cameras_batched.argtypes = [pd, u8, dp, dp, dp, ip, vp, C.c_size_t, vp]
+    lib.msckf_probe_fp64.restype = C.c_int
+    lib.msckf_probe_fp64.argtypes = [C.c_int, C.c_int, dp, C.POINTER(C.c_double), vp]
     if lib.msckf_abi_version() != 1:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib

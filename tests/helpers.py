@@ -24,7 +24,7 @@ def compare_update_outputs(out, ref, chi2_table, tol_state=1e-9, tol_gamma=1e-6,
     assert (out["out_dof"][v] == ref["out_dof"][v]).all(), f"{label}: dof differs"
     errs["idp_m"] = rel_err(out["out_idp_m"], ref["out_idp_m"])
     errs["idp_rho"] = rel_err(out["out_idp_rho"], ref["out_idp_rho"])
-    assert errs["idp_m"] < 1e-11 and errs["idp_rho"] < 1e-11, f"{label}: triangulation {errs}"
+    assert errs["idp_m"] < tol_state and errs["idp_rho"] < tol_state, f"{label}: triangulation {errs}"
     if v.any():
         g_ref = ref["out_gamma"][v]
         g_out = out["out_gamma"][v]

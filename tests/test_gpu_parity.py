@@ -65,7 +65,7 @@ def test_front_stage_vs_golden(golden_dir):
         v = c["out_valid"]
         assert (out["out_valid"] == v).all() and (out["out_lost"] == c["out_lost"]).all()
         assert (out["out_dof"][v] == c["out_dof"][v]).all()
-        assert rel_err(out["out_idp_m"], c["out_idp_m"]) < 1e-12 and rel_err(out["out_idp_rho"], c["out_idp_rho"]) < 1e-12
+        assert rel_err(out["out_idp_m"], c["out_idp_m"]) < 1e-9 and rel_err(out["out_idp_rho"], c["out_idp_rho"]) < 1e-9
         if v.any():
             g = c["out_gamma"][v]
             assert np.max(np.abs(out["out_gamma"][v] - g) / np.maximum(np.abs(g), 1e-3)) < 1e-7
@@ -143,11 +143,13 @@ def test_edge_cases(golden_dir):
     c_ = clone()
     c_["lost_cnt"][:] = 5
     c_["tracked_cnt"][:] = 1
-    # (d) two observations from the same pose (parallel rays, rank-deficient H_f -> larger null space)
+    # (d) zero baseline: every window pose identical and two identical rays per track (parallel rays, rank-deficient
+    #     H_f -> the null space grows to 2M - 2, SURVEY.md section 8a edge cases)
     d_ = clone()
     d_["feat_len"][:] = 2
-    d_["obs_slot"][:, 1] = d_["obs_slot"][:, 0]
-    d_["obs_uv"][:, 1] = d_["obs_uv"][:, 0]
+    d_["cam_R"][:] = d_["cam_R"][0]
+    d_["cam_t"][:] = d_["cam_t"][0]
+    d_["obs_uv"][:, 1] = d_["obs_uv"][:, 0] + np.array([1.5, -0.7])
     d_["obs_dir"][:, 1] = d_["obs_dir"][:, 0]
     d_["lost_cnt"][:] = 5
     d_["tracked_cnt"][:] = 10
