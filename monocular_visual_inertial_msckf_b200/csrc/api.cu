@@ -6,6 +6,9 @@
 static std::atomic<long long> g_launches{0};
 void msckf_count_launch(int n) { g_launches += n; }
 int tsqr_max_cams();
+bool gram_supported(const msckf_dims& d);
+size_t info_scratch_doubles(const msckf_dims& d);
+cudaError_t launch_update_info(const ApplyArgs& a, int n_ctas, cudaStream_t s);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -22,7 +25,8 @@ WsLayout msckf_ws_layout(const msckf_dims& d, int mode) {
     w.nacc = off;     off = align256(off + (size_t)d.B * sizeof(int));
     w.nrej = off;     off = align256(off + (size_t)d.B * sizeof(int));
     w.n_update_ctas = apply_num_ctas(d);
-    w.scratch_per_cta = align256(apply_scratch_doubles(d) * sizeof(double));
+    const size_t sd = apply_scratch_doubles(d) > info_scratch_doubles(d) ? apply_scratch_doubles(d) : info_scratch_doubles(d);
+    w.scratch_per_cta = align256(sd * sizeof(double));
     w.scratch = off;  off = align256(off + (size_t)w.n_update_ctas * w.scratch_per_cta);
     w.total = off;
     (void)mode;
@@ -97,6 +101,7 @@ int msckf_compress_batched(const msckf_dims* dims, const msckf_update_params* pa
         !workspace)
         return MSCKF_EINVAL;
     if (dims->N > msckf_max_cameras(params->compress_mode)) return MSCKF_ECAPACITY;
+    if (params->compress_mode != MSCKF_COMPRESS_QR && !gram_supported(*dims)) return MSCKF_ECAPACITY;
     const WsLayout w = msckf_ws_layout(*dims, params->compress_mode);
     if (workspace_bytes < w.total) return MSCKF_EWORKSPACE;
     char* ws = (char*)workspace;
@@ -123,7 +128,8 @@ int msckf_apply_update_batched(const msckf_dims* dims, const msckf_update_params
     a.n_cams = n_cams; a.T_H = T_H; a.r_n = r_n; a.n_accepted = n_accepted; a.delta_x = delta_x;
     a.scratch = (double*)((char*)workspace + w.scratch);
     a.scratch_per_cta = w.scratch_per_cta / sizeof(double);
-    return (int)launch_apply(a, w.n_update_ctas, (cudaStream_t)stream);
+    if (params->compress_mode == MSCKF_COMPRESS_QR) return (int)launch_apply(a, w.n_update_ctas, (cudaStream_t)stream);
+    return (int)launch_update_info(a, w.n_update_ctas, (cudaStream_t)stream);
 }
 
 int msckf_update_batched(const msckf_dims* dims, const msckf_update_params* params, const double* chi2_table,

@@ -38,17 +38,21 @@ def _summarise(all_errs):
     return {k: max(e.get(k, 0) for e in all_errs) for k in keys}
 
 
+MODES = [pytest.param(_lib.COMPRESS_QR, id="qr"), pytest.param(_lib.COMPRESS_GRAM, id="gram")]
+
+
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["small_updates.npz", "mid_48x10_updates.npz", "baseline_256x30_updates.npz"])
-def test_update_vs_golden(golden_dir, name):
+def test_update_vs_golden(golden_dir, name, mode):
     cases, _ = _load(golden_dir, name)
-    flt = _batch_from_cases(cases)
+    flt = _batch_from_cases(cases, mode)
     flt.update()
     torch.cuda.synchronize()
     errs = []
     for b, c in enumerate(cases):
         out = flt.case_outputs(b, c)
         errs.append(compare_update_outputs(out, c, CHI, label=f"{name}#{c['call_index']}"))
-    print(name, _summarise(errs))
+    print(name, "gram" if mode else "qr", _summarise(errs))
 
 
 def test_front_stage_vs_golden(golden_dir):
@@ -75,10 +79,12 @@ def test_front_stage_vs_golden(golden_dir):
     assert n_checked > 1000
 
 
-def test_compress_invariants_vs_oracle(golden_dir):
-    """row 9: T_H^T T_H = sum_j H_o^T H_o and T_H^T r_n = sum_j H_o^T r_o (the basis-invariant content of the QR)."""
+@pytest.mark.parametrize("mode", MODES)
+def test_compress_invariants_vs_oracle(golden_dir, mode):
+    """row 9: T_H^T T_H = sum_j H_o^T H_o and T_H^T r_n = sum_j H_o^T r_o (the basis-invariant content of the QR);
+    in information form the compression stage returns exactly those two sums (G, g)."""
     cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
-    flt = _batch_from_cases(cases)
+    flt = _batch_from_cases(cases, mode, pad_N=1 if mode else 0)
     flt.front()
     T_H, r_n = flt.compress()
     torch.cuda.synchronize()
@@ -91,14 +97,20 @@ def test_compress_invariants_vs_oracle(golden_dir):
         g = sum(ref["inter"]["Htr"][i] for i in acc)[15:]
         T = T_H[b, :cc, :cc].cpu().numpy()
         rn = r_n[b, :cc].cpu().numpy()
-        assert np.allclose(np.tril(T, -1), 0.0)
-        assert rel_err(T.T @ T, G) < 1e-11
-        assert rel_err(T.T @ rn, g) < 1e-10
+        if mode == _lib.COMPRESS_QR:
+            assert np.allclose(np.tril(T, -1), 0.0)
+            assert rel_err(T.T @ T, G) < 1e-11
+            assert rel_err(T.T @ rn, g) < 1e-10
+        else:
+            assert np.array_equal(T, T.T)
+            assert rel_err(T, G) < 1e-12
+            assert rel_err(rn, g) < 1e-11
         assert int(flt.n_accepted[b]) == len(acc)
         assert (T_H[b, cc:, :] == 0).all() and (T_H[b, :, cc:] == 0).all()
 
 
-def test_update_matches_oracle_on_perturbed_inputs(golden_dir):
+@pytest.mark.parametrize("mode", MODES)
+def test_update_matches_oracle_on_perturbed_inputs(golden_dir, mode):
     """Same seeded perturbation handed to the oracle and to the GPU (inputs the reference run never saw)."""
     cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
     rng = np.random.default_rng(7)
@@ -113,7 +125,7 @@ def test_update_matches_oracle_on_perturbed_inputs(golden_dir):
         c.update(ref)
         c["out_n_rejected"] = ref["out_n_rejected"]
         pert.append(c)
-    flt = _batch_from_cases(pert)
+    flt = _batch_from_cases(pert, mode)
     flt.update()
     torch.cuda.synchronize()
     n_rej = 0
@@ -123,7 +135,8 @@ def test_update_matches_oracle_on_perturbed_inputs(golden_dir):
     assert n_rej > 0
 
 
-def test_edge_cases(golden_dir):
+@pytest.mark.parametrize("mode", MODES)
+def test_edge_cases(golden_dir, mode):
     cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
     base = cases[0]
 
@@ -160,7 +173,7 @@ def test_edge_cases(golden_dir):
     for c in (a, b_, c_, d_, e_):
         # the per-case params differ (min_parallax): run them as separate single-filter batches
         ref = o.update_case(c) if c["feat_len"].max() > 0 else None
-        flt = _batch_from_cases([c])
+        flt = _batch_from_cases([c], mode)
         flt.update()
         torch.cuda.synchronize()
         out = flt.case_outputs(0, c)
@@ -171,7 +184,9 @@ def test_edge_cases(golden_dir):
     assert not ob["out_valid"].any() and not ob["out_updated"] and rel_err(ob["out_P"], b_["P"]) == 0.0
     assert not oc["out_valid"].any() and oc["out_lost"].all() and rel_err(oc["out_P"], c_["P"]) == 0.0
     assert (od["out_dof"] == rd["out_dof"]).all() and (rd["out_dof"][rd["out_valid"]] == 2).all()
-    compare_update_outputs(od, rd, CHI, label="rank-deficient")
+    # information form on a rank-deficient, zero-baseline problem: delta_x (1e-4 of the state) carries ~1e-9 of ITS OWN
+    # scale, i.e. ~1e-13 of the state, which is what the 1e-9 bar is about
+    compare_update_outputs(od, rd, CHI, tol_dx=1e-9 if mode == _lib.COMPRESS_QR else 1e-8, label="rank-deficient")
     assert not oe["out_valid"].any() and not oe["out_updated"]
 
 
@@ -267,7 +282,8 @@ def test_window_surgery_vs_oracle(golden_dir):
     assert rel_err(flt.cam_t[0, :len(keep)].cpu().numpy(), cam_t_ref) < 1e-15
 
 
-def test_full_size_properties(golden_dir):
+@pytest.mark.parametrize("mode", MODES)
+def test_full_size_properties(golden_dir, mode):
     """BASELINE shape (256 features x 30 poses) replicated over a batch with per-filter pixel noise: size-independent
     properties -- P+ symmetric, trace reduced, invariance to the order of the features, determinism."""
     cases, _ = _load(golden_dir, "baseline_256x30_updates.npz")
@@ -285,7 +301,7 @@ def test_full_size_properties(golden_dir):
     for k in ("feat_len", "obs_uv", "obs_dir", "obs_conf", "obs_slot", "idp_base", "idp_anchor_slot", "idp_m", "idp_rho",
               "lost_cnt", "tracked_cnt"):
         batch[1][k] = batch[1][k][perm]
-    flt = _batch_from_cases(batch)
+    flt = _batch_from_cases(batch, mode)
     flt.update()
     torch.cuda.synchronize()
     P = flt.P.cpu().numpy()
@@ -299,7 +315,7 @@ def test_full_size_properties(golden_dir):
     assert rel_err(flt.delta_x[1].cpu().numpy(), flt.delta_x[0].cpu().numpy()) < 1e-9
     assert (flt.feat_status[1].cpu().numpy() == flt.feat_status[0].cpu().numpy()[perm]).all()
     # determinism: a second run on identical inputs is bit-identical
-    flt2 = _batch_from_cases(batch)
+    flt2 = _batch_from_cases(batch, mode)
     flt2.update()
     torch.cuda.synchronize()
     assert torch.equal(flt2.P, flt.P) and torch.equal(flt2.delta_x, flt.delta_x)

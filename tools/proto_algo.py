@@ -42,6 +42,59 @@ def semidef_chol_upper(G, tol=1e-14):
     return R
 
 
+def semidef_chol_lower_panel(Pp, c):
+    """first c columns of the Cholesky factor of the PSD matrix Pp (n x n), zero column on a non-positive pivot."""
+    n = Pp.shape[0]
+    L = np.zeros((n, c))
+    W = Pp.copy()
+    for k in range(c):
+        p = W[k, k]
+        if p <= 0:
+            continue
+        L[k:, k] = W[k:, k] / np.sqrt(p)
+        W[k + 1:, k + 1:] -= np.outer(L[k + 1:, k], L[k + 1:, k])
+    return L
+
+
+def info_update(P, G, g, sigma, mode):
+    d = P.shape[0]; c = d - 15
+    s2 = sigma ** 2
+    if mode == "white":
+        # order [C; I]: U~ = P[:, C] L^-T
+        perm = np.r_[15:d, 0:15]
+        Pp = P[np.ix_(perm, perm)]
+        Lp = semidef_chol_lower_panel(Pp, c)          # (d x c): rows 0:c = L, rows c: = U~_I
+        L = Lp[:c]; UI = Lp[c:]
+        Gt = L.T @ G @ L
+        Gt = (Gt + Gt.T) / 2
+        B = s2 * np.eye(c) + Gt
+        CB = np.linalg.cholesky(B)
+        Wp = np.linalg.solve(CB, Lp.T).T               # U~ C_B^-T  (d x c) in permuted row order
+        Pn_p = s2 * Wp @ Wp.T
+        Pn_p[c:, c:] += Pp[c:, c:] - UI @ UI.T
+        inv = np.argsort(perm)
+        Pn = Pn_p[np.ix_(inv, inv)]
+        y = np.linalg.solve(CB, L.T @ g)
+        dx = (Wp @ y)[inv]
+        return (Pn + Pn.T) / 2, dx
+    Pcc = P[15:, 15:]; Pc = P[:, 15:]
+    A = s2 * np.eye(c) + G @ Pcc
+    import scipy.linalg as sl
+    lu = sl.lu_factor(A)
+    X = sl.lu_solve(lu, G)
+    mg = sl.lu_solve(lu, g)
+    dx = Pc @ mg
+    if mode == "lu_direct":
+        Z = (X + X.T) / 2
+    else:
+        Mi = sl.lu_solve(lu, np.eye(c))
+        E = X @ Pcc + s2 * Mi
+        Z = X + X.T - X @ E.T
+        Z = (Z + Z.T) / 2
+    Pn = P - Pc @ Z @ Pc.T
+    return (Pn + Pn.T) / 2, dx
+
+
 def run(case, mode="gram"):
     valid, lost, m_new, rho_new = o.select_and_triangulate(case)
     P = np.array(case["P"], float)
@@ -92,6 +145,9 @@ def run(case, mode="gram"):
         rows.append(Hs - Q1 @ W); rhs.append(rt)
     out = dict(out_valid=valid, out_lost=lost, out_idp_m=m_new, out_idp_rho=rho_new, out_gamma=gamma, out_dof=dof, out_gate=gate)
     if not gate.any():
+        return out
+    if mode in ("white", "lu", "lu_direct"):
+        out["out_P"], out["out_delta_x"] = info_update(P, G, g, sigma, mode)
         return out
     if mode == "qr":
         Hs = np.vstack(rows); rs = np.concatenate(rhs)
