@@ -7,6 +7,8 @@ static std::atomic<long long> g_launches{0};
 void msckf_count_launch(int n) { g_launches += n; }
 int tsqr_max_cams();
 bool gram_supported(const msckf_dims& d);
+bool front_warp_supported(const msckf_dims& d);
+cudaError_t launch_front_warp(const FrontArgs& a, cudaStream_t s);
 size_t info_scratch_doubles(const msckf_dims& d);
 cudaError_t launch_update_info(const ApplyArgs& a, int n_ctas, cudaStream_t s);
 
@@ -88,6 +90,8 @@ int msckf_front_batched(const msckf_dims* dims, const msckf_update_params* param
     FrontArgs a = make_front(dims, params, chi2_table, chi2_len, P, cam_R, cam_t, n_cams, feat_len, obs_uv, obs_dir,
                              obs_conf, obs_slot, idp_base, idp_anchor_slot, idp_m, idp_rho, lost_cnt, tracked_cnt,
                              feat_status, gamma, dof, (char*)workspace, w);
+    // warp-per-feature kernel when the track length / window fit its tile budget, CTA-per-feature kernel otherwise
+    if (front_warp_supported(*dims)) return (int)launch_front_warp(a, (cudaStream_t)stream);
     return (int)launch_front(a, (cudaStream_t)stream);
 }
 

@@ -55,10 +55,13 @@ def test_update_vs_golden(golden_dir, name, mode):
     print(name, "gram" if mode else "qr", _summarise(errs))
 
 
-def test_front_stage_vs_golden(golden_dir):
-    """rows 3-8 alone: selection, triangulation, gamma/dof/gate per feature, state untouched."""
+@pytest.mark.parametrize("pad_M", [pytest.param(2, id="warp-per-feature"), pytest.param(30, id="cta-per-feature")])
+def test_front_stage_vs_golden(golden_dir, pad_M):
+    """rows 3-8 alone: selection, triangulation, gamma/dof/gate per feature, state untouched.  The observation capacity
+    picks the kernel: <= 32 observations per track -> warp-per-feature kernel, more -> CTA-per-feature kernel."""
     cases, _ = _load(golden_dir, "small_updates.npz")
-    flt = _batch_from_cases(cases, pad_F=3, pad_M=2, pad_N=1)
+    flt = _batch_from_cases(cases, pad_F=3, pad_M=pad_M, pad_N=1)
+    assert (flt.M <= 32) == (pad_M == 2)
     P0 = flt.P.clone()
     flt.front()
     torch.cuda.synchronize()
