@@ -145,11 +145,11 @@ __device__ __noinline__ void gemm(Smem& sm, int M, int N, int K, const double* _
 }
 
 // In-place blocked right-looking Cholesky of the lower triangle of the n x n matrix S (leading dimension lds), factoring
-// only the first ncf columns; the trailing updates still cover all n rows/columns, so on return S[:, :ncf] holds the
-// first ncf columns of L and S[ncf:, ncf:] holds the Schur complement.  A non-positive pivot zeroes its column (positive
+// only the first ncf columns; the trailing updates cover all n rows and the columns below ncu.  With ncu = n, on return
+// S[:, :ncf] holds the first ncf columns of L and S[ncf:, ncf:] holds the Schur complement.  A non-positive pivot zeroes its column (positive
 // SEMI-definite input, e.g. a covariance with exactly correlated clones).  Linv (may be null) receives the inverse of
 // every NB x NB diagonal block of L, [block][NB * NB] row-major.
-static __device__ __noinline__ void cholesky(Smem& sm, double* S, int lds, int n, int ncf, double* Linv) {
+static __device__ __noinline__ void cholesky(Smem& sm, double* S, int lds, int n, int ncf, int ncu, double* Linv) {
     const int tid = threadIdx.x;
     double(*D)[NB + 1] = sm.D;
     double(*Di)[NB + 1] = sm.Di;
@@ -217,11 +217,11 @@ static __device__ __noinline__ void cholesky(Smem& sm, double* S, int lds, int n
                 if (c < nb) S[(size_t)i * lds + kb + c] = y[c];
         }
         __syncthreads();
-        const int n2 = n - kb - nb;
-        if (n2 > 0) {   // trailing update, lower triangle: S22 -= L21 L21^T
+        const int n2 = n - kb - nb, c2 = ncu - kb - nb;
+        if (n2 > 0 && c2 > 0) {   // trailing update, lower triangle, columns < ncu: S22 -= L21 L21^T
             double* S22 = S + (size_t)(kb + nb) * lds + kb + nb;
             const double* L21 = S + (size_t)(kb + nb) * lds + kb;
-            gemm<true, true>(sm, n2, n2, nb, L21, lds, L21, lds, MASK_NONE, MASK_NONE, true,
+            gemm<true, true>(sm, n2, c2, nb, L21, lds, L21, lds, MASK_NONE, MASK_NONE, true,
                              [=](int i, int j, double v) { if (j <= i) S22[(size_t)i * lds + j] -= v; });
         }
     }
@@ -262,6 +262,42 @@ static __device__ __noinline__ void trsm_right_lt(Smem& sm, double* X, int ldx, 
         }
     }
     __syncthreads();
+}
+
+constexpr int WB = 64;   // block-column width of the left-looking drivers (one 64-wide tile column of gemm())
+
+// Left-looking blocked Cholesky (same contract as cholesky() with ncu = n): every 64-wide block column is first updated
+// with ALL previously factored columns in one long-K GEMM (pipelined, written once), then factored by the right-looking
+// routine restricted to the block column.  Three sequential GEMM phases at n = 195 instead of twelve rank-16
+// read-modify-write sweeps of the trailing matrix.
+static __device__ __noinline__ void cholesky_ll(Smem& sm, double* S, int lds, int n, int ncf, double* Linv) {
+    for (int kb = 0; kb < ncf; kb += WB) {
+        const int w = min(WB, ncf - kb);
+        double* Skk = S + (size_t)kb * lds + kb;
+        if (kb > 0)
+            gemm<true, true>(sm, n - kb, w, kb, S + (size_t)kb * lds, lds, S + (size_t)kb * lds, lds, MASK_NONE, MASK_NONE,
+                             true, [=](int i, int j, double v) { if (j <= i) Skk[(size_t)i * lds + j] -= v; });
+        cholesky(sm, Skk, lds, n - kb, w, w, Linv ? Linv + (size_t)(kb / NB) * NB * NB : nullptr);
+    }
+    if (n > ncf) {   // Schur complement of the unfactored trailing block
+        double* S22 = S + (size_t)ncf * lds + ncf;
+        const double* L21 = S + (size_t)ncf * lds;
+        gemm<true, true>(sm, n - ncf, n - ncf, ncf, L21, lds, L21, lds, MASK_NONE, MASK_NONE, true,
+                         [=](int i, int j, double v) { if (j <= i) S22[(size_t)i * lds + j] -= v; });
+    }
+}
+
+// Left-looking X <- X C^-T (same contract as trsm_right_lt()).
+static __device__ __noinline__ void trsm_right_lt_ll(Smem& sm, double* X, int ldx, int m, const double* C, int ldc, int n,
+                                                     const double* Linv) {
+    for (int kb = 0; kb < n; kb += WB) {
+        const int w = min(WB, n - kb);
+        double* Xk = X + kb;
+        if (kb > 0)
+            gemm<true, true>(sm, m, w, kb, X, ldx, C + (size_t)kb * ldc, ldc, MASK_NONE, MASK_NONE, false,
+                             [=](int i, int j, double v) { Xk[(size_t)i * ldx + j] -= v; });
+        trsm_right_lt(sm, Xk, ldx, m, C + (size_t)kb * ldc + kb, ldc, w, Linv + (size_t)(kb / NB) * NB * NB);
+    }
 }
 
 // y <- C^-1 y for the lower-triangular Cholesky factor C (n x n), using the diagonal-block inverses.  y in global/shared.

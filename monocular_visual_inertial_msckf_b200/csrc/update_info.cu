@@ -23,7 +23,7 @@ namespace {
 using dense::NT;
 using dense::NB;
 
-__global__ void __launch_bounds__(NT) update_info_kernel(const ApplyArgs a) {
+__global__ void __launch_bounds__(NT, 2) update_info_kernel(const ApplyArgs a) {
     extern __shared__ double smem_raw[];
     dense::Smem& sm = *reinterpret_cast<dense::Smem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(NT) update_info_kernel(const ApplyArgs a) {
         }
         __syncthreads();
         // ---- L' and the Schur complement S_I ----
-        dense::cholesky(sm, Pp, ldp, d, c, nullptr);
+        dense::cholesky_ll(sm, Pp, ldp, d, c, nullptr);
         // ---- y = L^T g ; make L explicitly lower triangular (the solve below treats L' as a full d x c matrix) ----
         for (int j = tid; j < c; j += NT) {
             double acc = 0.0;
@@ -78,9 +78,9 @@ __global__ void __launch_bounds__(NT) update_info_kernel(const ApplyArgs a) {
         dense::gemm<false, false>(sm, c, c, c, Pp, ldp, T1, ccap, dense::MASK_K_GE_X, dense::MASK_NONE, true,
                                   [=](int i, int j, double v) { if (j <= i) Bm[(size_t)i * ccap + j] = v + (i == j ? s2 : 0.0); });
         // ---- B = C_B C_B^T ; y <- C_B^-1 y ; W = L' C_B^-T (in place) ----
-        dense::cholesky(sm, Bm, ccap, c, c, Linv);
+        dense::cholesky_ll(sm, Bm, ccap, c, c, Linv);
         dense::trsv_lower(sm, Bm, ccap, c, Linv, y);
-        dense::trsm_right_lt(sm, Pp, ldp, d, Bm, ccap, c, Linv);
+        dense::trsm_right_lt_ll(sm, Pp, ldp, d, Bm, ccap, c, Linv);
         // ---- dx = W y (back to the reference's state order) ----
         for (int i = tid; i < ldp; i += NT) {
             double acc = 0.0;
@@ -130,13 +130,18 @@ size_t info_scratch_doubles(const msckf_dims& d) {
 }
 
 cudaError_t launch_update_info(const ApplyArgs& a, int n_ctas, cudaStream_t s) {
-    static bool configured = false;
+    static int resident = 0;   // persistent grid = exactly the CTAs that fit on the device at once (no second wave)
     const size_t smem = sizeof(dense::Smem);
-    if (!configured) {
+    if (resident == 0) {
         cudaError_t e = cudaFuncSetAttribute(update_info_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, update_info_kernel, NT, smem);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
     }
+    if (n_ctas > resident) n_ctas = resident;
     update_info_kernel<<<n_ctas, NT, smem, s>>>(a);
     msckf_count_launch(1);
     return cudaGetLastError();
