@@ -80,6 +80,29 @@ def algorithmic_qr_flops_per_filter(rows, N):
     return 2.0 * rows * c * c - (2.0 / 3.0) * c ** 3
 
 
+def algorithmic_front_flops_per_feature(M):
+    """Rows 3-8 for one track of M observations (kernel table): assembling K = H_x P H_x^T + s^2 I from
+    M (M + 1) / 2 pairs of 2x6 . 6x6 . 6x2 blocks (96 multiply-adds each), the Cholesky of the 2M x 2M matrix with the 4
+    appended rows (n^3 / 3 + 4 n^2), and ~300 flops per observation of geometry.  Lower than SURVEY.md's 0.35-0.45 MFLOP
+    estimate (which assumed the two-sided projection); the smaller figure is used so the fraction is not flattered."""
+    n = 2 * M
+    return 192.0 * (M * (M + 1) / 2) + n ** 3 / 3.0 + 4.0 * n * n + 300.0 * M
+
+
+def algorithmic_gram_flops_per_filter(n_acc, N):
+    """Information-form compression: one rank-3 symmetric update of the 6N x 6N matrix per accepted feature."""
+    c = 6 * N
+    return 2.0 * 3.0 * n_acc * c * (c + 1) / 2.0
+
+
+def algorithmic_info_update_flops_per_filter(N):
+    """update_info.cu: Cholesky panel of P (c^3/3 + 15 c^2), L^T G L (c^3 + c^3/3), Cholesky of B (c^3/3),
+    W = L' C^-T (d c^2), P+ = s^2 W W^T lower (d^2 c)."""
+    c = 6.0 * N
+    d = c + 15.0
+    return c ** 3 / 3 + 15 * c * c + c ** 3 + c ** 3 / 3 + c ** 3 / 3 + d * c * c + d * d * c
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port on the host cores)
 # ----------------------------------------------------------------------------------------------------------------------
@@ -182,6 +205,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from monocular_visual_inertial_msckf_b200 import BatchedMSCKF, UpdateParams, _lib
+    from monocular_visual_inertial_msckf_b200.sharding import gather_filter_results, max_over_ranks, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -207,8 +231,9 @@ def run_gpu(args):
     h_qc = torch.empty((B, 4), dtype=torch.float64)
     uvn, smn, qcn = h_uv.numpy(), h_samples.numpy(), h_qc.numpy()
     t_start = 1.0
+    first_filter, _ = shard_range(B * world, rank, world)       # contiguous shard of the Monte-Carlo batch (weak scaling)
     for b in range(B):
-        uvn[b], smn[b], qcn[b], t_start = filter_inputs(base, rank * B + b)
+        uvn[b], smn[b], qcn[b], t_start = filter_inputs(base, first_filter + b)
 
     def rep(x, dtype):
         x = np.asarray(x)
@@ -299,12 +324,7 @@ def run_gpu(args):
             fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks(e0.elapsed_time(e1), device=dev)
 
     # ---- warm-up, then the timed K steps ----
     for _ in range(max(args.warmup, 3)):
@@ -365,7 +385,7 @@ def run_gpu(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        flt.lib.msckf_probe_fp64(148 * 8, 40000, C.c_void_p(sink.data_ptr()), C.byref(flops),
+        flt.lib.msckf_probe_fp64(148 * 8, 20000, C.c_void_p(sink.data_ptr()), C.byref(flops),
                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
         e1.record()
         torch.cuda.synchronize()
@@ -379,8 +399,8 @@ def run_gpu(args):
 
     if world > 1:
         # final gather of per-filter results (positions), outside the timed region
-        gathered = [torch.empty_like(flt.imu_state) for _ in range(world)] if rank == 0 else None
-        dist.gather(flt.imu_state, gathered, dst=0)
+        gathered = gather_filter_results(flt.imu_state, B * world, dst=0)
+        assert rank != 0 or gathered.shape[0] == B * world
         tot = torch.tensor([n_acc, n_rej, rows], dtype=torch.float64, device=dev)
         dist.all_reduce(tot)
         n_acc, n_rej, rows = [int(x) for x in tot.tolist()]
@@ -404,13 +424,20 @@ def run_gpu(args):
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     step_bytes = algorithmic_bytes_per_filter_step(F, M, N, N_IMU) * B
     rows_per_rank = rows / world
+    acc_per_rank = n_acc / world
+    stage_flops = dict(front=algorithmic_front_flops_per_feature(M) * B * F)
     if args.mode == "qr":
-        dom_name, dom_ms = "tsqr_kernel", stage_ms["compress"]
-        dom_flops = algorithmic_qr_flops_per_filter(rows_per_rank / B, N) * B
+        stage_flops["compress"] = algorithmic_qr_flops_per_filter(rows_per_rank / B, N) * B
+        stage_flops["apply"] = 8.0 * (15 + 6 * N) ** 3 * B
+        names = dict(front="front_warp_kernel", compress="tsqr_kernel", apply="apply_kernel")
     else:
-        dom_name, dom_ms = "apply_kernel", stage_ms["apply"]
-        dom_flops = 8.0 * (15 + 6 * N) ** 3 * B
+        stage_flops["compress"] = algorithmic_gram_flops_per_filter(acc_per_rank / B, N) * B
+        stage_flops["apply"] = algorithmic_info_update_flops_per_filter(N) * B
+        names = dict(front="front_warp_kernel", compress="gram_kernel", apply="update_info_kernel")
+    dom = max(("front", "compress", "apply"), key=lambda k: stage_ms[k])      # the dominant kernel of the step
+    dom_name, dom_ms, dom_flops = names[dom], stage_ms[dom], stage_flops[dom]
     achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12
+    stage_tflops = {names[k]: stage_flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in stage_flops}
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom_name)
@@ -419,8 +446,11 @@ def run_gpu(args):
     roofline = dict(bound="tensor", pipe="fp64 (DFMA/DMMA share one nominal peak on B200; tcgen05 has no f64 kind)",
                     kernel=dom_name, achieved=achieved_tf, peak=fp64_peak, unit="TFLOP/s",
                     frac=achieved_tf / fp64_peak if fp64_peak else None, traffic=traffic,
-                    peak_source="measured in this run by msckf_probe_fp64 (8 independent DFMA chains per thread)",
-                    kernel_ms=dom_ms, flops_per_launch=dom_flops, stage_ms=stage_ms,
+                    peak_source="measured in this run by msckf_probe_fp64 (8 independent DMMA.8x8x4 chains per warp; "
+                                "DFMA chains give the same 36-37 TFLOP/s, profiles/fp64_probe.txt)",
+                    kernel_ms=dom_ms, flops_per_launch=dom_flops, stage_ms=stage_ms, stage_tflops=stage_tflops,
+                    step_flops=dict(achieved=sum(stage_flops.values()) / (sec / args.steps) / 1e12, unit="TFLOP/s",
+                                    flops_per_filter_step=sum(stage_flops.values()) / B),
                     step_hbm=dict(bound="hbm", achieved=step_bytes / (sec / args.steps) / 1e9, peak=hbm_peak, unit="GB/s",
                                   frac=step_bytes / (sec / args.steps) / 1e9 / hbm_peak, peak_source=hbm_src,
                                   bytes_per_filter_step=algorithmic_bytes_per_filter_step(F, M, N, N_IMU)))
@@ -493,7 +523,9 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--filters", type=int, default=4096, help="filters per GPU")
-    ap.add_argument("--mode", default="qr", choices=["qr", "gram"])
+    ap.add_argument("--mode", default="gram", choices=["qr", "gram"],
+                    help="compression of the stacked rows: gram = information form (default, fastest, same results to "
+                         "1e-12), qr = explicit Householder TSQR as the reference's np.linalg.qr")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -175,8 +175,9 @@ int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* re
                                  double* cam_R, double* cam_t, double* P, int* n_cams,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
-/* Diagnostic: launches n_ctas x 256 threads of 8 independent FP64 FMA chains of length iters (the measured FP64-pipe
- * roofline denominator; MEASURED_PEAKS.json has no FP64 figure).  *flops_out_host receives the FLOP count. */
+/* Diagnostic: launches n_ctas x 256 threads, every warp running 8 independent FP64 tensor-instruction (DMMA.8x8x4) chains
+ * of length iters (the measured FP64-pipe roofline denominator; MEASURED_PEAKS.json has no FP64 figure).
+ * *flops_out_host receives the FLOP count. */
 int msckf_probe_fp64(int n_ctas, int iters, double* sink, double* flops_out_host, void* stream);
 
 /* Number of kernels launched by this library since load (the benchmark reports it as gpu_launches). */

@@ -1,0 +1,116 @@
+"""GPU: the drop-in filter class (reference API: MSCKF.process_imu / get_valid_features / update on Feature / Camera / IMU
+objects) against the golden vectors captured from the unmodified reference.  These read like the reference's own calls:
+build the objects the reference holds, call the method, compare the objects' state."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import rel_err
+from oracle import msckf_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+from monocular_visual_inertial_msckf_b200 import (MSCKF, Camera, Feature, IMUMeasurement, InverseDepthPoint,  # noqa: E402
+                                                  Isometry3D, Line, MSCKFParameters, _lib)
+
+
+def filter_from_case(c, mode):
+    """The reference's objects exactly as they were when the golden case was captured (tools/make_golden.py)."""
+    p = MSCKFParameters(K=np.array(c["K"], float), width=int(c["width"]), height=int(c["height"]),
+                        sigma_image=float(c["sigma"]), W_gravity=np.array(c["gravity"], float),
+                        use_parallax=bool(c["use_parallax"]), min_parallax=float(c["min_parallax"]),
+                        min_number_of_frames_to_be_lost=int(c["min_lost"]),
+                        min_number_of_frames_to_be_tracked=int(c["min_tracked"]))
+    f = MSCKF(p)
+    f.compress_mode = mode
+    imu = f.state.imu
+    imu.T_W_Ii = Isometry3D(np.array(c["imu_R"], float), np.array(c["imu_t"], float))
+    imu.v_W_Ii = np.array(c["imu_v"], float)
+    imu.gyroscope_bias = np.array(c["imu_bg"], float)
+    imu.accelerometer_bias = np.array(c["imu_ba"], float)
+    f.state.covariance = np.array(c["P"], float)
+    n = int(c["n_cams"])
+    ids = [1000 + 7 * s for s in range(n)]          # camera keys are imu ids, not slots (MSCKF.py:255)
+    for s in range(n):
+        f.state.cameras[ids[s]] = Camera(p.K, p.width, p.height, Isometry3D(np.array(c["cam_R"][s], float), np.array(c["cam_t"][s], float)))
+    feats = {}
+    for j in range(len(c["feat_len"])):
+        m = int(c["feat_len"][j])
+        ft = Feature()
+        for i in range(m):
+            s = int(c["obs_slot"][j, i])
+            ft.keypoints.append(np.array(c["obs_uv"][j, i], float))
+            ft.scores.append(float(c["obs_conf"][j, i]))
+            ft.camera_indices.append(ids[s])
+            ft.lines.append(Line(f.state.cameras[ids[s]].T_W_Ci.t, np.array(c["obs_dir"][j, i], float), float(c["obs_conf"][j, i])))
+        a = int(c["idp_anchor_slot"][j])
+        idp = InverseDepthPoint(f.state.cameras[ids[a]].T_W_Ci if a >= 0 else Isometry3D(np.eye(3), np.array(c["idp_base"][j], float)))
+        idp.m = np.array(c["idp_m"][j], float)
+        idp.rho = float(c["idp_rho"][j])
+        ft.inverse_depth_point = idp
+        ft.lost_for_n_frames = int(c["lost_cnt"][j])
+        ft.tracked_for_n_frames = int(c["tracked_cnt"][j])
+        feats[int(c["feat_ids"][j])] = ft
+    return f, feats, ids
+
+
+@pytest.mark.parametrize("mode", [pytest.param(_lib.COMPRESS_QR, id="qr"), pytest.param(_lib.COMPRESS_GRAM, id="gram")])
+@pytest.mark.parametrize("name,stride", [("small_updates.npz", 4), ("baseline_256x30_updates.npz", 1)])
+def test_get_valid_features_and_update_like_the_reference(golden_dir, name, stride, mode):
+    cases, _ = o.load_cases(os.path.join(golden_dir, name))
+    n_updated = 0
+    for c in cases[::stride]:
+        f, feats, ids = filter_from_case(c, mode)
+        keys = list(feats.keys())
+        valid, lost = f.get_valid_features(feats)
+        assert [k in valid for k in keys] == list(c["out_valid"]) and [k in lost for k in keys] == list(c["out_lost"])
+        assert rel_err(np.stack([feats[k].inverse_depth_point.m for k in keys]), c["out_idp_m"]) < 1e-9
+        assert rel_err(np.array([feats[k].inverse_depth_point.rho for k in keys]), c["out_idp_rho"]) < 1e-9
+        P_before = f.state.covariance.copy()
+        f.update(valid)
+        assert f.number_of_residuals_discarded_for_gasting_test == int(c["out_n_rejected"])
+        if not c["out_updated"]:
+            assert np.array_equal(f.state.covariance, P_before)
+            continue
+        n_updated += 1
+        assert rel_err(f.state.covariance, c["out_P"]) < 1e-9
+        assert rel_err(f.state.imu.T_W_Ii.R, c["out_imu_R"]) < 1e-9 and rel_err(f.state.imu.T_W_Ii.t, c["out_imu_t"]) < 1e-9
+        assert rel_err(f.state.imu.v_W_Ii, c["out_imu_v"]) < 1e-9
+        assert rel_err(f.state.imu.gyroscope_bias, c["out_imu_bg"]) < 1e-9
+        assert rel_err(f.state.imu.accelerometer_bias, c["out_imu_ba"]) < 1e-9
+        cams = list(f.state.cameras.values())
+        assert rel_err(np.stack([cam.T_W_Ci.R for cam in cams]), c["out_cam_R"]) < 1e-9
+        assert rel_err(np.stack([cam.T_W_Ci.t for cam in cams]), c["out_cam_t"]) < 1e-9
+        # aliasing survives the correction: Line.base / InverseDepthPoint.base still ARE the camera position arrays
+        for ft in feats.values():
+            for ln, cid in zip(ft.lines, ft.camera_indices):
+                assert ln.base is f.state.cameras[cid].T_W_Ci.t
+            assert all(cam.T_W_Ci_null is cam.T_W_Ci for cam in cams)
+    assert n_updated >= 3
+
+
+def test_process_imu_like_the_reference(golden_dir):
+    cases, _ = o.load_cases(os.path.join(golden_dir, "small_propagate.npz"))
+    for c in cases[::5]:
+        p = MSCKFParameters(W_gravity=np.array(c["gravity"], float))
+        f = MSCKF(p)
+        f.continuous_noise_covariance = np.diag(np.asarray(c["Qc_diag"], float))
+        imu = f.state.imu
+        imu.T_W_Ii = Isometry3D(np.array(c["imu_R"], float), np.array(c["imu_t"], float))
+        imu.v_W_Ii = np.array(c["imu_v"], float)
+        imu.gyroscope_bias = np.array(c["imu_bg"], float)
+        imu.accelerometer_bias = np.array(c["imu_ba"], float)
+        imu.T_W_Ii_null = Isometry3D(np.array(c["null_R"], float), np.array(c["null_t"], float))
+        imu.v_W_Ii_null = np.array(c["null_v"], float)
+        imu.timestamp = float(c["timestamp"])
+        d = c["P"].shape[0]
+        f.state.covariance = np.array(c["P"], float)
+        for s in range((d - 15) // 6):
+            f.state.cameras[s] = Camera(p.K, p.width, p.height, Isometry3D())
+        s = np.asarray(c["sample"], float)
+        f.process_imu(IMUMeasurement(float(s[0]), s[1:4].copy(), s[4:7].copy()))
+        assert rel_err(f.state.covariance, c["out_P"]) < 1e-12
+        assert rel_err(imu.T_W_Ii.R, c["out_imu_R"]) < 1e-13 and rel_err(imu.T_W_Ii.t, c["out_imu_t"]) < 1e-13
+        assert rel_err(imu.v_W_Ii, c["out_imu_v"]) < 1e-13
+        assert imu.T_W_Ii_null is imu.T_W_Ii and imu.v_W_Ii_null is imu.v_W_Ii and imu.timestamp == float(s[0])
