@@ -115,7 +115,7 @@ __device__ void svals3_w(double* G, double* sv) {
                     be += G[k * 3 + q] * G[k * 3 + q];
                     ga += G[k * 3 + p] * G[k * 3 + q];
                 }
-                if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+                if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
                 rotated = true;
                 const double zeta = (be - al) / (2.0 * ga);
                 const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -437,16 +437,23 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
                     }
                 }
             }
-            double G3[9], sv[3];
+            // rank by SciPy's rule s > eps max(3, 2M) s_max on the singular values of the 3x3 factor.  Column pivoting
+            // bounds s_min >= |r33| / 4 and s_max <= sqrt(6) |r11|, so |r33| > 1e-10 |r11| already proves rank 3 (the
+            // threshold is ~1e-14 s_max); only doubtful factors pay for the Jacobi SVD.
+            if (n2 >= 3 && fabs(R3[8]) > 1e-10 * fabs(R3[0])) {
+                rank = 3;
+            } else {
+                double G3[9], sv[3];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) G3[k] = R3[k];
-            svals3_w(G3, sv);
-            const double smax = fmax(sv[0], fmax(sv[1], sv[2]));
-            const double tol = 2.220446049250313e-16 * (double)(n2 > 3 ? n2 : 3) * smax;   // scipy null_space rcond
-            rank = 0;
+                for (int k = 0; k < 9; ++k) G3[k] = R3[k];
+                svals3_w(G3, sv);
+                const double smax = fmax(sv[0], fmax(sv[1], sv[2]));
+                const double tol = 2.220446049250313e-16 * (double)(n2 > 3 ? n2 : 3) * smax;   // scipy null_space rcond
+                rank = 0;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) rank += (sv[k] > tol) ? 1 : 0;
-            if (rank > n2) rank = n2;
+                for (int k = 0; k < 3; ++k) rank += (sv[k] > tol) ? 1 : 0;
+                if (rank > n2) rank = n2;
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 if (c >= rank) { Hf[0][c] = 0.0; Hf[1][c] = 0.0; }
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
         //      remaining matrix and then shifts the trailing tiles up-left by one, so the loop body is one fixed piece of
         //      code (statically indexed registers) that stays in the instruction cache. ----
         // gamma = y.y - b^T (V V^T)^-1 b with y = row 0 of the appended tile row, V = rows 1..3, b = V y
-        double yy = 0.0, bq[3] = {0, 0, 0}, Mq[6] = {0, 0, 0, 0, 0, 0};
+        double gr0 = 0.0, gr1 = 0.0;   // accumulator tile of [y; V] [y; V]^T (rows/cols 0..3 are meaningful)
 #pragma unroll 1
         for (int bk = 0; bk < Tn; ++bk) {
             const int rem = Tn - bk;
@@ -675,16 +682,9 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
                     }
                 }
             }
-            // the finished tile of the appended rows: y and V entries of this block column
-#pragma unroll
-            for (int x = 0; x < 2; ++x) {
-                const double e = Ga[0][x];
-                const double y = shfl_d(e, t), v1 = shfl_d(e, 4 + t), v2 = shfl_d(e, 8 + t), v3 = shfl_d(e, 12 + t);
-                yy += y * y;
-                bq[0] += v1 * y; bq[1] += v2 * y; bq[2] += v3 * y;
-                Mq[0] += v1 * v1; Mq[1] += v1 * v2; Mq[2] += v1 * v3;
-                Mq[3] += v2 * v2; Mq[4] += v2 * v3; Mq[5] += v3 * v3;
-            }
+            // the finished tile of the appended rows (y and V entries of this block column) enters their Gram matrix
+            dense::dmma(gr0, gr1, Ga[0][0], Ga[0][0]);
+            dense::dmma(gr0, gr1, Ga[0][1], Ga[0][1]);
             // shift the trailing matrix up-left by one tile
 #pragma unroll
             for (int I = 1; I < TC; ++I) {
@@ -697,15 +697,16 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
                 Ga[I - 1][1] = Ga[I][1];
             }
         }
-        // every lane holds the partial sums of its column pair (same for all g): reduce over t
-#pragma unroll
-        for (int o2 = 1; o2 <= 2; o2 <<= 1) {
-            yy += __shfl_xor_sync(0xffffffffu, yy, o2);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) bq[k] += __shfl_xor_sync(0xffffffffu, bq[k], o2);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) Mq[k] += __shfl_xor_sync(0xffffffffu, Mq[k], o2);
-        }
+        // Gram tile element (m, n) sits in lane 4 m + (n >> 1), register n & 1:  yy = (0,0), b_q = (q,0), M_qp = (q,p)
+        const double yy = shfl_d(gr0, 0);
+        double bq[3], Mq[6];
+        bq[0] = shfl_d(gr0, 4); bq[1] = shfl_d(gr0, 8); bq[2] = shfl_d(gr0, 12);
+        Mq[0] = shfl_d(gr1, 4);                                    // (1,1)
+        Mq[1] = shfl_d(gr0, 5);                                    // (1,2)
+        Mq[2] = shfl_d(gr1, 5);                                    // (1,3)
+        Mq[3] = shfl_d(gr0, 9);                                    // (2,2)
+        Mq[4] = shfl_d(gr1, 9);                                    // (2,3)
+        Mq[5] = shfl_d(gr1, 13);                                   // (3,3)
         double gam = yy;
         {   // Cholesky solve on the leading rank x rank block of V V^T
             double l00 = 0, l10 = 0, l11 = 0, l20 = 0, l21 = 0, l22 = 0, z0 = 0, z1 = 0, z2 = 0;
