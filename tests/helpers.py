@@ -48,3 +48,50 @@ def compare_update_outputs(out, ref, chi2_table, tol_state=1e-9, tol_gamma=1e-6,
             assert errs[k] < tol_state, f"{label}: {k} rel err {errs[k]}"
         assert errs["delta_x"] < tol_dx, f"{label}: delta_x rel err {errs['delta_x']}"
     return errs
+
+
+def make_case(F, M, N, seed=0, outlier_frac=0.05):
+    """A self-consistent packed update case of arbitrary shape (F tracks x M observations, N-pose window) for sizes the
+    golden fixtures do not hold: poses on a smooth arc, landmarks 6-14 m ahead, every track observed in M consecutive
+    window slots, a random SPD covariance with realistic scales.  The oracle supplies the expected outputs."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[320.0, 0, 320], [0, 320.0, 240], [0, 0, 1]])
+    Kinv = np.linalg.inv(K)
+    Rbc = np.array([[0.0, 0, 1], [-1, 0, 0], [0, -1, 0]])
+    cam_R = np.zeros((N, 3, 3))
+    cam_t = np.zeros((N, 3))
+    for s in range(N):
+        a = 0.01 * s
+        Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+        cam_R[s] = Rz @ Rbc
+        cam_t[s] = [0.05 * s, 0.6 * np.sin(0.15 * s), 0.1 * np.cos(0.1 * s)]
+    d = 15 + 6 * N
+    Q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    P = (Q * 10.0 ** rng.uniform(-7, -4, d)) @ Q.T
+    P = (P + P.T) / 2
+    c = dict(K=K, Kinv=Kinv, width=640, height=480, sigma=0.1, gravity=np.array([0.0, 0.0, -9.81]), min_lost=2,
+             min_tracked=3, use_parallax=1, min_parallax=1e9, n_cams=N, cam_R=cam_R, cam_t=cam_t,
+             imu_R=cam_R[-1] @ Rbc.T, imu_t=cam_t[-1].copy(), imu_v=np.array([0.3, 0.1, 0.0]),
+             imu_bg=1e-3 * rng.standard_normal(3), imu_ba=1e-2 * rng.standard_normal(3), P=P,
+             feat_ids=np.arange(F, dtype=np.int64), feat_len=np.full(F, M, np.int32), obs_uv=np.zeros((F, M, 2)),
+             obs_dir=np.zeros((F, M, 3)), obs_conf=rng.uniform(0.7, 1.0, (F, M)), obs_slot=np.zeros((F, M), np.int32),
+             idp_base=np.zeros((F, 3)), idp_anchor_slot=np.zeros(F, np.int32), idp_m=np.zeros((F, 3)),
+             idp_rho=np.full(F, 0.1), lost_cnt=np.full(F, 5, np.int32), tracked_cnt=np.full(F, M, np.int32), call_index=0)
+    for j in range(F):
+        depth = rng.uniform(6, 14)
+        p = np.array([depth, depth * np.tan(rng.uniform(-0.3, 0.3)), depth * np.tan(rng.uniform(-0.25, 0.25))])
+        s0 = rng.integers(0, N - M + 1)
+        bad = rng.random() < outlier_frac
+        for i in range(M):
+            s = s0 + i
+            pc = cam_R[s].T @ (p - cam_t[s])
+            uv = (K @ pc)[:2] / pc[2] + 0.1 * rng.standard_normal(2)
+            if bad and i % 3 == 0:
+                uv += 80.0 * rng.standard_normal(2)
+            c["obs_uv"][j, i] = uv
+            c["obs_dir"][j, i] = cam_R[s] @ (Kinv @ np.array([uv[0], uv[1], 1.0]))
+            c["obs_slot"][j, i] = s
+        c["idp_anchor_slot"][j] = s0
+        c["idp_base"][j] = cam_t[s0]
+        c["idp_m"][j] = c["obs_dir"][j, 0] / np.linalg.norm(c["obs_dir"][j, 0])
+    return c

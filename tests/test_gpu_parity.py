@@ -322,3 +322,24 @@ def test_full_size_properties(golden_dir, mode):
     flt2.update()
     torch.cuda.synchronize()
     assert torch.equal(flt2.P, flt.P) and torch.equal(flt2.delta_x, flt.delta_x)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("F,M,N", [(24, 12, 36), (16, 40, 40), (40, 33, 34)])
+def test_large_windows_vs_oracle(mode, F, M, N):
+    """Windows / tracks beyond the warp-per-feature kernel's tile budget (N > 31 or M > 32): CTA-per-feature front end,
+    multi-pass information accumulation (6N > 192), larger update factorisations -- against the oracle on synthetic
+    cases (the golden fixtures stop at N = 31)."""
+    from helpers import make_case
+    if mode == _lib.COMPRESS_QR and N > _lib.load_library().msckf_max_cameras(_lib.COMPRESS_QR):
+        pytest.skip("explicit-QR kernel keeps R in one SM's shared memory: N <= %d" % _lib.load_library().msckf_max_cameras(0))
+    cases = [make_case(F, M, N, seed=s) for s in (1, 2)]
+    refs = [o.update_case(c) for c in cases]
+    flt = _batch_from_cases(cases, mode)
+    flt.update()
+    torch.cuda.synchronize()
+    n_rej = 0
+    for b, (c, ref) in enumerate(zip(cases, refs)):
+        compare_update_outputs(flt.case_outputs(b, c), ref, CHI, label=f"synthetic F{F} M{M} N{N} #{b}")
+        n_rej += ref["out_n_rejected"]
+        assert ref["out_updated"]
