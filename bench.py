@@ -221,7 +221,8 @@ def run_gpu(args):
     M = base["obs_uv"].shape[1]
     N = int(base["n_cams"])
     mode = _lib.COMPRESS_QR if args.mode == "qr" else _lib.COMPRESS_GRAM
-    par = UpdateParams.from_case(base, mode)
+    gate = _lib.GATE_BOUNDS if args.gate == "bounds" else _lib.GATE_EXACT
+    par = UpdateParams.from_case(base, mode, gate)
     flt = BatchedMSCKF(B, F, M, N, par, device=dev)
 
     # ---- host-side inputs (pinned): what a caller hands over every step ----
@@ -339,6 +340,22 @@ def run_gpu(args):
     n_acc = int(flt.n_accepted.sum().item())
     n_rej = int(flt.n_rejected.sum().item())
     rows = 2 * int((flt.feat_len * ((flt.feat_status & 0xF) == 1)).sum().item())
+
+    # ---- the same step with the gate's exact early-out (MSCKF_GATE_BOUNDS), reported beside the headline ----
+    gate_bounds = None
+    if args.gate == "exact" and mode == _lib.COMPRESS_GRAM:
+        status_exact = (flt.feat_status & 0xF).clone()
+        flt.cpar.gate_mode = _lib.GATE_BOUNDS
+        for _ in range(2):
+            step_resident()
+        ms_b = timed(step_resident, args.steps)
+        n_flag = int(((flt.feat_status & _lib.FEAT_GAMMA_BOUND) != 0).sum().item())
+        same = bool(torch.equal(flt.feat_status & 0xF, status_exact))
+        flt.cpar.gate_mode = _lib.GATE_EXACT
+        gate_bounds = dict(value=B * world * F * args.steps / (ms_b * 1e-3), unit="feature-updates/s",
+                           ms_per_step=ms_b / args.steps, decided_by_bounds_rank0=n_flag, features_rank0=B * F,
+                           identical_decisions=same)
+        step_resident()      # leave the exact-mode outputs in place for the statistics below
 
     # ---- per-kernel durations (CUDA events on the launching stream), one extra pass outside the timed region ----
     def time_stage(fn, reps=3):
@@ -474,10 +491,10 @@ def run_gpu(args):
         config=dict(workload=f"BASELINE.json configs[3] shape: {B} filters/GPU x {F} features x {N}-pose window "
                              f"(d={15 + 6 * N}), {N_IMU} IMU samples/frame, FP64; steady-state snapshot replicated with "
                              f"per-filter pixel noise", filters_per_gpu=B, features=F, obs_per_feature=M, window=N,
-                    compress=args.mode, l2="inputs larger than L2 (%.1f GB touched per step)" % (
+                    compress=args.mode, gate=args.gate, l2="inputs larger than L2 (%.1f GB touched per step)" % (
                         (step_bytes + 2 * flt.P.numel() * 8) / 1e9),
                     accepted_features=n_acc, gated_out=n_rej),
-        roofline=roofline, cpu_baseline=cpu,
+        roofline=roofline, cpu_baseline=cpu, gate_bounds=gate_bounds,
         e2e=dict(value=feats_per_step * e2e_steps / e2e_sec, unit="feature-updates/s", h2d_bytes_per_step=h2d_bytes * world,
                  d2h_bytes_per_step=d2h_bytes * world, ms_per_step=ms_e2e / e2e_steps, steps=e2e_steps,
                  filter_steps_per_s=Btot * e2e_steps / e2e_sec),
@@ -526,6 +543,9 @@ if __name__ == "__main__":
     ap.add_argument("--mode", default="gram", choices=["qr", "gram"],
                     help="compression of the stacked rows: gram = information form (default, fastest, same results to "
                          "1e-12), qr = explicit Householder TSQR as the reference's np.linalg.qr")
+    ap.add_argument("--gate", default="exact", choices=["exact", "bounds"],
+                    help="exact: every selected feature goes through the full Mahalanobis test (headline); bounds: same "
+                         "decisions, features decided by the exact bounds skip the factorisation (reported beside it)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

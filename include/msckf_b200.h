@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 1
+#define MSCKF_B200_ABI_VERSION 2
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
@@ -40,6 +40,15 @@ extern "C" {
 #define MSCKF_FEAT_GATED_OUT 2     /* valid but rejected by gating_test (MSCKF.py:577-579) */
 #define MSCKF_FEAT_LOST_DISCARD 3  /* lost before it was tracked long enough (MSCKF.py:467-469) */
 #define MSCKF_FEAT_LOST_FLAG 0x10  /* OR-ed in when the feature is in the reference's `lost_features` dict */
+#define MSCKF_FEAT_GAMMA_BOUND 0x20 /* OR-ed in when the gate was decided by the exact bounds below (gate_mode 1):
+                                      gamma[] then holds the bound that decided it, not the Mahalanobis distance */
+
+/* how the chi-square gate (MSCKF.gating_test, MSCKF.py:561-568) is evaluated */
+#define MSCKF_GATE_EXACT 0     /* gamma = r_o^T (H_o P H_o^T + sigma^2 I)^-1 r_o for every selected feature */
+#define MSCKF_GATE_BOUNDS 1    /* same DECISIONS: |r_o|^2 / (sigma^2 + tr(H_x P H_x^T)) <= gamma <= |r_o|^2 / sigma^2 holds
+                                  exactly (H_o P H_o^T is positive semi-definite with largest eigenvalue below that trace),
+                                  so a feature whose upper bound passes / whose lower bound fails is decided without the
+                                  factorisation; every other feature gets the exact test */
 
 /* how the surviving rows are compressed before the Kalman update (row 9) */
 #define MSCKF_COMPRESS_QR 0    /* Householder TSQR of the stacked rows: T_H = R, r_n = Q^T r (MSCKF.py:594-598) */
@@ -64,6 +73,7 @@ typedef struct msckf_update_params {
     int use_parallax;        /* MSCKF.py:114 */
     double min_parallax_deg; /* MSCKF.py:115 */
     int compress_mode;       /* MSCKF_COMPRESS_* */
+    int gate_mode;           /* MSCKF_GATE_* */
 } msckf_update_params;
 
 /* imu_state: [B][21] = R_W_I (9, row-major), t (3), v (3), b_g (3), b_a (3)       (IMU.py:13-41)
@@ -97,7 +107,8 @@ int msckf_max_cameras(int compress_mode);
  * In/out: P, imu_state, cam_R, cam_t.   n_cams[B] is read only.
  * Outputs:
  *   feat_status[B][F]         MSCKF_FEAT_* | MSCKF_FEAT_LOST_FLAG
- *   gamma[B][F], dof[B][F]    Mahalanobis distance and degrees of freedom of each valid feature (NaN / 0 else)
+ *   gamma[B][F], dof[B][F]    Mahalanobis distance (or deciding bound, see MSCKF_FEAT_GAMMA_BOUND) and degrees of
+ *                             freedom of each valid feature (NaN / 0 else)
  *   delta_x[B][ldp]           the correction that was applied (zeros when nothing was accepted)
  *   n_accepted[B], n_rejected[B]   features stacked / gated out (the reference's discard counter, MSCKF.py:578)
  * ------------------------------------------------------------------------------------------------------------- */

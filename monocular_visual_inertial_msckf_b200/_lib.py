@@ -9,6 +9,8 @@ COMPRESS_QR = 0
 COMPRESS_GRAM = 1
 
 FEAT_SKIPPED, FEAT_ACCEPTED, FEAT_GATED_OUT, FEAT_LOST_DISCARD, FEAT_LOST_FLAG = 0, 1, 2, 3, 0x10
+FEAT_GAMMA_BOUND = 0x20
+GATE_EXACT, GATE_BOUNDS = 0, 1
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -23,7 +25,7 @@ class Params(C.Structure):
     _fields_ = [("K", C.c_double * 9), ("Kinv", C.c_double * 9), ("width", C.c_int), ("height", C.c_int),
                 ("sigma_image", C.c_double), ("gravity", C.c_double * 3), ("min_lost", C.c_int),
                 ("min_tracked", C.c_int), ("use_parallax", C.c_int), ("min_parallax_deg", C.c_double),
-                ("compress_mode", C.c_int)]
+                ("compress_mode", C.c_int), ("gate_mode", C.c_int)]
 
 
 # every symbol include/msckf_b200.h declares
@@ -80,7 +82,7 @@ def load_library():
     lib.msckf_remove_cameras_batched.argtypes = [pd, u8, dp, dp, dp, ip, vp, C.c_size_t, vp]
     lib.msckf_probe_fp64.restype = C.c_int
     lib.msckf_probe_fp64.argtypes = [C.c_int, C.c_int, dp, C.POINTER(C.c_double), vp]
-    if lib.msckf_abi_version() != 1:
+    if lib.msckf_abi_version() != 2:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib
     return lib

@@ -37,6 +37,7 @@ class UpdateParams:
     use_parallax: bool = True
     min_parallax: float = 45.0
     compress_mode: int = _lib.COMPRESS_QR
+    gate_mode: int = _lib.GATE_EXACT
 
     def to_c(self):
         p = _lib.Params()
@@ -54,15 +55,16 @@ class UpdateParams:
         p.use_parallax = int(bool(self.use_parallax))
         p.min_parallax_deg = float(self.min_parallax)
         p.compress_mode = int(self.compress_mode)
+        p.gate_mode = int(self.gate_mode)
         return p
 
     @staticmethod
-    def from_case(c, compress_mode=_lib.COMPRESS_QR):
+    def from_case(c, compress_mode=_lib.COMPRESS_QR, gate_mode=_lib.GATE_EXACT):
         return UpdateParams(K=np.array(c["K"], float), width=int(c["width"]), height=int(c["height"]),
                             sigma_image=float(c["sigma"]), gravity=np.array(c["gravity"], float),
                             min_lost=int(c["min_lost"]), min_tracked=int(c["min_tracked"]),
                             use_parallax=bool(c["use_parallax"]), min_parallax=float(c["min_parallax"]),
-                            compress_mode=compress_mode)
+                            compress_mode=compress_mode, gate_mode=gate_mode)
 
 
 def _ptr(t):

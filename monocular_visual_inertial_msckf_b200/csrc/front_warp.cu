@@ -502,6 +502,36 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
             continue;
         }
 
+        // ---- exact early-out (MSCKF_GATE_BOUNDS): |r~|^2 / (s^2 + tr S_x) <= gamma <= |r~|^2 / s^2 ----
+        if (a.par.gate_mode == MSCKF_GATE_BOUNDS) {
+            double trs = 0.0;
+            if (live) {
+                const double* Pd = sP + (size_t)(o.slot * (o.slot + 1) / 2 + o.slot) * 36;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) { v0 += Pd[r * 6 + c] * Hx[0][c]; v1 += Pd[r * 6 + c] * Hx[1][c]; }
+                    trs += Hx[0][r] * v0 + Hx[1][r] * v1;
+                }
+            }
+            trs = warp_sum_all(trs);
+            const double rr = warp_sum_all(rt0 * rt0 + rt1 * rt1);
+            const double crit = (dofv < a.chi2_len) ? a.chi2_table[dofv] : nan("");
+            const double gub = rr / s2, glb = rr / (s2 + trs);
+            const bool acc = gub <= crit, rej = glb > crit;
+            if (acc || rej) {
+                if (lane == 0) {
+                    a.feat_status[fj] = (unsigned char)((acc ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) |
+                                                        (code & MSCKF_FEAT_LOST_FLAG) | MSCKF_FEAT_GAMMA_BOUND);
+                    a.gamma[fj] = acc ? gub : glb;
+                    a.dof[fj] = dofv;
+                    a.fac_rank[fj] = rank;
+                }
+                continue;
+            }
+        }
+
         // ---- K = H_x P H_x^T + sigma^2 I in accumulator-fragment layout; appended tile row [r~; Q1^T] ----
         // (runtime loop over tile rows + a switch that files the finished row into the statically indexed register
         //  array: the fully unrolled form of this kernel was 400 KB of SASS and stalled 70% of the time on instruction

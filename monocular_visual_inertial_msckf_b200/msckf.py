@@ -154,6 +154,7 @@ class B200UpdateMixin:
     """process_imu / get_valid_features / update of the reference's MSCKF, executed by the CUDA library."""
 
     compress_mode = _lib.COMPRESS_GRAM   # or _lib.COMPRESS_QR: explicit Householder TSQR like np.linalg.qr
+    gate_mode = _lib.GATE_BOUNDS         # the reference's gating_test only returns the decision; GATE_EXACT also works
     device = "cuda"
 
     # -- device context (capacities grow in steps so that consecutive frames reuse the buffers) --------------------
@@ -165,7 +166,7 @@ class B200UpdateMixin:
                                   min_lost=int(self.min_number_of_frames_to_be_lost),
                                   min_tracked=int(self.min_number_of_frames_to_be_tracked),
                                   use_parallax=bool(self.use_parallax), min_parallax=float(self.min_parallax),
-                                  compress_mode=self.compress_mode)
+                                  compress_mode=self.compress_mode, gate_mode=self.gate_mode)
             Fc, Mc, Nc = _round_up(F, 64), _round_up(M, 8), max(int(N), 1)   # N exact: the warp-per-feature kernel needs N <= 31
             if ctx is not None:
                 Fc, Mc, Nc = max(Fc, ctx.F), max(Mc, ctx.M), max(Nc, ctx.N)

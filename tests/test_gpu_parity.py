@@ -343,3 +343,44 @@ def test_large_windows_vs_oracle(mode, F, M, N):
         compare_update_outputs(flt.case_outputs(b, c), ref, CHI, label=f"synthetic F{F} M{M} N{N} #{b}")
         n_rej += ref["out_n_rejected"]
         assert ref["out_updated"]
+
+
+@pytest.mark.parametrize("name", ["small_updates.npz", "baseline_256x30_updates.npz"])
+def test_gate_bounds_mode_gives_identical_decisions_and_state(golden_dir, name):
+    """MSCKF_GATE_BOUNDS: features whose upper bound passes / lower bound fails skip the factorisation; the decisions,
+    the update and the covariance are the reference's; the reported gamma of such a feature is the deciding bound."""
+    cases, _ = _load(golden_dir, name)
+    F = max(len(c["feat_len"]) for c in cases)
+    M = max(c["obs_uv"].shape[1] for c in cases)
+    N = max(int(c["n_cams"]) for c in cases)
+    par = UpdateParams.from_case(cases[0], _lib.COMPRESS_GRAM, _lib.GATE_BOUNDS)
+    flt = BatchedMSCKF(len(cases), F, M, N, par)
+    flt.load_cases(cases)
+    flt.update()
+    torch.cuda.synchronize()
+    n_bound = n_full = 0
+    for b, c in enumerate(cases):
+        out = flt.case_outputs(b, c)
+        st = flt.feat_status[b, :len(c["feat_len"])].cpu().numpy()
+        flagged = (st & _lib.FEAT_GAMMA_BOUND) != 0
+        v = np.asarray(c["out_valid"], bool)
+        assert not flagged[~v].any()
+        crit = CHI[c["out_dof"]]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            decided = ~(np.abs(c["out_gamma"] / crit - 1.0) <= 1e-6)
+        assert (out["out_gate"][v & decided] == c["out_gate"][v & decided]).all()
+        acc_b, rej_b = flagged & out["out_gate"], flagged & ~out["out_gate"]
+        assert (out["out_gamma"][acc_b] >= c["out_gamma"][acc_b] * (1 - 1e-12)).all()      # upper bound decided "accept"
+        assert (out["out_gamma"][rej_b] <= c["out_gamma"][rej_b] * (1 + 1e-12)).all()      # lower bound decided "reject"
+        exact = v & ~flagged
+        if exact.any():
+            g = c["out_gamma"][exact]
+            assert np.max(np.abs(out["out_gamma"][exact] - g) / np.maximum(np.abs(g), 1e-3)) < 1e-6
+        n_bound += int(flagged.sum())
+        n_full += int(exact.sum())
+        if (out["out_gate"][v] == c["out_gate"][v]).all():
+            assert out["out_n_rejected"] == c["out_n_rejected"]
+            for k in ("out_P", "out_imu_t", "out_imu_v", "out_cam_t", "out_cam_R"):
+                assert rel_err(out[k], c[k]) < 1e-9, (k, rel_err(out[k], c[k]))
+    print(name, "decided by bounds:", n_bound, "full test:", n_full)
+    assert n_bound > 0
