@@ -295,22 +295,19 @@ def run_gpu(args):
     h_out_nacc = torch.empty((B,), dtype=torch.int32).pin_memory()
     d2h_bytes = sum(t.numel() * t.element_size() for t in (h_out_state, h_out_camt, h_out_status, h_out_nacc))
 
+    host_in = dict(obs_uv=h_uv, obs_dir=h_dir, obs_conf=h_conf, obs_slot=h_slot, feat_len=h_len, lost_cnt=h_lost,
+                   tracked_cnt=h_trk, idp_anchor_slot=h_anchor, idp_base=h_base, idp_m=h_m, idp_rho=h_rho)
+    host_out = dict(imu_state=h_out_state, cam_t=h_out_camt, feat_status=h_out_status, n_accepted=h_out_nacc)
+
     def step_e2e():
-        # the caller's host buffers -> device, the step, the result back to the host
-        for dst, src in step_inputs:
-            dst.copy_(src, non_blocking=True)
-        samples_dev.copy_(h_samples, non_blocking=True)
+        # the caller's host buffers -> device, the step, the results back to the host: ONE C-ABI call
+        # (msckf_filter_step_host) that pipelines upload / kernels / download over chunks of filters
         flt.P.copy_(P0)
         flt.imu_state.copy_(imu0)
         flt.cam_R.copy_(camR0)
         flt.cam_t.copy_(camt0)
         flt.imu_time.copy_(time0)
-        flt.propagate(samples_dev)
-        flt.update()
-        h_out_state.copy_(flt.imu_state, non_blocking=True)
-        h_out_camt.copy_(flt.cam_t, non_blocking=True)
-        h_out_status.copy_(flt.feat_status, non_blocking=True)
-        h_out_nacc.copy_(flt.n_accepted, non_blocking=True)
+        flt.step_host(host_in, h_samples, host_out, chunk_filters=args.chunk, overlap_previous=True)
 
     def barrier():
         if world > 1:
@@ -497,6 +494,7 @@ def run_gpu(args):
         roofline=roofline, cpu_baseline=cpu, gate_bounds=gate_bounds,
         e2e=dict(value=feats_per_step * e2e_steps / e2e_sec, unit="feature-updates/s", h2d_bytes_per_step=h2d_bytes * world,
                  d2h_bytes_per_step=d2h_bytes * world, ms_per_step=ms_e2e / e2e_steps, steps=e2e_steps,
+                 call="msckf_filter_step_host", chunk_filters=args.chunk,
                  filter_steps_per_s=Btot * e2e_steps / e2e_sec),
         gpu_launches=int(launches), clocks=clocks, setup_s=setup_s)
     print(json.dumps(line))
@@ -546,6 +544,8 @@ if __name__ == "__main__":
     ap.add_argument("--gate", default="exact", choices=["exact", "bounds"],
                     help="exact: every selected feature goes through the full Mahalanobis test (headline); bounds: same "
                          "decisions, features decided by the exact bounds skip the factorisation (reported beside it)")
+    ap.add_argument("--chunk", type=int, default=592,
+                    help="filters per upload/compute/download chunk of the end-to-end (host-buffer) step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 2
+#define MSCKF_B200_ABI_VERSION 3
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
@@ -185,6 +185,55 @@ size_t msckf_remove_workspace_bytes(const msckf_dims* dims);
 int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* remove_mask,
                                  double* cam_R, double* cam_t, double* P, int* n_cams,
                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * msckf_filter_step_host  <->  one camera-frame step of B filters driven from HOST buffers: the n_samples
+ * MSCKF.process_imu calls since the last frame (MSCKF.py:160-248) followed by get_valid_features + update + correct
+ * (MSCKF.py:458-495, 570-661).  This is the call a host-side owner of the tracks (the reference keeps them in Python
+ * objects) makes once per frame.
+ *
+ * The batch is cut into chunks of `chunk_filters` filters.  For every chunk the library copies the host inputs to the
+ * caller's device buffers on an internal copy stream, runs propagate + update of that chunk on `stream`, and copies the
+ * requested results back on a second internal stream, so the PCIe transfers of chunk k+1 / k-1 overlap the kernels of
+ * chunk k.  On return everything is enqueued; `stream` has been made to wait for the last device-to-host copy, so
+ * synchronising `stream` makes all host outputs valid.
+ *
+ *   dev   device buffers of the whole batch (layouts as in msckf_update_batched / msckf_propagate_batched)
+ *   io    host buffers in the same layouts.  A NULL input pointer means "already resident in dev, do not copy";
+ *         a NULL output pointer means "not wanted".  Pinned memory is needed for the copies to be asynchronous.
+ *   chunk_filters  <= 0: one chunk.  A multiple of the resident update-CTA count (2 x SM count) avoids tail waves.
+ *   overlap_previous  non-zero: the uploads of this call may start while work enqueued on `stream` BEFORE the call is
+ *         still running, ordered only after the previous msckf_filter_step_host call's kernels of the same chunk (the
+ *         caller promises nothing else on `stream` still reads the device track buffers).  Zero: uploads start after
+ *         everything already enqueued on `stream`.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct msckf_device_buffers {
+    double* P; double* imu_state; double* imu_null; double* imu_time; const double* Qc_diag;
+    double* cam_R; double* cam_t; const int* n_cams;
+    int* feat_len; double* obs_uv; double* obs_dir; double* obs_conf; int* obs_slot;
+    double* idp_base; int* idp_anchor_slot; double* idp_m; double* idp_rho; int* lost_cnt; int* tracked_cnt;
+    unsigned char* feat_status; double* gamma; int* dof; double* delta_x; int* n_accepted; int* n_rejected;
+    double* imu_samples;     /* [B][n_samples][7] device staging for the IMU samples (may be NULL if n_samples == 0) */
+} msckf_device_buffers;
+
+typedef struct msckf_host_step {
+    /* inputs (host) */
+    const int* feat_len; const double* obs_uv; const double* obs_dir; const double* obs_conf; const int* obs_slot;
+    const double* idp_base; const int* idp_anchor_slot; const double* idp_m; const double* idp_rho;
+    const int* lost_cnt; const int* tracked_cnt;
+    const double* imu_samples; int n_samples;     /* n_samples == 0: no propagation */
+    int use_null_state;                           /* 0: null state = state on entry (see msckf_propagate_batched) */
+    double gravity[3];
+    /* outputs (host) */
+    double* imu_state; double* cam_R; double* cam_t; double* idp_m_out; double* idp_rho_out;
+    unsigned char* feat_status; double* gamma; double* delta_x; int* n_accepted; int* n_rejected;
+} msckf_host_step;
+
+int msckf_filter_step_host(const msckf_dims* dims, const msckf_update_params* params,
+                           const double* chi2_table, int chi2_len,
+                           const msckf_device_buffers* dev, const msckf_host_step* io,
+                           int chunk_filters, int overlap_previous,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* Diagnostic: launches n_ctas x 256 threads, every warp running 8 independent FP64 tensor-instruction (DMMA.8x8x4) chains
  * of length iters (the measured FP64-pipe roofline denominator; MEASURED_PEAKS.json has no FP64 figure).

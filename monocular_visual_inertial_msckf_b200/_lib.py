@@ -28,12 +28,34 @@ class Params(C.Structure):
                 ("compress_mode", C.c_int), ("gate_mode", C.c_int)]
 
 
+class DeviceBuffers(C.Structure):
+    """msckf_device_buffers (include/msckf_b200.h): device pointers of the whole batch."""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "P", "imu_state", "imu_null", "imu_time", "Qc_diag", "cam_R", "cam_t", "n_cams",
+        "feat_len", "obs_uv", "obs_dir", "obs_conf", "obs_slot", "idp_base", "idp_anchor_slot", "idp_m", "idp_rho",
+        "lost_cnt", "tracked_cnt", "feat_status", "gamma", "dof", "delta_x", "n_accepted", "n_rejected", "imu_samples")]
+
+
+HOST_INPUTS = ("feat_len", "obs_uv", "obs_dir", "obs_conf", "obs_slot", "idp_base", "idp_anchor_slot", "idp_m",
+               "idp_rho", "lost_cnt", "tracked_cnt")
+HOST_OUTPUTS = ("imu_state", "cam_R", "cam_t", "idp_m_out", "idp_rho_out", "feat_status", "gamma", "delta_x",
+                "n_accepted", "n_rejected")
+
+
+class HostStep(C.Structure):
+    """msckf_host_step (include/msckf_b200.h): host pointers of one camera-frame step."""
+    _fields_ = ([(n, C.c_void_p) for n in HOST_INPUTS] +
+                [("imu_samples", C.c_void_p), ("n_samples", C.c_int), ("use_null_state", C.c_int),
+                 ("gravity", C.c_double * 3)] +
+                [(n, C.c_void_p) for n in HOST_OUTPUTS])
+
+
 # every symbol include/msckf_b200.h declares
 EXPORTS = [
     "msckf_abi_version", "msckf_max_obs_per_feature", "msckf_max_cameras", "msckf_update_workspace_bytes",
     "msckf_update_batched", "msckf_front_batched", "msckf_compress_batched", "msckf_apply_update_batched",
     "msckf_propagate_batched", "msckf_augment_batched", "msckf_remove_workspace_bytes",
-    "msckf_remove_cameras_batched", "msckf_launch_count", "msckf_probe_fp64",
+    "msckf_remove_cameras_batched", "msckf_launch_count", "msckf_probe_fp64", "msckf_filter_step_host",
 ]
 
 
@@ -82,7 +104,10 @@ def load_library():
     lib.msckf_remove_cameras_batched.argtypes = [pd, u8, dp, dp, dp, ip, vp, C.c_size_t, vp]
     lib.msckf_probe_fp64.restype = C.c_int
     lib.msckf_probe_fp64.argtypes = [C.c_int, C.c_int, dp, C.POINTER(C.c_double), vp]
-    if lib.msckf_abi_version() != 2:
+    lib.msckf_filter_step_host.restype = C.c_int
+    lib.msckf_filter_step_host.argtypes = [pd, pp, dp, C.c_int, C.POINTER(DeviceBuffers), C.POINTER(HostStep), C.c_int,
+                                           C.c_int, vp, C.c_size_t, vp]
+    if lib.msckf_abi_version() != 3:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib
     return lib

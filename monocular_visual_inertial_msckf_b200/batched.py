@@ -127,6 +127,7 @@ class BatchedMSCKF:
             raise ValueError("unsupported dimensions")
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dv)
         self._remove_ws = None
+        self._samples_dev = None
         self.Qc_diag = z(B, 4)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -185,6 +186,54 @@ class BatchedMSCKF:
                                               _ptr(self.imu_null) if use_null_state else C.c_void_p(0),
                                               _ptr(self.P), _ptr(self.n_cams), self._stream())
         _lib.check(rc, "msckf_propagate_batched")
+
+    def step_host(self, host_in, host_samples=None, host_out=None, chunk_filters=592, overlap_previous=False,
+                  use_null_state=False):
+        """One camera-frame step of every filter driven from HOST buffers (msckf_filter_step_host): the IMU samples
+        since the last frame are propagated, then get_valid_features + update + correct run, chunk by chunk, with the
+        uploads / downloads of neighbouring chunks overlapping the kernels.
+
+        host_in:  dict name -> host tensor for any of _lib.HOST_INPUTS (the track arrays, [B, ...] in the device
+                  layout; pinned memory makes the copies asynchronous); missing names stay as resident on the device.
+        host_samples: [B, n, 7] host tensor of IMU samples (timestamp, omega, acc) or None.
+        host_out: dict name -> host tensor for any of _lib.HOST_OUTPUTS.
+        Results are valid once the current stream is synchronised."""
+        io = _lib.HostStep()
+        shapes = dict(feat_len=self.feat_len, obs_uv=self.obs_uv, obs_dir=self.obs_dir, obs_conf=self.obs_conf,
+                      obs_slot=self.obs_slot, idp_base=self.idp_base, idp_anchor_slot=self.idp_anchor_slot,
+                      idp_m=self.idp_m, idp_rho=self.idp_rho, lost_cnt=self.lost_cnt, tracked_cnt=self.tracked_cnt,
+                      imu_state=self.imu_state, cam_R=self.cam_R, cam_t=self.cam_t, idp_m_out=self.idp_m,
+                      idp_rho_out=self.idp_rho, feat_status=self.feat_status, gamma=self.gamma, delta_x=self.delta_x,
+                      n_accepted=self.n_accepted, n_rejected=self.n_rejected)
+        for group, names in ((host_in or {}, _lib.HOST_INPUTS), (host_out or {}, _lib.HOST_OUTPUTS)):
+            for k, t in group.items():
+                if k not in names:
+                    raise KeyError(f"{k} is not a host {'input' if names is _lib.HOST_INPUTS else 'output'} of step_host")
+                d = shapes[k]
+                if t.device.type != "cpu" or t.dtype != d.dtype or tuple(t.shape) != tuple(d.shape) or not t.is_contiguous():
+                    raise ValueError(f"{k}: expected a contiguous host tensor of shape {tuple(d.shape)}, dtype {d.dtype}")
+                setattr(io, k, t.data_ptr())
+        n = 0
+        if host_samples is not None:
+            if (host_samples.device.type != "cpu" or host_samples.dtype != torch.float64 or host_samples.dim() != 3 or
+                    host_samples.shape[0] != self.B or host_samples.shape[2] != 7 or not host_samples.is_contiguous()):
+                raise ValueError("host_samples: expected a contiguous [B, n, 7] float64 host tensor")
+            n = int(host_samples.shape[1])
+            if self._samples_dev is None or self._samples_dev.shape[1] != n:     # device staging, [B][n][7] exactly
+                self._samples_dev = torch.empty(self.B, n, 7, dtype=torch.float64, device=self.device)
+            io.imu_samples = host_samples.data_ptr()
+        io.n_samples = n
+        io.use_null_state = int(bool(use_null_state))
+        for i in range(3):
+            io.gravity[i] = float(self.params.gravity[i])
+        dev = _lib.DeviceBuffers()
+        for k, _ in _lib.DeviceBuffers._fields_:
+            t = self._samples_dev if k == "imu_samples" else getattr(self, k)
+            setattr(dev, k, t.data_ptr() if t is not None else None)
+        rc = self.lib.msckf_filter_step_host(C.byref(self.dims), C.byref(self.cpar), _ptr(self.chi2), self.chi2_len,
+                                             C.byref(dev), C.byref(io), int(chunk_filters), int(bool(overlap_previous)),
+                                             _ptr(self.workspace), self.workspace.numel(), self._stream())
+        _lib.check(rc, "msckf_filter_step_host")
 
     def augment(self, R_I_C, t_I_C, active=None):
         T = (C.c_double * 12)(*[float(x) for x in np.asarray(R_I_C, float).flatten()],

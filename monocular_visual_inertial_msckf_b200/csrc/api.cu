@@ -197,3 +197,126 @@ int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* re
 }
 
 }  // extern "C"
+
+// ---- host-buffer step: chunked upload / compute / download pipeline ------------------------------------------------
+namespace {
+constexpr int HS_MAX_CHUNKS = 256;
+struct HostStepCtx {
+    int device = -1;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_entry = nullptr, ev_out_done = nullptr;
+    cudaEvent_t ev_in[HS_MAX_CHUNKS] = {}, ev_done[HS_MAX_CHUNKS] = {};
+    int n_events = 0;
+};
+HostStepCtx g_hs[16];
+
+cudaError_t hs_ctx(HostStepCtx** out, int n_chunks) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 16) return cudaErrorInvalidDevice;
+    HostStepCtx& c = g_hs[dev];
+    if (c.device != dev) {
+        if ((e = cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&c.ev_entry, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&c.ev_out_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+        c.device = dev;
+    }
+    for (; c.n_events < n_chunks; ++c.n_events) {
+        if ((e = cudaEventCreateWithFlags(&c.ev_in[c.n_events], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&c.ev_done[c.n_events], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    *out = &c;
+    return cudaSuccess;
+}
+
+template <class T>
+cudaError_t hs_copy(T* dst, const T* src, size_t per_filter, int b0, int nb, cudaMemcpyKind kind, cudaStream_t s) {
+    if (!dst || !src || per_filter == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst + (size_t)b0 * per_filter, src + (size_t)b0 * per_filter, (size_t)nb * per_filter * sizeof(T),
+                           kind, s);
+}
+}  // namespace
+
+extern "C" int msckf_filter_step_host(const msckf_dims* dims, const msckf_update_params* params, const double* chi2_table,
+                                      int chi2_len, const msckf_device_buffers* dev, const msckf_host_step* io,
+                                      int chunk_filters, int overlap_previous, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!params || !chi2_table || !dev || !io || !workspace) return MSCKF_EINVAL;
+    if (io->n_samples < 0 || (io->n_samples > 0 && (!dev->imu_samples || !dev->imu_time || !dev->Qc_diag))) return MSCKF_EINVAL;
+    const int B = dims->B, F = dims->F, M = dims->M, N = dims->N, ldp = dims->ldp;
+    if (chunk_filters <= 0 || chunk_filters > B) chunk_filters = B;
+    const int n_chunks = (B + chunk_filters - 1) / chunk_filters;
+    if (n_chunks > HS_MAX_CHUNKS) return MSCKF_ECAPACITY;
+    HostStepCtx* cx = nullptr;
+    cudaError_t e = hs_ctx(&cx, n_chunks);
+    if (e != cudaSuccess) return (int)e;
+    cudaStream_t sc = (cudaStream_t)stream;
+    const size_t FM = (size_t)F * M;
+#define HS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+    if (!overlap_previous) {
+        HS_TRY(cudaEventRecord(cx->ev_entry, sc));
+        HS_TRY(cudaStreamWaitEvent(cx->s_in, cx->ev_entry, 0));
+    }
+    for (int k = 0; k < n_chunks; ++k) {
+        const int b0 = k * chunk_filters, nb = (b0 + chunk_filters <= B) ? chunk_filters : B - b0;
+        // ---- uploads of this chunk (after the previous call's kernels of the same chunk released the buffers) ----
+        HS_TRY(cudaStreamWaitEvent(cx->s_in, cx->ev_done[k], 0));
+        const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
+        HS_TRY(hs_copy(dev->feat_len, io->feat_len, F, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->obs_uv, io->obs_uv, FM * 2, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->obs_dir, io->obs_dir, FM * 3, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->obs_conf, io->obs_conf, FM, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->obs_slot, io->obs_slot, FM, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->idp_base, io->idp_base, (size_t)F * 3, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->idp_anchor_slot, io->idp_anchor_slot, F, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->idp_m, io->idp_m, (size_t)F * 3, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->idp_rho, io->idp_rho, F, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->lost_cnt, io->lost_cnt, F, b0, nb, H2D, cx->s_in));
+        HS_TRY(hs_copy(dev->tracked_cnt, io->tracked_cnt, F, b0, nb, H2D, cx->s_in));
+        if (io->n_samples > 0) HS_TRY(hs_copy(dev->imu_samples, io->imu_samples, (size_t)io->n_samples * 7, b0, nb, H2D, cx->s_in));
+        HS_TRY(cudaEventRecord(cx->ev_in[k], cx->s_in));
+        // ---- kernels of this chunk on the caller's stream ----
+        HS_TRY(cudaStreamWaitEvent(sc, cx->ev_in[k], 0));
+        msckf_dims cd = *dims;
+        cd.B = nb;
+        const size_t o1 = b0;
+        if (io->n_samples > 0) {
+            rc = msckf_propagate_batched(&cd, io->n_samples, dev->imu_samples + o1 * io->n_samples * 7, dev->imu_time + o1,
+                                         dev->Qc_diag + o1 * 4, io->gravity, dev->imu_state + o1 * MSCKF_IMU_STATE_DOUBLES,
+                                         (io->use_null_state && dev->imu_null) ? dev->imu_null + o1 * MSCKF_IMU_NULL_DOUBLES : nullptr,
+                                         dev->P + o1 * ldp * ldp, dev->n_cams + o1, stream);
+            if (rc) return rc;
+        }
+        rc = msckf_update_batched(&cd, params, chi2_table, chi2_len, dev->P + o1 * ldp * ldp,
+                                  dev->imu_state + o1 * MSCKF_IMU_STATE_DOUBLES, dev->cam_R + o1 * N * 9, dev->cam_t + o1 * N * 3,
+                                  dev->n_cams + o1, dev->feat_len + o1 * F, dev->obs_uv + o1 * FM * 2, dev->obs_dir + o1 * FM * 3,
+                                  dev->obs_conf + o1 * FM, dev->obs_slot + o1 * FM, dev->idp_base + o1 * F * 3,
+                                  dev->idp_anchor_slot + o1 * F, dev->idp_m + o1 * F * 3, dev->idp_rho + o1 * F,
+                                  dev->lost_cnt + o1 * F, dev->tracked_cnt + o1 * F, dev->feat_status + o1 * F,
+                                  dev->gamma + o1 * F, dev->dof + o1 * F, dev->delta_x + o1 * ldp, dev->n_accepted + o1,
+                                  dev->n_rejected + o1, workspace, workspace_bytes, stream);
+        if (rc) return rc;
+        HS_TRY(cudaEventRecord(cx->ev_done[k], sc));
+        // ---- downloads of this chunk ----
+        HS_TRY(cudaStreamWaitEvent(cx->s_out, cx->ev_done[k], 0));
+        const cudaMemcpyKind D2H = cudaMemcpyDeviceToHost;
+        HS_TRY(hs_copy(io->imu_state, (const double*)dev->imu_state, MSCKF_IMU_STATE_DOUBLES, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->cam_R, (const double*)dev->cam_R, (size_t)N * 9, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->cam_t, (const double*)dev->cam_t, (size_t)N * 3, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->idp_m_out, (const double*)dev->idp_m, (size_t)F * 3, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->idp_rho_out, (const double*)dev->idp_rho, F, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->feat_status, (const unsigned char*)dev->feat_status, F, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->gamma, (const double*)dev->gamma, F, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->delta_x, (const double*)dev->delta_x, ldp, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->n_accepted, (const int*)dev->n_accepted, 1, b0, nb, D2H, cx->s_out));
+        HS_TRY(hs_copy(io->n_rejected, (const int*)dev->n_rejected, 1, b0, nb, D2H, cx->s_out));
+    }
+    HS_TRY(cudaEventRecord(cx->ev_out_done, cx->s_out));
+    HS_TRY(cudaStreamWaitEvent(sc, cx->ev_out_done, 0));
+#undef HS_TRY
+    return 0;
+}

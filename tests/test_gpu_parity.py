@@ -384,3 +384,58 @@ def test_gate_bounds_mode_gives_identical_decisions_and_state(golden_dir, name):
                 assert rel_err(out[k], c[k]) < 1e-9, (k, rel_err(out[k], c[k]))
     print(name, "decided by bounds:", n_bound, "full test:", n_full)
     assert n_bound > 0
+
+
+@pytest.mark.parametrize("chunk", [2, 3, 0])
+def test_step_host_pipeline_equals_resident_calls(golden_dir, chunk):
+    """msckf_filter_step_host (host buffers in, chunked upload / kernels / download, results out) gives bit-identical
+    results to propagate() + update() on resident inputs, for ragged chunking, and matches the golden update."""
+    cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
+    cases = (cases * 3)[:7]
+    B = len(cases)
+    mode = _lib.COMPRESS_GRAM
+    ref = _batch_from_cases(cases, mode)
+    flt = _batch_from_cases(cases, mode)
+    n = 4
+    rng = np.random.default_rng(5)
+    samples = torch.zeros(B, n, 7, dtype=torch.float64)
+    samples[:, :, 0] = torch.arange(1, n + 1, dtype=torch.float64) * 0.005
+    samples[:, :, 1:4] = torch.from_numpy(0.02 * rng.standard_normal((B, n, 3)))
+    samples[:, :, 4:7] = torch.from_numpy(np.array([0.0, 0.0, 9.81]) + 0.1 * rng.standard_normal((B, n, 3)))
+    for f in (ref, flt):
+        f.Qc_diag[:] = torch.tensor([1e-8, 1e-10, 1e-6, 1e-8], dtype=torch.float64)
+    # resident path
+    ref.propagate(samples.cuda())
+    ref.update()
+    # host path: every track array comes from (pinned) host memory; the device copies are scrambled first
+    host_in = {k: getattr(flt, k).cpu().pin_memory() for k in _lib.HOST_INPUTS}
+    for k in _lib.HOST_INPUTS:
+        getattr(flt, k).fill_(0)
+    host_out = dict(imu_state=torch.empty(B, 21, dtype=torch.float64).pin_memory(),
+                    cam_R=torch.empty(B, flt.N, 9, dtype=torch.float64).pin_memory(),
+                    cam_t=torch.empty(B, flt.N, 3, dtype=torch.float64).pin_memory(),
+                    idp_m_out=torch.empty(B, flt.F, 3, dtype=torch.float64).pin_memory(),
+                    idp_rho_out=torch.empty(B, flt.F, dtype=torch.float64).pin_memory(),
+                    feat_status=torch.empty(B, flt.F, dtype=torch.uint8).pin_memory(),
+                    gamma=torch.empty(B, flt.F, dtype=torch.float64).pin_memory(),
+                    delta_x=torch.empty(B, flt.ldp, dtype=torch.float64).pin_memory(),
+                    n_accepted=torch.empty(B, dtype=torch.int32).pin_memory(),
+                    n_rejected=torch.empty(B, dtype=torch.int32).pin_memory())
+    for rep in range(2):      # second call exercises the cross-call event ordering (overlap_previous)
+        if rep == 1:
+            fresh = _batch_from_cases(cases, mode)
+            for k in ("P", "imu_state", "cam_R", "cam_t", "imu_time", "imu_null"):
+                getattr(flt, k).copy_(getattr(fresh, k))
+        flt.step_host(host_in, samples.pin_memory(), host_out, chunk_filters=chunk, overlap_previous=(rep == 1))
+        torch.cuda.synchronize()
+        for k, dev_name in (("imu_state", "imu_state"), ("cam_R", "cam_R"), ("cam_t", "cam_t"), ("idp_m_out", "idp_m"),
+                            ("idp_rho_out", "idp_rho"), ("feat_status", "feat_status"), ("delta_x", "delta_x"),
+                            ("n_accepted", "n_accepted"), ("n_rejected", "n_rejected")):
+            assert torch.equal(host_out[k], getattr(ref, dev_name).cpu()), (k, rep)
+        g_host, g_ref = host_out["gamma"].numpy(), ref.gamma.cpu().numpy()
+        assert np.array_equal(np.isnan(g_host), np.isnan(g_ref)) and np.array_equal(g_host[~np.isnan(g_host)], g_ref[~np.isnan(g_ref)])
+        assert torch.equal(flt.P, ref.P)
+    with pytest.raises(KeyError):
+        flt.step_host(dict(P=torch.zeros(1)))
+    with pytest.raises(ValueError):
+        flt.step_host(dict(obs_uv=torch.zeros(1, dtype=torch.float64)))
