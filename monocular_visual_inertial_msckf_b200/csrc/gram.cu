@@ -18,9 +18,10 @@
 
 namespace {
 
-constexpr int GT = 256;        // threads per CTA (8 warps, 2 per SM sub-partition)
-constexpr int UMAX = 20;       // (2 tile rows x 1 tile column) units per warp per pass -> 40 accumulator tiles
-constexpr int IMAX = 7;        // D/g items per thread: 27 N_cams / 256 <= 7 for N <= 64
+constexpr int GT = 512;        // threads per CTA (16 warps, 4 per SM sub-partition; <= 128 registers per thread)
+constexpr int GW = GT / 32;
+constexpr int UG = 5;          // units per branch-free group of the tensor loop
+constexpr int UMAX = 10;       // (2 tile rows x 1 tile column) units per warp per pass -> 20 accumulator tiles
 
 __device__ __forceinline__ void cp_async16(void* s, const void* g) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
@@ -33,23 +34,67 @@ __device__ __forceinline__ void cp_async4(void* s, const void* g) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-struct GramSmem {
-    double* panel;      // [3 PF][LD]
-    double* rawA[2];    // [PF][Mcap][12]
-    double* rawQ[2];    // [PF][Mcap][6]
-    double* rawR[2];    // [PF][Mcap][2]
-    int* rawS[2];       // [PF][Mcap]
-    double* Dg;         // [Ncap][27]
-    int* acc_list;      // [F]
-    int* flen;          // [2][PF]
-    signed char* inv;   // [PF][Ncap]
-};
+// shared-memory fragment load at a 32-bit shared address plus a compile-time byte offset.  Volatile on purpose: the
+// loads of a group of units must be ISSUED before the group's tensor instructions (the compiler otherwise sinks each
+// load to just before its use and the warp stalls on every one of them).
+template <int IMM>
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
 
 __device__ __forceinline__ int strip_len(int p, int T) { return min(2 * p + 2, T); }
 
-__global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const int PF, const int LD) {
+// Panel leading dimensions are = 4 mod 16: the DMMA fragment loads [k = t][x = g] of a half-warp then touch 16 distinct
+// 8-byte bank pairs (t * 4 + g); the r01k profile of the previous layout (= 8 mod 16) showed 42% conflicted wavefronts.
+
+// Folds one k-panel (KW rows) into this warp's accumulator tiles.  wbase = shared address of panel element [t][g].
+template <int KW, int LDW, int KK = 0>
+__device__ __forceinline__ void gram_tensor_loop(unsigned wbase, int p0, int J0, int nu, unsigned newstrip,
+                                                 double (&acc)[UMAX][2][2]) {
+    if constexpr (KK < KW) {
+        constexpr int KOFF = KK * LDW * 8;
+        unsigned abase = wbase + 128u * p0;
+        unsigned offb = 64u * J0;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int u0g = 0; u0g < UMAX; u0g += UG) {
+            if (u0g < nu) {
+                double bf[UG];
+#pragma unroll
+                for (int v = 0; v < UG; ++v) {
+                    const int u = u0g + v;
+                    if (u > 0 && ((newstrip >> u) & 1u)) offb = 0;
+                    bf[v] = lds_f64<KOFF>(wbase + offb);
+                    offb += 64u;
+                }
+#pragma unroll
+                for (int v = 0; v < UG; ++v) {
+                    const int u = u0g + v;
+                    if ((newstrip >> u) & 1u) {
+                        a0 = lds_f64<KOFF>(abase);
+                        a1 = lds_f64<KOFF + 64>(abase);
+                        abase += 128u;
+                    }
+                    dense::dmma(acc[u][0][0], acc[u][0][1], a0, bf[v]);
+                    dense::dmma(acc[u][1][0], acc[u][1][1], a1, bf[v]);
+                }
+            }
+        }
+        gram_tensor_loop<KW, LDW, KK + 4>(wbase, p0, J0, nu, newstrip, acc);
+    }
+}
+
+// NMAX = pose capacity of this instantiation (32 or 64): fixes the panels' leading dimensions at compile time, so the
+// k step of every operand load is an immediate offset.  PF = features per panel (8, or 4 when the tracks are long).
+template <int NMAX, int PF>
+__global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a) {
+    constexpr int SMAX = NMAX / GW;                     // window slots per warp for the D / g tiles
+    constexpr int LDW = 6 * NMAX + 4, LDX = 8 * NMAX + 4;   // mod 16 == 4 (see ld_pad4)
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     const int F = a.dims.F, Mcap = a.dims.M, Ncap = a.dims.N;
     const int nc = a.n_cams[b];
     const int c = 6 * nc;
@@ -57,22 +102,25 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const
     const int T = (c + 7) >> 3;            // 8 x 8 output tiles per side
     const int T2 = (T + 1) >> 1;           // 2-row strips
 
+    // shared-memory carve-up (offsets, not pointers: a table of generic pointers would pin two dozen registers)
+    //   panelW [3 PF][LDW]   rows of W = Q1^T H_x of the panel's features (k-panel of W^T W)
+    //   panelX [2 PF][LDX]   rows [A_i | r~_i | 0] per window slot, 8 columns per slot (k-panel of D and g)
+    //   stage[2]             prefetched factors of a panel: A [PF][Mcap][12], Q [PF][Mcap][6], r~ [PF][Mcap][2], slot [PF][Mcap]
+    //   Dg [Ncap][48]        D_s (6 x 6, row stride 8; column 6 = g_s)
+    //   acc_list [F], flen [2][PF] (int), seen [PF][Ncap] (bytes: this (feature, slot) pair has an observation)
     extern __shared__ double smem[];
-    GramSmem S;
-    {
-        double* p = smem;
-        S.panel = p;            p += (size_t)3 * PF * LD;
-        for (int s = 0; s < 2; ++s) { S.rawA[s] = p; p += (size_t)PF * Mcap * 12; }
-        for (int s = 0; s < 2; ++s) { S.rawQ[s] = p; p += (size_t)PF * Mcap * 6; }
-        for (int s = 0; s < 2; ++s) { S.rawR[s] = p; p += (size_t)PF * Mcap * 2; }
-        S.Dg = p;               p += (size_t)Ncap * 27;
-        int* q = (int*)p;
-        for (int s = 0; s < 2; ++s) { S.rawS[s] = q; q += PF * Mcap; }
-        S.acc_list = q;         q += F;
-        S.flen = q;             q += 2 * PF;
-        S.inv = (signed char*)q;
-    }
-    __shared__ int s_wcnt[GT / 32];
+    const int PM = PF * Mcap;
+    double* const panelW = smem;
+    double* const panelX = smem + 3 * PF * LDW;
+    auto rawA = [&](int st) { return smem + (3 * PF * LDW + 2 * PF * LDX) + (size_t)st * PM * 21; };
+    auto rawQ = [&](int st) { return rawA(st) + PM * 12; };
+    auto rawR = [&](int st) { return rawA(st) + PM * 18; };
+    auto rawS = [&](int st) { return reinterpret_cast<int*>(rawA(st) + PM * 20); };
+    double* const Dg = rawA(2);
+    int* const acc_list = reinterpret_cast<int*>(Dg + Ncap * 48);
+    int* const flen = acc_list + F;
+    unsigned char* const seen = reinterpret_cast<unsigned char*>(flen + 2 * PF);
+    __shared__ int s_wcnt[GW];
     __shared__ int s_tot[2];
 
     // ---- ordered list of the features that passed the gate (stacking order = feature order, MSCKF.py:573-588) ----
@@ -89,8 +137,8 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const
         __syncthreads();
         int off = nacc;
         for (int w = 0; w < warp; ++w) off += s_wcnt[w];
-        if (ok) S.acc_list[off + __popc(bal & ((1u << lane) - 1u))] = j;
-        for (int w = 0; w < GT / 32; ++w) nacc += s_wcnt[w];
+        if (ok) acc_list[off + __popc(bal & ((1u << lane) - 1u))] = j;
+        for (int w = 0; w < GW; ++w) nacc += s_wcnt[w];
         __syncthreads();
     }
     if (nrej_local) atomicAdd(&s_tot[1], nrej_local);
@@ -109,55 +157,65 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const
     const int npanels = (nacc + PF - 1) / PF;
     int U = 0;
     for (int p = 0; p < T2; ++p) U += strip_len(p, T);
-    const int npass = (U + 8 * UMAX - 1) / (8 * UMAX);
+    const int npass = (U + GW * UMAX - 1) / (GW * UMAX);
     const int upp = (U + npass - 1) / npass;
+    constexpr int KW = 3 * PF, KX = 2 * PF;      // k extents of the two panels (multiples of 4)
 
-    // asynchronous prefetch of one panel's compact factors
+    // asynchronous prefetch of one panel's compact factors: warp f fetches feature f
     auto prefetch = [&](int pi, int st) {
-        for (int f = 0; f < PF; ++f) {
+        for (int f = warp; f < PF; f += GW) {
             const int k = pi * PF + f;
-            const int j = (k < nacc) ? S.acc_list[k] : -1;
+            const int j = (k < nacc) ? acc_list[k] : -1;
             const int M = (j >= 0) ? min(a.feat_len[(size_t)b * F + j], Mcap) : 0;
-            if (tid == 0) S.flen[st * PF + f] = M;
+            if (lane == 0) flen[st * PF + f] = M;
             if (M <= 0) continue;
             const size_t fj = (size_t)b * F + j;
             const double* gA = a.fac_A + fj * (size_t)Mcap * 12;
             const double* gQ = a.fac_Q + fj * (size_t)Mcap * 6;
             const double* gR = a.fac_rt + fj * (size_t)Mcap * 2;
             const int* gS = a.obs_slot + fj * (size_t)Mcap;
-            double* sA = S.rawA[st] + (size_t)f * Mcap * 12;
-            double* sQ = S.rawQ[st] + (size_t)f * Mcap * 6;
-            double* sR = S.rawR[st] + (size_t)f * Mcap * 2;
-            int* sS = S.rawS[st] + f * Mcap;
-            for (int it = tid; it < 11 * M; it += GT) {
-                if (it < 6 * M) cp_async16(sA + 2 * it, gA + 2 * it);
-                else if (it < 9 * M) cp_async16(sQ + 2 * (it - 6 * M), gQ + 2 * (it - 6 * M));
-                else if (it < 10 * M) cp_async16(sR + 2 * (it - 9 * M), gR + 2 * (it - 9 * M));
-                else cp_async4(sS + (it - 10 * M), gS + (it - 10 * M));
+            double* sA = rawA(st) + (size_t)f * Mcap * 12;
+            double* sQ = rawQ(st) + (size_t)f * Mcap * 6;
+            double* sR = rawR(st) + (size_t)f * Mcap * 2;
+            int* sS = rawS(st) + f * Mcap;
+            for (int it = lane; it < 6 * M; it += 32) cp_async16(sA + 2 * it, gA + 2 * it);
+            for (int it = lane; it < 3 * M; it += 32) cp_async16(sQ + 2 * it, gQ + 2 * it);
+            for (int it = lane; it < M; it += 32) {
+                cp_async16(sR + 2 * it, gR + 2 * it);
+                cp_async4(sS + it, gS + it);
             }
         }
         cp_async_commit();
     };
 
-    double dg[IMAX];
-    const int nitems = nc * 27;
+    for (int e = tid; e < PF * Ncap; e += GT) seen[e] = 0;
 
     for (int pass = 0; pass < npass; ++pass) {
-        // this warp's contiguous range of units in the linearised (strip, column) order
+        // this warp's contiguous range of units in the linearised (strip, column) order; the per-unit operand offsets
+        // are the same for every k step of every panel, so they are worked out once, into registers
         const int ubeg = pass * upp, uend = min(U, ubeg + upp);
-        const int upw = (uend - ubeg + 7) >> 3;
+        const int upw = (uend - ubeg + GW - 1) / GW;
         const int u0 = min(uend, ubeg + warp * upw);
         const int nu = min(uend, u0 + upw) - u0;
         int p0 = 0, J0 = u0;
         while (p0 < T2 && J0 >= strip_len(p0, T)) { J0 -= strip_len(p0, T); ++p0; }
+        unsigned newstrip = 0;       // bit u: unit u is the first of a strip (reload the two A fragments, column 0)
+        {
+            int p = p0, J = J0;
+#pragma unroll
+            for (int u = 0; u < UMAX; ++u) {
+                if (u == 0 || J == 0) newstrip |= 1u << u;
+                if (u < nu && ++J == strip_len(p, T)) { J = 0; ++p; }
+            }
+        }
+        const bool doX = pass == 0;
 
         double acc[UMAX][2][2];
 #pragma unroll
         for (int u = 0; u < UMAX; ++u) acc[u][0][0] = acc[u][0][1] = acc[u][1][0] = acc[u][1][1] = 0.0;
-        if (pass == 0) {
+        double accX[SMAX][2];
 #pragma unroll
-            for (int k = 0; k < IMAX; ++k) dg[k] = 0.0;
-        }
+        for (int k = 0; k < SMAX; ++k) accX[k][0] = accX[k][1] = 0.0;
 
         __syncthreads();
         prefetch(0, 0);
@@ -167,71 +225,72 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const
         for (int pi = 0; pi < npanels; ++pi) {
             const int st = pi & 1;
             if (pi + 1 < npanels) prefetch(pi + 1, st ^ 1);
-            // ---- zero the K-panel and the slot -> observation map ----
-            for (int e = tid; e < 3 * PF * LD; e += GT) S.panel[e] = 0.0;
-            for (int e = tid; e < PF * Ncap; e += GT) S.inv[e] = -1;
-            __syncthreads();
-            // ---- scatter W rows: W[q][6 s + e] = Q1[2i][q] A[2i][e] + Q1[2i+1][q] A[2i+1][e] ----
+            // ---- scatter: W[3f+q][6 s + e] = Q1[2i][q] A[2i][e] + Q1[2i+1][q] A[2i+1][e];  X[2f+r][8 s + .] = [A[2i+r] | r~ | 0]
             for (int it = tid; it < PF * Mcap; it += GT) {
                 const int f = it / Mcap, i = it - f * Mcap;
-                if (i >= S.flen[st * PF + f]) continue;
-                const int s = S.rawS[st][f * Mcap + i];
+                if (i >= flen[st * PF + f]) continue;
+                const int s = rawS(st)[f * Mcap + i];
                 if (s < 0 || s >= nc) continue;
-                const double* A = S.rawA[st] + ((size_t)f * Mcap + i) * 12;
-                const double* Q = S.rawQ[st] + ((size_t)f * Mcap + i) * 6;
-                S.inv[f * Ncap + s] = (signed char)i;
-#pragma unroll
+                // (operands are re-read from shared memory per output row: the 80 accumulator registers of the tensor
+                //  loop stay live across this phase, so it must get by with few registers)
+                const double2* A2 = reinterpret_cast<const double2*>(rawA(st) + ((size_t)f * Mcap + i) * 12);
+                const double* Q = rawQ(st) + ((size_t)f * Mcap + i) * 6;
+                seen[f * Ncap + s] = 1;
+#pragma unroll 1
                 for (int q = 0; q < 3; ++q) {
-                    double* dst = S.panel + (size_t)(3 * f + q) * LD + 6 * s;
+                    double2* dst = reinterpret_cast<double2*>(panelW + (size_t)(3 * f + q) * LDW + 6 * s);
                     const double q0 = Q[q], q1 = Q[3 + q];
 #pragma unroll
-                    for (int e = 0; e < 6; ++e) dst[e] = q0 * A[e] + q1 * A[6 + e];
+                    for (int k = 0; k < 3; ++k) {
+                        const double2 x = A2[k], y = A2[3 + k];
+                        dst[k] = make_double2(q0 * x.x + q1 * y.x, q0 * x.y + q1 * y.y);
+                    }
                 }
-            }
-            __syncthreads();
-            // ---- W^T W on the tensor pipe ----
-            {
-                const int g = lane >> 2, t = lane & 3;
-                for (int kk = 0; kk < 3 * PF; kk += 4) {
-                    const double* row = S.panel + (size_t)(kk + t) * LD + g;
-                    int p = p0, J = J0;
-                    double a0 = row[16 * p], a1 = row[16 * p + 8];
+                if (doX) {
+                    const double* R = rawR(st) + ((size_t)f * Mcap + i) * 2;
+#pragma unroll 1
+                    for (int r = 0; r < 2; ++r) {
+                        double2* dst = reinterpret_cast<double2*>(panelX + (size_t)(2 * f + r) * LDX + 8 * s);
 #pragma unroll
-                    for (int u = 0; u < UMAX; ++u) {
-                        if (u < nu) {
-                            const double bf = row[8 * J];
-                            dense::dmma(acc[u][0][0], acc[u][0][1], a0, bf);
-                            dense::dmma(acc[u][1][0], acc[u][1][1], a1, bf);
-                            if (++J == strip_len(p, T)) {
-                                J = 0;
-                                ++p;
-                                if (p < T2) { a0 = row[16 * p]; a1 = row[16 * p + 8]; }
-                            }
-                        }
+                        for (int k = 0; k < 3; ++k) dst[k] = A2[3 * r + k];
+                        dst[3] = make_double2(R[r], 0.0);
                     }
                 }
             }
-            // ---- D = sum A_i^T A_i (6 x 6 lower per slot) and g = sum A_i^T r~_i, in feature order ----
-            if (pass == 0) {
+            __syncthreads();
+            // ---- (feature, slot) pairs without an observation contribute zero rows ----
+            for (int it = tid; it < PF * nc; it += GT) {
+                const int f = it / nc, s = it - f * nc;
+                if (seen[f * Ncap + s]) { seen[f * Ncap + s] = 0; continue; }
 #pragma unroll
-                for (int k = 0; k < IMAX; ++k) {
-                    const int item = tid + k * GT;
-                    if (item < nitems) {
-                        const int s = item / 27, e = item - 27 * s;
-                        int ea = 0, eb = 0;
-                        if (e < 21) { while ((ea + 1) * (ea + 2) / 2 <= e) ++ea; eb = e - ea * (ea + 1) / 2; } else ea = e - 21;
-                        double v = dg[k];
-                        for (int f = 0; f < PF; ++f) {
-                            const int i = S.inv[f * Ncap + s];
-                            if (i < 0) continue;
-                            const double* A = S.rawA[st] + ((size_t)f * Mcap + i) * 12;
-                            if (e < 21) v += A[ea] * A[eb] + A[6 + ea] * A[6 + eb];
-                            else {
-                                const double* R = S.rawR[st] + ((size_t)f * Mcap + i) * 2;
-                                v += A[ea] * R[0] + A[6 + ea] * R[1];
-                            }
+                for (int q = 0; q < 3; ++q) {
+                    double2* dst = reinterpret_cast<double2*>(panelW + (size_t)(3 * f + q) * LDW + 6 * s);
+                    dst[0] = dst[1] = dst[2] = make_double2(0.0, 0.0);
+                }
+                if (doX) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        double2* dst = reinterpret_cast<double2*>(panelX + (size_t)(2 * f + r) * LDX + 8 * s);
+                        dst[0] = dst[1] = dst[2] = dst[3] = make_double2(0.0, 0.0);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- W^T W on the tensor pipe: per k step, the B fragments of a group of units are loaded first, then the
+            //      tensor instructions are issued back to back (no branch per unit; units beyond nu work on dead tiles) ----
+            gram_tensor_loop<KW, LDW>((unsigned)__cvta_generic_to_shared(panelW) + (unsigned)(t * LDW + g) * 8u, p0, J0, nu,
+                                      newstrip, acc);
+            // ---- D_s = sum A_i^T A_i and g_s = sum A_i^T r~_i: one 8 x 8 tile per window slot, operand A == operand B ----
+            if (doX) {
+                const double* xrow = panelX + (size_t)t * LDX + g + 8 * warp;
+#pragma unroll
+                for (int kk = 0; kk < KX; kk += 4) {
+#pragma unroll
+                    for (int k = 0; k < SMAX; ++k) {
+                        if (warp + GW * k < nc) {
+                            const double x = xrow[kk * LDX + 8 * GW * k];
+                            dense::dmma(accX[k][0], accX[k][1], x, x);
                         }
-                        dg[k] = v;
                     }
                 }
             }
@@ -239,25 +298,28 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const
             __syncthreads();
         }
 
-        if (pass == 0) {
+        if (doX) {
 #pragma unroll
-            for (int k = 0; k < IMAX; ++k) {
-                const int item = tid + k * GT;
-                if (item < nitems) S.Dg[item] = dg[k];
+            for (int k = 0; k < SMAX; ++k) {
+                const int s = warp + GW * k;
+                if (s < nc && g < 6) {   // rows 6, 7 of the tile are by-products (r~^T A, 0)
+                    Dg[s * 48 + g * 8 + 2 * t] = accX[k][0];
+                    Dg[s * 48 + g * 8 + 2 * t + 1] = accX[k][1];
+                }
             }
             __syncthreads();
             for (int e = tid; e < ccap; e += GT) {
                 const int s = e / 6, aa = e - 6 * s;
-                gout[e] = (s < nc) ? S.Dg[s * 27 + 21 + aa] : 0.0;
+                gout[e] = (s < nc) ? Dg[s * 48 + aa * 8 + 6] : 0.0;
             }
         }
         // ---- G = D - W^T W: lower tiles written with their mirror image ----
         {
-            const int g = lane >> 2, t = lane & 3;
             int p = p0, J = J0;
 #pragma unroll
             for (int u = 0; u < UMAX; ++u) {
                 if (u < nu) {
+                    if (u > 0 && ((newstrip >> u) & 1u)) { ++p; J = 0; }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int I = 2 * p + h;
@@ -271,7 +333,7 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const
                                     const int s = r / 6;
                                     if (col >= 6 * s) {
                                         const int ea = r - 6 * s, eb = col - 6 * s;
-                                        v += S.Dg[s * 27 + ea * (ea + 1) / 2 + eb];
+                                        v += Dg[s * 48 + ea * 8 + eb];
                                     }
                                     Gout[(size_t)r * ccap + col] = v;
                                     Gout[(size_t)col * ccap + r] = v;
@@ -279,7 +341,7 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const
                             }
                         }
                     }
-                    if (++J == strip_len(p, T)) { J = 0; ++p; }
+                    ++J;
                 }
             }
         }
@@ -293,19 +355,31 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a, const
     }
 }
 
-struct GramPlan { int PF, LD; size_t smem; };
+struct GramPlan { int NMAX, PF; size_t smem; };
 
 GramPlan gram_plan(const msckf_dims& d) {
     GramPlan best{0, 0, 0};
-    const int T = (6 * d.N + 7) / 8, T2 = (T + 1) / 2;
-    const int LD = 16 * T2 + 8;                        // LD mod 16 == 8: conflict-free DMMA fragment loads
-    for (int PF = 8; PF >= 1; PF >>= 1) {
-        if ((3 * PF) % 4 != 0 && PF != 4 && PF != 8) continue;
-        size_t doubles = (size_t)3 * PF * LD + (size_t)2 * PF * d.M * 20 + (size_t)d.N * 27;
-        size_t bytes = doubles * 8 + ((size_t)2 * PF * d.M + d.F + 2 * PF) * 4 + (size_t)PF * d.N + 64;
-        if (bytes <= 227 * 1024) { best = GramPlan{PF, LD, bytes}; break; }
+    if (d.N > 64) return best;
+    const int NMAX = d.N <= 32 ? 32 : 64;
+    const int LDW = 6 * NMAX + 4, LDX = 8 * NMAX + 4;
+    for (int PF = 8; PF >= 4; PF >>= 1) {
+        size_t doubles = (size_t)3 * PF * LDW + (size_t)2 * PF * LDX + (size_t)2 * PF * d.M * 21 + (size_t)d.N * 48;
+        size_t bytes = doubles * 8 + ((size_t)d.F + 2 * PF) * 4 + (size_t)PF * d.N + 64;
+        if (bytes <= 227 * 1024) { best = GramPlan{NMAX, PF, bytes}; break; }
     }
     return best;
+}
+
+template <int NMAX, int PF>
+cudaError_t gram_launch(const CompressArgs& a, size_t smem, cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gram_kernel<NMAX, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    gram_kernel<NMAX, PF><<<a.dims.B, GT, smem, s>>>(a);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -315,13 +389,7 @@ bool gram_supported(const msckf_dims& d) { return gram_plan(d).PF >= 4; }
 cudaError_t launch_compress_gram(const CompressArgs& a, cudaStream_t s) {
     const GramPlan pl = gram_plan(a.dims);
     if (pl.PF < 4) return cudaErrorInvalidConfiguration;
-    static size_t configured = 0;
-    if (pl.smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-        if (e != cudaSuccess) return e;
-        configured = pl.smem;
-    }
-    gram_kernel<<<a.dims.B, GT, pl.smem, s>>>(a, pl.PF, pl.LD);
     msckf_count_launch(1);
-    return cudaGetLastError();
+    if (pl.NMAX == 32) return pl.PF == 8 ? gram_launch<32, 8>(a, pl.smem, s) : gram_launch<32, 4>(a, pl.smem, s);
+    return pl.PF == 8 ? gram_launch<64, 8>(a, pl.smem, s) : gram_launch<64, 4>(a, pl.smem, s);
 }
