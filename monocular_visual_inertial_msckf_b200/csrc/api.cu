@@ -1,6 +1,7 @@
 // C-ABI entry points of libmsckf_b200.so (declared in include/msckf_b200.h).  Argument checking + workspace carve-up +
 // kernel launches on the caller's stream; no allocation, no synchronisation, no torch types.
 #include <atomic>
+#include <cstdlib>
 #include "msckf_common.cuh"
 
 static std::atomic<long long> g_launches{0};
@@ -11,6 +12,9 @@ bool front_warp_supported(const msckf_dims& d);
 cudaError_t launch_front_warp(const FrontArgs& a, cudaStream_t s);
 size_t info_scratch_doubles(const msckf_dims& d);
 cudaError_t launch_update_info(const ApplyArgs& a, int n_ctas, cudaStream_t s);
+bool update_smem_supported(const msckf_dims& d);
+size_t update_smem_scratch_doubles(const msckf_dims& d);
+cudaError_t launch_update_smem(const ApplyArgs& a, int n_ctas, cudaStream_t s);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -27,7 +31,8 @@ WsLayout msckf_ws_layout(const msckf_dims& d, int mode) {
     w.nacc = off;     off = align256(off + (size_t)d.B * sizeof(int));
     w.nrej = off;     off = align256(off + (size_t)d.B * sizeof(int));
     w.n_update_ctas = apply_num_ctas(d);
-    const size_t sd = apply_scratch_doubles(d) > info_scratch_doubles(d) ? apply_scratch_doubles(d) : info_scratch_doubles(d);
+    size_t sd = apply_scratch_doubles(d) > info_scratch_doubles(d) ? apply_scratch_doubles(d) : info_scratch_doubles(d);
+    if (update_smem_supported(d) && update_smem_scratch_doubles(d) > sd) sd = update_smem_scratch_doubles(d);
     w.scratch_per_cta = align256(sd * sizeof(double));
     w.scratch = off;  off = align256(off + (size_t)w.n_update_ctas * w.scratch_per_cta);
     w.total = off;
@@ -133,6 +138,7 @@ int msckf_apply_update_batched(const msckf_dims* dims, const msckf_update_params
     a.scratch = (double*)((char*)workspace + w.scratch);
     a.scratch_per_cta = w.scratch_per_cta / sizeof(double);
     if (params->compress_mode == MSCKF_COMPRESS_QR) return (int)launch_apply(a, w.n_update_ctas, (cudaStream_t)stream);
+    if (update_smem_supported(*dims) && !getenv("MSCKF_UPDATE_L2")) return (int)launch_update_smem(a, w.n_update_ctas, (cudaStream_t)stream);
     return (int)launch_update_info(a, w.n_update_ctas, (cudaStream_t)stream);
 }
 
