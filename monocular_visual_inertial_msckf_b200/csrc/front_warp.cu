@@ -35,7 +35,6 @@ struct WarpScratch {
     double A[2 * FW_MAX_OBS][6];     // observability-projected Jacobian rows
     double aug[2 * FW_MAX_OBS][4];   // r~, Q1[:, 0..2] per measurement row
     double2 rowbuf[TC][32];          // one tile row of K in accumulator-fragment layout (staging for the registers)
-    int slot[FW_MAX_OBS];
 };
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -98,6 +97,29 @@ __device__ void sym3_eig_w(const double* a, double* lam, double* V) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) V[r * 3 + k] = Q[r][k];
     }
+}
+
+// p = X^-1 y for a comfortably non-singular symmetric positive definite 3x3 X (a = [xx, xy, xz, yy, yz, zz]) by LDL^T.
+// Returns false when det(X) <= 1e-9 tr(X)^3 (lambda_min / lambda_max could be below ~1e-9): only then can the 1e-15
+// singular-value cut-off of np.linalg.pinv (geometry.py:299) matter, and the caller takes the eigen-decomposition path.
+__device__ __forceinline__ bool sym3_solve_spd(const double* a, const double* y, double* p) {
+    const double d0 = a[0];
+    if (!(d0 > 0.0)) return false;
+    const double i0 = 1.0 / d0;
+    const double l10 = a[1] * i0, l20 = a[2] * i0;
+    const double d1 = a[3] - l10 * a[1];
+    if (!(d1 > 0.0)) return false;
+    const double i1 = 1.0 / d1;
+    const double e21 = a[4] - l20 * a[1];
+    const double l21 = e21 * i1;
+    const double d2 = a[5] - l20 * a[2] - l21 * e21;
+    const double tr = a[0] + a[3] + a[5];
+    if (!(d2 > 0.0) || !(d0 * d1 * d2 > 1e-9 * tr * tr * tr)) return false;
+    const double z0 = y[0], z1 = y[1] - l10 * z0, z2 = y[2] - l20 * z0 - l21 * z1;
+    p[2] = z2 / d2;
+    p[1] = z1 * i1 - l21 * p[2];
+    p[0] = z0 * i0 - l10 * p[1] - l20 * p[2];
+    return true;
 }
 
 // singular values of a 3x3 matrix G (row-major, destroyed) by one-sided Jacobi
@@ -198,6 +220,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
 
     const double s2 = a.par.sigma_image * a.par.sigma_image;
     const double g0 = a.par.gravity[0], g1 = a.par.gravity[1], g2 = a.par.gravity[2];
+    const bool cos_ok = a.par.min_parallax_deg > 0.0 && a.par.min_parallax_deg < 180.0;
+    const double cos_thr = cos_ok ? cos(a.par.min_parallax_deg * (3.14159265358979323846 / 180.0)) : 0.0;
 
     ObsRegs nxt;
     int Mn = 0;
@@ -243,10 +267,18 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
                 if (a.par.use_parallax && M > 1) {
                     const double ax = shfl_d(o.dx, 0), ay = shfl_d(o.dy, 0), az = shfl_d(o.dz, 0);
                     const double bx = shfl_d(o.dx, M - 1), by = shfl_d(o.dy, M - 1), bz = shfl_d(o.dz, M - 1);
-                    const double n1 = sqrt(ax * ax + ay * ay + az * az), n2_ = sqrt(bx * bx + by * by + bz * bz);
-                    double dp = (ax / n1) * (bx / n2_) + (ay / n1) * (by / n2_) + (az / n1) * (bz / n2_);
-                    dp = fmin(1.0, fmax(-1.0, dp));
-                    enough = acos(dp) * (180.0 / 3.14159265358979323846) > a.par.min_parallax_deg;
+                    // acos(dp) in degrees > min_parallax  <=>  dp < cos(min_parallax): decided on the cosine unless it sits
+                    // within 1e-9 of the threshold, where the reference's own expression is evaluated (geometry.py:237-256)
+                    const double na = ax * ax + ay * ay + az * az, nb = bx * bx + by * by + bz * bz;
+                    const double dq = (ax * bx + ay * by + az * bz) * fast_rsqrt(na * nb);
+                    if (cos_ok && na * nb > 0.0 && fabs(dq - cos_thr) > 1e-9) {
+                        enough = dq < cos_thr;
+                    } else {
+                        const double n1 = sqrt(na), n2_ = sqrt(nb);
+                        double dp = (ax / n1) * (bx / n2_) + (ay / n1) * (by / n2_) + (az / n1) * (bz / n2_);
+                        dp = fmin(1.0, fmax(-1.0, dp));
+                        enough = acos(dp) * (180.0 / 3.14159265358979323846) > a.par.min_parallax_deg;
+                    }
                 }
                 code = (lost || enough) ? (MSCKF_FEAT_ACCEPTED | (lost ? MSCKF_FEAT_LOST_FLAG : 0)) : MSCKF_FEAT_SKIPPED;
             }
@@ -280,17 +312,20 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
             }
 #pragma unroll
             for (int k = 0; k < 9; ++k) term[k] = warp_sum_all(live ? term[k] : 0.0);
-            double lam[3], V[9];
-            sym3_eig_w(term, lam, V);
-            const double lmax = fmax(fabs(lam[0]), fmax(fabs(lam[1]), fabs(lam[2])));
             double p[3] = {0, 0, 0};
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (fabs(lam[k]) > 1e-15 * lmax) {   // np.linalg.pinv default rcond
-                    const double coef = (V[0 + k] * term[6] + V[3 + k] * term[7] + V[6 + k] * term[8]) / lam[k];
-                    p[0] += coef * V[0 + k];
-                    p[1] += coef * V[3 + k];
-                    p[2] += coef * V[6 + k];
+            if (!sym3_solve_spd(term, term + 6, p)) {   // (nearly) singular X: pinv with its singular-value cut-off
+                double lam[3], V[9];
+                sym3_eig_w(term, lam, V);
+                const double lmax = fmax(fabs(lam[0]), fmax(fabs(lam[1]), fabs(lam[2])));
+                p[0] = p[1] = p[2] = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < 3; ++k) {
+                    if (fabs(lam[k]) > 1e-15 * lmax) {   // np.linalg.pinv default rcond
+                        const double coef = (V[0 + k] * term[6] + V[3 + k] * term[7] + V[6 + k] * term[8]) / lam[k];
+                        p[0] += coef * V[0 + k];
+                        p[1] += coef * V[3 + k];
+                        p[2] += coef * V[6 + k];
+                    }
                 }
             }
             // first observing camera (MSCKF.py:481-488)
@@ -486,7 +521,6 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
             fR[0] = rt0; fR[1] = rt1;
             ws->aug[2 * lane][0] = rt0;
             ws->aug[2 * lane + 1][0] = rt1;
-            ws->slot[lane] = o.slot;
         }
         __syncwarp();
 
@@ -539,59 +573,97 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
         const int Tn = (n2 + 7) >> 3;
         double S[NTILE][2];
         double Ga[TC][2];
+        // Each lane computes one whole 2x2 block  A_i P[s_i, s_k] A_k^T  (so every 6x6 block of P is read from shared
+        // memory by exactly one lane): row observation i = 4 I + (g >> 1), column observation k = 4 J + t, and the low bit
+        // of g picks the tile J = 2 Jp + h of a PAIR of tiles handled per pass.  One exchange with lane ^ 4 then puts row
+        // 2 i + (g & 1) of both tiles into the accumulator-fragment layout.
+        const int h = g & 1;
+        unsigned sk_lo = 0, sk_hi = 0;      // slots of this lane's column observations k = 4 J + t, one byte per J
+#pragma unroll
+        for (int J = 0; J < TC; ++J) {
+            const int s_k = __shfl_sync(0xffffffffu, o.slot, (4 * J + t) & 31) & 0xff;
+            if (J < 4) sk_lo |= (unsigned)s_k << (8 * J); else sk_hi |= (unsigned)s_k << (8 * (J - 4));
+        }
 #pragma unroll 1
         for (int I = 0; I < Tn; ++I) {
-            const int i = 4 * I + (g >> 1), comp = g & 1;
+            const int i = 4 * I + (g >> 1);
             const bool iv = i < M;
-            double ai[6];
+            const int si = __shfl_sync(0xffffffffu, o.slot, i & 31);
+            double ai[2][6];
+            {
+                const double2* Ai = reinterpret_cast<const double2*>(&ws->A[2 * (iv ? i : 0)][0]);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) ai[k] = iv ? ws->A[2 * i + comp][k] : 0.0;
-            const int si = iv ? ws->slot[i] : 0;
+                for (int c2 = 0; c2 < 6; ++c2) {
+                    const double2 x = Ai[c2];
+                    ai[c2 / 3][2 * (c2 % 3)] = iv ? x.x : 0.0;
+                    ai[c2 / 3][2 * (c2 % 3) + 1] = iv ? x.y : 0.0;
+                }
+            }
 #pragma unroll 1
-            for (int J = 0; J <= I; ++J) {
-                double o0 = 0.0, o1 = 0.0;
+            for (int Jp = 0; 2 * Jp <= I; ++Jp) {
+                const int J = 2 * Jp + h;
                 const int k = 4 * J + t;
-                if (iv && k < M && !(I == J && k > i)) {
-                    const int sk = ws->slot[k];
-                    double v[6];
+                double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
+                if (iv && J <= I && k < M && !(I == J && k > i)) {
+                    const int sk = (int)(((J < 4 ? sk_lo : sk_hi) >> (8 * (J & 3))) & 0xffu);
+                    double v0[6], v1[6];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) { v0[c] = 0.0; v1[c] = 0.0; }
                     if (si >= sk) {
                         const double2* Pb = reinterpret_cast<const double2*>(sP + (size_t)(si * (si + 1) / 2 + sk) * 36);
-#pragma unroll
-                        for (int c2 = 0; c2 < 3; ++c2) { v[2 * c2] = 0.0; v[2 * c2 + 1] = 0.0; }
 #pragma unroll
                         for (int r = 0; r < 6; ++r) {
 #pragma unroll
                             for (int c2 = 0; c2 < 3; ++c2) {
                                 const double2 pv = Pb[r * 3 + c2];
-                                v[2 * c2] += ai[r] * pv.x;
-                                v[2 * c2 + 1] += ai[r] * pv.y;
+                                v0[2 * c2] += ai[0][r] * pv.x;
+                                v0[2 * c2 + 1] += ai[0][r] * pv.y;
+                                v1[2 * c2] += ai[1][r] * pv.x;
+                                v1[2 * c2 + 1] += ai[1][r] * pv.y;
                             }
                         }
                     } else {   // transposed block (slots not increasing with the observation index)
-                        const double* Pb = sP + (size_t)(sk * (sk + 1) / 2 + si) * 36;
+                        const double2* Pb = reinterpret_cast<const double2*>(sP + (size_t)(sk * (sk + 1) / 2 + si) * 36);
 #pragma unroll
                         for (int c = 0; c < 6; ++c) {
-                            double acc = 0.0;
 #pragma unroll
-                            for (int r = 0; r < 6; ++r) acc += ai[r] * Pb[c * 6 + r];
-                            v[c] = acc;
+                            for (int r2 = 0; r2 < 3; ++r2) {
+                                const double2 pv = Pb[c * 3 + r2];
+                                v0[c] += ai[0][2 * r2] * pv.x + ai[0][2 * r2 + 1] * pv.y;
+                                v1[c] += ai[1][2 * r2] * pv.x + ai[1][2 * r2 + 1] * pv.y;
+                            }
                         }
                     }
                     const double2* Ak = reinterpret_cast<const double2*>(&ws->A[2 * k][0]);
 #pragma unroll
                     for (int c2 = 0; c2 < 3; ++c2) {
                         const double2 x0 = Ak[c2], x1 = Ak[3 + c2];
-                        o0 += v[2 * c2] * x0.x + v[2 * c2 + 1] * x0.y;
-                        o1 += v[2 * c2] * x1.x + v[2 * c2 + 1] * x1.y;
+                        o00 += v0[2 * c2] * x0.x + v0[2 * c2 + 1] * x0.y;
+                        o01 += v0[2 * c2] * x1.x + v0[2 * c2 + 1] * x1.y;
+                        o10 += v1[2 * c2] * x0.x + v1[2 * c2 + 1] * x0.y;
+                        o11 += v1[2 * c2] * x1.x + v1[2 * c2 + 1] * x1.y;
                     }
                 }
-                if (I == J) {   // sigma^2 on the diagonal, identity on padded rows
+                // even lanes (h = 0) computed tile 2 Jp and keep its row 2 i; odd lanes computed tile 2 Jp + 1 and keep its
+                // row 2 i + 1; the other row of each block goes to the partner lane
+                const double r0 = __shfl_xor_sync(0xffffffffu, h ? o00 : o10, 4);
+                const double r1 = __shfl_xor_sync(0xffffffffu, h ? o01 : o11, 4);
+                double e0 = h ? r0 : o00, e1 = h ? r1 : o01;       // fragment of tile 2 Jp
+                double f0 = h ? o10 : r0, f1 = h ? o11 : r1;       // fragment of tile 2 Jp + 1
+                {   // sigma^2 on the diagonal, identity on padded rows
                     const int row = 8 * I + g;
                     const double dg = (row < n2) ? s2 : 1.0;
-                    if (g == 2 * t) o0 += dg;
-                    if (g == 2 * t + 1) o1 += dg;
+                    if (2 * Jp == I) {
+                        if (g == 2 * t) e0 += dg;
+                        if (g == 2 * t + 1) e1 += dg;
+                    }
+                    if (2 * Jp + 1 == I) {
+                        if (g == 2 * t) f0 += dg;
+                        if (g == 2 * t + 1) f1 += dg;
+                    }
                 }
-                ws->rowbuf[J][lane] = make_double2(o0, o1);
+                ws->rowbuf[2 * Jp][lane] = make_double2(e0, e1);
+                if (2 * Jp + 1 <= I) ws->rowbuf[2 * Jp + 1][lane] = make_double2(f0, f1);
             }
             // the finished tile row goes from the staging buffer into the statically indexed register array
             switch (I) {
