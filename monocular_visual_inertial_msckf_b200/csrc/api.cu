@@ -10,6 +10,10 @@ int tsqr_max_cams();
 bool gram_supported(const msckf_dims& d);
 bool front_warp_supported(const msckf_dims& d);
 cudaError_t launch_front_warp(const FrontArgs& a, cudaStream_t s);
+bool front_split_supported(const msckf_dims& d);
+int front_split_sub_filters(const msckf_dims& d);
+size_t front_split_tile_bytes(const msckf_dims& d);
+cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, cudaStream_t s);
 size_t info_scratch_doubles(const msckf_dims& d);
 cudaError_t launch_update_info(const ApplyArgs& a, int n_ctas, cudaStream_t s);
 bool update_smem_supported(const msckf_dims& d);
@@ -35,6 +39,11 @@ WsLayout msckf_ws_layout(const msckf_dims& d, int mode) {
     if (update_smem_supported(d) && update_smem_scratch_doubles(d) > sd) sd = update_smem_scratch_doubles(d);
     w.scratch_per_cta = align256(sd * sizeof(double));
     w.scratch = off;  off = align256(off + (size_t)w.n_update_ctas * w.scratch_per_cta);
+    if (front_split_supported(d)) {
+        w.k_tiles = off;    off = align256(off + front_split_tile_bytes(d));
+        w.pend_list = off;  off = align256(off + (size_t)front_split_sub_filters(d) * d.F * sizeof(int));
+        w.pend_count = off; off = align256(off + sizeof(int));
+    }
     w.total = off;
     (void)mode;
     return w;
@@ -96,6 +105,10 @@ int msckf_front_batched(const msckf_dims* dims, const msckf_update_params* param
                              obs_conf, obs_slot, idp_base, idp_anchor_slot, idp_m, idp_rho, lost_cnt, tracked_cnt,
                              feat_status, gamma, dof, (char*)workspace, w);
     // warp-per-feature kernel when the track length / window fit its tile budget, CTA-per-feature kernel otherwise
+    // split front end (assembly kernel + factorisation kernel) by default; MSCKF_FRONT_FUSED=1 selects the fused kernel
+    if (front_split_supported(*dims) && !getenv("MSCKF_FRONT_FUSED"))
+        return (int)launch_front_split(a, (double2*)((char*)workspace + w.k_tiles), (int*)((char*)workspace + w.pend_list),
+                                       (int*)((char*)workspace + w.pend_count), (cudaStream_t)stream);
     if (front_warp_supported(*dims)) return (int)launch_front_warp(a, (cudaStream_t)stream);
     return (int)launch_front(a, (cudaStream_t)stream);
 }

@@ -22,138 +22,22 @@
 // No explicit null-space basis, no dense 2M x d Jacobian, no projected 2M x 2M matrix is ever formed.
 #include "msckf_common.cuh"
 #include "dense.cuh"
+#include "front_geom.cuh"
 
 namespace {
+
+using namespace fgeom;
 
 constexpr int FW_THREADS = 256;
 constexpr int FW_WARPS = FW_THREADS / 32;
 constexpr int TC = 8;                         // 8x8 tile columns -> up to 64 measurement rows (32 observations)
 constexpr int NTILE = TC * (TC + 1) / 2;
-constexpr int FW_MAX_OBS = 4 * TC;
 
 struct WarpScratch {
     double A[2 * FW_MAX_OBS][6];     // observability-projected Jacobian rows
     double aug[2 * FW_MAX_OBS][4];   // r~, Q1[:, 0..2] per measurement row
     double2 rowbuf[TC][32];          // one tile row of K in accumulator-fragment layout (staging for the registers)
 };
-
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-// 1/sqrt(x) for x > 0 (0 for x <= 0): hardware seed (MUFU.RSQ64H, ~2^-22) + two Newton steps, no slow-path branch
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double hx = 0.5 * x;
-    y = y * fma(-hx * y, y, 1.5);
-    y = y * fma(-hx * y, y, 1.5);
-    return x > 0.0 ? y : 0.0;
-}
-
-__device__ __forceinline__ double warp_sum_all(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// cyclic Jacobi eigen-decomposition of a symmetric 3x3 (a = [xx, xy, xz, yy, yz, zz]); V columns = eigenvectors
-__device__ void sym3_eig_w(const double* a, double* lam, double* V) {
-    double A[3][3] = {{a[0], a[1], a[2]}, {a[1], a[3], a[4]}, {a[2], a[4], a[5]}};
-    double Q[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-        const double dia = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
-        if (off <= 1e-300 || off <= 1e-18 * dia) break;
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-            for (int q = p + 1; q < 3; ++q) {
-                if (A[p][q] == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double akp = A[k][p], akq = A[k][q];
-                    A[k][p] = c * akp - s * akq;
-                    A[k][q] = s * akp + c * akq;
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double apk = A[p][k], aqk = A[q][k];
-                    A[p][k] = c * apk - s * aqk;
-                    A[q][k] = s * apk + c * aqk;
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double qkp = Q[k][p], qkq = Q[k][q];
-                    Q[k][p] = c * qkp - s * qkq;
-                    Q[k][q] = s * qkp + c * qkq;
-                }
-            }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        lam[k] = A[k][k];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) V[r * 3 + k] = Q[r][k];
-    }
-}
-
-// p = X^-1 y for a comfortably non-singular symmetric positive definite 3x3 X (a = [xx, xy, xz, yy, yz, zz]) by LDL^T.
-// Returns false when det(X) <= 1e-9 tr(X)^3 (lambda_min / lambda_max could be below ~1e-9): only then can the 1e-15
-// singular-value cut-off of np.linalg.pinv (geometry.py:299) matter, and the caller takes the eigen-decomposition path.
-__device__ __forceinline__ bool sym3_solve_spd(const double* a, const double* y, double* p) {
-    const double d0 = a[0];
-    if (!(d0 > 0.0)) return false;
-    const double i0 = 1.0 / d0;
-    const double l10 = a[1] * i0, l20 = a[2] * i0;
-    const double d1 = a[3] - l10 * a[1];
-    if (!(d1 > 0.0)) return false;
-    const double i1 = 1.0 / d1;
-    const double e21 = a[4] - l20 * a[1];
-    const double l21 = e21 * i1;
-    const double d2 = a[5] - l20 * a[2] - l21 * e21;
-    const double tr = a[0] + a[3] + a[5];
-    if (!(d2 > 0.0) || !(d0 * d1 * d2 > 1e-9 * tr * tr * tr)) return false;
-    const double z0 = y[0], z1 = y[1] - l10 * z0, z2 = y[2] - l20 * z0 - l21 * z1;
-    p[2] = z2 / d2;
-    p[1] = z1 * i1 - l21 * p[2];
-    p[0] = z0 * i0 - l10 * p[1] - l20 * p[2];
-    return true;
-}
-
-// singular values of a 3x3 matrix G (row-major, destroyed) by one-sided Jacobi
-__device__ void svals3_w(double* G, double* sv) {
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        bool rotated = false;
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-            for (int q = p + 1; q < 3; ++q) {
-                double al = 0, be = 0, ga = 0;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    al += G[k * 3 + p] * G[k * 3 + p];
-                    be += G[k * 3 + q] * G[k * 3 + q];
-                    ga += G[k * 3 + p] * G[k * 3 + q];
-                }
-                if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
-                rotated = true;
-                const double zeta = (be - al) / (2.0 * ga);
-                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double gp = G[k * 3 + p], gq = G[k * 3 + q];
-                    G[k * 3 + p] = c * gp - s * gq;
-                    G[k * 3 + q] = s * gp + c * gq;
-                }
-            }
-        if (!rotated) break;
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) sv[c] = sqrt(G[c] * G[c] + G[3 + c] * G[3 + c] + G[6 + c] * G[6 + c]);
-}
 
 // files one finished tile row (tiles (I, 0..I)) into the statically indexed lower-triangular register array
 template <int I>
@@ -163,25 +47,6 @@ __device__ __forceinline__ void file_row(double (&S)[NTILE][2], const double2 (*
         const double2 v = rowbuf[J][lane];
         S[I * (I + 1) / 2 + J][0] = v.x;
         S[I * (I + 1) / 2 + J][1] = v.y;
-    }
-}
-
-struct ObsRegs {
-    double u, v, dx, dy, dz, cf;
-    int slot;
-};
-
-__device__ __forceinline__ void load_obs(ObsRegs& o, const FrontArgs& a, size_t fj, int M, int lane) {
-    const int Mcap = a.dims.M;
-    if (lane < M) {
-        const double2 uv = *reinterpret_cast<const double2*>(a.obs_uv + (fj * Mcap + lane) * 2);
-        o.u = uv.x; o.v = uv.y;
-        const double* d = a.obs_dir + (fj * Mcap + lane) * 3;
-        o.dx = d[0]; o.dy = d[1]; o.dz = d[2];
-        o.cf = a.obs_conf[fj * Mcap + lane];
-        o.slot = a.obs_slot[fj * Mcap + lane];
-    } else {
-        o.u = o.v = 0.0; o.dx = o.dy = 0.0; o.dz = 1.0; o.cf = 0.0; o.slot = 0;
     }
 }
 
@@ -218,10 +83,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
     }
     __syncthreads();
 
-    const double s2 = a.par.sigma_image * a.par.sigma_image;
-    const double g0 = a.par.gravity[0], g1 = a.par.gravity[1], g2 = a.par.gravity[2];
-    const bool cos_ok = a.par.min_parallax_deg > 0.0 && a.par.min_parallax_deg < 180.0;
-    const double cos_thr = cos_ok ? cos(a.par.min_parallax_deg * (3.14159265358979323846 / 180.0)) : 0.0;
+    const GeoConsts gc = make_geo_consts(a);
+    const double s2 = gc.s2;
 
     ObsRegs nxt;
     int Mn = 0;
@@ -256,33 +119,11 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
         const int n2 = 2 * M;
         const bool live = lane < M;
 
-        // ---- selection (MSCKF.py:463-479) ----
-        int code;
-        {
-            const bool lost = a.lost_cnt[fj] >= a.par.min_lost;
-            if (lost && a.tracked_cnt[fj] < a.par.min_tracked) {
-                code = MSCKF_FEAT_LOST_DISCARD | MSCKF_FEAT_LOST_FLAG;
-            } else {
-                bool enough = false;
-                if (a.par.use_parallax && M > 1) {
-                    const double ax = shfl_d(o.dx, 0), ay = shfl_d(o.dy, 0), az = shfl_d(o.dz, 0);
-                    const double bx = shfl_d(o.dx, M - 1), by = shfl_d(o.dy, M - 1), bz = shfl_d(o.dz, M - 1);
-                    // acos(dp) in degrees > min_parallax  <=>  dp < cos(min_parallax): decided on the cosine unless it sits
-                    // within 1e-9 of the threshold, where the reference's own expression is evaluated (geometry.py:237-256)
-                    const double na = ax * ax + ay * ay + az * az, nb = bx * bx + by * by + bz * bz;
-                    const double dq = (ax * bx + ay * by + az * bz) * fast_rsqrt(na * nb);
-                    if (cos_ok && na * nb > 0.0 && fabs(dq - cos_thr) > 1e-9) {
-                        enough = dq < cos_thr;
-                    } else {
-                        const double n1 = sqrt(na), n2_ = sqrt(nb);
-                        double dp = (ax / n1) * (bx / n2_) + (ay / n1) * (by / n2_) + (az / n1) * (bz / n2_);
-                        dp = fmin(1.0, fmax(-1.0, dp));
-                        enough = acos(dp) * (180.0 / 3.14159265358979323846) > a.par.min_parallax_deg;
-                    }
-                }
-                code = (lost || enough) ? (MSCKF_FEAT_ACCEPTED | (lost ? MSCKF_FEAT_LOST_FLAG : 0)) : MSCKF_FEAT_SKIPPED;
-            }
-        }
+
+        // ---- selection, triangulation, residual / Jacobian blocks, basis of range(H_f), r~ (front_geom.cuh) ----
+        double Hx[2][6], Hf[2][3], rt0, rt1;
+        int rank;
+        const int code = feature_geometry(a, gc, fj, M, lane, o, sR, sT, Hx, Hf, rt0, rt1, rank);
         if ((code & 0xF) != MSCKF_FEAT_ACCEPTED) {
             if (lane == 0) {
                 a.feat_status[fj] = (unsigned char)code;
@@ -293,217 +134,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
             continue;
         }
 
-        const double* R = sR + 9 * o.slot;
-        const double* tt = sT + 3 * o.slot;
-
-        // ---- triangulation: X = sum c (I - d d^T), y = sum c (I - d d^T) t_slot, p = pinv(X) y (geometry.py:286-299) ----
-        double rho, m0, m1, m2, b0, b1, b2;
-        {
-            double term[9];
-            {
-                const double nn = sqrt(o.dx * o.dx + o.dy * o.dy + o.dz * o.dz);
-                const double ux = o.dx / nn, uy = o.dy / nn, uz = o.dz / nn;
-                const double c = live ? o.cf : 0.0;
-                term[0] = c * (1.0 - ux * ux); term[1] = c * (0.0 - ux * uy); term[2] = c * (0.0 - ux * uz);
-                term[3] = c * (1.0 - uy * uy); term[4] = c * (0.0 - uy * uz); term[5] = c * (1.0 - uz * uz);
-                term[6] = term[0] * tt[0] + term[1] * tt[1] + term[2] * tt[2];
-                term[7] = term[1] * tt[0] + term[3] * tt[1] + term[4] * tt[2];
-                term[8] = term[2] * tt[0] + term[4] * tt[1] + term[5] * tt[2];
-            }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) term[k] = warp_sum_all(live ? term[k] : 0.0);
-            double p[3] = {0, 0, 0};
-            if (!sym3_solve_spd(term, term + 6, p)) {   // (nearly) singular X: pinv with its singular-value cut-off
-                double lam[3], V[9];
-                sym3_eig_w(term, lam, V);
-                const double lmax = fmax(fabs(lam[0]), fmax(fabs(lam[1]), fabs(lam[2])));
-                p[0] = p[1] = p[2] = 0.0;
-#pragma unroll 1
-                for (int k = 0; k < 3; ++k) {
-                    if (fabs(lam[k]) > 1e-15 * lmax) {   // np.linalg.pinv default rcond
-                        const double coef = (V[0 + k] * term[6] + V[3 + k] * term[7] + V[6 + k] * term[8]) / lam[k];
-                        p[0] += coef * V[0 + k];
-                        p[1] += coef * V[3 + k];
-                        p[2] += coef * V[6 + k];
-                    }
-                }
-            }
-            // first observing camera (MSCKF.py:481-488)
-            const int s0 = __shfl_sync(0xffffffffu, o.slot, 0);
-            const double* R0 = sR + 9 * s0;
-            const double* t0 = sT + 3 * s0;
-            const double q0 = p[0] - t0[0], q1 = p[1] - t0[1], q2 = p[2] - t0[2];
-            const double cx = R0[0] * q0 + R0[3] * q1 + R0[6] * q2;
-            const double cy = R0[1] * q0 + R0[4] * q1 + R0[7] * q2;
-            const double cz = R0[2] * q0 + R0[5] * q1 + R0[8] * q2;
-            rho = a.idp_rho[fj];
-            m0 = a.idp_m[fj * 3]; m1 = a.idp_m[fj * 3 + 1]; m2 = a.idp_m[fj * 3 + 2];
-            if (cz > 0.0) {
-                const double* K = a.par.K;
-                const double iw = K[6] * cx + K[7] * cy + K[8] * cz;
-                const double iu = (K[0] * cx + K[1] * cy + K[2] * cz) / iw;
-                const double iv = (K[3] * cx + K[4] * cy + K[5] * cz) / iw;
-                if (!(iu < 0.0 || iu >= (double)a.par.width || iv < 0.0 || iv >= (double)a.par.height)) {
-                    const double* Ki = a.par.Kinv;
-                    const double vx = Ki[0] * iu + Ki[1] * iv + Ki[2];
-                    const double vy = Ki[3] * iu + Ki[4] * iv + Ki[5];
-                    const double vz = Ki[6] * iu + Ki[7] * iv + Ki[8];
-                    const double wx = R0[0] * vx + R0[1] * vy + R0[2] * vz;
-                    const double wy = R0[3] * vx + R0[4] * vy + R0[5] * vz;
-                    const double wz = R0[6] * vx + R0[7] * vy + R0[8] * vz;
-                    const double wn = sqrt(wx * wx + wy * wy + wz * wz);
-                    rho = 1.0 / cz;                      // InverseDepthPoint.update, geometry.py:61-71
-                    m0 = wx / wn; m1 = wy / wn; m2 = wz / wn;
-                    if (lane == 0) {
-                        a.idp_rho[fj] = rho;
-                        a.idp_m[fj * 3] = m0; a.idp_m[fj * 3 + 1] = m1; a.idp_m[fj * 3 + 2] = m2;
-                    }
-                }
-            }
-            const int as = a.idp_anchor_slot[fj];
-            const double* base = (as >= 0) ? (sT + 3 * as) : (a.idp_base + fj * 3);
-            b0 = base[0]; b1 = base[1]; b2 = base[2];
-        }
-
-        // ---- residual and Jacobian blocks of this lane's observation (MSCKF.py:505-544, Camera.py:54-67) ----
-        double Hx[2][6], Hf[2][3], res[2];
-        {
-            const double q0 = rho * (b0 - tt[0]) + m0, q1 = rho * (b1 - tt[1]) + m1, q2 = rho * (b2 - tt[2]) + m2;
-            const double f0 = R[0] * q0 + R[3] * q1 + R[6] * q2;
-            const double f1 = R[1] * q0 + R[4] * q1 + R[7] * q2;
-            const double f2 = R[2] * q0 + R[5] * q1 + R[8] * q2;
-            const double w0 = (R[0] * f0 + R[1] * f1 + R[2] * f2 + tt[0]) - tt[0];
-            const double w1 = (R[3] * f0 + R[4] * f1 + R[5] * f2 + tt[1]) - tt[1];
-            const double w2 = (R[6] * f0 + R[7] * f1 + R[8] * f2 + tt[2]) - tt[2];
-            const double* Ki = a.par.Kinv;
-            const double zx = Ki[0] * o.u + Ki[1] * o.v + Ki[2];
-            const double zy = Ki[3] * o.u + Ki[4] * o.v + Ki[5];
-            const double zw = Ki[6] * o.u + Ki[7] * o.v + Ki[8];
-            res[0] = zx / zw - f0 / f2;
-            res[1] = zy / zw - f1 / f2;
-            const double J00 = 1.0 / f2, J02 = -f0 / (f2 * f2), J11 = 1.0 / f2, J12 = -f1 / (f2 * f2);
-            Hx[0][0] = J02 * (-f1);
-            Hx[0][1] = J00 * (-f2) + J02 * f0;
-            Hx[0][2] = J00 * f1;
-            Hx[1][0] = J11 * f2 + J12 * (-f1);
-            Hx[1][1] = J12 * f0;
-            Hx[1][2] = J11 * (-f0);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                Hf[0][k] = J00 * R[3 * k + 0] + J02 * R[3 * k + 2];
-                Hf[1][k] = J11 * R[3 * k + 1] + J12 * R[3 * k + 2];
-                Hx[0][3 + k] = -Hf[0][k];
-                Hx[1][3 + k] = -Hf[1][k];
-            }
-            double u6[6];
-            u6[0] = R[0] * g0 + R[3] * g1 + R[6] * g2;
-            u6[1] = R[1] * g0 + R[4] * g1 + R[7] * g2;
-            u6[2] = R[2] * g0 + R[5] * g1 + R[8] * g2;
-            u6[3] = w1 * g2 - w2 * g1;
-            u6[4] = w2 * g0 - w0 * g2;
-            u6[5] = w0 * g1 - w1 * g0;
-            double den = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) den += u6[k] * u6[k];
-            if (den > 1e-6) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    double au = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) au += Hx[r][k] * u6[k];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) Hx[r][k] = Hx[r][k] - (au * u6[k]) / den;
-                }
-            }
-            if (!live) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    res[r] = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) Hx[r][k] = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) Hf[r][k] = 0.0;
-                }
-            }
-        }
-
-        // ---- orthonormal basis of range(H_f): column-pivoted Gram-Schmidt with re-orthogonalisation ----
-        int rank;
-        {
-            double R3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            bool stop = false;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (stop) break;
-                double nrm[3] = {0, 0, 0};
-                int piv = k;
-                double best = -1.0;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (c < k) continue;
-                    nrm[c] = warp_sum_all(Hf[0][c] * Hf[0][c] + Hf[1][c] * Hf[1][c]);
-                    if (nrm[c] > best) { best = nrm[c]; piv = c; }
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (c > k && c == piv) {
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) { const double tmp = Hf[r][k]; Hf[r][k] = Hf[r][c]; Hf[r][c] = tmp; }
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) {
-                            if (r < k) { const double tmp = R3[r * 3 + k]; R3[r * 3 + k] = R3[r * 3 + c]; R3[r * 3 + c] = tmp; }
-                        }
-                    }
-                }
-                const double nk = sqrt(best);
-                R3[k * 3 + k] = nk;
-                if (!(nk > 0.0)) { stop = true; break; }
-                const double ink = 1.0 / nk;
-                Hf[0][k] *= ink; Hf[1][k] *= ink;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (c <= k) continue;
-#pragma unroll
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const double h = warp_sum_all(Hf[0][k] * Hf[0][c] + Hf[1][k] * Hf[1][c]);
-                        Hf[0][c] -= h * Hf[0][k];
-                        Hf[1][c] -= h * Hf[1][k];
-                        R3[k * 3 + c] += h;
-                    }
-                }
-            }
-            // rank by SciPy's rule s > eps max(3, 2M) s_max on the singular values of the 3x3 factor.  Column pivoting
-            // bounds s_min >= |r33| / 4 and s_max <= sqrt(6) |r11|, so |r33| > 1e-10 |r11| already proves rank 3 (the
-            // threshold is ~1e-14 s_max); only doubtful factors pay for the Jacobi SVD.
-            if (n2 >= 3 && fabs(R3[8]) > 1e-10 * fabs(R3[0])) {
-                rank = 3;
-            } else {
-                double G3[9], sv[3];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) G3[k] = R3[k];
-                svals3_w(G3, sv);
-                const double smax = fmax(sv[0], fmax(sv[1], sv[2]));
-                const double tol = 2.220446049250313e-16 * (double)(n2 > 3 ? n2 : 3) * smax;   // scipy null_space rcond
-                rank = 0;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) rank += (sv[k] > tol) ? 1 : 0;
-                if (rank > n2) rank = n2;
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                if (c >= rank) { Hf[0][c] = 0.0; Hf[1][c] = 0.0; }
-        }
         const int dofv = n2 - rank;
-
-        // ---- r~ = r - Q1 Q1^T r ----
-        double rt0, rt1;
-        {
-            double w[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) w[c] = warp_sum_all(Hf[0][c] * res[0] + Hf[1][c] * res[1]);
-            rt0 = res[0] - (Hf[0][0] * w[0] + Hf[0][1] * w[1] + Hf[0][2] * w[2]);
-            rt1 = res[1] - (Hf[1][0] * w[0] + Hf[1][1] * w[1] + Hf[1][2] * w[2]);
-        }
 
         // ---- factors for the compression stage + the warp's shared scratch ----
         __syncwarp();

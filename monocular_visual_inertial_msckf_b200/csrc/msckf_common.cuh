@@ -8,6 +8,7 @@
 
 #define MSCKF_MAX_OBS 64          // observation capacity per feature supported by the front-end kernel
 #define MSCKF_TSQR_MAX_COLS 256   // 6 N + 1 columns (R | rhs) handled by one TSQR CTA  -> N <= 42
+#define MSCKF_FEAT_PENDING 0x40   // internal feat_status value between the two kernels of the split front end
 #define MSCKF_MAX_CAMS 64         // pose capacity of the dense-update kernels (d <= 399)
 
 // Workspace carve-up shared by msckf_*_workspace_bytes and the launches.  All offsets in bytes, 256-aligned.
@@ -23,6 +24,9 @@ struct WsLayout {
     size_t scratch;   // [n_cta][scratch_per_cta] dense-update scratch of the persistent update CTAs
     size_t scratch_per_cta;
     int n_update_ctas;
+    size_t k_tiles;   // [sub][F][1280] double2: per-feature K tiles of the split front end (front_split.cu); 0 bytes if unused
+    size_t pend_list; // [sub][F] int   features waiting for the factorisation kernel
+    size_t pend_count;// int
     size_t total;
 };
 

@@ -55,10 +55,15 @@ def test_update_vs_golden(golden_dir, name, mode):
     print(name, "gram" if mode else "qr", _summarise(errs))
 
 
-@pytest.mark.parametrize("pad_M", [pytest.param(2, id="warp-per-feature"), pytest.param(30, id="cta-per-feature")])
-def test_front_stage_vs_golden(golden_dir, pad_M):
+@pytest.mark.parametrize("pad_M,fused", [pytest.param(2, False, id="split-assembly+factorisation"),
+                                         pytest.param(2, True, id="fused-warp-per-feature"),
+                                         pytest.param(30, False, id="cta-per-feature")])
+def test_front_stage_vs_golden(golden_dir, pad_M, fused, monkeypatch):
     """rows 3-8 alone: selection, triangulation, gamma/dof/gate per feature, state untouched.  The observation capacity
-    picks the kernel: <= 32 observations per track -> warp-per-feature kernel, more -> CTA-per-feature kernel."""
+    picks the kernel: <= 32 observations per track -> warp-per-feature kernels (assembly + factorisation pair by default,
+    the fused kernel with MSCKF_FRONT_FUSED=1), more -> CTA-per-feature kernel."""
+    if fused:
+        monkeypatch.setenv("MSCKF_FRONT_FUSED", "1")
     cases, _ = _load(golden_dir, "small_updates.npz")
     flt = _batch_from_cases(cases, pad_F=3, pad_M=pad_M, pad_N=1)
     assert (flt.M <= 32) == (pad_M == 2)
