@@ -80,6 +80,18 @@ def algorithmic_qr_flops_per_filter(rows, N):
     return 2.0 * rows * c * c - (2.0 / 3.0) * c ** 3
 
 
+def algorithmic_asm_flops_per_feature(M):
+    """front_asm_kernel: K = H_x P H_x^T + s^2 I from M (M + 1) / 2 pairs of 2x6 . 6x6 . 6x2 blocks (96 multiply-adds each)
+    + ~300 flops per observation of geometry (triangulation, residual, Jacobians, basis of range(H_f))."""
+    return 192.0 * (M * (M + 1) / 2) + 300.0 * M
+
+
+def algorithmic_chol_flops_per_feature(M):
+    """front_chol_kernel: Cholesky of the 2M x 2M matrix with the 4 appended rows [r~; Q1^T]: n^3 / 3 + 4 n^2."""
+    n = 2 * M
+    return n ** 3 / 3.0 + 4.0 * n * n
+
+
 def algorithmic_front_flops_per_feature(M):
     """Rows 3-8 for one track of M observations (kernel table): assembling K = H_x P H_x^T + s^2 I from
     M (M + 1) / 2 pairs of 2x6 . 6x6 . 6x2 blocks (96 multiply-adds each), the Cholesky of the 2M x 2M matrix with the 4
@@ -373,6 +385,22 @@ def run_gpu(args):
     stage_ms = {}
     prep = lambda: None  # noqa: E731
     stage_ms["front"] = time_stage(flt.front)
+    # the two kernels of the split front end, timed by the library's own events on the launching stream
+    import ctypes as C
+    flt.lib.msckf_set_stage_timing(1)
+    best = (1e30, 1e30)
+    for _ in range(3):
+        restore()
+        flt.propagate(samples_dev)
+        flt.front()
+        a_ms, c_ms = C.c_double(0), C.c_double(0)
+        n_sub = flt.lib.msckf_front_stage_ms(C.byref(a_ms), C.byref(c_ms))
+        if n_sub > 0 and a_ms.value + c_ms.value < sum(best):
+            best = (a_ms.value, c_ms.value)
+    flt.lib.msckf_set_stage_timing(0)
+    split_front = best[0] < 1e29
+    if split_front:
+        stage_ms["front_asm"], stage_ms["front_chol"] = best
     prep = flt.front
     stage_ms["compress"] = time_stage(flt.compress)
     prep = lambda: (flt.front(), flt.compress())  # noqa: E731
@@ -440,15 +468,22 @@ def run_gpu(args):
     rows_per_rank = rows / world
     acc_per_rank = n_acc / world
     stage_flops = dict(front=algorithmic_front_flops_per_feature(M) * B * F)
+    if split_front:
+        code = flt.feat_status & 0xF
+        n_chol = int((((code == 1) | (code == 2)) & ((flt.feat_status & _lib.FEAT_GAMMA_BOUND) == 0) & (flt.dof > 0)).sum().item())
+        stage_flops = dict(front_asm=algorithmic_asm_flops_per_feature(M) * B * F,
+                           front_chol=algorithmic_chol_flops_per_feature(M) * n_chol)
     if args.mode == "qr":
         stage_flops["compress"] = algorithmic_qr_flops_per_filter(rows_per_rank / B, N) * B
         stage_flops["apply"] = 8.0 * (15 + 6 * N) ** 3 * B
-        names = dict(front="front_warp_kernel", compress="tsqr_kernel", apply="apply_kernel")
+        names = dict(front="front_warp_kernel", front_asm="front_asm_kernel", front_chol="front_chol_kernel",
+                     compress="tsqr_kernel", apply="apply_kernel")
     else:
         stage_flops["compress"] = algorithmic_gram_flops_per_filter(acc_per_rank / B, N) * B
         stage_flops["apply"] = algorithmic_info_update_flops_per_filter(N) * B
-        names = dict(front="front_warp_kernel", compress="gram_kernel", apply="update_info_kernel")
-    dom = max(("front", "compress", "apply"), key=lambda k: stage_ms[k])      # the dominant kernel of the step
+        names = dict(front="front_warp_kernel", front_asm="front_asm_kernel", front_chol="front_chol_kernel",
+                     compress="gram_kernel", apply="update_smem_kernel")
+    dom = max(stage_flops, key=lambda k: stage_ms[k])      # the dominant kernel of the step
     dom_name, dom_ms, dom_flops = names[dom], stage_ms[dom], stage_flops[dom]
     achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12
     stage_tflops = {names[k]: stage_flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in stage_flops}

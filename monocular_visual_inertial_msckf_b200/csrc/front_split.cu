@@ -220,14 +220,20 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
 
             // ---- K = H_x P H_x^T + sigma^2 I, one lower 2x2 block per lane per pass ----
             const int npairs = Mp * (Mp + 1) / 2;
+            // (the pair descriptor of the next pass is fetched while this one is computed)
+            unsigned ik_n = lut[lane < npairs ? lane : 0];
+            int si_n = __shfl_sync(0xffffffffu, o.slot, ik_n & 0xff), sk_n = __shfl_sync(0xffffffffu, o.slot, ik_n >> 8);
 #pragma unroll 1
             for (int p0 = 0; p0 < npairs; p0 += 32) {
-                const int p = p0 + lane;
-                const bool act = p < npairs;
-                const unsigned ik = lut[act ? p : 0];
-                const int i = ik & 0xff, k = ik >> 8;
-                const int si = __shfl_sync(0xffffffffu, o.slot, i);
-                const int sk = __shfl_sync(0xffffffffu, o.slot, k);
+                const bool act = p0 + lane < npairs;
+                const int i = ik_n & 0xff, k = ik_n >> 8;
+                const int si = si_n, sk = sk_n;
+                {
+                    const int pn = p0 + 32 + lane;
+                    ik_n = lut[pn < npairs ? pn : 0];
+                    si_n = __shfl_sync(0xffffffffu, o.slot, ik_n & 0xff);
+                    sk_n = __shfl_sync(0xffffffffu, o.slot, ik_n >> 8);
+                }
                 if (!act) continue;
                 double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
                 if (i < M) {
@@ -264,8 +270,8 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
 #pragma unroll
                             for (int r2 = 0; r2 < 3; ++r2) {
                                 const double2 pv = Pb[c * 3 + r2];
-                                v0[c] += ai[0][2 * r2] * pv.x + ai[0][2 * r2 + 1] * pv.y;
-                                v1[c] += ai[1][2 * r2] * pv.x + ai[1][2 * r2 + 1] * pv.y;
+                                v0[c] = fma(ai[0][2 * r2 + 1], pv.y, fma(ai[0][2 * r2], pv.x, v0[c]));
+                                v1[c] = fma(ai[1][2 * r2 + 1], pv.y, fma(ai[1][2 * r2], pv.x, v1[c]));
                             }
                         }
                     }
@@ -273,10 +279,10 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
 #pragma unroll
                     for (int c2 = 0; c2 < 3; ++c2) {
                         const double2 x0 = Ak[c2], x1 = Ak[3 + c2];
-                        o00 += v0[2 * c2] * x0.x + v0[2 * c2 + 1] * x0.y;
-                        o01 += v0[2 * c2] * x1.x + v0[2 * c2 + 1] * x1.y;
-                        o10 += v1[2 * c2] * x0.x + v1[2 * c2 + 1] * x0.y;
-                        o11 += v1[2 * c2] * x1.x + v1[2 * c2 + 1] * x1.y;
+                        o00 = fma(v0[2 * c2 + 1], x0.y, fma(v0[2 * c2], x0.x, o00));
+                        o01 = fma(v0[2 * c2 + 1], x1.y, fma(v0[2 * c2], x1.x, o01));
+                        o10 = fma(v1[2 * c2 + 1], x0.y, fma(v1[2 * c2], x0.x, o10));
+                        o11 = fma(v1[2 * c2 + 1], x1.y, fma(v1[2 * c2], x1.x, o11));
                     }
                     if (i == k) { o00 += s2; o11 += s2; }
                 } else if (i == k) {   // padded measurement rows: identity
@@ -530,6 +536,37 @@ size_t front_split_tile_bytes(const msckf_dims& d) {
     return (size_t)front_split_sub_filters(d) * d.F * KT_D2 * sizeof(double2);
 }
 
+// optional per-kernel timing (msckf_set_stage_timing / msckf_front_stage_ms): CUDA events on the launching stream around
+// the two kernels of every sub-batch
+namespace {
+constexpr int MAX_SUB = 64;
+bool g_timing = false;
+cudaEvent_t g_ev[MAX_SUB][3];
+int g_ev_created = 0, g_ev_used = 0;
+}  // namespace
+
+extern "C" int msckf_set_stage_timing(int on) {
+    g_timing = on != 0;
+    g_ev_used = 0;
+    return 0;
+}
+
+extern "C" int msckf_front_stage_ms(double* asm_ms, double* chol_ms) {
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < g_ev_used; ++k) {
+        float t0 = 0.f, t1 = 0.f;
+        cudaError_t e = cudaEventSynchronize(g_ev[k][2]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t0, g_ev[k][0], g_ev[k][1]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t1, g_ev[k][1], g_ev[k][2]);
+        if (e != cudaSuccess) return (int)e;
+        a += t0;
+        c += t1;
+    }
+    if (asm_ms) *asm_ms = a;
+    if (chol_ms) *chol_ms = c;
+    return g_ev_used;
+}
+
 cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, cudaStream_t s) {
     const size_t smem = front_asm_smem(a.dims);
     static size_t configured = 0;
@@ -540,10 +577,19 @@ cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list
     }
     const int sub = front_split_sub_filters(a.dims);
     const int F = a.dims.F;
+    if (g_timing) g_ev_used = 0;
     for (int b0 = 0; b0 < a.dims.B; b0 += sub) {
         const int nb = (b0 + sub <= a.dims.B) ? sub : a.dims.B - b0;
         cudaError_t e = cudaMemsetAsync(pend_count, 0, sizeof(int), s);
         if (e != cudaSuccess) return e;
+        const bool timed = g_timing && g_ev_used < MAX_SUB;
+        const int slot = g_ev_used;
+        if (timed) {
+            for (; g_ev_created <= slot; ++g_ev_created)
+                for (int q = 0; q < 3; ++q)
+                    if ((e = cudaEventCreate(&g_ev[g_ev_created][q])) != cudaSuccess) return e;
+            cudaEventRecord(g_ev[slot][0], s);
+        }
         // feature chunks per filter so that the CTAs come in >= ~12 waves of 148 (each warp keeps >= 2 features)
         int chunks = (12 * 148 + nb - 1) / nb;
         int fpc = (F + chunks - 1) / chunks;
@@ -553,11 +599,16 @@ cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list
         front_asm_kernel<<<grid, FA_THREADS, smem, s>>>(a, Kbuf, pend_list, pend_count, b0, fpc);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        if (timed) cudaEventRecord(g_ev[slot][1], s);
         front_chol_kernel<<<148 * 4, FC_THREADS, 0, s>>>(Kbuf, pend_list, pend_count, a.feat_len, a.fac_rank, a.dof,
                                                         a.chi2_table, a.chi2_len, a.feat_status, a.gamma, (size_t)b0 * F);
         msckf_count_launch(2);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        if (timed) {
+            cudaEventRecord(g_ev[slot][2], s);
+            ++g_ev_used;
+        }
     }
     return cudaSuccess;
 }
