@@ -10,6 +10,7 @@ timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench
 tail -c 3000 $OUT/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'front_warp|gram_kernel|update_smem|update_info' -c 3 \
-    -o $OUT/prof python bench.py --steps 1 --warmup 1 --filters 592 --no-cpu > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+# one launch of every kernel of the step at the launch shape of the full-size run (1024 filters = one front-end sub-batch)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'propagate|front_asm|front_chol|gram_kernel|update_smem|update_info' -c 5 \
+    -o $OUT/prof python bench.py --steps 1 --warmup 1 --filters 1024 --no-cpu > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT

@@ -80,6 +80,6 @@ if __name__ == "__main__":
                      "`python bench.py --steps 2 --warmup 1 --no-cpu`\n\n" + launch_shares(l) + "\n")
     rep = os.path.join(src, "prof.ncu-rep")
     if os.path.exists(rep):
-        parts.append("## `ncu --set full --clock-control none` (reduced batch, see tools/gpu_check.sh)\n" + full_metrics(rep) + "\n")
+        parts.append("## `ncu --set full --clock-control none`, one launch per kernel at 1024 filters (= one front-end sub-batch of the 4096-filter step; tools/gpu_check.sh)\n" + full_metrics(rep) + "\n")
     open(dst + "_summary.md", "w").write("\n".join(parts))
     print("wrote", dst + "_summary.md")
