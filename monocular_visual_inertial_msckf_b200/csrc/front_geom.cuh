@@ -12,13 +12,13 @@ constexpr int FW_MAX_OBS = 32;   // one lane per observation
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// 1/sqrt(x) for x > 0 (0 for x <= 0): hardware seed (MUFU.RSQ64H, ~2^-22) + two Newton steps, no slow-path branch
+// 1/sqrt(x) for x > 0 (0 for x <= 0): hardware seed (MUFU.RSQ64H, ~2^-22) + one third-order step, no slow-path branch
 __device__ __forceinline__ double fast_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double hx = 0.5 * x;
-    y = y * fma(-hx * y, y, 1.5);
-    y = y * fma(-hx * y, y, 1.5);
+    // one cubically convergent step: e = 1 - x y^2, y <- y (1 + e/2 + 3 e^2/8); seed error 2^-22 -> ~2^-64
+    const double e = fma(-(x * y), y, 1.0);
+    y = fma(y * e, fma(0.375, e, 0.5), y);
     return x > 0.0 ? y : 0.0;
 }
 

@@ -34,12 +34,12 @@ constexpr int FA_THREADS = 512;
 constexpr int FA_WARPS = FA_THREADS / 32;
 constexpr int FC_THREADS = 128;
 constexpr int FC_WARPS = FC_THREADS / 32;
-constexpr int TC = 8;                          // 8x8 tile columns -> up to 64 measurement rows (32 observations)
+constexpr int TC = 9;                          // 8x8 tile columns: up to 64 measurement rows (32 observations) + 4 appended rows
 constexpr int NTILE = TC * (TC + 1) / 2;
 constexpr int PB = 38;                         // doubles per staged 6x6 block of P (stride 76 words = 12 mod 32)
 constexpr int AR = 14;                         // doubles per observation's 2x6 block in the warp scratch (28 words)
-constexpr int KT_D2 = NTILE * 32 + TC * 16;    // double2 per feature in the tile buffer: 36 K tiles + 8 appended half tiles
-constexpr int MAX_PAIRS = FW_MAX_OBS * (FW_MAX_OBS + 1) / 2;
+constexpr int KT_D2 = NTILE * 32;               // double2 per feature slot in the tile buffer (45 tiles; M = 30 uses 36)
+constexpr int MAX_PAIRS = (4 * TC) * (4 * TC + 1) / 2;   // 2x2 blocks of the lower triangle of the padded matrix
 
 __device__ __forceinline__ int tile_index(int I, int J) { return I * (I + 1) / 2 + J; }
 
@@ -209,13 +209,19 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                 pend_list[atomicAdd(pend_count, 1)] = fl;
             }
             double2* Kt = Kbuf + (size_t)fl * KT_D2;
-            const int Tn = (n2 + 7) >> 3, Mp = 4 * Tn;
-            // appended tile row [r~; Q1^T]: column pair (2 i, 2 i + 1) of rows 0..3 -> half tile J = i / 4, lane 4 g + (i & 3)
-            if (lane < Mp) {
-                double2* Gt = Kt + NTILE * 32 + (lane >> 2) * 16 + (lane & 3);
-                Gt[0] = live ? make_double2(rt0, rt1) : make_double2(0.0, 0.0);
+            // Padded matrix of the factorisation kernel: rows [0, n2) measurement rows, [n2, a4) identity (a4 = n2 rounded up
+            // to a multiple of 4), [a4, a4 + 4) the appended rows [r~; Q1^T] (they never straddle a tile row and their
+            // diagonal block is zero: after the factorisation of the columns < a4 it holds minus their Gram matrix), rest
+            // zero.  At M = 30 the appended rows fill the four padding rows of the eighth tile row.
+            const int a4 = (n2 + 3) & ~3;
+            const int Tn = (a4 + 4 + 7) >> 3, Mp = 4 * Tn;
+            const int rr = a4 - 8 * (Tn - 1);          // local row of the first appended row in the last tile row: 0 or 4
+            const int ia = a4 >> 1;                     // the appended rows as two observation-sized row pairs ia, ia + 1
+            if (live) {   // columns (2 lane, 2 lane + 1) of the four appended rows
+                double2* Gt = Kt + tile_index(Tn - 1, lane >> 2) * 32 + 4 * rr + (lane & 3);
+                Gt[0] = make_double2(rt0, rt1);
 #pragma unroll
-                for (int q = 0; q < 3; ++q) Gt[4 * (q + 1)] = live ? make_double2(Hf[0][q], Hf[1][q]) : make_double2(0.0, 0.0);
+                for (int q = 0; q < 3; ++q) Gt[4 * (q + 1)] = make_double2(Hf[0][q], Hf[1][q]);
             }
 
             // ---- K = H_x P H_x^T + sigma^2 I, one lower 2x2 block per lane per pass ----
@@ -285,15 +291,17 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                         o11 = fma(v1[2 * c2 + 1], x1.y, fma(v1[2 * c2], x1.x, o11));
                     }
                     if (i == k) { o00 += s2; o11 += s2; }
-                } else if (i == k) {   // padded measurement rows: identity
+                } else if (i == k && i < ia) {   // padding between the measurement rows and the appended rows: identity
                     o00 = 1.0; o11 = 1.0;
                 }
                 // rows 2 i, 2 i + 1 / columns 2 k, 2 k + 1  ->  tile (i / 4, k / 4), lanes 4 (2 (i & 3) + row) + (k & 3)
                 const int I = i >> 2, J = k >> 2;
                 double2* T = Kt + tile_index(I, J) * 32;
                 const int l0 = 8 * (i & 3) + (k & 3);
-                T[l0] = make_double2(o00, o01);
-                T[l0 + 4] = make_double2(o10, o11);
+                if (!(i >= ia && i < ia + 2 && k < M)) {   // (appended rows x measurement columns were written above)
+                    T[l0] = make_double2(o00, o01);
+                    T[l0 + 4] = make_double2(o10, o11);
+                }
                 if (I == J && i != k) {   // the mirrored block of a diagonal tile is never read as data: keep it defined
                     const int l1 = 8 * (k & 3) + (i & 3);
                     T[l1] = make_double2(0.0, 0.0);
@@ -350,16 +358,41 @@ __device__ __forceinline__ void diag_tile_inverse(double D0, double D1, const in
     bf1 = (g & 1) ? v11 : v10;
 }
 
+// the first `npass` column pairs of a diagonal tile, no inverse (last tile row: the columns left of the appended rows)
+__device__ __forceinline__ void diag_tile_partial(double& D0, double& D1, const int g, const int t, const int npass) {
+#pragma unroll 1
+    for (int tk = 0; tk < npass; ++tk) {
+        {
+            const int k = 2 * tk;
+            const double rs = fast_rsqrt(shfl_d(D0, k * 4 + tk));
+            const double colv = (g > k) ? D0 * rs : 0.0;
+            const double lg = shfl_d(colv, g * 4 + tk);
+            const double lc0 = shfl_d(colv, (2 * t) * 4 + tk);
+            const double lc1 = shfl_d(colv, (2 * t + 1) * 4 + tk);
+            D0 -= lg * lc0;
+            D1 -= lg * lc1;
+        }
+        {
+            const int k = 2 * tk + 1;
+            const double rs = fast_rsqrt(shfl_d(D1, k * 4 + tk));
+            const double colv = (g > k) ? D1 * rs : 0.0;
+            const double lg = shfl_d(colv, g * 4 + tk);
+            const double lc0 = shfl_d(colv, (2 * t) * 4 + tk);
+            const double lc1 = shfl_d(colv, (2 * t + 1) * 4 + tk);
+            D0 -= lg * lc0;
+            D1 -= lg * lc1;
+        }
+    }
+}
+
 struct CholRegs {
     double L[TC][TC][2];   // finished tiles L[I][c], I > c (statically indexed; live only while later columns need them)
-    double Ga[TC][2];      // finished tiles of the appended rows [y; V]
     double Cn[TC][2];      // prefetched tiles of the next block column (rows I >= column)
-    double Gn[2];          // prefetched appended tile of the next block column
 };
 
 // loads block column BK (static position; the feature's own tile column is BK - off) into the prefetch registers
 template <int BK, int off>
-__device__ __forceinline__ void load_column(CholRegs& r, const double2* __restrict__ Kt, const int lane) {
+__device__ __forceinline__ void load_column(CholRegs& r, const double2* __restrict__ Kt) {
     constexpr int J = BK - off;
 #pragma unroll
     for (int I = BK; I < TC; ++I) {
@@ -367,24 +400,20 @@ __device__ __forceinline__ void load_column(CholRegs& r, const double2* __restri
         r.Cn[I][0] = v.x;
         r.Cn[I][1] = v.y;
     }
-    double2 v = make_double2(0.0, 0.0);
-    if (lane < 16) v = __ldcs(Kt + NTILE * 32 + J * 16);
-    r.Gn[0] = v.x;
-    r.Gn[1] = v.y;
 }
 
-// Left-looking block column BK: C[I] = K[I][BK] - sum_{c < BK} L[I][c] L[BK][c]^T, factor the diagonal tile, solve the
-// panel; the appended rows ride along.  Only BK (8 - BK) + (8 - BK) tiles are live (<= 20 of 36), and the next column's
-// tiles are in flight while this one is computed.
+// Left-looking block column BK: C[I] = K[I][BK] - sum_{c < BK} L[I][c] L[BK][c]^T, then (BK < TC - 1) factor the diagonal
+// tile and solve the panel.  Only BK (9 - BK) + (9 - BK) tiles are live (<= 25 of 45), and the next column's tiles are in
+// flight while this one is computed.  The last block column (BK = TC - 1) is the tile that holds the appended rows: its
+// updated diagonal tile is returned in (D0, D1).
 template <int BK, int off>
-__device__ __forceinline__ void chol_block_column(CholRegs& r, const double2* __restrict__ Kt, const int lane,
-                                                  const int g, const int t, double& gr0, double& gr1) {
+__device__ __forceinline__ void chol_block_column(CholRegs& r, const double2* __restrict__ Kt, const int g, const int t,
+                                                  double& D0, double& D1) {
     if (BK < off) return;
-    double C[TC][2], Gb[2];
+    double C[TC][2];
 #pragma unroll
     for (int I = BK; I < TC; ++I) { C[I][0] = r.Cn[I][0]; C[I][1] = r.Cn[I][1]; }
-    Gb[0] = r.Gn[0]; Gb[1] = r.Gn[1];
-    if (BK + 1 < TC) load_column<(BK + 1 < TC) ? BK + 1 : BK, off>(r, Kt, lane);
+    if (BK + 1 < TC) load_column<(BK + 1 < TC) ? BK + 1 : BK, off>(r, Kt);
 #pragma unroll
     for (int c = 0; c < BK; ++c) {
         if (c >= off) {   // columns left of the feature's first one were never produced
@@ -394,9 +423,12 @@ __device__ __forceinline__ void chol_block_column(CholRegs& r, const double2* __
                 dense::dmma(C[I][0], C[I][1], r.L[I][c][0], nb0);
                 dense::dmma(C[I][0], C[I][1], r.L[I][c][1], nb1);
             }
-            dense::dmma(Gb[0], Gb[1], r.Ga[c][0], nb0);
-            dense::dmma(Gb[0], Gb[1], r.Ga[c][1], nb1);
         }
+    }
+    if (BK == TC - 1) {
+        D0 = C[BK][0];
+        D1 = C[BK][1];
+        return;
     }
     double bf0, bf1;
     diag_tile_inverse(C[BK][0], C[BK][1], g, t, bf0, bf1);
@@ -408,32 +440,22 @@ __device__ __forceinline__ void chol_block_column(CholRegs& r, const double2* __
         r.L[I][BK][0] = n0;
         r.L[I][BK][1] = n1;
     }
-    {
-        double n0 = 0.0, n1 = 0.0;
-        dense::dmma(n0, n1, Gb[0], bf0);
-        dense::dmma(n0, n1, Gb[1], bf1);
-        r.Ga[BK][0] = n0;
-        r.Ga[BK][1] = n1;
-        // the finished tile of the appended rows (y and V entries of this block column) enters their Gram matrix
-        dense::dmma(gr0, gr1, n0, n0);
-        dense::dmma(gr0, gr1, n1, n1);
-    }
 }
 
-// the whole factorisation of a feature whose first tile column sits at the static position OFF = 8 - (tile rows)
+// the whole factorisation of a feature whose first tile column sits at the static position OFF = 9 - (tile rows)
 template <int OFF>
-__device__ __forceinline__ void chol_feature(const double2* __restrict__ Kt, const int lane, const int g, const int t,
-                                             double& gr0, double& gr1) {
+__device__ __forceinline__ void chol_feature(const double2* __restrict__ Kt, const int g, const int t, double& D0, double& D1) {
     CholRegs r;
-    load_column<OFF, OFF>(r, Kt, lane);
-    chol_block_column<0, OFF>(r, Kt, lane, g, t, gr0, gr1);
-    chol_block_column<1, OFF>(r, Kt, lane, g, t, gr0, gr1);
-    chol_block_column<2, OFF>(r, Kt, lane, g, t, gr0, gr1);
-    chol_block_column<3, OFF>(r, Kt, lane, g, t, gr0, gr1);
-    chol_block_column<4, OFF>(r, Kt, lane, g, t, gr0, gr1);
-    chol_block_column<5, OFF>(r, Kt, lane, g, t, gr0, gr1);
-    chol_block_column<6, OFF>(r, Kt, lane, g, t, gr0, gr1);
-    chol_block_column<7, OFF>(r, Kt, lane, g, t, gr0, gr1);
+    load_column<OFF, OFF>(r, Kt);
+    chol_block_column<0, OFF>(r, Kt, g, t, D0, D1);
+    chol_block_column<1, OFF>(r, Kt, g, t, D0, D1);
+    chol_block_column<2, OFF>(r, Kt, g, t, D0, D1);
+    chol_block_column<3, OFF>(r, Kt, g, t, D0, D1);
+    chol_block_column<4, OFF>(r, Kt, g, t, D0, D1);
+    chol_block_column<5, OFF>(r, Kt, g, t, D0, D1);
+    chol_block_column<6, OFF>(r, Kt, g, t, D0, D1);
+    chol_block_column<7, OFF>(r, Kt, g, t, D0, D1);
+    chol_block_column<8, OFF>(r, Kt, g, t, D0, D1);
 }
 
 __global__ void __launch_bounds__(FC_THREADS, 4)
@@ -449,34 +471,39 @@ front_chol_kernel(const double2* __restrict__ Kbuf, const int* __restrict__ pend
         const int fl = pend_list[q];
         const size_t fj = fbase + (size_t)fl;
         const int n2 = 2 * feat_len[fj];
-        const int Tn = (n2 + 7) >> 3, off = TC - Tn;
+        const int a4 = (n2 + 3) & ~3;                       // first appended row (front_asm_kernel)
+        const int Tn = (a4 + 4 + 7) >> 3, off = TC - Tn;
+        const int rr = a4 - 8 * (Tn - 1);                   // its local row in the last tile row: 0 or 4
         const double2* Kt = Kbuf + (size_t)fl * KT_D2 + lane;
         // tile (I, J) of the feature sits at the static position (I + off, J + off): the factorisation then ends at the
         // bottom-right corner for every track length and every register index is static
-        double gr0 = 0.0, gr1 = 0.0;   // accumulator tile of [y; V] [y; V]^T (rows/cols 0..3 are meaningful)
+        double D0 = 0.0, D1 = 0.0;
         switch (off) {
-            case 0: chol_feature<0>(Kt, lane, g, t, gr0, gr1); break;
-            case 1: chol_feature<1>(Kt, lane, g, t, gr0, gr1); break;
-            case 2: chol_feature<2>(Kt, lane, g, t, gr0, gr1); break;
-            case 3: chol_feature<3>(Kt, lane, g, t, gr0, gr1); break;
-            case 4: chol_feature<4>(Kt, lane, g, t, gr0, gr1); break;
-            case 5: chol_feature<5>(Kt, lane, g, t, gr0, gr1); break;
-            case 6: chol_feature<6>(Kt, lane, g, t, gr0, gr1); break;
-            default: chol_feature<7>(Kt, lane, g, t, gr0, gr1); break;
+            case 0: chol_feature<0>(Kt, g, t, D0, D1); break;
+            case 1: chol_feature<1>(Kt, g, t, D0, D1); break;
+            case 2: chol_feature<2>(Kt, g, t, D0, D1); break;
+            case 3: chol_feature<3>(Kt, g, t, D0, D1); break;
+            case 4: chol_feature<4>(Kt, g, t, D0, D1); break;
+            case 5: chol_feature<5>(Kt, g, t, D0, D1); break;
+            case 6: chol_feature<6>(Kt, g, t, D0, D1); break;
+            case 7: chol_feature<7>(Kt, g, t, D0, D1); break;
+            default: chol_feature<8>(Kt, g, t, D0, D1); break;
         }
+        // the measurement columns of the last tile row, then its 4x4 block at (rr, rr) holds MINUS the Gram matrix of
+        // [y; V] = [r~; Q1^T] L^-T:  yy = (0,0), b_q = (q,0), M_qp = (q,p), q >= p (lower triangle of the tile)
+        diag_tile_partial(D0, D1, g, t, rr >> 1);
+        const int l0 = 4 * rr + (rr >> 1);                  // lane of element (rr, rr)
+        const double yy = -shfl_d(D0, l0);
+        double bq[3], Mq[6];
+        bq[0] = -shfl_d(D0, l0 + 4); bq[1] = -shfl_d(D0, l0 + 8); bq[2] = -shfl_d(D0, l0 + 12);
+        Mq[0] = -shfl_d(D1, l0 + 4);                               // (1,1)
+        Mq[1] = -shfl_d(D1, l0 + 8);                               // (2,1)
+        Mq[2] = -shfl_d(D1, l0 + 12);                              // (3,1)
+        Mq[3] = -shfl_d(D0, l0 + 9);                               // (2,2)
+        Mq[4] = -shfl_d(D0, l0 + 13);                              // (3,2)
+        Mq[5] = -shfl_d(D1, l0 + 13);                              // (3,3)
         const int rank = fac_rank[fj], dofv = dof[fj];
         const int st = feat_status[fj];
-
-        // Gram tile element (m, n) sits in lane 4 m + (n >> 1), register n & 1:  yy = (0,0), b_q = (q,0), M_qp = (q,p)
-        const double yy = shfl_d(gr0, 0);
-        double bq[3], Mq[6];
-        bq[0] = shfl_d(gr0, 4); bq[1] = shfl_d(gr0, 8); bq[2] = shfl_d(gr0, 12);
-        Mq[0] = shfl_d(gr1, 4);                                    // (1,1)
-        Mq[1] = shfl_d(gr0, 5);                                    // (1,2)
-        Mq[2] = shfl_d(gr1, 5);                                    // (1,3)
-        Mq[3] = shfl_d(gr0, 9);                                    // (2,2)
-        Mq[4] = shfl_d(gr1, 9);                                    // (2,3)
-        Mq[5] = shfl_d(gr1, 13);                                   // (3,3)
         double gam = yy;
         {   // Cholesky solve on the leading rank x rank block of V V^T
             double l00 = 0, l10 = 0, l11 = 0, l20 = 0, l21 = 0, l22 = 0, z0 = 0, z1 = 0, z2 = 0;

@@ -350,6 +350,44 @@ def test_large_windows_vs_oracle(mode, F, M, N):
         assert ref["out_updated"]
 
 
+@pytest.mark.parametrize("fused", [pytest.param(False, id="split"), pytest.param(True, id="fused")])
+@pytest.mark.parametrize("F,M,N", [(40, 32, 32), (24, 31, 31), (24, 29, 32), (48, 30, 30)])
+def test_warp_front_end_capacity_edges(F, M, N, fused, monkeypatch):
+    """The warp-per-feature front ends at the edges of their tile budget (M = 32: no padding rows in the last tile row;
+    N = 32: the staged covariance block fills the shared memory), with RAGGED track lengths 1..M in one batch (every
+    tile count of the factorisation kernel) and tracks whose observations are stored newest-first (slots decreasing with
+    the observation index: the transposed-block path of the assembly) -- against the oracle."""
+    from helpers import make_case
+    if fused:
+        monkeypatch.setenv("MSCKF_FRONT_FUSED", "1")
+        if N > 31:
+            pytest.skip("the fused kernel's staged window stops at 31 poses")
+    cases = []
+    for seed in (3, 4):
+        c = make_case(F, M, N, seed=seed)
+        rng = np.random.default_rng(100 + seed)
+        for j in range(F):
+            if j % 3 == 1:                                  # ragged: keep the first L observations
+                c["feat_len"][j] = int(rng.integers(1, M + 1))
+                c["tracked_cnt"][j] = c["feat_len"][j]
+            if j % 4 == 2:                                  # newest-first storage order
+                L = int(c["feat_len"][j])
+                for k in ("obs_uv", "obs_dir", "obs_conf", "obs_slot"):
+                    c[k][j, :L] = c[k][j, :L][::-1].copy()
+                c["idp_anchor_slot"][j] = c["obs_slot"][j, 0]
+                c["idp_base"][j] = c["cam_t"][c["obs_slot"][j, 0]]
+                c["idp_m"][j] = c["obs_dir"][j, 0] / np.linalg.norm(c["obs_dir"][j, 0])
+        cases.append(c)
+    refs = [o.update_case(c) for c in cases]
+    flt = _batch_from_cases(cases, _lib.COMPRESS_GRAM)
+    assert flt.M <= 32 and flt.N <= 32
+    flt.update()
+    torch.cuda.synchronize()
+    for b, (c, ref) in enumerate(zip(cases, refs)):
+        compare_update_outputs(flt.case_outputs(b, c), ref, CHI, label=f"edge F{F} M{M} N{N} #{b}")
+        assert ref["out_updated"]
+
+
 @pytest.mark.parametrize("name", ["small_updates.npz", "baseline_256x30_updates.npz"])
 def test_gate_bounds_mode_gives_identical_decisions_and_state(golden_dir, name):
     """MSCKF_GATE_BOUNDS: features whose upper bound passes / lower bound fails skip the factorisation; the decisions,
