@@ -212,7 +212,8 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
         double term[9];
         {
             const double nn = sqrt(o.dx * o.dx + o.dy * o.dy + o.dz * o.dz);
-            const double ux = o.dx / nn, uy = o.dy / nn, uz = o.dz / nn;
+            const double inn = 1.0 / nn;
+            const double ux = o.dx * inn, uy = o.dy * inn, uz = o.dz * inn;
             const double c = live ? o.cf : 0.0;
             term[0] = c * (1.0 - ux * ux); term[1] = c * (0.0 - ux * uy); term[2] = c * (0.0 - ux * uz);
             term[3] = c * (1.0 - uy * uy); term[4] = c * (0.0 - uy * uz); term[5] = c * (1.0 - uz * uz);
@@ -251,8 +252,9 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
         if (cz > 0.0) {
             const double* K = a.par.K;
             const double iw = K[6] * cx + K[7] * cy + K[8] * cz;
-            const double iu = (K[0] * cx + K[1] * cy + K[2] * cz) / iw;
-            const double iv = (K[3] * cx + K[4] * cy + K[5] * cz) / iw;
+            const double iiw = 1.0 / iw;
+            const double iu = (K[0] * cx + K[1] * cy + K[2] * cz) * iiw;
+            const double iv = (K[3] * cx + K[4] * cy + K[5] * cz) * iiw;
             if (!(iu < 0.0 || iu >= (double)a.par.width || iv < 0.0 || iv >= (double)a.par.height)) {
                 const double* Ki = a.par.Kinv;
                 const double vx = Ki[0] * iu + Ki[1] * iv + Ki[2];
@@ -263,7 +265,8 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
                 const double wz = R0[6] * vx + R0[7] * vy + R0[8] * vz;
                 const double wn = sqrt(wx * wx + wy * wy + wz * wz);
                 rho = 1.0 / cz;                      // InverseDepthPoint.update, geometry.py:61-71
-                m0 = wx / wn; m1 = wy / wn; m2 = wz / wn;
+                const double iwn = 1.0 / wn;
+                m0 = wx * iwn; m1 = wy * iwn; m2 = wz * iwn;
                 if (lane == 0) {
                     a.idp_rho[fj] = rho;
                     a.idp_m[fj * 3] = m0; a.idp_m[fj * 3 + 1] = m1; a.idp_m[fj * 3 + 2] = m2;
@@ -290,9 +293,11 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
         const double zx = Ki[0] * o.u + Ki[1] * o.v + Ki[2];
         const double zy = Ki[3] * o.u + Ki[4] * o.v + Ki[5];
         const double zw = Ki[6] * o.u + Ki[7] * o.v + Ki[8];
-        res[0] = zx / zw - f0 / f2;
-        res[1] = zy / zw - f1 / f2;
-        const double J00 = 1.0 / f2, J02 = -f0 / (f2 * f2), J11 = 1.0 / f2, J12 = -f1 / (f2 * f2);
+        // (one reciprocal per denominator: the quotients differ from the reference's divisions by an ulp, far inside 1e-9)
+        const double izw = 1.0 / zw, if2 = 1.0 / f2;
+        res[0] = zx * izw - f0 * if2;
+        res[1] = zy * izw - f1 * if2;
+        const double J00 = if2, J02 = -f0 * (if2 * if2), J11 = if2, J12 = -f1 * (if2 * if2);
         Hx[0][0] = J02 * (-f1);
         Hx[0][1] = J00 * (-f2) + J02 * f0;
         Hx[0][2] = J00 * f1;
@@ -317,13 +322,14 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
 #pragma unroll
         for (int k = 0; k < 6; ++k) den += u6[k] * u6[k];
         if (den > 1e-6) {
+            const double iden = 1.0 / den;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 double au = 0.0;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) au += Hx[r][k] * u6[k];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) Hx[r][k] = Hx[r][k] - (au * u6[k]) / den;
+                for (int k = 0; k < 6; ++k) Hx[r][k] = Hx[r][k] - (au * u6[k]) * iden;
             }
         }
         if (!live) {
