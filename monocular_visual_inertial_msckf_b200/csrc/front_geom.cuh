@@ -22,6 +22,16 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     return x > 0.0 ? y : 0.0;
 }
 
+// 1/x for finite non-zero x: hardware seed (MUFU.RCP64H) + two Newton steps, no slow-path branch (x = 0 gives NaN where
+// the IEEE division gives inf; every caller's downstream comparison treats both as "not valid")
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
 __device__ __forceinline__ double warp_sum_all(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -78,18 +88,18 @@ __device__ inline void sym3_eig_w(const double* a, double* lam, double* V) {
 __device__ __forceinline__ bool sym3_solve_spd(const double* a, const double* y, double* p) {
     const double d0 = a[0];
     if (!(d0 > 0.0)) return false;
-    const double i0 = 1.0 / d0;
+    const double i0 = fast_rcp(d0);
     const double l10 = a[1] * i0, l20 = a[2] * i0;
     const double d1 = a[3] - l10 * a[1];
     if (!(d1 > 0.0)) return false;
-    const double i1 = 1.0 / d1;
+    const double i1 = fast_rcp(d1);
     const double e21 = a[4] - l20 * a[1];
     const double l21 = e21 * i1;
     const double d2 = a[5] - l20 * a[2] - l21 * e21;
     const double tr = a[0] + a[3] + a[5];
     if (!(d2 > 0.0) || !(d0 * d1 * d2 > 1e-9 * tr * tr * tr)) return false;
     const double z0 = y[0], z1 = y[1] - l10 * z0, z2 = y[2] - l20 * z0 - l21 * z1;
-    p[2] = z2 / d2;
+    p[2] = z2 * fast_rcp(d2);
     p[1] = z1 * i1 - l21 * p[2];
     p[0] = z0 * i0 - l10 * p[1] - l20 * p[2];
     return true;
@@ -211,8 +221,7 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
     {
         double term[9];
         {
-            const double nn = sqrt(o.dx * o.dx + o.dy * o.dy + o.dz * o.dz);
-            const double inn = 1.0 / nn;
+            const double inn = fast_rsqrt(o.dx * o.dx + o.dy * o.dy + o.dz * o.dz);
             const double ux = o.dx * inn, uy = o.dy * inn, uz = o.dz * inn;
             const double c = live ? o.cf : 0.0;
             term[0] = c * (1.0 - ux * ux); term[1] = c * (0.0 - ux * uy); term[2] = c * (0.0 - ux * uz);
@@ -252,7 +261,7 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
         if (cz > 0.0) {
             const double* K = a.par.K;
             const double iw = K[6] * cx + K[7] * cy + K[8] * cz;
-            const double iiw = 1.0 / iw;
+            const double iiw = fast_rcp(iw);
             const double iu = (K[0] * cx + K[1] * cy + K[2] * cz) * iiw;
             const double iv = (K[3] * cx + K[4] * cy + K[5] * cz) * iiw;
             if (!(iu < 0.0 || iu >= (double)a.par.width || iv < 0.0 || iv >= (double)a.par.height)) {
@@ -263,9 +272,8 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
                 const double wx = R0[0] * vx + R0[1] * vy + R0[2] * vz;
                 const double wy = R0[3] * vx + R0[4] * vy + R0[5] * vz;
                 const double wz = R0[6] * vx + R0[7] * vy + R0[8] * vz;
-                const double wn = sqrt(wx * wx + wy * wy + wz * wz);
                 rho = 1.0 / cz;                      // InverseDepthPoint.update, geometry.py:61-71
-                const double iwn = 1.0 / wn;
+                const double iwn = fast_rsqrt(wx * wx + wy * wy + wz * wz);
                 m0 = wx * iwn; m1 = wy * iwn; m2 = wz * iwn;
                 if (lane == 0) {
                     a.idp_rho[fj] = rho;
@@ -294,7 +302,7 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
         const double zy = Ki[3] * o.u + Ki[4] * o.v + Ki[5];
         const double zw = Ki[6] * o.u + Ki[7] * o.v + Ki[8];
         // (one reciprocal per denominator: the quotients differ from the reference's divisions by an ulp, far inside 1e-9)
-        const double izw = 1.0 / zw, if2 = 1.0 / f2;
+        const double izw = fast_rcp(zw), if2 = fast_rcp(f2);
         res[0] = zx * izw - f0 * if2;
         res[1] = zy * izw - f1 * if2;
         const double J00 = if2, J02 = -f0 * (if2 * if2), J11 = if2, J12 = -f1 * (if2 * if2);
@@ -322,7 +330,7 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
 #pragma unroll
         for (int k = 0; k < 6; ++k) den += u6[k] * u6[k];
         if (den > 1e-6) {
-            const double iden = 1.0 / den;
+            const double iden = fast_rcp(den);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 double au = 0.0;
@@ -371,10 +379,10 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
                     }
                 }
             }
-            const double nk = sqrt(best);
+            const double ink = fast_rsqrt(best);
+            const double nk = best * ink;
             R3[k * 3 + k] = nk;
             if (!(nk > 0.0)) { stop = true; break; }
-            const double ink = 1.0 / nk;
             Hf[0][k] *= ink; Hf[1][k] *= ink;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {

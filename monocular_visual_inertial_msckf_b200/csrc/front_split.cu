@@ -505,29 +505,15 @@ front_chol_kernel(const double2* __restrict__ Kbuf, const int* __restrict__ pend
         const int rank = fac_rank[fj], dofv = dof[fj];
         const int st = feat_status[fj];
         double gam = yy;
-        {   // Cholesky solve on the leading rank x rank block of V V^T
-            double l00 = 0, l10 = 0, l11 = 0, l20 = 0, l21 = 0, l22 = 0, z0 = 0, z1 = 0, z2 = 0;
-            if (rank >= 1 && Mq[0] > 0.0) {
-                l00 = sqrt(Mq[0]);
-                z0 = bq[0] / l00;
-                if (rank >= 2) {
-                    l10 = Mq[1] / l00;
-                    const double d1 = Mq[3] - l10 * l10;
-                    if (d1 > 0.0) {
-                        l11 = sqrt(d1);
-                        z1 = (bq[1] - l10 * z0) / l11;
-                        if (rank >= 3) {
-                            l20 = Mq[2] / l00;
-                            l21 = (Mq[4] - l20 * l10) / l11;
-                            const double d2 = Mq[5] - l20 * l20 - l21 * l21;
-                            if (d2 > 0.0) {
-                                l22 = sqrt(d2);
-                                z2 = (bq[2] - l20 * z0 - l21 * z1) / l22;
-                            }
-                        }
-                    }
-                }
-            }
+        {   // Cholesky solve on the leading rank x rank block of V V^T (reciprocal square roots: 0 for a non-positive pivot)
+            const double r0 = (rank >= 1) ? fast_rsqrt(Mq[0]) : 0.0;
+            const double z0 = bq[0] * r0;
+            const double l10 = Mq[1] * r0, l20 = Mq[2] * r0;
+            const double r1 = (rank >= 2 && r0 > 0.0) ? fast_rsqrt(Mq[3] - l10 * l10) : 0.0;
+            const double z1 = (bq[1] - l10 * z0) * r1;
+            const double l21 = (Mq[4] - l20 * l10) * r1;
+            const double r2 = (rank >= 3 && r1 > 0.0) ? fast_rsqrt(Mq[5] - l20 * l20 - l21 * l21) : 0.0;
+            const double z2 = (bq[2] - l20 * z0 - l21 * z1) * r2;
             gam = yy - (z0 * z0 + z1 * z1 + z2 * z2);
         }
         if (lane == 0) {
