@@ -222,10 +222,14 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                 Gt[0] = make_double2(rt0, rt1);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) Gt[4 * (q + 1)] = make_double2(Hf[0][q], Hf[1][q]);
+                if ((lane >> 2) == Tn - 1) {   // measurement rows of the same (diagonal) tile: define the mirrored blocks
+                    double2* Tm = Kt + tile_index(Tn - 1, Tn - 1) * 32 + 8 * (lane & 3) + (ia & 3);
+                    Tm[0] = Tm[1] = Tm[4] = Tm[5] = make_double2(0.0, 0.0);
+                }
             }
 
             // ---- K = H_x P H_x^T + sigma^2 I, one lower 2x2 block per lane per pass ----
-            const int npairs = Mp * (Mp + 1) / 2;
+            const int npairs = M * (M + 1) / 2;     // measurement rows only; the few padding blocks follow below
             // (the pair descriptor of the next pass is fetched while this one is computed)
             unsigned ik_n = lut[lane < npairs ? lane : 0];
             int si_n = __shfl_sync(0xffffffffu, o.slot, ik_n & 0xff), sk_n = __shfl_sync(0xffffffffu, o.slot, ik_n >> 8);
@@ -242,7 +246,7 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                 }
                 if (!act) continue;
                 double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
-                if (i < M) {
+                {
                     double ai[2][6];
                     {
                         const double2* Ai = reinterpret_cast<const double2*>(wsA + i * AR);
@@ -291,21 +295,35 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                         o11 = fma(v1[2 * c2 + 1], x1.y, fma(v1[2 * c2], x1.x, o11));
                     }
                     if (i == k) { o00 += s2; o11 += s2; }
-                } else if (i == k && i < ia) {   // padding between the measurement rows and the appended rows: identity
-                    o00 = 1.0; o11 = 1.0;
                 }
                 // rows 2 i, 2 i + 1 / columns 2 k, 2 k + 1  ->  tile (i / 4, k / 4), lanes 4 (2 (i & 3) + row) + (k & 3)
                 const int I = i >> 2, J = k >> 2;
                 double2* T = Kt + tile_index(I, J) * 32;
                 const int l0 = 8 * (i & 3) + (k & 3);
-                if (!(i >= ia && i < ia + 2 && k < M)) {   // (appended rows x measurement columns were written above)
-                    T[l0] = make_double2(o00, o01);
-                    T[l0 + 4] = make_double2(o10, o11);
-                }
+                T[l0] = make_double2(o00, o01);
+                T[l0 + 4] = make_double2(o10, o11);
                 if (I == J && i != k) {   // the mirrored block of a diagonal tile is never read as data: keep it defined
                     const int l1 = 8 * (k & 3) + (i & 3);
                     T[l1] = make_double2(0.0, 0.0);
                     T[l1 + 4] = make_double2(0.0, 0.0);
+                }
+            }
+            // ---- the padding row pairs i = M .. Mp-1 (at most 7): identity before the appended rows, zero after; the
+            //      blocks (appended rows x measurement columns) were written above ----
+            for (int i = M; i < Mp; ++i) {
+                const bool appended = i >= ia && i < ia + 2;
+                for (int k = (appended ? M : 0) + lane; k <= i; k += 32) {
+                    const double dg = (i == k && i < ia) ? 1.0 : 0.0;
+                    const int I = i >> 2, J = k >> 2;
+                    double2* T = Kt + tile_index(I, J) * 32;
+                    const int l0 = 8 * (i & 3) + (k & 3);
+                    T[l0] = make_double2(dg, 0.0);
+                    T[l0 + 4] = make_double2(0.0, dg);
+                    if (I == J && i != k) {
+                        const int l1 = 8 * (k & 3) + (i & 3);
+                        T[l1] = make_double2(0.0, 0.0);
+                        T[l1 + 4] = make_double2(0.0, 0.0);
+                    }
                 }
             }
         }
