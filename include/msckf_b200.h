@@ -187,6 +187,28 @@ int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* re
                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * msckf_select_poorest_cameras_batched  <->  MSCKF.prune_poorest_camera_states, selection part (MSCKF.py:712-733)
+ *
+ * Per filter: observations per window slot are counted over all tracks; the (up to) `max_select` slots (the reference
+ * uses 2) with the fewest observations -- ties in the order in which the cameras first appear while walking the tracks,
+ * as the reference's dict + stable sort produce -- are marked in remove_mask[B][N]; feat_touch[B][F] marks the tracks
+ * observing a selected camera (the reference's `features_to_process`, which get one last update before the cameras go).
+ *
+ * msckf_drop_observations_batched  <->  MSCKF.remove_cameras, track part (MSCKF.py:760-770)
+ *
+ * The observations made from the slots marked in remove_mask leave every track (order kept, in place), the remaining
+ * obs_slot values and idp_anchor_slot are renumbered to the window after the deletion, an anchor on a deleted camera
+ * becomes -1 with idp_base frozen at that camera's position, feat_len is updated (0 = the reference deletes the track).
+ * Call it BEFORE msckf_remove_cameras_batched (it reads cam_t / n_cams of the window before the deletion).
+ * ------------------------------------------------------------------------------------------------------------- */
+int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select, const int* n_cams, const int* feat_len,
+                                         const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch,
+                                         void* stream);
+int msckf_drop_observations_batched(const msckf_dims* dims, const unsigned char* remove_mask, const int* n_cams,
+                                    const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                    int* obs_slot, double* idp_base, int* idp_anchor_slot, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * msckf_filter_step_host  <->  one camera-frame step of B filters driven from HOST buffers: the n_samples
  * MSCKF.process_imu calls since the last frame (MSCKF.py:160-248) followed by get_valid_features + update + correct
  * (MSCKF.py:458-495, 570-661).  This is the call a host-side owner of the tracks (the reference keeps them in Python

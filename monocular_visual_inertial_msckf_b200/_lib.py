@@ -56,7 +56,8 @@ EXPORTS = [
     "msckf_update_batched", "msckf_front_batched", "msckf_compress_batched", "msckf_apply_update_batched",
     "msckf_propagate_batched", "msckf_augment_batched", "msckf_remove_workspace_bytes",
     "msckf_remove_cameras_batched", "msckf_launch_count", "msckf_probe_fp64", "msckf_filter_step_host",
-    "msckf_set_stage_timing", "msckf_front_stage_ms",
+    "msckf_set_stage_timing", "msckf_front_stage_ms", "msckf_select_poorest_cameras_batched",
+    "msckf_drop_observations_batched",
 ]
 
 
@@ -108,6 +109,10 @@ def load_library():
     lib.msckf_filter_step_host.restype = C.c_int
     lib.msckf_filter_step_host.argtypes = [pd, pp, dp, C.c_int, C.POINTER(DeviceBuffers), C.POINTER(HostStep), C.c_int,
                                            C.c_int, vp, C.c_size_t, vp]
+    lib.msckf_select_poorest_cameras_batched.restype = C.c_int
+    lib.msckf_select_poorest_cameras_batched.argtypes = [pd, C.c_int, ip, ip, ip, u8, u8, vp]
+    lib.msckf_drop_observations_batched.restype = C.c_int
+    lib.msckf_drop_observations_batched.argtypes = [pd, u8, ip, dp, ip, dp, dp, dp, ip, dp, ip, vp]
     lib.msckf_set_stage_timing.restype = C.c_int
     lib.msckf_set_stage_timing.argtypes = [C.c_int]
     lib.msckf_front_stage_ms.restype = C.c_int

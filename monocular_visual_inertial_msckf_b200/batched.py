@@ -253,6 +253,38 @@ class BatchedMSCKF:
                                                    _ptr(self._remove_ws), self._remove_ws.numel(), self._stream())
         _lib.check(rc, "msckf_remove_cameras_batched")
 
+    def select_poorest_cameras(self, max_select=2):
+        """MSCKF.prune_poorest_camera_states' selection (MSCKF.py:712-733) for every filter: returns
+        (remove_mask [B, N] uint8, feat_touch [B, F] uint8) on the device."""
+        mask = torch.empty((self.B, self.N), dtype=torch.uint8, device=self.device)
+        touch = torch.empty((self.B, self.F), dtype=torch.uint8, device=self.device)
+        rc = self.lib.msckf_select_poorest_cameras_batched(C.byref(self.dims), int(max_select), _ptr(self.n_cams),
+                                                           _ptr(self.feat_len), _ptr(self.obs_slot), _ptr(mask), _ptr(touch),
+                                                           self._stream())
+        _lib.check(rc, "msckf_select_poorest_cameras_batched")
+        return mask, touch
+
+    def drop_observations(self, mask):
+        """Track part of MSCKF.remove_cameras (MSCKF.py:760-770); call before remove_cameras(mask)."""
+        rc = self.lib.msckf_drop_observations_batched(C.byref(self.dims), _ptr(mask), _ptr(self.n_cams), _ptr(self.cam_t),
+                                                      _ptr(self.feat_len), _ptr(self.obs_uv), _ptr(self.obs_dir),
+                                                      _ptr(self.obs_conf), _ptr(self.obs_slot), _ptr(self.idp_base),
+                                                      _ptr(self.idp_anchor_slot), self._stream())
+        _lib.check(rc, "msckf_drop_observations_batched")
+
+    def prune_poorest_camera_states(self, max_select=2):
+        """MSCKF.prune_poorest_camera_states (MSCKF.py:710-737) for every filter, everything resident: select the two
+        cameras with the fewest observations, one last update with the tracks that observe them, then delete those
+        cameras from the tracks, the window and the covariance.  Returns the (remove_mask, feat_touch) that were used."""
+        mask, touch = self.select_poorest_cameras(max_select)
+        full_len = self.feat_len.clone()
+        self.feat_len.mul_(touch.to(torch.int32))         # features_to_process: the other tracks sit this update out
+        self.update()
+        self.feat_len.copy_(full_len)
+        self.drop_observations(mask)
+        self.remove_cameras(mask)
+        return mask, touch
+
     # ------------------------------------------------------------------------------------------------------------
     def load_cases(self, cases):
         """Fill filter b from packed case dict cases[b] (the layout of tests/golden and tools/make_golden.py)."""

@@ -19,6 +19,11 @@ cudaError_t launch_update_info(const ApplyArgs& a, int n_ctas, cudaStream_t s);
 bool update_smem_supported(const msckf_dims& d);
 size_t update_smem_scratch_doubles(const msckf_dims& d);
 cudaError_t launch_update_smem(const ApplyArgs& a, int n_ctas, cudaStream_t s);
+cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, const int* n_cams, const int* feat_len,
+                                  const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch, cudaStream_t s);
+cudaError_t launch_drop_observations(const msckf_dims& d, const unsigned char* remove_mask, const int* n_cams,
+                                     const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                     int* obs_slot, double* idp_base, int* idp_anchor_slot, cudaStream_t s);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -213,6 +218,28 @@ int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* re
     if (dims->N > 128) return MSCKF_ECAPACITY;
     if (workspace_bytes < msckf_remove_workspace_bytes(dims)) return MSCKF_EWORKSPACE;
     return (int)launch_remove(*dims, remove_mask, cam_R, cam_t, P, n_cams, (double*)workspace, (cudaStream_t)stream);
+}
+
+int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select, const int* n_cams, const int* feat_len,
+                                         const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch,
+                                         void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (max_select < 0 || !n_cams || !feat_len || !obs_slot || !remove_mask || !feat_touch) return MSCKF_EINVAL;
+    return (int)launch_select_poorest(*dims, max_select, n_cams, feat_len, obs_slot, remove_mask, feat_touch,
+                                      (cudaStream_t)stream);
+}
+
+int msckf_drop_observations_batched(const msckf_dims* dims, const unsigned char* remove_mask, const int* n_cams,
+                                    const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                    int* obs_slot, double* idp_base, int* idp_anchor_slot, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!remove_mask || !n_cams || !cam_t || !feat_len || !obs_uv || !obs_dir || !obs_conf || !obs_slot || !idp_base ||
+        !idp_anchor_slot)
+        return MSCKF_EINVAL;
+    return (int)launch_drop_observations(*dims, remove_mask, n_cams, cam_t, feat_len, obs_uv, obs_dir, obs_conf, obs_slot,
+                                         idp_base, idp_anchor_slot, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,145 @@
+// "Next rows" of SURVEY.md section 8f, rows 1-2: the window selection and the track surgery that sit between two updates,
+// on the struct-of-arrays tracks in HBM (integer / byte work, one pass over the tracks each):
+//   select_poorest_kernel     <-> MSCKF.prune_poorest_camera_states, selection part (reference src/msckf/MSCKF.py:712-733)
+//   drop_observations_kernel  <-> MSCKF.remove_cameras, track part (MSCKF.py:760-770) + the slot renumbering implied by
+//                                 `del self.state.cameras[...]` (MSCKF.py:758, slots are dict positions, MSCKF.py:539)
+#include "msckf_common.cuh"
+
+namespace {
+
+constexpr int TT = 256;
+
+// One CTA per filter.  Observations per window slot are counted with shared-memory atomics together with the slot's first
+// appearance in track order (the reference builds a dict while walking the tracks, so cameras enter it in that order, and
+// Python's stable `sorted` keeps it among equal counts); the `max_select` smallest (count, first appearance) pairs win.
+__global__ void __launch_bounds__(TT) select_poorest_kernel(msckf_dims dims, int max_select, const int* __restrict__ n_cams,
+                                                            const int* __restrict__ feat_len, const int* __restrict__ obs_slot,
+                                                            unsigned char* __restrict__ remove_mask,
+                                                            unsigned char* __restrict__ feat_touch) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int F = dims.F, M = dims.M, N = dims.N;
+    __shared__ int s_count[MSCKF_MAX_CAMS], s_first[MSCKF_MAX_CAMS];
+    __shared__ unsigned char s_sel[MSCKF_MAX_CAMS];
+    const int nc = min(n_cams[b], N);
+    for (int s = tid; s < N; s += TT) { s_count[s] = 0; s_first[s] = 0x7fffffff; s_sel[s] = 0; }
+    __syncthreads();
+    const int* len = feat_len + (size_t)b * F;
+    const int* slot = obs_slot + (size_t)b * F * M;
+    for (int e = tid; e < F * M; e += TT) {
+        const int j = e / M, i = e - j * M;
+        if (i < len[j]) {
+            const int s = slot[e];
+            if (s >= 0 && s < nc) {
+                atomicAdd(&s_count[s], 1);
+                atomicMin(&s_first[s], e);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int pick = 0; pick < max_select; ++pick) {
+            int best = -1;
+            for (int s = 0; s < nc; ++s) {
+                if (s_sel[s] || s_count[s] == 0) continue;
+                if (best < 0 || s_count[s] < s_count[best] || (s_count[s] == s_count[best] && s_first[s] < s_first[best])) best = s;
+            }
+            if (best < 0) break;
+            s_sel[best] = 1;
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < N; s += TT) remove_mask[(size_t)b * N + s] = s_sel[s];
+    for (int j = tid; j < F; j += TT) {
+        unsigned char t = 0;
+        const int n = min(len[j], M);
+        for (int i = 0; i < n; ++i) {
+            const int s = slot[(size_t)j * M + i];
+            if (s >= 0 && s < nc && s_sel[s]) { t = 1; break; }
+        }
+        feat_touch[(size_t)b * F + j] = t;
+    }
+}
+
+// One warp per track, lane = observation (chunks of 32 for longer tracks): observations of removed slots leave the track,
+// the rest keep their order (ballot + popc compaction, in place) and are renumbered; an inverse-depth anchor on a removed
+// camera is frozen at that camera's position (InverseDepthPoint.base keeps aliasing the deleted camera's array,
+// src/utils/geometry.py:55).  Must run BEFORE msckf_remove_cameras_batched compacts cam_t / n_cams.
+__global__ void __launch_bounds__(TT) drop_observations_kernel(msckf_dims dims, const unsigned char* __restrict__ remove_mask,
+                                                               const int* __restrict__ n_cams, const double* __restrict__ cam_t,
+                                                               int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                                               int* obs_slot, double* idp_base, int* idp_anchor_slot) {
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int F = dims.F, M = dims.M, N = dims.N;
+    __shared__ unsigned char s_rm[MSCKF_MAX_CAMS];
+    __shared__ unsigned char s_shift[MSCKF_MAX_CAMS];
+    const int nc = min(n_cams[b], N);
+    if (tid < N) s_rm[tid] = (tid < nc) ? remove_mask[(size_t)b * N + tid] : 0;
+    __syncthreads();
+    if (tid < N) {
+        int c = 0;
+        for (int s = 0; s <= tid; ++s) c += s_rm[s] ? 1 : 0;
+        s_shift[tid] = (unsigned char)c;
+    }
+    __syncthreads();
+    const int j = blockIdx.x * (TT / 32) + (tid >> 5);
+    if (j >= F) return;
+    const size_t fj = (size_t)b * F + j;
+    const int n = min(feat_len[fj], M);
+    int off = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool live = i < n;
+        const size_t e = fj * M + i;
+        int s = 0;
+        double u = 0, v = 0, d0 = 0, d1 = 0, d2 = 0, cf = 0;
+        if (live) {
+            s = obs_slot[e];
+            u = obs_uv[e * 2]; v = obs_uv[e * 2 + 1];
+            d0 = obs_dir[e * 3]; d1 = obs_dir[e * 3 + 1]; d2 = obs_dir[e * 3 + 2];
+            cf = obs_conf[e];
+        }
+        const bool keep = live && !(s >= 0 && s < nc && s_rm[s]);
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) {
+            const size_t w = fj * M + off + __popc(km & ((1u << lane) - 1u));
+            obs_slot[w] = (s >= 0 && s < nc) ? s - (int)s_shift[s] : s;
+            obs_uv[w * 2] = u; obs_uv[w * 2 + 1] = v;
+            obs_dir[w * 3] = d0; obs_dir[w * 3 + 1] = d1; obs_dir[w * 3 + 2] = d2;
+            obs_conf[w] = cf;
+        }
+        off += __popc(km);
+    }
+    if (lane == 0) {
+        feat_len[fj] = off;
+        const int a = idp_anchor_slot[fj];
+        if (a >= 0 && a < nc) {
+            if (s_rm[a]) {
+                idp_anchor_slot[fj] = -1;
+                for (int k = 0; k < 3; ++k) idp_base[fj * 3 + k] = cam_t[((size_t)b * N + a) * 3 + k];
+            } else {
+                idp_anchor_slot[fj] = a - (int)s_shift[a];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, const int* n_cams, const int* feat_len,
+                                  const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch, cudaStream_t s) {
+    select_poorest_kernel<<<d.B, TT, 0, s>>>(d, max_select, n_cams, feat_len, obs_slot, remove_mask, feat_touch);
+    msckf_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_drop_observations(const msckf_dims& d, const unsigned char* remove_mask, const int* n_cams,
+                                     const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                     int* obs_slot, double* idp_base, int* idp_anchor_slot, cudaStream_t s) {
+    if (d.F == 0) return cudaSuccess;
+    dim3 grid((d.F + TT / 32 - 1) / (TT / 32), d.B);
+    drop_observations_kernel<<<grid, TT, 0, s>>>(d, remove_mask, n_cams, cam_t, feat_len, obs_uv, obs_dir, obs_conf, obs_slot,
+                                                 idp_base, idp_anchor_slot);
+    msckf_count_launch(1);
+    return cudaGetLastError();
+}

@@ -290,6 +290,109 @@ def test_window_surgery_vs_oracle(golden_dir):
     assert rel_err(flt.cam_t[0, :len(keep)].cpu().numpy(), cam_t_ref) < 1e-15
 
 
+def _load_tracks(flt, cases):
+    """tracks + window positions of packed surgery cases (tools/make_golden.py::pack_tracks) into a BatchedMSCKF"""
+    for b, c in enumerate(cases):
+        f, m, n = c["obs_slot"].shape[0], c["obs_slot"].shape[1], int(c["n_cams"])
+        flt.n_cams[b] = n
+        flt.feat_len[b].zero_()
+        flt.feat_len[b, :f] = torch.from_numpy(c["feat_len"])
+        flt.obs_slot[b, :f, :m] = torch.from_numpy(np.maximum(c["obs_slot"], 0))
+        flt.obs_uv[b, :f, :m] = torch.from_numpy(c["obs_uv"])
+        flt.obs_dir[b, :f, :m] = torch.from_numpy(c["obs_dir"])
+        flt.obs_conf[b, :f, :m] = torch.from_numpy(c["obs_conf"])
+        flt.idp_base[b, :f] = torch.from_numpy(c["idp_base"])
+        flt.idp_anchor_slot[b, :f] = torch.from_numpy(c["idp_anchor_slot"])
+        flt.cam_t[b, :n] = torch.from_numpy(c["cam_t"])
+
+
+def _surgery_batch(cases):
+    F = max(c["obs_slot"].shape[0] for c in cases) + 3
+    M = max(c["obs_slot"].shape[1] for c in cases) + 1
+    N = max(int(c["n_cams"]) for c in cases) + 1
+    flt = BatchedMSCKF(len(cases), F, M, N, UpdateParams())
+    _load_tracks(flt, cases)
+    return flt
+
+
+def test_prune_selection_vs_golden(golden_dir):
+    """next rows: the camera / track selection of prune_poorest_camera_states on device, bit-exact against every
+    selection the reference made in the small run (ties included)."""
+    cases, _ = _load(golden_dir, "small_prune_select.npz")
+    flt = _surgery_batch(cases)
+    mask, touch = flt.select_poorest_cameras(2)
+    torch.cuda.synchronize()
+    mask, touch = mask.cpu().numpy().astype(bool), touch.cpu().numpy().astype(bool)
+    for b, c in enumerate(cases):
+        n, f = int(c["n_cams"]), len(c["feat_len"])
+        assert (mask[b, :n] == c["out_remove_mask"]).all() and not mask[b, n:].any(), c["call_index"]
+        assert (touch[b, :f] == c["out_feat_touch"]).all() and not touch[b, f:].any(), c["call_index"]
+
+
+def test_drop_observations_vs_golden(golden_dir):
+    """next rows: the track part of remove_cameras on device (compaction in place, slot renumbering, frozen anchors),
+    bit-exact against every remove_cameras call of the small run; then the window / covariance part on the same mask."""
+    cases, _ = _load(golden_dir, "small_prune_drop.npz")
+    flt = _surgery_batch(cases)
+    mask = torch.zeros((flt.B, flt.N), dtype=torch.uint8, device="cuda")
+    for b, c in enumerate(cases):
+        mask[b, :int(c["n_cams"])] = torch.from_numpy(c["remove_mask"].astype(np.uint8))
+    flt.drop_observations(mask)
+    flt.remove_cameras(mask)
+    torch.cuda.synchronize()
+    ln, sl = flt.feat_len.cpu().numpy(), flt.obs_slot.cpu().numpy()
+    uv, dr, cf = flt.obs_uv.cpu().numpy(), flt.obs_dir.cpu().numpy(), flt.obs_conf.cpu().numpy()
+    an, bs = flt.idp_anchor_slot.cpu().numpy(), flt.idp_base.cpu().numpy()
+    n_checked = 0
+    for b, c in enumerate(cases):
+        f = len(c["feat_len"])
+        assert (ln[b, :f] == c["out_feat_len"]).all() and (ln[b, f:] == 0).all(), c["call_index"]
+        assert int(flt.n_cams[b]) == int(c["out_n_cams"])
+        for j in range(f):
+            n = int(c["out_feat_len"][j])
+            if n == 0:
+                continue
+            assert (sl[b, j, :n] == c["out_obs_slot"][j, :n]).all()
+            assert np.array_equal(uv[b, j, :n], c["out_obs_uv"][j, :n]) and np.array_equal(dr[b, j, :n], c["out_obs_dir"][j, :n])
+            assert np.array_equal(cf[b, j, :n], c["out_obs_conf"][j, :n])
+            assert an[b, j] == c["out_idp_anchor_slot"][j] and np.array_equal(bs[b, j], c["out_idp_base"][j])
+            n_checked += n
+    assert n_checked > 5000
+
+
+def test_prune_flow_vs_oracle(golden_dir):
+    """prune_poorest_camera_states end to end on resident state (select -> update with the touched tracks -> drop ->
+    remove) against the oracle's composition of the same reference steps."""
+    cases, _ = _load(golden_dir, "mid_48x10_updates.npz")
+    cases = [c for c in cases if int(c["n_cams"]) >= 4][:2]
+    flt = _batch_from_cases(cases, _lib.COMPRESS_GRAM)
+    mask, touch = flt.prune_poorest_camera_states()
+    torch.cuda.synchronize()
+    mask, touch = mask.cpu().numpy().astype(bool), touch.cpu().numpy().astype(bool)
+    for b, c in enumerate(cases):
+        n, f = int(c["n_cams"]), len(c["feat_len"])
+        m_ref, t_ref = o.select_poorest_cameras(c)
+        assert (mask[b, :n] == m_ref).all() and (touch[b, :f] == t_ref).all()
+        sub = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in c.items()}
+        sub["feat_len"] = np.where(t_ref, c["feat_len"], 0).astype(np.int32)
+        ref = o.update_case(sub)
+        P = ref["out_P"]
+        for s in sorted(np.nonzero(m_ref)[0], reverse=True):
+            P = o.remove_camera_covariance(P, int(s))
+        keep = ~m_ref
+        d = P.shape[0]
+        assert int(flt.n_cams[b]) == int(keep.sum())
+        assert rel_err(flt.P[b, :d, :d].cpu().numpy(), P) < 1e-9
+        assert rel_err(flt.cam_t[b, :keep.sum()].cpu().numpy(), ref["out_cam_t"][keep]) < 1e-9
+        after = dict(c)
+        after["cam_t"] = ref["out_cam_t"]
+        tr = o.drop_observations(after, m_ref)
+        assert (flt.feat_len[b, :f].cpu().numpy() == tr["feat_len"]).all()
+        sl = flt.obs_slot[b].cpu().numpy()
+        for j in range(f):
+            assert (sl[j, :tr["feat_len"][j]] == tr["obs_slot"][j, :tr["feat_len"][j]]).all()
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_full_size_properties(golden_dir, mode):
     """BASELINE shape (256 features x 30 poses) replicated over a batch with per-filter pixel noise: size-independent
@@ -330,11 +433,12 @@ def test_full_size_properties(golden_dir, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("F,M,N", [(24, 12, 36), (16, 40, 40), (40, 33, 34)])
+@pytest.mark.parametrize("F,M,N", [(24, 12, 36), (16, 40, 40), (40, 33, 34), (48, 60, 60)])
 def test_large_windows_vs_oracle(mode, F, M, N):
     """Windows / tracks beyond the warp-per-feature kernel's tile budget (N > 31 or M > 32): CTA-per-feature front end,
     multi-pass information accumulation (6N > 192), larger update factorisations -- against the oracle on synthetic
-    cases (the golden fixtures stop at N = 31)."""
+    cases (the golden fixtures stop at N = 31).  (48, 60, 60) is the per-feature / per-filter shape of BASELINE.json's
+    stress config (60-pose window, state 375, 60 observations per track)."""
     from helpers import make_case
     if mode == _lib.COMPRESS_QR and N > _lib.load_library().msckf_max_cameras(_lib.COMPRESS_QR):
         pytest.skip("explicit-QR kernel keeps R in one SM's shared memory: N <= %d" % _lib.load_library().msckf_max_cameras(0))

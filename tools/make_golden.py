@@ -197,6 +197,114 @@ class Capture:
         return out
 
 
+def pack_tracks(f):
+    """All tracks of the filter in the SoA layout (dict order), slots = position in the insertion-ordered camera dict."""
+    cams = list(f.state.cameras.items())
+    cam_ids = [k for k, _ in cams]
+    feats = f.features
+    F = len(feats)
+    M = max([len(ft.keypoints) for ft in feats.values()] + [1])
+    c = dict(n_cams=len(cams), feat_ids=np.array(list(feats.keys()), np.int64), feat_len=np.zeros(F, np.int32),
+             obs_uv=np.zeros((F, M, 2)), obs_dir=np.zeros((F, M, 3)), obs_conf=np.zeros((F, M)),
+             obs_slot=-np.ones((F, M), np.int32), idp_base=np.zeros((F, 3)), idp_anchor_slot=-np.ones(F, np.int32),
+             cam_t=np.stack([cam.T_W_Ci.t for _, cam in cams]).astype(float) if cams else np.zeros((0, 3)))
+    for j, ft in enumerate(feats.values()):
+        n = len(ft.keypoints)
+        c["feat_len"][j] = n
+        for i in range(n):
+            c["obs_uv"][j, i] = ft.keypoints[i]
+            c["obs_dir"][j, i] = ft.lines[i].direction
+            c["obs_conf"][j, i] = ft.lines[i].confidence
+            c["obs_slot"][j, i] = cam_ids.index(ft.camera_indices[i])
+        c["idp_base"][j] = ft.inverse_depth_point.base
+        for s, (_, cam) in enumerate(cams):
+            if ft.inverse_depth_point.base is cam.T_W_Ci.t:
+                c["idp_anchor_slot"][j] = s
+    return c
+
+
+class SurgeryCapture:
+    """prune_poorest_camera_states (selection, MSCKF.py:710-727) and remove_cameras (track part, MSCKF.py:751-770)."""
+
+    def __init__(self, f):
+        self.f = f
+        self.select_cases, self.drop_cases = [], []
+        self._orig_prune, self._orig_remove = f.prune_poorest_camera_states, f.remove_cameras
+        self._orig_gvf = f.get_valid_features
+        self._in_prune = None
+        f.prune_poorest_camera_states = self.prune
+        f.remove_cameras = self.remove
+        f.get_valid_features = self.gvf
+
+    def prune(self):
+        c = pack_tracks(self.f)
+        c["call_index"] = len(self.select_cases)
+        self._in_prune = c
+        out = self._orig_prune()
+        self._in_prune = None
+        self.select_cases.append(c)
+        return out
+
+    def gvf(self, features):
+        c = self._in_prune
+        if c is not None and "out_feat_touch" not in c:
+            c["out_feat_touch"] = np.array([k in features for k in c["feat_ids"]], bool)
+        return self._orig_gvf(features)
+
+    def remove(self, cameras):
+        f = self.f
+        cam_ids = list(f.state.cameras.keys())
+        if self._in_prune is not None:
+            m = np.zeros(len(cam_ids), bool)
+            for k in cameras.keys():
+                m[cam_ids.index(k)] = True
+            self._in_prune["out_remove_mask"] = m
+            self._in_prune.setdefault("out_feat_touch", np.zeros(len(self._in_prune["feat_ids"]), bool))
+        c = pack_tracks(f)
+        c["call_index"] = len(self.drop_cases)
+        c["remove_mask"] = np.array([k in cameras for k in cam_ids], bool)
+        out = self._orig_remove(cameras)
+        after = pack_tracks(f)
+        F, M = c["obs_slot"].shape
+        for k in ("feat_len", "obs_uv", "obs_dir", "obs_conf", "obs_slot", "idp_base", "idp_anchor_slot"):
+            c["out_" + k] = np.zeros_like(c[k]) if k != "obs_slot" else -np.ones_like(c[k])
+        pos = {int(fid): j for j, fid in enumerate(c["feat_ids"])}
+        for j2, fid in enumerate(after["feat_ids"]):
+            j = pos[int(fid)]
+            n = int(after["feat_len"][j2])
+            c["out_feat_len"][j] = n
+            for k in ("obs_uv", "obs_dir", "obs_conf", "obs_slot"):
+                c["out_" + k][j, :n] = after[k][j2, :n]
+            c["out_idp_base"][j] = after["idp_base"][j2]
+            c["out_idp_anchor_slot"][j] = after["idp_anchor_slot"][j2]
+        c["out_n_cams"] = after["n_cams"]
+        self.drop_cases.append(c)
+        return out
+
+
+def fixture_prune(ns):
+    """Window / track surgery cases from the `small` run: every prune selection and every remove_cameras call."""
+    kw = dict(seed=42, n_frames=60, n_landmarks=40, noise_level="mid", p_drop=0.06, p_outlier=0.03, shuffle=True)
+    seq = synth.make_sequence(**kw)
+    fp = dict(min_parallax=2.0, max_number_of_camera_states=8, epipolar_rejection_threshold=1e9,
+              homography_rejection_threshold=1e9, min_number_of_frames_to_be_tracked=3)
+    params, pd = make_params(ns, seq, **fp)
+    f = ns.MSCKF(parameters=params, rr=None)
+    cap = SurgeryCapture(f)
+    image = np.zeros((seq.height, seq.width, 3), np.uint8)
+    frame_at = {fr.imu_index: fr for fr in seq.frames}
+    for i in range(len(seq.imu)):
+        row = seq.imu[i]
+        f.imu_callback(ns.IMUMeasurement(row[0], row[1:4].copy(), row[4:7].copy()))
+        fr = frame_at.get(i)
+        if fr is not None:
+            f.feature_callback(image, ns.CameraMeasurement(keypoints=fr.keypoints.copy(), descriptors=fr.descriptors.copy(),
+                                                           scores=fr.scores.copy()))
+    extra = seq_spec(**kw)
+    save_cases(os.path.join(GOLDEN, "small_prune_select.npz"), cap.select_cases, extra)
+    save_cases(os.path.join(GOLDEN, "small_prune_drop.npz"), cap.drop_cases, extra)
+
+
 def make_params(ns, seq, **kw):
     sa, sg, sba, sbg = synth.NOISE_LEVELS[seq.noise_level]
     p = dict(K=seq.K, width=seq.width, height=seq.height, sigma_image=0.1, only_imu=False,
@@ -298,6 +406,8 @@ if __name__ == "__main__":
     np.random.seed(42)
     if args.only in (None, "small"):
         fixture_small(ns)
+    if args.only in (None, "prune"):
+        fixture_prune(ns)
     if args.only in (None, "mid"):
         # mid-size steady-state fixture (cheap to regenerate): F = 48, window 10
         KEEP_FROM[:] = [18, 14 * 9]
