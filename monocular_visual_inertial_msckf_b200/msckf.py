@@ -310,6 +310,68 @@ class B200UpdateMixin:
         self.state.covariance = ctx.P[0, :d, :d].cpu().numpy()
 
 
+    # -- window surgery: same names / arguments / side effects as the reference ---------
+    def state_augmentation(self) -> None:
+        """MSCKF.state_augmentation (MSCKF.py:250-265): the current camera pose enters the window under the key
+        `state.imu.id`, P <- [I; J] P [I; J]^T on the device (msckf_augment_batched)."""
+        imu = self.state.imu
+        T_I_C = imu.T_W_I.inv() * self.T_W_C
+        n = len(self.state.cameras)
+        ctx = self._b200_context(1, 2, n + 1)
+        self._upload_state(ctx)
+        ctx.augment(T_I_C.R, T_I_C.t)
+        d = 15 + 6 * (n + 1)
+        self.state.covariance = ctx.P[0, :d, :d].cpu().numpy()
+        R = ctx.cam_R[0, n].cpu().numpy().reshape(3, 3).copy()
+        t = ctx.cam_t[0, n].cpu().numpy().copy()
+        self.state.cameras[imu.id] = Camera(self.K, self.width, self.height, Isometry3D(R, t))
+
+    def remove_cameras(self, cameras: Dict[int, "Camera"]) -> None:
+        """MSCKF.remove_cameras (MSCKF.py:751-770): covariance rows / columns and poses of `cameras` leave the window
+        (msckf_remove_cameras_batched), their observations leave every track, empty tracks are deleted."""
+        if len(cameras) == 0:
+            return
+        ids = list(self.state.cameras.keys())
+        n = len(ids)
+        ctx = self._b200_context(1, 2, n)
+        self._upload_state(ctx)
+        mask = torch.zeros((1, ctx.N), dtype=torch.uint8)
+        for k in cameras.keys():
+            mask[0, ids.index(k)] = 1
+        ctx.remove_cameras(mask.to(ctx.device))
+        d = 15 + 6 * (n - int(mask.sum()))
+        self.state.covariance = ctx.P[0, :d, :d].cpu().numpy()
+        for k in cameras.keys():
+            del self.state.cameras[k]
+        emptied = []
+        for index, ft in self.features.items():
+            for k in cameras.keys():
+                if k in ft.camera_indices:
+                    i = ft.camera_indices.index(k)
+                    for lst in (ft.keypoints, ft.descriptors, ft.scores, ft.camera_indices, ft.lines):
+                        if i < len(lst):
+                            del lst[i]
+            if len(ft.camera_indices) == 0:
+                emptied.append(index)
+        for index in emptied:
+            del self.features[index]
+
+    def prune_poorest_camera_states(self) -> None:
+        """MSCKF.prune_poorest_camera_states (MSCKF.py:710-737): the two cameras observed by the fewest tracks get one
+        last update with the tracks that see them and are removed."""
+        per_camera: Dict[int, int] = {}
+        for ft in self.features.values():
+            for k in ft.camera_indices:
+                per_camera[k] = per_camera.get(k, 0) + 1
+        chosen = [k for k, _ in sorted(per_camera.items(), key=lambda kv: kv[1])][:2]
+        cams = {k: self.state.cameras[k] for k in chosen}
+        touched = {i: ft for i, ft in self.features.items() if any(k in cams for k in ft.camera_indices)}
+        valid, _ = self.get_valid_features(touched)
+        if len(valid) > 0:
+            self.update(valid)
+        self.remove_cameras(cams)
+
+
 class MSCKF(B200UpdateMixin):
     """Stand-alone filter object with the reference's constructor signature and state layout for this path
     (reference MSCKF.__init__, MSCKF.py:80-132; track management / feature extraction are not part of this package)."""

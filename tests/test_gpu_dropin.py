@@ -114,3 +114,41 @@ def test_process_imu_like_the_reference(golden_dir):
         assert rel_err(imu.T_W_Ii.R, c["out_imu_R"]) < 1e-13 and rel_err(imu.T_W_Ii.t, c["out_imu_t"]) < 1e-13
         assert rel_err(imu.v_W_Ii, c["out_imu_v"]) < 1e-13
         assert imu.T_W_Ii_null is imu.T_W_Ii and imu.v_W_Ii_null is imu.v_W_Ii and imu.timestamp == float(s[0])
+
+
+def test_window_surgery_like_the_reference(golden_dir):
+    """state_augmentation / prune_poorest_camera_states / remove_cameras of the drop-in class on the reference's object
+    model, against the oracle's restatement of the same reference steps."""
+    cases, _ = o.load_cases(os.path.join(golden_dir, "mid_48x10_updates.npz"))
+    c = cases[0]
+    f, feats, ids = filter_from_case(c, _lib.COMPRESS_GRAM)
+    f.features = feats
+    n = int(c["n_cams"])
+    # --- augmentation: a new pose under the key imu.id, P grows by one 6x6 block (MSCKF.py:250-265) ---
+    f.state.imu.id = 4242
+    f.state.imu.T_W_I = Isometry3D(np.eye(3), np.zeros(3))
+    P0 = f.state.covariance.copy()
+    T_I_C = f.state.imu.T_W_I.inv() * f.T_W_C
+    f.state_augmentation()
+    assert list(f.state.cameras.keys())[-1] == 4242 and len(f.state.cameras) == n + 1
+    assert rel_err(f.state.covariance, o.augment_covariance(P0, T_I_C.R, T_I_C.t, f.state.imu.T_W_Ii.R)) < 1e-12
+    new_cam = f.state.cameras[4242].T_W_Ci
+    ref_pose = f.state.imu.T_W_Ii * T_I_C
+    assert rel_err(new_cam.R, ref_pose.R) < 1e-13 and rel_err(new_cam.t, ref_pose.t) < 1e-13
+    # --- prune: selection as the reference's dict + stable sort, one last update, removal ---
+    tracks = {k: list(ft.camera_indices) for k, ft in f.features.items()}
+    m_ref, t_ref = o.select_poorest_cameras(c)
+    chosen = [ids[s] for s in np.nonzero(m_ref)[0]]
+    P1 = f.state.covariance.copy()
+    f.prune_poorest_camera_states()
+    assert all(k not in f.state.cameras for k in chosen) and len(f.state.cameras) == n + 1 - len(chosen)
+    assert f.state.covariance.shape[0] == P1.shape[0] - 6 * len(chosen)
+    for k, ft in f.features.items():
+        assert ft.camera_indices == [cid for cid in tracks[k] if cid not in chosen]
+        assert len(ft.keypoints) == len(ft.camera_indices) == len(ft.lines)
+    assert all(len(tracks[k]) > 0 and all(cid in chosen for cid in tracks[k]) for k in tracks if k not in f.features)
+    # --- remove_cameras alone: covariance rows / columns of that slot disappear (MSCKF.py:753-757) ---
+    P2 = f.state.covariance.copy()
+    first = list(f.state.cameras.keys())[0]
+    f.remove_cameras({first: f.state.cameras[first]})
+    assert rel_err(f.state.covariance, o.remove_camera_covariance(P2, 0)) == 0.0
