@@ -141,10 +141,19 @@ __device__ inline void svals3_w(double* G, double* sv) {
 struct ObsRegs {
     double u, v, dx, dy, dz, cf;
     int slot;
+    // the track's own scalars, fetched with the observations so that their latency is hidden behind the previous
+    // feature: fd = idp_rho (lane 0), idp_m (lanes 1-3), idp_base (lanes 4-6); fi = lost_cnt, tracked_cnt, idp_anchor_slot
+    double fd;
+    int fi;
 };
 
 __device__ __forceinline__ void load_obs(ObsRegs& o, const FrontArgs& a, size_t fj, int M, int lane) {
     const int Mcap = a.dims.M;
+    o.fd = 0.0;
+    o.fi = 0;
+    if (lane == 0) { o.fd = a.idp_rho[fj]; o.fi = a.lost_cnt[fj]; }
+    else if (lane < 4) { o.fd = a.idp_m[fj * 3 + lane - 1]; o.fi = (lane == 1) ? a.tracked_cnt[fj] : ((lane == 2) ? a.idp_anchor_slot[fj] : 0); }
+    else if (lane < 7) o.fd = a.idp_base[fj * 3 + lane - 4];
     if (lane < M) {
         const double2 uv = *reinterpret_cast<const double2*>(a.obs_uv + (fj * Mcap + lane) * 2);
         o.u = uv.x; o.v = uv.y;
@@ -187,8 +196,8 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
     // ---- selection (MSCKF.py:463-479) ----
     int code;
     {
-        const bool lost = a.lost_cnt[fj] >= a.par.min_lost;
-        if (lost && a.tracked_cnt[fj] < a.par.min_tracked) {
+        const bool lost = __shfl_sync(0xffffffffu, o.fi, 0) >= a.par.min_lost;
+        if (lost && __shfl_sync(0xffffffffu, o.fi, 1) < a.par.min_tracked) {
             code = MSCKF_FEAT_LOST_DISCARD | MSCKF_FEAT_LOST_FLAG;
         } else {
             bool enough = false;
@@ -256,8 +265,8 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
         const double cx = R0[0] * q0 + R0[3] * q1 + R0[6] * q2;
         const double cy = R0[1] * q0 + R0[4] * q1 + R0[7] * q2;
         const double cz = R0[2] * q0 + R0[5] * q1 + R0[8] * q2;
-        rho = a.idp_rho[fj];
-        m0 = a.idp_m[fj * 3]; m1 = a.idp_m[fj * 3 + 1]; m2 = a.idp_m[fj * 3 + 2];
+        rho = shfl_d(o.fd, 0);
+        m0 = shfl_d(o.fd, 1); m1 = shfl_d(o.fd, 2); m2 = shfl_d(o.fd, 3);
         if (cz > 0.0) {
             const double* K = a.par.K;
             const double iw = K[6] * cx + K[7] * cy + K[8] * cz;
@@ -281,9 +290,10 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
                 }
             }
         }
-        const int as = a.idp_anchor_slot[fj];
-        const double* base = (as >= 0) ? (sT + 3 * as) : (a.idp_base + fj * 3);
-        b0 = base[0]; b1 = base[1]; b2 = base[2];
+        const int as = __shfl_sync(0xffffffffu, o.fi, 2);
+        const double e0 = shfl_d(o.fd, 4), e1 = shfl_d(o.fd, 5), e2 = shfl_d(o.fd, 6);
+        if (as >= 0) { b0 = sT[3 * as]; b1 = sT[3 * as + 1]; b2 = sT[3 * as + 2]; }
+        else { b0 = e0; b1 = e1; b2 = e2; }
     }
 
 

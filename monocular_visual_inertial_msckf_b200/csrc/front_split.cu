@@ -202,11 +202,12 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
 
             // ---- pending: the factorisation kernel finishes this feature ----
             const int fl = bl * F + j;
+            int pend_pos = 0;     // (the list position is consumed after the pair loop: the atomic's latency stays hidden)
             if (lane == 0) {
                 a.feat_status[fj] = (unsigned char)(MSCKF_FEAT_PENDING | (code & MSCKF_FEAT_LOST_FLAG));
                 a.dof[fj] = dofv;
                 a.fac_rank[fj] = rank;
-                pend_list[atomicAdd(pend_count, 1)] = fl;
+                pend_pos = atomicAdd(pend_count, 1);
             }
             double2* Kt = Kbuf + (size_t)fl * KT_D2;
             // Padded matrix of the factorisation kernel: rows [0, n2) measurement rows, [n2, a4) identity (a4 = n2 rounded up
@@ -326,6 +327,7 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                     }
                 }
             }
+            if (lane == 0) pend_list[pend_pos] = fl;
         }
     }
 }
