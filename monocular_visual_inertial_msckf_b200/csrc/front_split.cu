@@ -22,6 +22,7 @@
 //
 // gamma = y.y - (V^T y)^T (V^T V)^-1 (V^T y),  y = L^-1 r~,  V = L^-1 Q1  (basis-free form of the projected Mahalanobis
 // distance).
+#include <cstdlib>
 #include "msckf_common.cuh"
 #include "dense.cuh"
 #include "front_geom.cuh"
@@ -59,7 +60,8 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
     double* sR = sP + (size_t)(Ncap * (Ncap + 1) / 2) * PB;         // [Ncap][9]
     double* sT = sR + (size_t)Ncap * 9;                             // [Ncap][3]
     double* wsA = sT + (size_t)Ncap * 3 + (size_t)warp * (FW_MAX_OBS * AR);   // 16-byte aligned (12 Ncap doubles of poses)
-    unsigned short* lut = reinterpret_cast<unsigned short*>(sT + (size_t)Ncap * 3 + (size_t)FA_WARPS * (FW_MAX_OBS * AR));
+    const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
+    unsigned short* lut = reinterpret_cast<unsigned short*>(sT + (size_t)Ncap * 3 + (size_t)nwarps * (FW_MAX_OBS * AR));
 
     const int f_begin = blockIdx.x * feats_per_cta;
     const int f_end = min(F, f_begin + feats_per_cta);
@@ -69,7 +71,7 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
     {
         const double* P = a.P + (size_t)b * ldp * ldp;
         const int c = 6 * nc;
-        for (int row = warp; row < c; row += FA_WARPS) {
+        for (int row = warp; row < c; row += nwarps) {
             const int ba = row / 6, r = row - 6 * ba;
             const double* Prow = P + (size_t)(15 + row) * ldp + 15;
             double* dst = sP + (size_t)tile_index(ba, 0) * PB + r * 6;
@@ -80,9 +82,9 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
         }
         const double* camR = a.cam_R + (size_t)b * Ncap * 9;
         const double* camt = a.cam_t + (size_t)b * Ncap * 3;
-        for (int e = tid; e < nc * 9; e += FA_THREADS) sR[e] = camR[e];
-        for (int e = tid; e < nc * 3; e += FA_THREADS) sT[e] = camt[e];
-        for (int p = tid; p < MAX_PAIRS; p += FA_THREADS) {
+        for (int e = tid; e < nc * 9; e += nthreads) sR[e] = camR[e];
+        for (int e = tid; e < nc * 3; e += nthreads) sT[e] = camt[e];
+        for (int p = tid; p < MAX_PAIRS; p += nthreads) {
             const int i = tri_row(p);
             lut[p] = (unsigned short)(i | ((p - tri(i)) << 8));
         }
@@ -102,12 +104,12 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
         }
     }
 
-    for (int j = f_begin + warp; j < f_end; j += FA_WARPS) {
+    for (int j = f_begin + warp; j < f_end; j += nwarps) {
         const size_t fj = (size_t)b * F + j;
         const ObsRegs o = nxt;
         const int M = Mn;
         {   // prefetch the next feature of this warp
-            const int jn = j + FA_WARPS;
+            const int jn = j + nwarps;
             if (jn < f_end) {
                 Mn = a.feat_len[(size_t)b * F + jn];
                 load_obs(nxt, a, (size_t)b * F + jn, min(max(Mn, 0), FW_MAX_OBS), lane);
@@ -545,8 +547,8 @@ front_chol_kernel(const double2* __restrict__ Kbuf, const int* __restrict__ pend
     }
 }
 
-size_t front_asm_smem(const msckf_dims& d) {
-    return ((size_t)(d.N * (d.N + 1) / 2) * PB + (size_t)d.N * 12 + (size_t)FA_WARPS * FW_MAX_OBS * AR) * sizeof(double) +
+size_t front_asm_smem(const msckf_dims& d, int warps = FA_WARPS) {
+    return ((size_t)(d.N * (d.N + 1) / 2) * PB + (size_t)d.N * 12 + (size_t)warps * FW_MAX_OBS * AR) * sizeof(double) +
            MAX_PAIRS * sizeof(unsigned short);
 }
 
