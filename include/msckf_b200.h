@@ -201,6 +201,20 @@ int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* re
  * becomes -1 with idp_base frozen at that camera's position, feat_len is updated (0 = the reference deletes the track).
  * Call it BEFORE msckf_remove_cameras_batched (it reads cam_t / n_cams of the window before the deletion).
  * ------------------------------------------------------------------------------------------------------------- */
+/* msckf_append_observations_batched  <->  MSCKF.add_camera_measurements, track bookkeeping after the matcher
+ * (MSCKF.py:400-438; the descriptor matching and the epipolar / homography tests stay on the host side)
+ *
+ * action[B][F] (u8) per track slot: 0 untouched, 1 lost this frame (lost_cnt += 1), 2 matched: (new_uv, new_conf) is
+ * appended with the ray R_newest K^-1 [u, v, 1] and the newest window slot, tracked_cnt += 1, lost_cnt = 0, 3 new track
+ * in this (empty) slot: one observation, inverse-depth point anchored on the newest camera, rho = 0.1, tracked_cnt = 1.
+ * Kinv_host: 9 doubles on the HOST.  A track already holding dims->M observations is left untouched and counted in
+ * *overflow_count (device int, incremented).  With this call a frame costs 25 B of input per track instead of the whole
+ * track. */
+int msckf_append_observations_batched(const msckf_dims* dims, const double* Kinv_host, const int* n_cams, const double* cam_R,
+                                      const double* cam_t, const unsigned char* action, const double* new_uv,
+                                      const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                      int* obs_slot, double* idp_base, int* idp_anchor_slot, double* idp_m, double* idp_rho,
+                                      int* lost_cnt, int* tracked_cnt, int* overflow_count, void* stream);
 int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select, const int* n_cams, const int* feat_len,
                                          const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch,
                                          void* stream);

@@ -57,7 +57,7 @@ EXPORTS = [
     "msckf_propagate_batched", "msckf_augment_batched", "msckf_remove_workspace_bytes",
     "msckf_remove_cameras_batched", "msckf_launch_count", "msckf_probe_fp64", "msckf_filter_step_host",
     "msckf_set_stage_timing", "msckf_front_stage_ms", "msckf_select_poorest_cameras_batched",
-    "msckf_drop_observations_batched",
+    "msckf_drop_observations_batched", "msckf_append_observations_batched",
 ]
 
 
@@ -113,6 +113,9 @@ def load_library():
     lib.msckf_select_poorest_cameras_batched.argtypes = [pd, C.c_int, ip, ip, ip, u8, u8, vp]
     lib.msckf_drop_observations_batched.restype = C.c_int
     lib.msckf_drop_observations_batched.argtypes = [pd, u8, ip, dp, ip, dp, dp, dp, ip, dp, ip, vp]
+    lib.msckf_append_observations_batched.restype = C.c_int
+    lib.msckf_append_observations_batched.argtypes = [pd, C.POINTER(C.c_double), ip, dp, dp, u8, dp, dp, ip, dp, dp, dp, ip, dp, ip,
+                                                      dp, dp, ip, ip, ip, vp]
     lib.msckf_set_stage_timing.restype = C.c_int
     lib.msckf_set_stage_timing.argtypes = [C.c_int]
     lib.msckf_front_stage_ms.restype = C.c_int

@@ -127,6 +127,7 @@ class BatchedMSCKF:
             raise ValueError("unsupported dimensions")
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dv)
         self._remove_ws = None
+        self._overflow = None
         self._samples_dev = None
         self.Qc_diag = z(B, 4)
 
@@ -252,6 +253,21 @@ class BatchedMSCKF:
                                                    _ptr(self.cam_t), _ptr(self.P), _ptr(self.n_cams),
                                                    _ptr(self._remove_ws), self._remove_ws.numel(), self._stream())
         _lib.check(rc, "msckf_remove_cameras_batched")
+
+    def append_observations(self, action, new_uv, new_conf):
+        """Track bookkeeping of MSCKF.add_camera_measurements after the matcher (MSCKF.py:400-438): action [B, F] uint8
+        (0 untouched, 1 lost this frame, 2 append, 3 new track), new_uv [B, F, 2], new_conf [B, F] on the device.
+        Returns the device int counting tracks that were full."""
+        if self._overflow is None:
+            self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        kinv = (C.c_double * 9)(*[float(self.cpar.Kinv[i]) for i in range(9)])
+        rc = self.lib.msckf_append_observations_batched(
+            C.byref(self.dims), kinv, _ptr(self.n_cams), _ptr(self.cam_R), _ptr(self.cam_t), _ptr(action), _ptr(new_uv),
+            _ptr(new_conf), _ptr(self.feat_len), _ptr(self.obs_uv), _ptr(self.obs_dir), _ptr(self.obs_conf),
+            _ptr(self.obs_slot), _ptr(self.idp_base), _ptr(self.idp_anchor_slot), _ptr(self.idp_m), _ptr(self.idp_rho),
+            _ptr(self.lost_cnt), _ptr(self.tracked_cnt), _ptr(self._overflow), self._stream())
+        _lib.check(rc, "msckf_append_observations_batched")
+        return self._overflow
 
     def select_poorest_cameras(self, max_select=2):
         """MSCKF.prune_poorest_camera_states' selection (MSCKF.py:712-733) for every filter: returns

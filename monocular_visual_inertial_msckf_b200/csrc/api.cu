@@ -21,6 +21,11 @@ size_t update_smem_scratch_doubles(const msckf_dims& d);
 cudaError_t launch_update_smem(const ApplyArgs& a, int n_ctas, cudaStream_t s);
 cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, const int* n_cams, const int* feat_len,
                                   const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch, cudaStream_t s);
+cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_host, const int* n_cams, const double* cam_R,
+                                       const double* cam_t, const unsigned char* action, const double* new_uv,
+                                       const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                       int* obs_slot, double* idp_base, int* idp_anchor_slot, double* idp_m, double* idp_rho,
+                                       int* lost_cnt, int* tracked_cnt, int* overflow, cudaStream_t s);
 cudaError_t launch_drop_observations(const msckf_dims& d, const unsigned char* remove_mask, const int* n_cams,
                                      const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
                                      int* obs_slot, double* idp_base, int* idp_anchor_slot, cudaStream_t s);
@@ -228,6 +233,22 @@ int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select,
     if (max_select < 0 || !n_cams || !feat_len || !obs_slot || !remove_mask || !feat_touch) return MSCKF_EINVAL;
     return (int)launch_select_poorest(*dims, max_select, n_cams, feat_len, obs_slot, remove_mask, feat_touch,
                                       (cudaStream_t)stream);
+}
+
+int msckf_append_observations_batched(const msckf_dims* dims, const double* Kinv_host, const int* n_cams, const double* cam_R,
+                                      const double* cam_t, const unsigned char* action, const double* new_uv,
+                                      const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                      int* obs_slot, double* idp_base, int* idp_anchor_slot, double* idp_m, double* idp_rho,
+                                      int* lost_cnt, int* tracked_cnt, int* overflow_count, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!Kinv_host || !n_cams || !cam_R || !cam_t || !action || !new_uv || !new_conf || !feat_len || !obs_uv || !obs_dir ||
+        !obs_conf || !obs_slot || !idp_base || !idp_anchor_slot || !idp_m || !idp_rho || !lost_cnt || !tracked_cnt ||
+        !overflow_count)
+        return MSCKF_EINVAL;
+    return (int)launch_append_observations(*dims, Kinv_host, n_cams, cam_R, cam_t, action, new_uv, new_conf, feat_len, obs_uv,
+                                           obs_dir, obs_conf, obs_slot, idp_base, idp_anchor_slot, idp_m, idp_rho, lost_cnt,
+                                           tracked_cnt, overflow_count, (cudaStream_t)stream);
 }
 
 int msckf_drop_observations_batched(const msckf_dims* dims, const unsigned char* remove_mask, const int* n_cams,

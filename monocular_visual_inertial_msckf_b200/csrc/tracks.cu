@@ -124,7 +124,77 @@ __global__ void __launch_bounds__(TT) drop_observations_kernel(msckf_dims dims, 
     }
 }
 
+// One thread per track slot: what add_camera_measurements does to a track once the matcher has decided (MSCKF.py:403-412
+// append, :400 / :437-438 lost this frame, :414-434 new track).  The new ray is R_newest K^-1 [u, v, 1] (Camera.py:29-44);
+// a new track's inverse-depth point is anchored on the newest camera with m from the ray's azimuth / elevation and
+// rho = 0.1 (geometry.py:53-59).  HBM traffic: 25 B in + 52 B out per touched track (one new observation each).
+struct Kinv9 { double k[9]; };
+__global__ void __launch_bounds__(TT) append_observations_kernel(msckf_dims dims, Kinv9 Ki, const int* __restrict__ n_cams,
+                                                                 const double* __restrict__ cam_R, const double* __restrict__ cam_t,
+                                                                 const unsigned char* __restrict__ action,
+                                                                 const double* __restrict__ new_uv, const double* __restrict__ new_conf,
+                                                                 int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                                                 int* obs_slot, double* idp_base, int* idp_anchor_slot, double* idp_m,
+                                                                 double* idp_rho, int* lost_cnt, int* tracked_cnt, int* overflow) {
+    const int b = blockIdx.y, j = blockIdx.x * TT + threadIdx.x;
+    const int F = dims.F, M = dims.M, N = dims.N;
+    if (j >= F) return;
+    const size_t fj = (size_t)b * F + j;
+    const int act = action[fj];
+    if (act == 0) return;
+    if (act == 1) { lost_cnt[fj] += 1; return; }
+    const int s = min(n_cams[b], N) - 1;
+    if (s < 0) return;
+    const int n = (act == 2) ? feat_len[fj] : 0;
+    if (n >= M) { atomicAdd(overflow, 1); return; }      // capacity of the track arrays exceeded: reported, track untouched
+    const double* R = cam_R + ((size_t)b * N + s) * 9;
+    const double u = new_uv[fj * 2], v = new_uv[fj * 2 + 1];
+    const double c0 = Ki.k[0] * u + Ki.k[1] * v + Ki.k[2];
+    const double c1 = Ki.k[3] * u + Ki.k[4] * v + Ki.k[5];
+    const double c2 = Ki.k[6] * u + Ki.k[7] * v + Ki.k[8];
+    const double w0 = R[0] * c0 + R[1] * c1 + R[2] * c2;
+    const double w1 = R[3] * c0 + R[4] * c1 + R[5] * c2;
+    const double w2 = R[6] * c0 + R[7] * c1 + R[8] * c2;
+    const size_t e = fj * M + n;
+    obs_uv[e * 2] = u; obs_uv[e * 2 + 1] = v;
+    obs_dir[e * 3] = w0; obs_dir[e * 3 + 1] = w1; obs_dir[e * 3 + 2] = w2;
+    obs_conf[e] = new_conf[fj];
+    obs_slot[e] = s;
+    feat_len[fj] = n + 1;
+    if (act == 2) {
+        tracked_cnt[fj] += 1;
+        lost_cnt[fj] = 0;
+    } else {
+        const double theta = atan2(w0, w2);
+        const double phi = atan2(-w1, sqrt(w0 * w0 + w2 * w2));
+        idp_m[fj * 3] = cos(phi) * sin(theta);
+        idp_m[fj * 3 + 1] = -sin(phi);
+        idp_m[fj * 3 + 2] = cos(phi) * cos(theta);
+        idp_rho[fj] = 0.1;
+        idp_anchor_slot[fj] = s;
+        for (int k = 0; k < 3; ++k) idp_base[fj * 3 + k] = cam_t[((size_t)b * N + s) * 3 + k];
+        tracked_cnt[fj] = 1;
+        lost_cnt[fj] = 0;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_host, const int* n_cams, const double* cam_R,
+                                       const double* cam_t, const unsigned char* action, const double* new_uv,
+                                       const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
+                                       int* obs_slot, double* idp_base, int* idp_anchor_slot, double* idp_m, double* idp_rho,
+                                       int* lost_cnt, int* tracked_cnt, int* overflow, cudaStream_t s) {
+    if (d.F == 0) return cudaSuccess;
+    Kinv9 Ki;
+    for (int k = 0; k < 9; ++k) Ki.k[k] = Kinv_host[k];
+    dim3 grid((d.F + TT - 1) / TT, d.B);
+    append_observations_kernel<<<grid, TT, 0, s>>>(d, Ki, n_cams, cam_R, cam_t, action, new_uv, new_conf, feat_len, obs_uv, obs_dir,
+                                                   obs_conf, obs_slot, idp_base, idp_anchor_slot, idp_m, idp_rho, lost_cnt,
+                                                   tracked_cnt, overflow);
+    msckf_count_launch(1);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, const int* n_cams, const int* feat_len,
                                   const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch, cudaStream_t s) {

@@ -360,6 +360,60 @@ def test_drop_observations_vs_golden(golden_dir):
     assert n_checked > 5000
 
 
+def test_track_append_vs_golden(golden_dir):
+    """next rows: the track bookkeeping of add_camera_measurements on device (append / lost / new track) against what
+    the reference did to its tracks in 30 frames of the small run."""
+    cases, _ = _load(golden_dir, "small_track_append.npz")
+    F = max(len(c["feat_ids"]) for c in cases) + 2
+    M = max(c["obs_slot"].shape[1] for c in cases)
+    N = max(int(c["n_cams"]) for c in cases)
+    flt = BatchedMSCKF(len(cases), F, M, N, UpdateParams(K=np.array(cases[0]["K"], float)))
+    action = torch.zeros((flt.B, F), dtype=torch.uint8, device="cuda")
+    new_uv = torch.zeros((flt.B, F, 2), dtype=torch.float64, device="cuda")
+    new_conf = torch.zeros((flt.B, F), dtype=torch.float64, device="cuda")
+    _load_tracks(flt, cases)
+    for b, c in enumerate(cases):
+        f, n = len(c["feat_ids"]), int(c["n_cams"])
+        flt.cam_R[b, :n] = torch.from_numpy(np.asarray(c["cam_R"], float).reshape(n, 9))
+        flt.idp_m[b, :f] = torch.from_numpy(c["idp_m"])
+        flt.idp_rho[b, :f] = torch.from_numpy(c["idp_rho"])
+        flt.lost_cnt[b, :f] = torch.from_numpy(c["lost_cnt"])
+        flt.tracked_cnt[b, :f] = torch.from_numpy(c["tracked_cnt"])
+        action[b, :f] = torch.from_numpy(c["action"])
+        new_uv[b, :f] = torch.from_numpy(c["new_uv"])
+        new_conf[b, :f] = torch.from_numpy(c["new_conf"])
+    overflow = flt.append_observations(action, new_uv, new_conf)
+    torch.cuda.synchronize()
+    assert int(overflow.item()) == 0
+    got = {k: getattr(flt, k).cpu().numpy() for k in ("feat_len", "obs_uv", "obs_dir", "obs_conf", "obs_slot", "idp_base",
+                                                      "idp_anchor_slot", "idp_m", "idp_rho", "lost_cnt", "tracked_cnt")}
+    n_app = 0
+    for b, c in enumerate(cases):
+        f = len(c["feat_ids"])
+        for k in ("feat_len", "idp_anchor_slot", "lost_cnt", "tracked_cnt", "idp_rho"):
+            assert np.array_equal(got[k][b, :f], c["out_" + k]), (c["call_index"], k)
+        assert (got["feat_len"][b, f:] == 0).all()
+        for j in range(f):
+            n = int(c["out_feat_len"][j])
+            assert (got["obs_slot"][b, j, :n] == c["out_obs_slot"][j, :n]).all()
+            assert np.array_equal(got["obs_uv"][b, j, :n], c["out_obs_uv"][j, :n])
+            assert np.array_equal(got["obs_conf"][b, j, :n], c["out_obs_conf"][j, :n])
+            assert rel_err(got["obs_dir"][b, j, :n], c["out_obs_dir"][j, :n]) < 1e-14
+            assert np.array_equal(got["idp_base"][b, j], c["out_idp_base"][j])
+            assert rel_err(got["idp_m"][b, j], c["out_idp_m"][j]) < 1e-14
+            n_app += int(c["action"][j] >= 2)
+    assert n_app > 1000
+    # a full track is reported, not overrun
+    full = BatchedMSCKF(1, 2, 2, 2, UpdateParams())
+    full.n_cams.fill_(2)
+    full.feat_len[0, 0] = 2
+    act = torch.tensor([[2, 0]], dtype=torch.uint8, device="cuda")
+    ov = full.append_observations(act, torch.zeros((1, 2, 2), dtype=torch.float64, device="cuda"),
+                                  torch.zeros((1, 2), dtype=torch.float64, device="cuda"))
+    torch.cuda.synchronize()
+    assert int(ov.item()) == 1 and int(full.feat_len[0, 0]) == 2
+
+
 def test_prune_flow_vs_oracle(golden_dir):
     """prune_poorest_camera_states end to end on resident state (select -> update with the touched tracks -> drop ->
     remove) against the oracle's composition of the same reference steps."""

@@ -207,7 +207,9 @@ def pack_tracks(f):
     c = dict(n_cams=len(cams), feat_ids=np.array(list(feats.keys()), np.int64), feat_len=np.zeros(F, np.int32),
              obs_uv=np.zeros((F, M, 2)), obs_dir=np.zeros((F, M, 3)), obs_conf=np.zeros((F, M)),
              obs_slot=-np.ones((F, M), np.int32), idp_base=np.zeros((F, 3)), idp_anchor_slot=-np.ones(F, np.int32),
-             cam_t=np.stack([cam.T_W_Ci.t for _, cam in cams]).astype(float) if cams else np.zeros((0, 3)))
+             cam_t=np.stack([cam.T_W_Ci.t for _, cam in cams]).astype(float) if cams else np.zeros((0, 3)),
+             cam_R=np.stack([cam.T_W_Ci.R for _, cam in cams]).astype(float) if cams else np.zeros((0, 3, 3)),
+             idp_m=np.zeros((F, 3)), idp_rho=np.zeros(F), lost_cnt=np.zeros(F, np.int32), tracked_cnt=np.zeros(F, np.int32))
     for j, ft in enumerate(feats.values()):
         n = len(ft.keypoints)
         c["feat_len"][j] = n
@@ -220,6 +222,10 @@ def pack_tracks(f):
         for s, (_, cam) in enumerate(cams):
             if ft.inverse_depth_point.base is cam.T_W_Ci.t:
                 c["idp_anchor_slot"][j] = s
+        c["idp_m"][j] = ft.inverse_depth_point.m
+        c["idp_rho"][j] = ft.inverse_depth_point.rho
+        c["lost_cnt"][j] = ft.lost_for_n_frames
+        c["tracked_cnt"][j] = ft.tracked_for_n_frames
     return c
 
 
@@ -235,6 +241,56 @@ class SurgeryCapture:
         f.prune_poorest_camera_states = self.prune
         f.remove_cameras = self.remove
         f.get_valid_features = self.gvf
+        self.append_cases = []
+        self._orig_add = f.add_camera_measurements
+        f.add_camera_measurements = self.add
+
+    def add(self, image, extracted_features=None):
+        """add_camera_measurements (MSCKF.py:268-448): the matching is out of scope; what it did to the tracks is
+        recovered by comparing them before / after: action 0 untouched, 1 lost this frame, 2 observation appended,
+        3 new track (appended to the dict)."""
+        f = self.f
+        before = pack_tracks(f)
+        out = self._orig_add(image, extracted_features)
+        after = pack_tracks(f)
+        Fb, Fa = len(before["feat_ids"]), len(after["feat_ids"])
+        assert list(after["feat_ids"][:Fb]) == list(before["feat_ids"])          # dict order: old tracks, then new ones
+        c = {k: before[k] for k in ("n_cams", "cam_R", "cam_t")}
+        c["K"] = np.array(f.K, float)
+        c["Kinv"] = np.linalg.inv(f.K)
+        c["call_index"] = len(self.append_cases)
+        c["feat_ids"] = after["feat_ids"]
+        Ma = after["obs_slot"].shape[1]
+        for k in ("feat_len", "obs_uv", "obs_dir", "obs_conf", "obs_slot", "idp_base", "idp_anchor_slot", "idp_m", "idp_rho",
+                  "lost_cnt", "tracked_cnt"):
+            a = after[k]
+            pre = np.zeros_like(a) if k != "obs_slot" else -np.ones_like(a)
+            if k == "idp_anchor_slot":
+                pre = -np.ones_like(a)
+            b = before[k]
+            if b.ndim >= 2 and k.startswith("obs_"):
+                pre[:Fb, :b.shape[1]] = b
+            else:
+                pre[:Fb] = b
+            c[k] = pre
+            c["out_" + k] = a
+        action = np.zeros(Fa, np.uint8)
+        new_uv = np.zeros((Fa, 2))
+        new_conf = np.zeros(Fa)
+        for j in range(Fa):
+            n1 = int(after["feat_len"][j])
+            if j >= Fb:
+                action[j] = 3
+            elif n1 > int(before["feat_len"][j]):
+                action[j] = 2
+            elif int(after["lost_cnt"][j]) > int(before["lost_cnt"][j]):
+                action[j] = 1
+            if action[j] >= 2:
+                new_uv[j] = after["obs_uv"][j, n1 - 1]
+                new_conf[j] = after["obs_conf"][j, n1 - 1]
+        c["action"], c["new_uv"], c["new_conf"] = action, new_uv, new_conf
+        self.append_cases.append(c)
+        return out
 
     def prune(self):
         c = pack_tracks(self.f)
@@ -303,6 +359,7 @@ def fixture_prune(ns):
     extra = seq_spec(**kw)
     save_cases(os.path.join(GOLDEN, "small_prune_select.npz"), cap.select_cases, extra)
     save_cases(os.path.join(GOLDEN, "small_prune_drop.npz"), cap.drop_cases, extra)
+    save_cases(os.path.join(GOLDEN, "small_track_append.npz"), cap.append_cases[::2], extra)
 
 
 def make_params(ns, seq, **kw):
