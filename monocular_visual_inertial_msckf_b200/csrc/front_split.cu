@@ -49,7 +49,7 @@ __device__ __forceinline__ int tile_index(int I, int J) { return I * (I + 1) / 2
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FA_THREADS, 1)
 front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict__ pend_list, int* __restrict__ pend_count,
-                 const int b0, const int feats_per_cta) {
+                 const int b0, const int feats_per_cta, const unsigned stagger_ns) {
     const int bl = blockIdx.y, b = b0 + bl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = a.dims.F, Mcap = a.dims.M, Ncap = a.dims.N, ldp = a.dims.ldp;
@@ -103,6 +103,11 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
             load_obs(nxt, a, (size_t)b * F + j0, min(max(Mn, 0), FW_MAX_OBS), lane);
         }
     }
+    // Every warp alternates between the geometry (no shared-memory traffic) and the pair loop (shared-memory bound), and
+    // all the warps of the CTA leave the barrier above in the same phase: staggering their start spreads the phases, so
+    // that the pair loops of some warps run under the geometry of the others instead of all of them queueing on the
+    // shared-memory pipe at once.
+    if (stagger_ns) __nanosleep(warp * stagger_ns);
 
     for (int j = f_begin + warp; j < f_end; j += nwarps) {
         const size_t fj = (size_t)b * F + j;
@@ -625,13 +630,16 @@ cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list
                     if ((e = cudaEventCreate(&g_ev[g_ev_created][q])) != cudaSuccess) return e;
             cudaEventRecord(g_ev[slot][0], s);
         }
-        // feature chunks per filter so that the CTAs come in >= ~12 waves of 148 (each warp keeps >= 2 features)
-        int chunks = (12 * 148 + nb - 1) / nb;
+        // feature chunks per filter so that the CTAs come in >= ~6 waves of 148 (each warp keeps >= 2 features): long CTAs
+        // amortise the staggered start of their warps (measured: 13.3 ms -> 12.0 ms per 4096 filters with both)
+        static const int waves = getenv("MSCKF_ASM_WAVES") ? atoi(getenv("MSCKF_ASM_WAVES")) : 6;
+        static const unsigned stagger_ns = getenv("MSCKF_ASM_STAGGER_NS") ? (unsigned)atoi(getenv("MSCKF_ASM_STAGGER_NS")) : 1500u;
+        int chunks = (waves * 148 + nb - 1) / nb;
         int fpc = (F + chunks - 1) / chunks;
         if (fpc < 2 * FA_WARPS) fpc = 2 * FA_WARPS;
         chunks = (F + fpc - 1) / fpc;
         dim3 grid(chunks, nb);
-        front_asm_kernel<<<grid, FA_THREADS, smem, s>>>(a, Kbuf, pend_list, pend_count, b0, fpc);
+        front_asm_kernel<<<grid, FA_THREADS, smem, s>>>(a, Kbuf, pend_list, pend_count, b0, fpc, stagger_ns);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (timed) cudaEventRecord(g_ev[slot][1], s);
