@@ -147,23 +147,26 @@ struct ObsRegs {
     int fi;
 };
 
+// All loads are unconditional (clamped indices, no register written on two paths): the prefetch of the next feature then
+// costs no scoreboard wait until the values are used.  Lanes beyond the track length get their neutral values from
+// mask_obs() when the feature is processed.
 __device__ __forceinline__ void load_obs(ObsRegs& o, const FrontArgs& a, size_t fj, int M, int lane) {
     const int Mcap = a.dims.M;
-    o.fd = 0.0;
-    o.fi = 0;
-    if (lane == 0) { o.fd = a.idp_rho[fj]; o.fi = a.lost_cnt[fj]; }
-    else if (lane < 4) { o.fd = a.idp_m[fj * 3 + lane - 1]; o.fi = (lane == 1) ? a.tracked_cnt[fj] : ((lane == 2) ? a.idp_anchor_slot[fj] : 0); }
-    else if (lane < 7) o.fd = a.idp_base[fj * 3 + lane - 4];
-    if (lane < M) {
-        const double2 uv = *reinterpret_cast<const double2*>(a.obs_uv + (fj * Mcap + lane) * 2);
-        o.u = uv.x; o.v = uv.y;
-        const double* d = a.obs_dir + (fj * Mcap + lane) * 3;
-        o.dx = d[0]; o.dy = d[1]; o.dz = d[2];
-        o.cf = a.obs_conf[fj * Mcap + lane];
-        o.slot = a.obs_slot[fj * Mcap + lane];
-    } else {
-        o.u = o.v = 0.0; o.dx = o.dy = 0.0; o.dz = 1.0; o.cf = 0.0; o.slot = 0;
-    }
+    const double* pd = (lane == 0 || lane >= 7) ? a.idp_rho + fj : (lane < 4 ? a.idp_m + fj * 3 + (lane - 1) : a.idp_base + fj * 3 + (lane - 4));
+    const int* pi = (lane == 1) ? a.tracked_cnt + fj : (lane == 2 ? a.idp_anchor_slot + fj : a.lost_cnt + fj);
+    o.fd = *pd;
+    o.fi = *pi;
+    const size_t e = fj * Mcap + (lane < M ? lane : 0);
+    const double2 uv = *reinterpret_cast<const double2*>(a.obs_uv + e * 2);
+    o.u = uv.x; o.v = uv.y;
+    const double* d = a.obs_dir + e * 3;
+    o.dx = d[0]; o.dy = d[1]; o.dz = d[2];
+    o.cf = a.obs_conf[e];
+    o.slot = a.obs_slot[e];
+}
+
+__device__ __forceinline__ void mask_obs(ObsRegs& o, int M, int lane) {
+    if (lane >= M) { o.u = o.v = 0.0; o.dx = o.dy = 0.0; o.dz = 1.0; o.cf = 0.0; o.slot = 0; }
 }
 
 struct GeoConsts {
@@ -175,7 +178,7 @@ __device__ __forceinline__ GeoConsts make_geo_consts(const FrontArgs& a) {
     GeoConsts c;
     c.s2 = a.par.sigma_image * a.par.sigma_image;
     c.g0 = a.par.gravity[0]; c.g1 = a.par.gravity[1]; c.g2 = a.par.gravity[2];
-    c.cos_ok = a.par.min_parallax_deg > 0.0 && a.par.min_parallax_deg < 180.0;
+    c.cos_ok = a.par.min_parallax_deg >= 0.0 && a.par.min_parallax_deg < 180.0;   // (0 degrees: cos = 1, same guard band)
     c.cos_thr = c.cos_ok ? cos(a.par.min_parallax_deg * (3.14159265358979323846 / 180.0)) : 0.0;
     return c;
 }

@@ -111,8 +111,9 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
 
     for (int j = f_begin + warp; j < f_end; j += nwarps) {
         const size_t fj = (size_t)b * F + j;
-        const ObsRegs o = nxt;
+        ObsRegs o = nxt;
         const int M = Mn;
+        mask_obs(o, M, lane);
         {   // prefetch the next feature of this warp
             const int jn = j + nwarps;
             if (jn < f_end) {

@@ -98,8 +98,9 @@ __global__ void __launch_bounds__(FW_THREADS, 1) front_warp_kernel(const FrontAr
 
     for (int j = f_begin + warp; j < f_end; j += FW_WARPS) {
         const size_t fj = (size_t)b * F + j;
-        const ObsRegs o = nxt;
+        ObsRegs o = nxt;
         const int M = Mn;
+        mask_obs(o, M, lane);
         {   // prefetch the next feature of this warp
             const int jn = j + FW_WARPS;
             if (jn < f_end) {
