@@ -40,7 +40,6 @@ constexpr int NTILE = TC * (TC + 1) / 2;
 constexpr int PB = 38;                         // doubles per staged 6x6 block of P (stride 76 words = 12 mod 32)
 constexpr int AR = 14;                         // doubles per observation's 2x6 block in the warp scratch (28 words)
 constexpr int KT_D2 = NTILE * 32;               // double2 per feature slot in the tile buffer (45 tiles; M = 30 uses 36)
-constexpr int MAX_PAIRS = (4 * TC) * (4 * TC + 1) / 2;   // 2x2 blocks of the lower triangle of the padded matrix
 
 __device__ __forceinline__ int tile_index(int I, int J) { return I * (I + 1) / 2 + J; }
 
@@ -61,7 +60,6 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
     double* sT = sR + (size_t)Ncap * 9;                             // [Ncap][3]
     double* wsA = sT + (size_t)Ncap * 3 + (size_t)warp * (FW_MAX_OBS * AR);   // 16-byte aligned (12 Ncap doubles of poses)
     const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
-    unsigned short* lut = reinterpret_cast<unsigned short*>(sT + (size_t)Ncap * 3 + (size_t)nwarps * (FW_MAX_OBS * AR));
 
     const int f_begin = blockIdx.x * feats_per_cta;
     const int f_end = min(F, f_begin + feats_per_cta);
@@ -84,10 +82,6 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
         const double* camt = a.cam_t + (size_t)b * Ncap * 3;
         for (int e = tid; e < nc * 9; e += nthreads) sR[e] = camR[e];
         for (int e = tid; e < nc * 3; e += nthreads) sT[e] = camt[e];
-        for (int p = tid; p < MAX_PAIRS; p += nthreads) {
-            const int i = tri_row(p);
-            lut[p] = (unsigned short)(i | ((p - tri(i)) << 8));
-        }
     }
     __syncthreads();
 
@@ -239,19 +233,27 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
 
             // ---- K = H_x P H_x^T + sigma^2 I, one lower 2x2 block per lane per pass ----
             const int npairs = M * (M + 1) / 2;     // measurement rows only; the few padding blocks follow below
-            // (the pair descriptor of the next pass is fetched while this one is computed)
-            unsigned ik_n = lut[lane < npairs ? lane : 0];
-            int si_n = __shfl_sync(0xffffffffu, o.slot, ik_n & 0xff), sk_n = __shfl_sync(0xffffffffu, o.slot, ik_n >> 8);
+            // Pair p = i (i + 1) / 2 + k and its window slots.  Under load every dependent shared-memory / shuffle access
+            // costs a full trip through the saturated memory-input queue, so the descriptor is pure arithmetic whenever
+            // the track's slots are consecutive (slot[i] = slot[0] + i: the normal case, a track is observed from every
+            // camera since its first one); otherwise the slots come from the lanes that hold them.
+            const int s0 = __shfl_sync(0xffffffffu, o.slot, 0);
+            const bool affine = __all_sync(0xffffffffu, !live || o.slot == s0 + lane);
 #pragma unroll 1
             for (int p0 = 0; p0 < npairs; p0 += 32) {
-                const bool act = p0 + lane < npairs;
-                const int i = ik_n & 0xff, k = ik_n >> 8;
-                const int si = si_n, sk = sk_n;
-                {
-                    const int pn = p0 + 32 + lane;
-                    ik_n = lut[pn < npairs ? pn : 0];
-                    si_n = __shfl_sync(0xffffffffu, o.slot, ik_n & 0xff);
-                    sk_n = __shfl_sync(0xffffffffu, o.slot, ik_n >> 8);
+                const int p = p0 + lane;
+                const bool act = p < npairs;
+                int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+                i -= (i * (i + 1) / 2 > p) ? 1 : 0;
+                i += ((i + 1) * (i + 2) / 2 <= p) ? 1 : 0;
+                const int k = p - i * (i + 1) / 2;
+                int si, sk;
+                if (affine) {
+                    si = s0 + i;
+                    sk = s0 + k;
+                } else {
+                    si = __shfl_sync(0xffffffffu, o.slot, i & 31);
+                    sk = __shfl_sync(0xffffffffu, o.slot, k & 31);
                 }
                 if (!act) continue;
                 double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
@@ -554,8 +556,7 @@ front_chol_kernel(const double2* __restrict__ Kbuf, const int* __restrict__ pend
 }
 
 size_t front_asm_smem(const msckf_dims& d, int warps = FA_WARPS) {
-    return ((size_t)(d.N * (d.N + 1) / 2) * PB + (size_t)d.N * 12 + (size_t)warps * FW_MAX_OBS * AR) * sizeof(double) +
-           MAX_PAIRS * sizeof(unsigned short);
+    return ((size_t)(d.N * (d.N + 1) / 2) * PB + (size_t)d.N * 12 + (size_t)warps * FW_MAX_OBS * AR) * sizeof(double);
 }
 
 }  // namespace
