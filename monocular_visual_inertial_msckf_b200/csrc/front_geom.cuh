@@ -32,6 +32,15 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return y;
 }
 
+// same without the x <= 0 guard: a non-positive (or NaN) pivot of a matrix that is positive definite by construction gives
+// NaN, which propagates to gamma and fails the gate instead of silently zeroing a column
+__device__ __forceinline__ double fast_rsqrt_spd(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
 __device__ __forceinline__ double warp_sum_all(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

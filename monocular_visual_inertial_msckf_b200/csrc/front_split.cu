@@ -355,7 +355,7 @@ __device__ __forceinline__ void diag_tile_inverse(double D0, double D1, const in
         {
             const int k = 2 * tk;
             const double piv = shfl_d(D0, k * 4 + tk);
-            const double rs = fast_rsqrt(piv);
+            const double rs = fast_rsqrt_spd(piv);
             const double colv = (g > k) ? D0 * rs : 0.0;      // column k of L below the diagonal
             const double xsel = x0 * rs;                       // column k of X L^-T
             if (t == tk) x0 = xsel;
@@ -369,7 +369,7 @@ __device__ __forceinline__ void diag_tile_inverse(double D0, double D1, const in
         {
             const int k = 2 * tk + 1;
             const double piv = shfl_d(D1, k * 4 + tk);
-            const double rs = fast_rsqrt(piv);
+            const double rs = fast_rsqrt_spd(piv);
             const double colv = (g > k) ? D1 * rs : 0.0;
             const double xsel = x1 * rs;
             if (t == tk) x1 = xsel;
@@ -394,7 +394,7 @@ __device__ __forceinline__ void diag_tile_partial(double& D0, double& D1, const 
     for (int tk = 0; tk < npass; ++tk) {
         {
             const int k = 2 * tk;
-            const double rs = fast_rsqrt(shfl_d(D0, k * 4 + tk));
+            const double rs = fast_rsqrt_spd(shfl_d(D0, k * 4 + tk));
             const double colv = (g > k) ? D0 * rs : 0.0;
             const double lg = shfl_d(colv, g * 4 + tk);
             const double lc0 = shfl_d(colv, (2 * t) * 4 + tk);
@@ -404,7 +404,7 @@ __device__ __forceinline__ void diag_tile_partial(double& D0, double& D1, const 
         }
         {
             const int k = 2 * tk + 1;
-            const double rs = fast_rsqrt(shfl_d(D1, k * 4 + tk));
+            const double rs = fast_rsqrt_spd(shfl_d(D1, k * 4 + tk));
             const double colv = (g > k) ? D1 * rs : 0.0;
             const double lg = shfl_d(colv, g * 4 + tk);
             const double lc0 = shfl_d(colv, (2 * t) * 4 + tk);
