@@ -250,11 +250,22 @@ __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
         for (int i = warp; i < nt * 8; i += UW) {
             const int si = smap(i), I = i >> 3;
             const double* Prow = P + (size_t)(si < 0 ? 0 : si) * ldp;
-            for (int j = lane; j < (I + 1) * 8; j += 32) {
+            // all the loads of the row are issued before the first store (one dependent load -> store per iteration left
+            // the global-memory latency exposed: 7 % of the kernel's stall samples, profiles/r01q)
+            constexpr int JU = (MAX_NT * 8 + 31) / 32;
+            double vv[JU];
+#pragma unroll
+            for (int u = 0; u < JU; ++u) {
+                const int j = lane + 32 * u;
                 const int sj = smap(j);
                 double v = 0.0;
-                if (j <= i) v = (si < 0 || sj < 0) ? ((i == j) ? 1.0 : 0.0) : Prow[sj];
-                T[toff(I, j >> 3) + swz(i & 7, j & 7)] = v;
+                if (j < (I + 1) * 8 && j <= i) v = (si < 0 || sj < 0) ? ((i == j) ? 1.0 : 0.0) : Prow[sj];
+                vv[u] = v;
+            }
+#pragma unroll
+            for (int u = 0; u < JU; ++u) {
+                const int j = lane + 32 * u;
+                if (j < (I + 1) * 8) T[toff(I, j >> 3) + swz(i & 7, j & 7)] = vv[u];
             }
         }
         for (int e = tid; e < 2 * KBR * LDG; e += UT) Gs[e] = 0.0;   // both stages (the solve below reuses them)
@@ -444,9 +455,11 @@ __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
                 const double* Yrow = Ybuf + (jp & 1) * MAX_NCP * TILE;
                 const double* Xb = Xbuf + (jp & 1) * TILE;
                 const double xb0 = Xb[swz(7 - 2 * t, 7 - g)], xb1 = Xb[swz(6 - 2 * t, 7 - g)];
-                for (int i = j; i < nt; ++i) {
-                    const int owner = (i >= 16) ? (nt - 1 - i) : 9 + (i % 7);
-                    if (owner != warp) continue;
+                // rows owned by this warp: i >= 16 -> warp nt-1-i, i < 16 -> warp 9 + (i % 7); enumerated directly
+                for (int q = 0; q < 4; ++q) {
+                    const int i = (q < 3) ? ((warp >= 9 && warp - 9 + 7 * q < 16) ? warp - 9 + 7 * q : -1)
+                                          : ((nt - 1 - warp >= 16) ? nt - 1 - warp : -1);
+                    if (i < j || i >= nt) continue;
                     double* p = T + toff(i, j) + swz(g, 2 * t);
                     double2 v = ld2(p);
                     double w0 = 0.0, w1 = 0.0;
