@@ -39,15 +39,15 @@ NOISE = [(1e-3, 1e-4, 1e-4, 1e-5), (5e-3, 5e-4, 5e-4, 5e-5), (1e-2, 1e-3, 1e-3, 
 # ----------------------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------------------
-def load_base_case():
+def load_base_case(n_cams=30):
     z = np.load(FIXTURE)
     n = int(z["n_cases"])
     best = None
     for i in range(n):
         c = {k[len(f"c{i}."):]: (z[k].item() if z[k].ndim == 0 else z[k]) for k in z.files if k.startswith(f"c{i}.")}
-        if int(c["n_cams"]) == 30:
+        if int(c["n_cams"]) == n_cams:
             best = c
-    assert best is not None, "fixture holds no 30-pose case"
+    assert best is not None, f"fixture holds no {n_cams}-pose case"
     return best
 
 
@@ -210,6 +210,36 @@ class ClockSampler:
         return out
 
 
+_ORIG_AFFINITY = []
+
+
+def pin_near_gpu(gpu_index):
+    """Restrict this rank to the CPU cores `nvidia-smi topo -m` lists as local to its GPU, BEFORE the pinned host buffers
+    are allocated (first touch then places them on that NUMA node): with 8 ranks uploading at once, cross-socket copies
+    are what limits the end-to-end step.  Best effort: any failure leaves the affinity untouched."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        avail = os.sched_getaffinity(0)
+        _ORIG_AFFINITY.append(set(avail))
+        for ln in out.splitlines():
+            parts = ln.split()
+            if not parts or parts[0] != f"GPU{gpu_index}":
+                continue
+            for tok in parts[1:]:
+                if tok[0].isdigit() and ("-" in tok or "," in tok):
+                    cores = set()
+                    for rng in tok.split(","):
+                        lo, _, hi = rng.partition("-")
+                        cores.update(range(int(lo), int(hi or lo) + 1))
+                    cores &= avail
+                    if len(cores) >= 2:
+                        os.sched_setaffinity(0, cores)
+                        return tok
+        return None
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
@@ -226,8 +256,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_near_gpu(local_rank) if world > 1 else None   # host buffers of a rank live on its GPU's NUMA node
 
-    base = load_base_case()
+    base = load_base_case(args.window)
     B = args.filters
     F = len(base["feat_len"])
     M = base["obs_uv"].shape[1]
@@ -568,6 +599,8 @@ def run_gpu(args):
     ncpu = os.cpu_count() or 1
     cpu = dict(value=None)
     if not args.no_cpu:
+        if _ORIG_AFFINITY:
+            os.sched_setaffinity(0, _ORIG_AFFINITY[0])      # the CPU arm uses every host core again
         nw = min(ncpu, 64)
         r = run_cpu(nw, 1)
         cpu = dict(value=r["feature_updates_per_s"], unit="feature-updates/s", cores=nw, kind="port",
@@ -599,7 +632,7 @@ def run_gpu(args):
                                  gate_decisions_equal_to_full_upload=inc_same, track_lengths_restored=inc_len_ok,
                                  note="tracks resident in HBM between frames: per step the host sends the new observation of "
                                       "every track (25 B) and the IMU samples instead of the whole tracks"),
-        gpu_launches=int(launches), clocks=clocks, setup_s=setup_s)
+        gpu_launches=int(launches), clocks=clocks, setup_s=setup_s, cpu_affinity_rank0=numa)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -647,6 +680,9 @@ if __name__ == "__main__":
     ap.add_argument("--gate", default="exact", choices=["exact", "bounds"],
                     help="exact: every selected feature goes through the full Mahalanobis test (headline); bounds: same "
                          "decisions, features decided by the exact bounds skip the factorisation (reported beside it)")
+    ap.add_argument("--window", type=int, default=30, choices=[30, 31],
+                    help="camera poses in the window of the snapshot: 30 (BASELINE.json) or 31 (the transient max + 1 window "
+                         "every other reference update sees, SURVEY.md section 8a)")
     ap.add_argument("--chunk", type=int, default=592,
                     help="filters per upload/compute/download chunk of the end-to-end (host-buffer) step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
