@@ -23,7 +23,8 @@ using dense::dmma;
 
 constexpr int UT = 512;                    // threads per CTA
 constexpr int UW = UT / 32;
-constexpr int MAX_NCP = 23;                // tile columns of the padded camera block: 6 N <= 184  ->  N <= 30
+constexpr int MAX_NCP = 24;                // tile columns of the padded camera block: 6 N <= 192  ->  N <= 32
+constexpr int DUAL_NCP = 23;               // up to here both row-block stages (G and T1 = G L) fit beside the tiles
 constexpr int MAX_NT = MAX_NCP + 2;        // + 2 tile rows for the 15 IMU error states (padded to 16)
 constexpr int MAX_TILES = MAX_NT * (MAX_NT + 1) / 2;
 constexpr int TILE = 64;
@@ -210,12 +211,18 @@ __device__ void chol_tiles(double* T, const int nt, const int ncf, double* Xs, d
     }
 }
 
+template <bool single>
 __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
     extern __shared__ double sm[];
-    double* T = sm;                                  // [MAX_TILES][64]
-    double* Gs = T + (size_t)MAX_TILES * TILE;       // [KBR][LDG]  row block of G          | Y row buffers of the solve
-    double* T1s = Gs + KBR * LDG;                    // [KBR][LDG]  row block of T1 = G L   |
-    double* Xs = T1s + KBR * LDG;                    // [2][64]     X = L_kk^-T of the current diagonal tile(s)
+    // Capacity-dependent carve-up: up to 23 tile columns (N <= 30) the row block of G and the row block of T1 = G L have a
+    // stage each (the next block of G streams in while B accumulates); with 24 (N = 31, 32) the tiles leave room for ONE
+    // stage, T1 overwrites the block of G it was computed from and the next block is fetched after the accumulation.
+    const int ncp_max = (6 * a.dims.N + 7) >> 3;
+    const int stage_doubles = single ? max(KBR * LDG, 2 * ncp_max * TILE + 2 * TILE) : 2 * KBR * LDG;
+    double* T = sm;                                  // [tri(ncp_max + 2)][64]
+    double* Gs = T + (size_t)tri(ncp_max + 2) * TILE;   // [KBR][LDG]  row block of G          | Y row buffers of the solve
+    double* T1s = single ? Gs : Gs + KBR * LDG;      // [KBR][LDG]  row block of T1 = G L   |
+    double* Xs = Gs + stage_doubles;                 // [2][64]     X = L_kk^-T of the current diagonal tile(s)
     double* gvec = Xs + 2 * TILE;                    // [VEC] g (padded)
     double* yvec = gvec + VEC;                       // [VEC] y = L^T g
     double* zvec = yvec + VEC;                       // [VEC] z = Y^-T y
@@ -268,7 +275,7 @@ __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
                 if (j < (I + 1) * 8) T[toff(I, j >> 3) + swz(i & 7, j & 7)] = vv[u];
             }
         }
-        for (int e = tid; e < 2 * KBR * LDG; e += UT) Gs[e] = 0.0;   // both stages (the solve below reuses them)
+        for (int e = tid; e < stage_doubles; e += UT) Gs[e] = 0.0;   // both stages (the solve below reuses them)
         for (int e = tid; e < VEC; e += UT) gvec[e] = (e < c) ? gv[e] : 0.0;
         __syncthreads();
 
@@ -313,44 +320,95 @@ __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
             cp_async_wait_all();
             __syncthreads();
             // T1[rows of this block][:] = G[rows][:] L ; warp w < ceil(ncp / 2) takes the tile columns w and ncp-1-w
-            if (warp < ((ncp + 1) >> 1)) {
+            if (!single) {
+                if (warp < ((ncp + 1) >> 1)) {
 #pragma unroll 1
-                for (int u = 0; u < 2; ++u) {
-                    const int j = u == 0 ? warp : ncp - 1 - warp;
-                    if (u == 1 && j <= warp) break;
-                    double r00 = 0.0, r01 = 0.0, r10 = 0.0, r11 = 0.0;
-                    double q00 = 0.0, q01 = 0.0, q10 = 0.0, q11 = 0.0;   // second accumulator set (odd k tiles): shorter chains
-                    int kt = j;
-                    for (; kt + 1 < ncp; kt += 2) {
-                        const double* La = T + toff(kt, j);
-                        const double* Lb = T + toff(kt + 1, j);
+                    for (int u = 0; u < 2; ++u) {
+                        const int j = u == 0 ? warp : ncp - 1 - warp;
+                        if (u == 1 && j <= warp) break;
+                        double r00 = 0.0, r01 = 0.0, r10 = 0.0, r11 = 0.0;
+                        double q00 = 0.0, q01 = 0.0, q10 = 0.0, q11 = 0.0;   // second accumulator set (odd k tiles): shorter chains
+                        int kt = j;
+                        for (; kt + 1 < ncp; kt += 2) {
+                            const double* La = T + toff(kt, j);
+                            const double* Lb = T + toff(kt + 1, j);
 #pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            const double bfa = La[swz(4 * s + t, g)];
-                            const double bfb = Lb[swz(4 * s + t, g)];
-                            const int ca = kt * 8 + 4 * s + t;
-                            dmma(r00, r01, Gs[g * LDG + ca], bfa);
-                            dmma(r10, r11, Gs[(8 + g) * LDG + ca], bfa);
-                            dmma(q00, q01, Gs[g * LDG + ca + 8], bfb);
-                            dmma(q10, q11, Gs[(8 + g) * LDG + ca + 8], bfb);
+                            for (int s = 0; s < 2; ++s) {
+                                const double bfa = La[swz(4 * s + t, g)];
+                                const double bfb = Lb[swz(4 * s + t, g)];
+                                const int ca = kt * 8 + 4 * s + t;
+                                dmma(r00, r01, Gs[g * LDG + ca], bfa);
+                                dmma(r10, r11, Gs[(8 + g) * LDG + ca], bfa);
+                                dmma(q00, q01, Gs[g * LDG + ca + 8], bfb);
+                                dmma(q10, q11, Gs[(8 + g) * LDG + ca + 8], bfb);
+                            }
                         }
-                    }
-                    if (kt < ncp) {
-                        const double* La = T + toff(kt, j);
+                        if (kt < ncp) {
+                            const double* La = T + toff(kt, j);
 #pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            const double bfa = La[swz(4 * s + t, g)];
-                            const int ca = kt * 8 + 4 * s + t;
-                            dmma(r00, r01, Gs[g * LDG + ca], bfa);
-                            dmma(r10, r11, Gs[(8 + g) * LDG + ca], bfa);
+                            for (int s = 0; s < 2; ++s) {
+                                const double bfa = La[swz(4 * s + t, g)];
+                                const int ca = kt * 8 + 4 * s + t;
+                                dmma(r00, r01, Gs[g * LDG + ca], bfa);
+                                dmma(r10, r11, Gs[(8 + g) * LDG + ca], bfa);
+                            }
                         }
+                        st2(T1s + g * LDG + j * 8 + 2 * t, r00 + q00, r01 + q01);
+                        st2(T1s + (8 + g) * LDG + j * 8 + 2 * t, r10 + q10, r11 + q11);
                     }
-                    st2(T1s + g * LDG + j * 8 + 2 * t, r00 + q00, r01 + q01);
-                    st2(T1s + (8 + g) * LDG + j * 8 + 2 * t, r10 + q10, r11 + q11);
                 }
+                __syncthreads();
+            } else {
+                // single stage: the results wait in registers until every warp is done with this block of G
+                double t1r[2][4];
+                int t1j[2] = {-1, -1};
+                if (warp < ((ncp + 1) >> 1)) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int j = u == 0 ? warp : ncp - 1 - warp;
+                        if (u == 1 && j <= warp) break;
+                        t1j[u] = j;
+                        double r00 = 0.0, r01 = 0.0, r10 = 0.0, r11 = 0.0;
+                        double q00 = 0.0, q01 = 0.0, q10 = 0.0, q11 = 0.0;   // second accumulator set (odd k tiles): shorter chains
+                        int kt = j;
+                        for (; kt + 1 < ncp; kt += 2) {
+                            const double* La = T + toff(kt, j);
+                            const double* Lb = T + toff(kt + 1, j);
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) {
+                                const double bfa = La[swz(4 * s + t, g)];
+                                const double bfb = Lb[swz(4 * s + t, g)];
+                                const int ca = kt * 8 + 4 * s + t;
+                                dmma(r00, r01, Gs[g * LDG + ca], bfa);
+                                dmma(r10, r11, Gs[(8 + g) * LDG + ca], bfa);
+                                dmma(q00, q01, Gs[g * LDG + ca + 8], bfb);
+                                dmma(q10, q11, Gs[(8 + g) * LDG + ca + 8], bfb);
+                            }
+                        }
+                        if (kt < ncp) {
+                            const double* La = T + toff(kt, j);
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) {
+                                const double bfa = La[swz(4 * s + t, g)];
+                                const int ca = kt * 8 + 4 * s + t;
+                                dmma(r00, r01, Gs[g * LDG + ca], bfa);
+                                dmma(r10, r11, Gs[(8 + g) * LDG + ca], bfa);
+                            }
+                        }
+                        t1r[u][0] = r00 + q00; t1r[u][1] = r01 + q01; t1r[u][2] = r10 + q10; t1r[u][3] = r11 + q11;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (t1j[u] >= 0) {
+                        st2(T1s + g * LDG + t1j[u] * 8 + 2 * t, t1r[u][0], t1r[u][1]);
+                        st2(T1s + (8 + g) * LDG + t1j[u] * 8 + 2 * t, t1r[u][2], t1r[u][3]);
+                    }
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            if (Kb + 1 < nsp) load_G_rows(Kb + 1);
+            if (!single && Kb + 1 < nsp) load_G_rows(Kb + 1);
             // B[I][J] += L[kt][I]^T T1[kt][J] for the two tile rows kt of this block
 #pragma unroll
             for (int s = 0; s < NSUP; ++s) {
@@ -379,6 +437,10 @@ __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
                         }
                     }
                 }
+            }
+            if (single && Kb + 1 < nsp) {
+                __syncthreads();                      // T1 (in the only stage) has been consumed
+                load_G_rows(Kb + 1);
             }
         }
         __syncthreads();
@@ -437,9 +499,9 @@ __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
         //      tiles Y[k][j] = flip-transpose(C[jp][ncp-1-k]) and streams through two shared-memory buffers ----
         {
             double* Ybuf = Gs;                         // [2][MAX_NCP * 64] + [2][64] for the diagonal inverses
-            double* Xbuf = Gs + 2 * MAX_NCP * TILE;
+            double* Xbuf = Gs + 2 * ncp_max * TILE;
             auto load_Y_row = [&](int jp) {
-                double* dst = Ybuf + (jp & 1) * MAX_NCP * TILE;
+                double* dst = Ybuf + (jp & 1) * ncp_max * TILE;
                 const double* src = Yg + (size_t)tri(jp) * TILE;
                 const int n = (jp + 1) * TILE / 2;
                 for (int x = tid; x < n; x += UT) cp_async16(dst + 2 * x, src + 2 * x);
@@ -452,7 +514,7 @@ __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
                 cp_async_wait_all();
                 __syncthreads();
                 if (jp + 1 < ncp) load_Y_row(jp + 1);
-                const double* Yrow = Ybuf + (jp & 1) * MAX_NCP * TILE;
+                const double* Yrow = Ybuf + (jp & 1) * ncp_max * TILE;
                 const double* Xb = Xbuf + (jp & 1) * TILE;
                 const double xb0 = Xb[swz(7 - 2 * t, 7 - g)], xb1 = Xb[swz(6 - 2 * t, 7 - g)];
                 // rows owned by this warp: i >= 16 -> warp nt-1-i, i < 16 -> warp 9 + (i % 7); enumerated directly
@@ -577,13 +639,18 @@ __global__ void __launch_bounds__(UT, 1) update_smem_kernel(const ApplyArgs a) {
     }
 }
 
-constexpr size_t US_SMEM = ((size_t)MAX_TILES * TILE + 2 * KBR * LDG + 2 * TILE + 3 * VEC + 208) * sizeof(double);
-static_assert(US_SMEM <= 227 * 1024, "update_smem shared memory");
-static_assert(2 * KBR * LDG >= 2 * MAX_NCP * TILE + 2 * TILE, "Y row buffers must fit the G/T1 stages");
+size_t us_smem_bytes(const msckf_dims& d) {
+    const size_t ncp = (6 * (size_t)d.N + 7) / 8, nt = ncp + 2;
+    const size_t stage = ncp > DUAL_NCP ? (KBR * LDG > 2 * ncp * TILE + 2 * TILE ? KBR * LDG : 2 * ncp * TILE + 2 * TILE) : 2 * KBR * LDG;
+    return (nt * (nt + 1) / 2 * TILE + stage + 2 * TILE + 3 * VEC + 208) * sizeof(double);
+}
+static_assert(2 * KBR * LDG >= 2 * DUAL_NCP * TILE + 2 * TILE, "Y row buffers must fit the G/T1 stages");
 
 }  // namespace
 
-bool update_smem_supported(const msckf_dims& d) { return 6 * d.N <= 8 * MAX_NCP && d.ldp >= 15 + 6 * d.N; }
+bool update_smem_supported(const msckf_dims& d) {
+    return 6 * d.N <= 8 * MAX_NCP && d.ldp >= 15 + 6 * d.N && us_smem_bytes(d) <= 227 * 1024;
+}
 
 size_t update_smem_scratch_doubles(const msckf_dims& d) {
     const size_t ncp = (6 * (size_t)d.N + 7) / 8, nt = ncp + 2;
@@ -592,16 +659,24 @@ size_t update_smem_scratch_doubles(const msckf_dims& d) {
 
 cudaError_t launch_update_smem(const ApplyArgs& a, int n_ctas, cudaStream_t s) {
     static int sms = 0;
+    static size_t configured = 0;
+    const size_t smem = us_smem_bytes(a.dims);
     if (sms == 0) {
-        cudaError_t e = cudaFuncSetAttribute(update_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)US_SMEM);
-        if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    const bool single = (6 * a.dims.N + 7) / 8 > DUAL_NCP;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(update_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(update_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
     int grid = a.dims.B < sms ? a.dims.B : sms;
     if (grid > n_ctas) grid = n_ctas;
-    update_smem_kernel<<<grid, UT, US_SMEM, s>>>(a);
+    if (single) update_smem_kernel<true><<<grid, UT, smem, s>>>(a);
+    else update_smem_kernel<false><<<grid, UT, smem, s>>>(a);
     msckf_count_launch(1);
     return cudaGetLastError();
 }
