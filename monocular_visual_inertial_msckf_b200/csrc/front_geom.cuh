@@ -47,6 +47,24 @@ __device__ __forceinline__ double warp_sum_all(double v) {
     return v;
 }
 
+// All-reduce of EIGHT values at once by recursive halving: every exchange step halves the number of values a lane still
+// carries (4 + 2 + 1 + 1 + 1 = 9 double shuffles), then each total is fetched from the lane that owns it (8 shuffles):
+// 17 instead of 40 trips through the shuffle / shared-memory queue, which is what the geometry waits for when the pair
+// loops of the other warps keep that queue full.
+__device__ __forceinline__ void warp_allreduce8(double (&v)[8], const int lane) {
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    double a[4], b[2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = (h16 ? v[4 + q] : v[q]) + __shfl_xor_sync(0xffffffffu, h16 ? v[q] : v[4 + q], 16);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) b[q] = (h8 ? a[2 + q] : a[q]) + __shfl_xor_sync(0xffffffffu, h8 ? a[q] : a[2 + q], 8);
+    double c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, h4 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __shfl_sync(0xffffffffu, c, 4 * i);
+}
+
 // cyclic Jacobi eigen-decomposition of a symmetric 3x3 (a = [xx, xy, xz, yy, yz, zz]); V columns = eigenvectors
 __device__ inline void sym3_eig_w(const double* a, double* lam, double* V) {
     double A[3][3] = {{a[0], a[1], a[2]}, {a[1], a[3], a[4]}, {a[2], a[4], a[5]}};
@@ -251,8 +269,16 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
             term[7] = term[1] * tt[0] + term[3] * tt[1] + term[4] * tt[2];
             term[8] = term[2] * tt[0] + term[4] * tt[1] + term[5] * tt[2];
         }
+        {
+            double t8[8];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) term[k] = warp_sum_all(live ? term[k] : 0.0);
+            for (int k = 0; k < 8; ++k) t8[k] = live ? term[k] : 0.0;
+            const double t9 = warp_sum_all(live ? term[8] : 0.0);
+            warp_allreduce8(t8, lane);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) term[k] = t8[k];
+            term[8] = t9;
+        }
         double p[3] = {0, 0, 0};
         if (!sym3_solve_spd(term, term + 6, p)) {   // (nearly) singular X: pinv with its singular-value cut-off
             double lam[3], V[9];
@@ -374,7 +400,77 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
         }
     }
 
-    // ---- orthonormal basis of range(H_f): column-pivoted Gram-Schmidt with re-orthogonalisation ----
+    // ---- orthonormal basis of range(H_f) and r~ = (I - Q1 Q1^T) r ----
+    // Fast path (well-conditioned H_f, the normal case): Cholesky-QR applied twice.  Two all-reduce rounds (the Gram matrix
+    // of H_f; then the Gram matrix of the first-pass Q together with Q^T r) replace the nine sequential reductions of the
+    // pivoted Gram-Schmidt below.  It is taken only when every Cholesky pivot of H_f^T H_f exceeds 1e-10 of its largest
+    // diagonal entry (sigma_min / sigma_max > ~1e-5: rank 3 by SciPy's rule with nine orders of magnitude to spare, and the
+    // second pass restores orthogonality to rounding); anything else goes through the Gram-Schmidt + SVD path.
+    bool fast_done = false;
+    if (n2 >= 3) {
+        double G[8];
+        G[0] = Hf[0][0] * Hf[0][0] + Hf[1][0] * Hf[1][0];
+        G[1] = Hf[0][0] * Hf[0][1] + Hf[1][0] * Hf[1][1];
+        G[2] = Hf[0][0] * Hf[0][2] + Hf[1][0] * Hf[1][2];
+        G[3] = Hf[0][1] * Hf[0][1] + Hf[1][1] * Hf[1][1];
+        G[4] = Hf[0][1] * Hf[0][2] + Hf[1][1] * Hf[1][2];
+        G[5] = Hf[0][2] * Hf[0][2] + Hf[1][2] * Hf[1][2];
+        G[6] = 0.0; G[7] = 0.0;
+        warp_allreduce8(G, lane);
+        const double gmax = fmax(G[0], fmax(G[3], G[5]));
+        // G = R^T R, R upper triangular
+        const double d0 = G[0];
+        const double i0 = fast_rsqrt(d0);
+        const double r01 = G[1] * i0, r02 = G[2] * i0;
+        const double d1 = G[3] - r01 * r01;
+        const double i1 = fast_rsqrt(d1);
+        const double r12 = (G[4] - r01 * r02) * i1;
+        const double d2 = G[5] - r02 * r02 - r12 * r12;
+        const double i2 = fast_rsqrt(d2);
+        if (d0 > 1e-10 * gmax && d1 > 1e-10 * gmax && d2 > 1e-10 * gmax && gmax < 1e300) {
+            // first-pass Q = H_f R^-1 (row by row)
+            double Q[2][3];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                Q[r][0] = Hf[r][0] * i0;
+                Q[r][1] = (Hf[r][1] - Q[r][0] * r01) * i1;
+                Q[r][2] = (Hf[r][2] - Q[r][0] * r02 - Q[r][1] * r12) * i2;
+            }
+            double S[8];
+            S[0] = Q[0][0] * Q[0][0] + Q[1][0] * Q[1][0];
+            S[1] = Q[0][0] * Q[0][1] + Q[1][0] * Q[1][1];
+            S[2] = Q[0][0] * Q[0][2] + Q[1][0] * Q[1][2];
+            S[3] = Q[0][1] * Q[0][1] + Q[1][1] * Q[1][1];
+            S[4] = Q[0][1] * Q[0][2] + Q[1][1] * Q[1][2];
+            S[5] = Q[0][2] * Q[0][2] + Q[1][2] * Q[1][2];
+            S[6] = Q[0][0] * res[0] + Q[1][0] * res[1];
+            S[7] = Q[0][1] * res[0] + Q[1][1] * res[1];
+            const double b2 = warp_sum_all(Q[0][2] * res[0] + Q[1][2] * res[1]);
+            warp_allreduce8(S, lane);
+            // second pass: S = R2^T R2 (close to the identity), Q <- Q R2^-1, w = Q^T r = R2^-T (Q1^T r)
+            const double j0 = fast_rsqrt(S[0]);
+            const double s01 = S[1] * j0, s02 = S[2] * j0;
+            const double j1 = fast_rsqrt(S[3] - s01 * s01);
+            const double s12 = (S[4] - s01 * s02) * j1;
+            const double j2 = fast_rsqrt(S[5] - s02 * s02 - s12 * s12);
+            const double w0 = S[6] * j0;
+            const double w1 = (S[7] - s01 * w0) * j1;
+            const double w2 = (b2 - s02 * w0 - s12 * w1) * j2;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                Hf[r][0] = Q[r][0] * j0;
+                Hf[r][1] = (Q[r][1] - Hf[r][0] * s01) * j1;
+                Hf[r][2] = (Q[r][2] - Hf[r][0] * s02 - Hf[r][1] * s12) * j2;
+            }
+            rank = 3;
+            rt0 = res[0] - (Hf[0][0] * w0 + Hf[0][1] * w1 + Hf[0][2] * w2);
+            rt1 = res[1] - (Hf[1][0] * w0 + Hf[1][1] * w1 + Hf[1][2] * w2);
+            fast_done = true;
+        }
+    }
+    if (fast_done) return code;
+
+    // ---- general path: column-pivoted Gram-Schmidt with re-orthogonalisation ----
     {
         double R3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         bool stop = false;
