@@ -414,6 +414,80 @@ def test_track_append_vs_golden(golden_dir):
     assert int(ov.item()) == 1 and int(full.feat_len[0, 0]) == 2
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_whole_run_trace_chained_on_device(golden_dir, mode):
+    """Sequence-level parity: a whole reference run replayed call by call with the filter state RESIDENT on the device
+    (540 process_imu, 59 state_augmentation, 85 get_valid_features + update + correct, 79 remove_cameras; only the tracks
+    of each update come from the host) reproduces the reference's state after every camera frame to 1e-9."""
+    tr = o.load_trace(os.path.join(golden_dir, "small_trace.npz"))
+    ini, cases = tr["init"], tr["cases"]
+    F = max(len(c["feat_len"]) for c in cases)
+    M = max(c["obs_uv"].shape[1] for c in cases)
+    N = max(int(c["n_cams"]) for c in cases)
+    par = UpdateParams.from_case(cases[0], mode)
+    par.gravity = np.array(ini["gravity"], float)
+    flt = BatchedMSCKF(1, F, M, N, par)
+    flt.P.zero_()
+    flt.P[0, :15, :15] = torch.from_numpy(np.asarray(ini["P"], float))
+    flt.imu_state[0] = torch.from_numpy(np.concatenate([np.asarray(ini["imu_R"], float).flatten(), ini["imu_t"], ini["imu_v"],
+                                                        ini["imu_bg"], ini["imu_ba"]]))
+    flt.imu_null[0] = torch.from_numpy(np.concatenate([np.asarray(ini["null_R"], float).flatten(), ini["null_t"], ini["null_v"]]))
+    flt.imu_time[0] = float(ini["timestamp"])
+    flt.Qc_diag[0] = torch.from_numpy(np.asarray(ini["Qc_diag"], float)[[0, 3, 6, 9]].copy())
+    flt.n_cams.zero_()
+    boundaries = {int(fr["op_index"]): i for i, fr in enumerate(tr["frames"])}
+    first, worst, n_updates = True, 0.0, 0
+    for n, (kind, idx) in enumerate(tr["ops"]):
+        if kind == 0:
+            smp = torch.from_numpy(np.asarray(tr["samples"][idx], float)).reshape(1, 1, 7).cuda()
+            flt.propagate(smp, use_null_state=first)     # afterwards the null state IS the state (aliasing, MSCKF.py:247-248)
+            first = False
+        elif kind == 1:
+            flt.augment(ini["R_I_C"], ini["t_I_C"])
+        elif kind == 2:
+            c = cases[idx]
+            assert int(flt.n_cams[0]) == int(c["n_cams"])
+            f, m = len(c["feat_len"]), c["obs_uv"].shape[1]
+            flt.feat_len.zero_()
+            if f:
+                flt.feat_len[0, :f] = torch.from_numpy(c["feat_len"])
+                flt.obs_uv[0, :f, :m] = torch.from_numpy(c["obs_uv"])
+                flt.obs_dir[0, :f, :m] = torch.from_numpy(c["obs_dir"])
+                flt.obs_conf[0, :f, :m] = torch.from_numpy(c["obs_conf"])
+                flt.obs_slot[0, :f, :m] = torch.from_numpy(np.maximum(c["obs_slot"], 0))
+                flt.idp_base[0, :f] = torch.from_numpy(c["idp_base"])
+                flt.idp_anchor_slot[0, :f] = torch.from_numpy(c["idp_anchor_slot"])
+                flt.idp_m[0, :f] = torch.from_numpy(c["idp_m"])
+                flt.idp_rho[0, :f] = torch.from_numpy(c["idp_rho"])
+                flt.lost_cnt[0, :f] = torch.from_numpy(c["lost_cnt"])
+                flt.tracked_cnt[0, :f] = torch.from_numpy(c["tracked_cnt"])
+            flt.update()
+            code = flt.feat_status[0, :f].cpu().numpy() & 0xF
+            assert (((code == 1) | (code == 2)) == c["out_valid"]).all()
+            n_updates += int(flt.n_accepted[0]) > 0
+        else:
+            mask = torch.zeros((1, flt.N), dtype=torch.uint8, device="cuda")
+            mk = tr["masks"][idx]
+            mask[0, :len(mk)] = torch.from_numpy(mk.astype(np.uint8))
+            flt.remove_cameras(mask)
+        if (n + 1) in boundaries:
+            fr = tr["frames"][boundaries[n + 1]]
+            d = fr["P"].shape[0]
+            nc = (d - 15) // 6
+            assert int(flt.n_cams[0]) == nc
+            st = flt.imu_state[0].cpu().numpy()
+            errs = [rel_err(flt.P[0, :d, :d].cpu().numpy(), fr["P"]), rel_err(st[:9].reshape(3, 3), fr["imu_R"]),
+                    rel_err(st[9:12], fr["imu_t"]), rel_err(st[12:15], fr["imu_v"]), rel_err(st[15:18], fr["imu_bg"]),
+                    rel_err(st[18:21], fr["imu_ba"])]
+            if nc:
+                errs += [rel_err(flt.cam_R[0, :nc].cpu().numpy().reshape(nc, 3, 3), fr["cam_R"]),
+                         rel_err(flt.cam_t[0, :nc].cpu().numpy(), fr["cam_t"])]
+            worst = max(worst, max(errs))
+            assert worst < 1e-9, (boundaries[n + 1], errs)
+    assert n_updates >= 40
+    print("chained device replay, worst relative error over", len(tr["frames"]), "frames:", worst)
+
+
 def test_prune_flow_vs_oracle(golden_dir):
     """prune_poorest_camera_states end to end on resident state (select -> update with the touched tracks -> drop ->
     remove) against the oracle's composition of the same reference steps."""

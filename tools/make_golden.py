@@ -338,6 +338,124 @@ class SurgeryCapture:
         return out
 
 
+class TraceCapture:
+    """Operation trace of a whole reference run for the chained (sequence-level) parity test: every process_imu sample,
+    every state_augmentation, every get_valid_features + update pair (tracks only -- the filter state is carried by
+    the replay) and every remove_cameras mask, in call order, plus the state at the first traced call and after every
+    camera frame."""
+
+    def __init__(self, ns, f):
+        self.ns, self.f = ns, f
+        self.ops = []            # (kind, payload index)
+        self.samples, self.masks, self.cases, self.frames = [], [], [], []
+        self.init = None
+        self._o_imu, self._o_aug = f.process_imu, f.state_augmentation
+        self._o_gvf, self._o_upd, self._o_rm = f.get_valid_features, f.update, f.remove_cameras
+        f.process_imu, f.state_augmentation = self.imu, self.aug
+        f.get_valid_features, f.update, f.remove_cameras = self.gvf, self.upd, self.rm
+        self._pending = None
+
+    def _state(self):
+        f = self.f
+        imu = f.state.imu
+        cams = list(f.state.cameras.values())
+        return dict(P=np.array(f.state.covariance, float), imu_R=np.array(imu.T_W_Ii.R, float), imu_t=np.array(imu.T_W_Ii.t, float),
+                    imu_v=np.array(imu.v_W_Ii, float), imu_bg=np.array(imu.gyroscope_bias, float),
+                    imu_ba=np.array(imu.accelerometer_bias, float), timestamp=float(imu.timestamp),
+                    null_R=np.array(imu.T_W_Ii_null.R, float), null_t=np.array(imu.T_W_Ii_null.t, float),
+                    null_v=np.array(imu.v_W_Ii_null, float),
+                    cam_R=np.stack([c.T_W_Ci.R for c in cams]).astype(float) if cams else np.zeros((0, 3, 3)),
+                    cam_t=np.stack([c.T_W_Ci.t for c in cams]).astype(float) if cams else np.zeros((0, 3)))
+
+    def imu(self, m):
+        if self.init is None:
+            f = self.f
+            self.init = self._state()
+            T_I_C = f.state.imu.T_W_I.inv() * f.T_W_C
+            self.init.update(Qc_diag=np.diag(f.continuous_noise_covariance).copy(), gravity=np.array(f.state.imu.W_gravity, float),
+                             R_I_C=np.array(T_I_C.R, float), t_I_C=np.array(T_I_C.t, float))
+        self.ops.append((0, len(self.samples)))
+        self.samples.append(np.concatenate([[m.timestamp], m.angular_velocity, m.linear_acceleration]))
+        return self._o_imu(m)
+
+    def aug(self):
+        self.ops.append((1, 0))
+        return self._o_aug()
+
+    def gvf(self, features):
+        c = pack_update_inputs(self.ns, self.f, features)
+        for k in ("P", "cam_R", "cam_t", "imu_R", "imu_t", "imu_v", "imu_bg", "imu_ba"):
+            c.pop(k)                                  # carried by the replay
+        self._pending = c
+        valid, lost = self._o_gvf(features)
+        c["out_valid"] = np.array([k in valid for k in features.keys()], bool)
+        if len(valid) == 0:                           # the reference does not call update(): selection only
+            c["n_valid"] = 0
+            self.ops.append((2, len(self.cases)))
+            self.cases.append(c)
+            self._pending = None
+        return valid, lost
+
+    def upd(self, features):
+        c = self._pending
+        out = self._o_upd(features)
+        if c is not None:
+            c["n_valid"] = len(features)
+            self.ops.append((2, len(self.cases)))
+            self.cases.append(c)
+            self._pending = None
+        return out
+
+    def rm(self, cameras):
+        ids = list(self.f.state.cameras.keys())
+        self.ops.append((3, len(self.masks)))
+        self.masks.append(np.array([k in cameras for k in ids], bool))
+        return self._o_rm(cameras)
+
+    def frame_done(self):
+        st = self._state()
+        self.frames.append(dict(op_index=len(self.ops), **st))
+
+
+def fixture_trace(ns):
+    """Whole-run operation trace of the small configuration (window 8, 40 landmarks, 60 frames)."""
+    kw = dict(seed=42, n_frames=60, n_landmarks=40, noise_level="mid", p_drop=0.06, p_outlier=0.03, shuffle=True)
+    seq = synth.make_sequence(**kw)
+    fp = dict(min_parallax=2.0, max_number_of_camera_states=8, epipolar_rejection_threshold=1e9,
+              homography_rejection_threshold=1e9, min_number_of_frames_to_be_tracked=3)
+    params, pd = make_params(ns, seq, **fp)
+    f = ns.MSCKF(parameters=params, rr=None)
+    cap = TraceCapture(ns, f)
+    image = np.zeros((seq.height, seq.width, 3), np.uint8)
+    frame_at = {fr.imu_index: fr for fr in seq.frames}
+    for i in range(len(seq.imu)):
+        row = seq.imu[i]
+        f.imu_callback(ns.IMUMeasurement(row[0], row[1:4].copy(), row[4:7].copy()))
+        fr = frame_at.get(i)
+        if fr is not None:
+            f.feature_callback(image, ns.CameraMeasurement(keypoints=fr.keypoints.copy(), descriptors=fr.descriptors.copy(),
+                                                           scores=fr.scores.copy()))
+            if cap.init is not None:
+                cap.frame_done()
+    flat = {"ops": np.array(cap.ops, np.int32), "samples": np.array(cap.samples), "n_cases": np.asarray(len(cap.cases)),
+            "n_masks": np.asarray(len(cap.masks)), "n_frames": np.asarray(len(cap.frames))}
+    for k, v in cap.init.items():
+        flat["init." + k] = np.asarray(v)
+    for i, m in enumerate(cap.masks):
+        flat[f"m{i}"] = m
+    for i, c in enumerate(cap.cases):
+        for k, v in c.items():
+            flat[f"c{i}.{k}"] = np.asarray(v)
+    for i, fr in enumerate(cap.frames):
+        for k, v in fr.items():
+            flat[f"f{i}.{k}"] = np.asarray(v)
+    path = os.path.join(GOLDEN, "small_trace.npz")
+    np.savez_compressed(path, **flat)
+    kinds = np.bincount(np.array(cap.ops)[:, 0], minlength=4)
+    print(f"wrote {path}: {len(cap.ops)} ops (imu {kinds[0]}, augment {kinds[1]}, update {kinds[2]}, remove {kinds[3]}), "
+          f"{len(cap.frames)} frames, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def fixture_prune(ns):
     """Window / track surgery cases from the `small` run: every prune selection and every remove_cameras call."""
     kw = dict(seed=42, n_frames=60, n_landmarks=40, noise_level="mid", p_drop=0.06, p_outlier=0.03, shuffle=True)
@@ -465,6 +583,8 @@ if __name__ == "__main__":
         fixture_small(ns)
     if args.only in (None, "prune"):
         fixture_prune(ns)
+    if args.only in (None, "trace"):
+        fixture_trace(ns)
     if args.only in (None, "mid"):
         # mid-size steady-state fixture (cheap to regenerate): F = 48, window 10
         KEEP_FROM[:] = [18, 14 * 9]
