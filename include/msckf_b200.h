@@ -215,9 +215,30 @@ int msckf_append_observations_batched(const msckf_dims* dims, const double* Kinv
                                       const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
                                       int* obs_slot, double* idp_base, int* idp_anchor_slot, double* idp_m, double* idp_rho,
                                       int* lost_cnt, int* tracked_cnt, int* overflow_count, void* stream);
-int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select, const int* n_cams, const int* feat_len,
-                                         const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch,
-                                         void* stream);
+int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select, int prune_above, const int* n_cams,
+                                         const int* feat_len, const int* obs_slot, unsigned char* remove_mask,
+                                         unsigned char* feat_touch, void* stream);
+/* (prune_above: filters whose window holds at most that many cameras select nothing -- MSCKF.feature_callback prunes only
+ * when len(cameras) > max_number_of_camera_states, MSCKF.py:157-158; pass -1 to select in every filter) */
+
+/* msckf_unobserved_cameras_batched  <->  MSCKF.get_cameras_without_features (called by remove_features, MSCKF.py:739-749):
+ * remove_mask[B][N] marks the window slots no track observes; filters with active[b] == 0 (active may be NULL) mark none. */
+int msckf_unobserved_cameras_batched(const msckf_dims* dims, const int* n_cams, const int* feat_len, const int* obs_slot,
+                                     const unsigned char* active, unsigned char* remove_mask, void* stream);
+
+/* msckf_compact_tracks_batched  <->  the `del self.features[...]` of MSCKF.remove_features (MSCKF.py:739-741) and of
+ * remove_cameras (tracks left without observations, MSCKF.py:768-772): the surviving tracks of every filter are copied, in
+ * order, to the front of a SECOND set of track arrays (the caller swaps the two sets); the rest of dst gets feat_len 0.
+ * drop_lost = 0: only empty slots (feat_len 0) go.  drop_lost = 1: in filters whose last update had at least one valid
+ * feature (feat_status ACCEPTED / GATED_OUT) the tracks flagged MSCKF_FEAT_LOST_FLAG go too (process_features,
+ * MSCKF.py:450-456); active_out[b] (may be NULL) = 1 for those filters. */
+typedef struct msckf_track_arrays {
+    int* feat_len; double* obs_uv; double* obs_dir; double* obs_conf; int* obs_slot; double* idp_base; int* idp_anchor_slot;
+    double* idp_m; double* idp_rho; int* lost_cnt; int* tracked_cnt;
+} msckf_track_arrays;
+int msckf_compact_tracks_batched(const msckf_dims* dims, int drop_lost, const unsigned char* feat_status,
+                                 const msckf_track_arrays* src, const msckf_track_arrays* dst, unsigned char* active_out,
+                                 void* stream);
 int msckf_drop_observations_batched(const msckf_dims* dims, const unsigned char* remove_mask, const int* n_cams,
                                     const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
                                     int* obs_slot, double* idp_base, int* idp_anchor_slot, void* stream);

@@ -50,6 +50,14 @@ class HostStep(C.Structure):
                 [(n, C.c_void_p) for n in HOST_OUTPUTS])
 
 
+TRACK_FIELDS = ("feat_len", "obs_uv", "obs_dir", "obs_conf", "obs_slot", "idp_base", "idp_anchor_slot", "idp_m", "idp_rho",
+                "lost_cnt", "tracked_cnt")
+
+
+class TrackArrays(C.Structure):   # msckf_track_arrays
+    _fields_ = [(n, C.c_void_p) for n in TRACK_FIELDS]
+
+
 # every symbol include/msckf_b200.h declares
 EXPORTS = [
     "msckf_abi_version", "msckf_max_obs_per_feature", "msckf_max_cameras", "msckf_update_workspace_bytes",
@@ -57,7 +65,8 @@ EXPORTS = [
     "msckf_propagate_batched", "msckf_augment_batched", "msckf_remove_workspace_bytes",
     "msckf_remove_cameras_batched", "msckf_launch_count", "msckf_probe_fp64", "msckf_filter_step_host",
     "msckf_set_stage_timing", "msckf_front_stage_ms", "msckf_select_poorest_cameras_batched",
-    "msckf_drop_observations_batched", "msckf_append_observations_batched",
+    "msckf_drop_observations_batched", "msckf_append_observations_batched", "msckf_unobserved_cameras_batched",
+    "msckf_compact_tracks_batched",
 ]
 
 
@@ -110,7 +119,11 @@ def load_library():
     lib.msckf_filter_step_host.argtypes = [pd, pp, dp, C.c_int, C.POINTER(DeviceBuffers), C.POINTER(HostStep), C.c_int,
                                            C.c_int, vp, C.c_size_t, vp]
     lib.msckf_select_poorest_cameras_batched.restype = C.c_int
-    lib.msckf_select_poorest_cameras_batched.argtypes = [pd, C.c_int, ip, ip, ip, u8, u8, vp]
+    lib.msckf_select_poorest_cameras_batched.argtypes = [pd, C.c_int, C.c_int, ip, ip, ip, u8, u8, vp]
+    lib.msckf_unobserved_cameras_batched.restype = C.c_int
+    lib.msckf_unobserved_cameras_batched.argtypes = [pd, ip, ip, ip, u8, u8, vp]
+    lib.msckf_compact_tracks_batched.restype = C.c_int
+    lib.msckf_compact_tracks_batched.argtypes = [pd, C.c_int, u8, C.POINTER(TrackArrays), C.POINTER(TrackArrays), u8, vp]
     lib.msckf_drop_observations_batched.restype = C.c_int
     lib.msckf_drop_observations_batched.argtypes = [pd, u8, ip, dp, ip, dp, dp, dp, ip, dp, ip, vp]
     lib.msckf_append_observations_batched.restype = C.c_int

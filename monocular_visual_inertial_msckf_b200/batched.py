@@ -128,6 +128,7 @@ class BatchedMSCKF:
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dv)
         self._remove_ws = None
         self._overflow = None
+        self._alt_tracks = None
         self._samples_dev = None
         self.Qc_diag = z(B, 4)
 
@@ -269,12 +270,13 @@ class BatchedMSCKF:
         _lib.check(rc, "msckf_append_observations_batched")
         return self._overflow
 
-    def select_poorest_cameras(self, max_select=2):
+    def select_poorest_cameras(self, max_select=2, prune_above=-1):
         """MSCKF.prune_poorest_camera_states' selection (MSCKF.py:712-733) for every filter: returns
-        (remove_mask [B, N] uint8, feat_touch [B, F] uint8) on the device."""
+        (remove_mask [B, N] uint8, feat_touch [B, F] uint8) on the device.  Filters whose window holds at most
+        `prune_above` cameras select nothing (MSCKF.py:157-158)."""
         mask = torch.empty((self.B, self.N), dtype=torch.uint8, device=self.device)
         touch = torch.empty((self.B, self.F), dtype=torch.uint8, device=self.device)
-        rc = self.lib.msckf_select_poorest_cameras_batched(C.byref(self.dims), int(max_select), _ptr(self.n_cams),
+        rc = self.lib.msckf_select_poorest_cameras_batched(C.byref(self.dims), int(max_select), int(prune_above), _ptr(self.n_cams),
                                                            _ptr(self.feat_len), _ptr(self.obs_slot), _ptr(mask), _ptr(touch),
                                                            self._stream())
         _lib.check(rc, "msckf_select_poorest_cameras_batched")
@@ -288,17 +290,69 @@ class BatchedMSCKF:
                                                       _ptr(self.idp_anchor_slot), self._stream())
         _lib.check(rc, "msckf_drop_observations_batched")
 
-    def prune_poorest_camera_states(self, max_select=2):
+    def _track_struct(self, tensors):
+        st = _lib.TrackArrays()
+        for n in _lib.TRACK_FIELDS:
+            setattr(st, n, tensors[n].data_ptr())
+        return st
+
+    def compact_tracks(self, drop_lost=False):
+        """Stable compaction of the track slots (MSCKF.remove_features / the track deletions of remove_cameras): the
+        survivors move, in order, to the front of a second set of track arrays, which then becomes the current one.
+        Returns active [B] uint8 (drop_lost: filters that deleted their lost tracks)."""
+        cur = {n: getattr(self, n) for n in _lib.TRACK_FIELDS}
+        if self._alt_tracks is None:
+            self._alt_tracks = {n: torch.zeros_like(t) for n, t in cur.items()}
+        active = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
+        a, b = self._track_struct(cur), self._track_struct(self._alt_tracks)
+        rc = self.lib.msckf_compact_tracks_batched(C.byref(self.dims), int(bool(drop_lost)), _ptr(self.feat_status), C.byref(a),
+                                                   C.byref(b), _ptr(active), self._stream())
+        _lib.check(rc, "msckf_compact_tracks_batched")
+        for n in _lib.TRACK_FIELDS:
+            setattr(self, n, self._alt_tracks[n])
+        self._alt_tracks = cur
+        return active
+
+    def unobserved_cameras(self, active=None):
+        """MSCKF.get_cameras_without_features (MSCKF.py:739-749): [B, N] uint8 mask of the window slots no track observes."""
+        mask = torch.empty((self.B, self.N), dtype=torch.uint8, device=self.device)
+        rc = self.lib.msckf_unobserved_cameras_batched(C.byref(self.dims), _ptr(self.n_cams), _ptr(self.feat_len),
+                                                       _ptr(self.obs_slot), _ptr(active), _ptr(mask), self._stream())
+        _lib.check(rc, "msckf_unobserved_cameras_batched")
+        return mask
+
+    def process_features(self):
+        """MSCKF.process_features (MSCKF.py:450-456) on resident tracks: one update with every track; filters that had a
+        valid feature then delete their lost tracks (remove_features) and the cameras nothing observes any more."""
+        self.update()
+        active = self.compact_tracks(drop_lost=True)
+        mask = self.unobserved_cameras(active)
+        self.drop_observations(mask)          # renumbers the slots of the surviving observations
+        self.remove_cameras(mask)
+
+    def frame_step(self, samples, R_I_C, t_I_C, action, new_uv, new_conf, max_cameras, use_null_state=False):
+        """One camera frame of every filter with everything resident (MSCKF.imu_callback x n + feature_callback,
+        MSCKF.py:135-158): the IMU samples since the last frame, state_augmentation, the track bookkeeping of
+        add_camera_measurements (the matcher's decisions come from the caller), process_features, and the pruning of the
+        two poorest cameras in the filters whose window exceeds max_cameras."""
+        self.propagate(samples, use_null_state=use_null_state)
+        self.augment(R_I_C, t_I_C)
+        self.append_observations(action, new_uv, new_conf)
+        self.process_features()
+        self.prune_poorest_camera_states(prune_above=max_cameras)
+
+    def prune_poorest_camera_states(self, max_select=2, prune_above=-1):
         """MSCKF.prune_poorest_camera_states (MSCKF.py:710-737) for every filter, everything resident: select the two
         cameras with the fewest observations, one last update with the tracks that observe them, then delete those
         cameras from the tracks, the window and the covariance.  Returns the (remove_mask, feat_touch) that were used."""
-        mask, touch = self.select_poorest_cameras(max_select)
+        mask, touch = self.select_poorest_cameras(max_select, prune_above)
         full_len = self.feat_len.clone()
         self.feat_len.mul_(touch.to(torch.int32))         # features_to_process: the other tracks sit this update out
         self.update()
         self.feat_len.copy_(full_len)
         self.drop_observations(mask)
         self.remove_cameras(mask)
+        self.compact_tracks(drop_lost=False)               # tracks left without observations are deleted (MSCKF.py:768-772)
         return mask, touch
 
     # ------------------------------------------------------------------------------------------------------------

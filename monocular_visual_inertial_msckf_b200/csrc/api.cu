@@ -19,8 +19,12 @@ cudaError_t launch_update_info(const ApplyArgs& a, int n_ctas, cudaStream_t s);
 bool update_smem_supported(const msckf_dims& d);
 size_t update_smem_scratch_doubles(const msckf_dims& d);
 cudaError_t launch_update_smem(const ApplyArgs& a, int n_ctas, cudaStream_t s);
-cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, const int* n_cams, const int* feat_len,
+cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, int prune_above, const int* n_cams, const int* feat_len,
                                   const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch, cudaStream_t s);
+cudaError_t launch_unobserved_cameras(const msckf_dims& d, const int* n_cams, const int* feat_len, const int* obs_slot,
+                                      const unsigned char* active, unsigned char* remove_mask, cudaStream_t s);
+cudaError_t launch_compact_tracks(const msckf_dims& d, int drop_lost, const unsigned char* feat_status, void* const* src,
+                                  void* const* dst, unsigned char* active_out, cudaStream_t s);
 cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_host, const int* n_cams, const double* cam_R,
                                        const double* cam_t, const unsigned char* action, const double* new_uv,
                                        const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
@@ -225,13 +229,36 @@ int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* re
     return (int)launch_remove(*dims, remove_mask, cam_R, cam_t, P, n_cams, (double*)workspace, (cudaStream_t)stream);
 }
 
-int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select, const int* n_cams, const int* feat_len,
-                                         const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch,
-                                         void* stream) {
+int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select, int prune_above, const int* n_cams,
+                                         const int* feat_len, const int* obs_slot, unsigned char* remove_mask,
+                                         unsigned char* feat_touch, void* stream) {
     int rc = check_dims(dims);
     if (rc) return rc;
     if (max_select < 0 || !n_cams || !feat_len || !obs_slot || !remove_mask || !feat_touch) return MSCKF_EINVAL;
-    return (int)launch_select_poorest(*dims, max_select, n_cams, feat_len, obs_slot, remove_mask, feat_touch,
+    return (int)launch_select_poorest(*dims, max_select, prune_above, n_cams, feat_len, obs_slot, remove_mask, feat_touch,
+                                      (cudaStream_t)stream);
+}
+
+int msckf_unobserved_cameras_batched(const msckf_dims* dims, const int* n_cams, const int* feat_len, const int* obs_slot,
+                                     const unsigned char* active, unsigned char* remove_mask, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!n_cams || !feat_len || !obs_slot || !remove_mask) return MSCKF_EINVAL;
+    return (int)launch_unobserved_cameras(*dims, n_cams, feat_len, obs_slot, active, remove_mask, (cudaStream_t)stream);
+}
+
+int msckf_compact_tracks_batched(const msckf_dims* dims, int drop_lost, const unsigned char* feat_status,
+                                 const msckf_track_arrays* src, const msckf_track_arrays* dst, unsigned char* active_out,
+                                 void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!src || !dst || (drop_lost && !feat_status)) return MSCKF_EINVAL;
+    const void* const* ps = (const void* const*)src;
+    const void* const* pq = (const void* const*)dst;
+    for (int k = 0; k < 11; ++k)
+        if (!ps[k] || !pq[k] || ps[k] == pq[k]) return MSCKF_EINVAL;
+    if ((size_t)dims->F * sizeof(int) > 48 * 1024) return MSCKF_ECAPACITY;
+    return (int)launch_compact_tracks(*dims, drop_lost, feat_status, (void* const*)src, (void* const*)dst, active_out,
                                       (cudaStream_t)stream);
 }
 

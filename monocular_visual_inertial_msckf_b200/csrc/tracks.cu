@@ -12,7 +12,8 @@ constexpr int TT = 256;
 // One CTA per filter.  Observations per window slot are counted with shared-memory atomics together with the slot's first
 // appearance in track order (the reference builds a dict while walking the tracks, so cameras enter it in that order, and
 // Python's stable `sorted` keeps it among equal counts); the `max_select` smallest (count, first appearance) pairs win.
-__global__ void __launch_bounds__(TT) select_poorest_kernel(msckf_dims dims, int max_select, const int* __restrict__ n_cams,
+__global__ void __launch_bounds__(TT) select_poorest_kernel(msckf_dims dims, int max_select, int prune_above,
+                                                            const int* __restrict__ n_cams,
                                                             const int* __restrict__ feat_len, const int* __restrict__ obs_slot,
                                                             unsigned char* __restrict__ remove_mask,
                                                             unsigned char* __restrict__ feat_touch) {
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(TT) select_poorest_kernel(msckf_dims dims, int
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && nc > prune_above) {      // MSCKF.feature_callback prunes only windows longer than the maximum (MSCKF.py:157-158)
         for (int pick = 0; pick < max_select; ++pick) {
             int best = -1;
             for (int s = 0; s < nc; ++s) {
@@ -178,7 +179,123 @@ __global__ void __launch_bounds__(TT) append_observations_kernel(msckf_dims dims
     }
 }
 
+// Window slots of a filter that no track observes any more (MSCKF.get_cameras_without_features, called by remove_features,
+// MSCKF.py:739-749): the same shared-memory histogram as the pruning selection, mask = (count == 0).
+__global__ void __launch_bounds__(TT) unobserved_cameras_kernel(msckf_dims dims, const int* __restrict__ n_cams,
+                                                                const int* __restrict__ feat_len, const int* __restrict__ obs_slot,
+                                                                const unsigned char* __restrict__ active,
+                                                                unsigned char* __restrict__ remove_mask) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int F = dims.F, M = dims.M, N = dims.N;
+    __shared__ int s_count[MSCKF_MAX_CAMS];
+    const int nc = min(n_cams[b], N);
+    for (int s = tid; s < N; s += TT) s_count[s] = 0;
+    __syncthreads();
+    const int* len = feat_len + (size_t)b * F;
+    const int* slot = obs_slot + (size_t)b * F * M;
+    for (int e = tid; e < F * M; e += TT) {
+        const int j = e / M, i = e - j * M;
+        if (i < len[j]) {
+            const int s = slot[e];
+            if (s >= 0 && s < nc) atomicAdd(&s_count[s], 1);
+        }
+    }
+    __syncthreads();
+    const bool on = active == nullptr || active[b] != 0;
+    for (int s = tid; s < N; s += TT) remove_mask[(size_t)b * N + s] = (on && s < nc && s_count[s] == 0) ? 1 : 0;
+}
+
+// Stable compaction of the track slots of every filter from one set of track arrays into another (the host swaps the two
+// sets afterwards): the reference deletes tracks from its insertion-ordered dict, so the survivors keep their order --
+// which the pruning selection's tie-break depends on.  A slot survives when it holds a track (feat_len > 0) and, with
+// drop_lost, when the track is not in the `lost_features` dict of the last update (MSCKF_FEAT_LOST_FLAG); drop_lost only
+// applies to filters that had at least one valid feature in that update (MSCKF.process_features, MSCKF.py:454-456).
+// active_out[b] = 1 when the filter deleted lost tracks (its unobserved cameras are removed next).
+struct TrackSet {
+    int* feat_len; double* obs_uv; double* obs_dir; double* obs_conf; int* obs_slot; double* idp_base; int* idp_anchor_slot;
+    double* idp_m; double* idp_rho; int* lost_cnt; int* tracked_cnt;
+};
+__global__ void __launch_bounds__(TT) compact_tracks_kernel(msckf_dims dims, int drop_lost, const unsigned char* __restrict__ feat_status,
+                                                            TrackSet src, TrackSet dst, unsigned char* __restrict__ active_out) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = dims.F, M = dims.M;
+    extern __shared__ int s_dest[];            // [F] destination slot of each surviving track, -1 otherwise
+    __shared__ int s_wsum[TT / 32];
+    __shared__ int s_base, s_any;
+    const size_t fb = (size_t)b * F;
+    if (tid == 0) { s_base = 0; s_any = 0; }
+    __syncthreads();
+    bool lost_rule = false;
+    if (drop_lost) {
+        int any = 0;
+        for (int j = tid; j < F; j += TT) {
+            const int code = feat_status[fb + j] & 0xF;
+            if (src.feat_len[fb + j] > 0 && (code == MSCKF_FEAT_ACCEPTED || code == MSCKF_FEAT_GATED_OUT)) any = 1;
+        }
+        if (any) atomicOr(&s_any, 1);
+        __syncthreads();
+        lost_rule = s_any != 0;
+    }
+    if (tid == 0 && active_out) active_out[b] = lost_rule ? 1 : 0;
+    for (int j0 = 0; j0 < F; j0 += TT) {          // block-wide exclusive scan of the keep flags, TT slots at a time
+        const int j = j0 + tid;
+        int keep = 0;
+        if (j < F) keep = (src.feat_len[fb + j] > 0 && !(lost_rule && (feat_status[fb + j] & MSCKF_FEAT_LOST_FLAG))) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_wsum[w];
+        if (j < F) s_dest[j] = keep ? off + __popc(bal & ((1u << lane) - 1u)) : -1;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < TT / 32; ++w) t += s_wsum[w]; s_base += t; }
+        __syncthreads();
+    }
+    const int n_kept = s_base;
+    for (int j = warp; j < F; j += TT / 32) {      // one warp per track
+        const int d = s_dest[j];
+        if (d < 0) continue;
+        const size_t sj = fb + j, dj = fb + d;
+        const int n = min(src.feat_len[sj], M);
+        for (int i = lane; i < n; i += 32) {
+            const size_t se = sj * M + i, de = dj * M + i;
+            dst.obs_uv[de * 2] = src.obs_uv[se * 2]; dst.obs_uv[de * 2 + 1] = src.obs_uv[se * 2 + 1];
+            dst.obs_dir[de * 3] = src.obs_dir[se * 3]; dst.obs_dir[de * 3 + 1] = src.obs_dir[se * 3 + 1];
+            dst.obs_dir[de * 3 + 2] = src.obs_dir[se * 3 + 2];
+            dst.obs_conf[de] = src.obs_conf[se];
+            dst.obs_slot[de] = src.obs_slot[se];
+        }
+        if (lane == 0) {
+            dst.feat_len[dj] = n;
+            dst.idp_anchor_slot[dj] = src.idp_anchor_slot[sj];
+            dst.idp_rho[dj] = src.idp_rho[sj];
+            dst.lost_cnt[dj] = src.lost_cnt[sj];
+            dst.tracked_cnt[dj] = src.tracked_cnt[sj];
+        }
+        if (lane < 3) { dst.idp_base[dj * 3 + lane] = src.idp_base[sj * 3 + lane]; dst.idp_m[dj * 3 + lane] = src.idp_m[sj * 3 + lane]; }
+    }
+    for (int j = n_kept + tid; j < F; j += TT) dst.feat_len[fb + j] = 0;
+}
+
 }  // namespace
+
+cudaError_t launch_unobserved_cameras(const msckf_dims& d, const int* n_cams, const int* feat_len, const int* obs_slot,
+                                      const unsigned char* active, unsigned char* remove_mask, cudaStream_t s) {
+    unobserved_cameras_kernel<<<d.B, TT, 0, s>>>(d, n_cams, feat_len, obs_slot, active, remove_mask);
+    msckf_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_tracks(const msckf_dims& d, int drop_lost, const unsigned char* feat_status, void* const* src,
+                                  void* const* dst, unsigned char* active_out, cudaStream_t s) {
+    TrackSet a{(int*)src[0], (double*)src[1], (double*)src[2], (double*)src[3], (int*)src[4], (double*)src[5], (int*)src[6],
+               (double*)src[7], (double*)src[8], (int*)src[9], (int*)src[10]};
+    TrackSet b{(int*)dst[0], (double*)dst[1], (double*)dst[2], (double*)dst[3], (int*)dst[4], (double*)dst[5], (int*)dst[6],
+               (double*)dst[7], (double*)dst[8], (int*)dst[9], (int*)dst[10]};
+    compact_tracks_kernel<<<d.B, TT, (size_t)d.F * sizeof(int), s>>>(d, drop_lost, feat_status, a, b, active_out);
+    msckf_count_launch(1);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_host, const int* n_cams, const double* cam_R,
                                        const double* cam_t, const unsigned char* action, const double* new_uv,
@@ -196,9 +313,9 @@ cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_h
     return cudaGetLastError();
 }
 
-cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, const int* n_cams, const int* feat_len,
+cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, int prune_above, const int* n_cams, const int* feat_len,
                                   const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch, cudaStream_t s) {
-    select_poorest_kernel<<<d.B, TT, 0, s>>>(d, max_select, n_cams, feat_len, obs_slot, remove_mask, feat_touch);
+    select_poorest_kernel<<<d.B, TT, 0, s>>>(d, max_select, prune_above, n_cams, feat_len, obs_slot, remove_mask, feat_touch);
     msckf_count_launch(1);
     return cudaGetLastError();
 }

@@ -465,7 +465,7 @@ def test_whole_run_trace_chained_on_device(golden_dir, mode):
             code = flt.feat_status[0, :f].cpu().numpy() & 0xF
             assert (((code == 1) | (code == 2)) == c["out_valid"]).all()
             n_updates += int(flt.n_accepted[0]) > 0
-        else:
+        elif kind == 3:
             mask = torch.zeros((1, flt.N), dtype=torch.uint8, device="cuda")
             mk = tr["masks"][idx]
             mask[0, :len(mk)] = torch.from_numpy(mk.astype(np.uint8))
@@ -486,6 +486,73 @@ def test_whole_run_trace_chained_on_device(golden_dir, mode):
             assert worst < 1e-9, (boundaries[n + 1], errs)
     assert n_updates >= 40
     print("chained device replay, worst relative error over", len(tr["frames"]), "frames:", worst)
+
+
+def test_whole_run_resident_frame_loop(golden_dir):
+    """The whole camera-frame loop on the device (BatchedMSCKF.frame_step: propagation, state augmentation, track
+    bookkeeping, process_features with deletion of the lost tracks and of the unobserved cameras, pruning of the two
+    poorest cameras with its last update) driven only by the IMU samples and the matcher's decisions of a reference run:
+    after every camera frame the filter state AND the tracks (order, lengths, slots, counters, anchors) equal the
+    reference's."""
+    tr = o.load_trace(os.path.join(golden_dir, "small_trace.npz"))
+    ini, cases, apps = tr["init"], tr["cases"], tr["appends"]
+    F = max(len(a["action"]) for a in apps) + 1
+    M = max(c["obs_uv"].shape[1] for c in cases) + 1
+    N = tr["max_cams"] + 1
+    par = UpdateParams.from_case(cases[0], _lib.COMPRESS_GRAM)
+    par.gravity = np.array(ini["gravity"], float)
+    B = 2                                                   # two identical filters: the batch path, not a special case
+    flt = BatchedMSCKF(B, F, M, N, par)
+    flt.P.zero_()
+    flt.P[:, :15, :15] = torch.from_numpy(np.asarray(ini["P"], float))
+    flt.imu_state[:] = torch.from_numpy(np.concatenate([np.asarray(ini["imu_R"], float).flatten(), ini["imu_t"], ini["imu_v"],
+                                                        ini["imu_bg"], ini["imu_ba"]]))
+    flt.imu_null[:] = torch.from_numpy(np.concatenate([np.asarray(ini["null_R"], float).flatten(), ini["null_t"], ini["null_v"]]))
+    flt.imu_time[:] = float(ini["timestamp"])
+    flt.Qc_diag[:] = torch.from_numpy(np.asarray(ini["Qc_diag"], float)[[0, 3, 6, 9]].copy())
+    flt.n_cams.zero_()
+    flt.feat_len.zero_()
+    ops = tr["ops"]
+    first, worst, start = True, 0.0, 0
+    for i, fr in enumerate(tr["frames"]):
+        seg = ops[start:int(fr["op_index"])]
+        start = int(fr["op_index"])
+        smp = np.array([tr["samples"][idx] for kind, idx in seg if kind == 0], float)
+        app = [idx for kind, idx in seg if kind == 4]
+        assert sum(1 for kind, _ in seg if kind == 1) == 1 and len(app) == 1
+        a = apps[app[0]]
+        fa = len(a["action"])
+        action = torch.zeros((B, F), dtype=torch.uint8, device="cuda")
+        new_uv = torch.zeros((B, F, 2), dtype=torch.float64, device="cuda")
+        new_conf = torch.zeros((B, F), dtype=torch.float64, device="cuda")
+        action[:, :fa] = torch.from_numpy(a["action"]).cuda()
+        new_uv[:, :fa] = torch.from_numpy(a["new_uv"]).cuda()
+        new_conf[:, :fa] = torch.from_numpy(a["new_conf"]).cuda()
+        samples = torch.from_numpy(smp).reshape(1, -1, 7).repeat(B, 1, 1).cuda()
+        flt.frame_step(samples, ini["R_I_C"], ini["t_I_C"], action, new_uv, new_conf, tr["max_cams"], use_null_state=first)
+        first = False
+        torch.cuda.synchronize()
+        d = fr["P"].shape[0]
+        nc = (d - 15) // 6
+        nf = len(fr["feat_len"])
+        for b in range(B):
+            assert int(flt.n_cams[b]) == nc, (i, int(flt.n_cams[b]), nc)
+            ln = flt.feat_len[b].cpu().numpy()
+            assert (ln[:nf] == fr["feat_len"]).all() and (ln[nf:] == 0).all(), i
+            sl = flt.obs_slot[b].cpu().numpy()
+            for j in range(nf):
+                assert (sl[j, :ln[j]] == fr["obs_slot"][j, :ln[j]]).all(), (i, j)
+            assert (flt.lost_cnt[b, :nf].cpu().numpy() == fr["lost_cnt"]).all(), i
+            assert (flt.tracked_cnt[b, :nf].cpu().numpy() == fr["tracked_cnt"]).all(), i
+            assert (flt.idp_anchor_slot[b, :nf].cpu().numpy() == fr["idp_anchor_slot"]).all(), i
+            st = flt.imu_state[b].cpu().numpy()
+            errs = [rel_err(flt.P[b, :d, :d].cpu().numpy(), fr["P"]), rel_err(st[:9].reshape(3, 3), fr["imu_R"]),
+                    rel_err(st[9:12], fr["imu_t"]), rel_err(st[12:15], fr["imu_v"]), rel_err(st[15:18], fr["imu_bg"]),
+                    rel_err(st[18:21], fr["imu_ba"]), rel_err(flt.cam_R[b, :nc].cpu().numpy().reshape(nc, 3, 3), fr["cam_R"]),
+                    rel_err(flt.cam_t[b, :nc].cpu().numpy(), fr["cam_t"])]
+            worst = max(worst, max(errs))
+            assert worst < 1e-9, (i, errs)
+    print("resident frame loop, worst relative error over", len(tr["frames"]), "frames:", worst)
 
 
 def test_prune_flow_vs_oracle(golden_dir):
@@ -515,10 +582,12 @@ def test_prune_flow_vs_oracle(golden_dir):
         after = dict(c)
         after["cam_t"] = ref["out_cam_t"]
         tr = o.drop_observations(after, m_ref)
-        assert (flt.feat_len[b, :f].cpu().numpy() == tr["feat_len"]).all()
+        keep = np.nonzero(tr["feat_len"] > 0)[0]                 # tracks left empty are deleted, the others keep their order
+        ln = flt.feat_len[b].cpu().numpy()
+        assert (ln[:len(keep)] == tr["feat_len"][keep]).all() and (ln[len(keep):] == 0).all()
         sl = flt.obs_slot[b].cpu().numpy()
-        for j in range(f):
-            assert (sl[j, :tr["feat_len"][j]] == tr["obs_slot"][j, :tr["feat_len"][j]]).all()
+        for d, j in enumerate(keep):
+            assert (sl[d, :tr["feat_len"][j]] == tr["obs_slot"][j, :tr["feat_len"][j]]).all()
 
 
 @pytest.mark.parametrize("mode", MODES)

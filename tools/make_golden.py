@@ -354,6 +354,34 @@ class TraceCapture:
         f.process_imu, f.state_augmentation = self.imu, self.aug
         f.get_valid_features, f.update, f.remove_cameras = self.gvf, self.upd, self.rm
         self._pending = None
+        self.appends = []
+        self._o_add = f.add_camera_measurements
+        f.add_camera_measurements = self.add
+
+    def add(self, image, extracted_features=None):
+        """what add_camera_measurements did to the tracks (the matching itself is out of scope): kind-4 op"""
+        f = self.f
+        before = pack_tracks(f)
+        out = self._o_add(image, extracted_features)
+        after = pack_tracks(f)
+        Fb, Fa = len(before["feat_ids"]), len(after["feat_ids"])
+        assert list(after["feat_ids"][:Fb]) == list(before["feat_ids"])
+        action = np.zeros(Fa, np.uint8)
+        new_uv, new_conf = np.zeros((Fa, 2)), np.zeros(Fa)
+        for j in range(Fa):
+            n1 = int(after["feat_len"][j])
+            if j >= Fb:
+                action[j] = 3
+            elif n1 > int(before["feat_len"][j]):
+                action[j] = 2
+            elif int(after["lost_cnt"][j]) > int(before["lost_cnt"][j]):
+                action[j] = 1
+            if action[j] >= 2:
+                new_uv[j] = after["obs_uv"][j, n1 - 1]
+                new_conf[j] = after["obs_conf"][j, n1 - 1]
+        self.ops.append((4, len(self.appends)))
+        self.appends.append(dict(action=action, new_uv=new_uv, new_conf=new_conf, feat_ids=after["feat_ids"]))
+        return out
 
     def _state(self):
         f = self.f
@@ -414,7 +442,10 @@ class TraceCapture:
 
     def frame_done(self):
         st = self._state()
-        self.frames.append(dict(op_index=len(self.ops), **st))
+        trk = pack_tracks(self.f)
+        self.frames.append(dict(op_index=len(self.ops), feat_ids=trk["feat_ids"], feat_len=trk["feat_len"],
+                                obs_slot=trk["obs_slot"], lost_cnt=trk["lost_cnt"], tracked_cnt=trk["tracked_cnt"],
+                                idp_anchor_slot=trk["idp_anchor_slot"], **st))
 
 
 def fixture_trace(ns):
@@ -443,6 +474,11 @@ def fixture_trace(ns):
         flat["init." + k] = np.asarray(v)
     for i, m in enumerate(cap.masks):
         flat[f"m{i}"] = m
+    flat["n_appends"] = np.asarray(len(cap.appends))
+    for i, a in enumerate(cap.appends):
+        for k, v in a.items():
+            flat[f"a{i}.{k}"] = np.asarray(v)
+    flat["max_number_of_camera_states"] = np.asarray(int(f.max_number_of_camera_states))
     for i, c in enumerate(cap.cases):
         for k, v in c.items():
             flat[f"c{i}.{k}"] = np.asarray(v)
@@ -451,7 +487,7 @@ def fixture_trace(ns):
             flat[f"f{i}.{k}"] = np.asarray(v)
     path = os.path.join(GOLDEN, "small_trace.npz")
     np.savez_compressed(path, **flat)
-    kinds = np.bincount(np.array(cap.ops)[:, 0], minlength=4)
+    kinds = np.bincount(np.array(cap.ops)[:, 0], minlength=5)
     print(f"wrote {path}: {len(cap.ops)} ops (imu {kinds[0]}, augment {kinds[1]}, update {kinds[2]}, remove {kinds[3]}), "
           f"{len(cap.frames)} frames, {os.path.getsize(path) / 1e6:.2f} MB")
 
