@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 3
+#define MSCKF_B200_ABI_VERSION 4
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
