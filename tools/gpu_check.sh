@@ -13,4 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # one launch of every kernel of the step at the launch shape of the full-size run (1024 filters = one front-end sub-batch)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'propagate|front_asm|front_chol|gram_kernel|update_smem|update_info' -c 5 \
     -o $OUT/prof python bench.py --steps 1 --warmup 1 --filters 1024 --no-cpu > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 300 python tools/tracks_probe.py 4096 > $OUT/tracks_probe.txt 2>&1; tail -9 $OUT/tracks_probe.txt
 ls -la $OUT
