@@ -76,12 +76,15 @@ __global__ void __launch_bounds__(WT) augment_kernel(msckf_dims dims, const doub
     if (tid == 0) n_cams[b] = n + 1;
 }
 
+constexpr int RCH = 16;
+
 __global__ void __launch_bounds__(WT) remove_kernel(msckf_dims dims, const unsigned char* __restrict__ mask, double* cam_R,
                                                     double* cam_t, double* Pall, int* n_cams, double* scratch) {
     const int tid = threadIdx.x;
     const int ldp = dims.ldp;
     __shared__ int keep[128];
     __shared__ int s_nkeep;
+    extern __shared__ double rows[];            // [RCH][d] staging of the rows being moved
     double* tmp = scratch + (size_t)blockIdx.x * ldp * ldp;
     for (int b = blockIdx.x; b < dims.B; b += gridDim.x) {
         const int n = n_cams[b];
@@ -95,21 +98,25 @@ __global__ void __launch_bounds__(WT) remove_kernel(msckf_dims dims, const unsig
         const int nk = s_nkeep;
         if (nk != n) {
             double* P = Pall + (size_t)b * ldp * ldp;
-            const int d = 15 + 6 * n, dn = 15 + 6 * nk;
-            for (int e = tid; e < d * d; e += WT) tmp[e] = P[(size_t)(e / d) * ldp + (e % d)];
-            __syncthreads();
-            for (int e = tid; e < dn * dn; e += WT) {
-                const int i = e / dn, j = e - i * dn;
-                const int si = i < 15 ? i : 15 + 6 * keep[(i - 15) / 6] + (i - 15) % 6;
-                const int sj = j < 15 ? j : 15 + 6 * keep[(j - 15) / 6] + (j - 15) % 6;
-                P[(size_t)i * ldp + j] = tmp[(size_t)si * d + sj];
+            const int dn = 15 + 6 * nk;
+            // In place, one pass: destination rows in increasing order, RCH rows at a time through shared memory.  A
+            // destination element (i, j) comes from (si, sj) with si >= i, sj >= j, so a chunk only overwrites rows whose
+            // content has already been consumed (by an earlier chunk, or by the loads of this chunk before the barrier).
+            for (int i0 = 0; i0 < dn; i0 += RCH) {
+                const int nr = min(RCH, dn - i0);
+                for (int e = tid; e < nr * dn; e += WT) {
+                    const int i = i0 + e / dn, j = e % dn;
+                    const int si = i < 15 ? i : 15 + 6 * keep[(i - 15) / 6] + (i - 15) % 6;
+                    const int sj = j < 15 ? j : 15 + 6 * keep[(j - 15) / 6] + (j - 15) % 6;
+                    rows[e] = P[(size_t)si * ldp + sj];
+                }
+                __syncthreads();
+                for (int e = tid; e < nr * dn; e += WT) P[(size_t)(i0 + e / dn) * ldp + e % dn] = rows[e];
+                __syncthreads();
             }
             // poses: compact through the scratch as well
-            double* pr = tmp + (size_t)d * d;
-            __syncthreads();
             for (int e = tid; e < n * 9; e += WT) tmp[e] = cam_R[(size_t)b * dims.N * 9 + e];
             for (int e = tid; e < n * 3; e += WT) tmp[n * 9 + e] = cam_t[(size_t)b * dims.N * 3 + e];
-            (void)pr;
             __syncthreads();
             for (int e = tid; e < nk * 9; e += WT) cam_R[(size_t)b * dims.N * 9 + e] = tmp[keep[e / 9] * 9 + e % 9];
             for (int e = tid; e < nk * 3; e += WT) cam_t[(size_t)b * dims.N * 3 + e] = tmp[n * 9 + keep[e / 3] * 3 + e % 3];
@@ -132,7 +139,14 @@ cudaError_t launch_augment(const msckf_dims& d, const double* T, const double* i
 cudaError_t launch_remove(const msckf_dims& d, const unsigned char* mask, double* cam_R, double* cam_t, double* P,
                           int* n_cams, double* scratch, cudaStream_t s) {
     const int ctas = d.B < 148 * 4 ? d.B : 148 * 4;
-    remove_kernel<<<ctas, WT, 0, s>>>(d, mask, cam_R, cam_t, P, n_cams, scratch);
+    const size_t smem = (size_t)RCH * (15 + 6 * d.N) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(remove_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    remove_kernel<<<ctas, WT, smem, s>>>(d, mask, cam_R, cam_t, P, n_cams, scratch);
     msckf_count_launch(1);
     return cudaGetLastError();
 }
