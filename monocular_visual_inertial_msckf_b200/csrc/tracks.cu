@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(TT) compact_tracks_kernel(msckf_dims dims, int
         __syncthreads();
         lost_rule = s_any != 0;
     }
-    if (tid == 0 && active_out) active_out[b] = lost_rule ? 1 : 0;
+    if (tid == 0 && active_out && blockIdx.y == 0) active_out[b] = lost_rule ? 1 : 0;
     for (int j0 = 0; j0 < F; j0 += TT) {          // block-wide exclusive scan of the keep flags, TT slots at a time
         const int j = j0 + tid;
         int keep = 0;
@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(TT) compact_tracks_kernel(msckf_dims dims, int
         __syncthreads();
     }
     const int n_kept = s_base;
-    for (int j = warp; j < F; j += TT / 32) {      // one warp per track
+    // every CTA of the filter repeats the (cheap) scan above and moves its own slice of the tracks
+    for (int j = blockIdx.y * (TT / 32) + warp; j < F; j += gridDim.y * (TT / 32)) {      // one warp per track
         const int d = s_dest[j];
         if (d < 0) continue;
         const size_t sj = fb + j, dj = fb + d;
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(TT) compact_tracks_kernel(msckf_dims dims, int
         }
         if (lane < 3) { dst.idp_base[dj * 3 + lane] = src.idp_base[sj * 3 + lane]; dst.idp_m[dj * 3 + lane] = src.idp_m[sj * 3 + lane]; }
     }
-    for (int j = n_kept + tid; j < F; j += TT) dst.feat_len[fb + j] = 0;
+    if (blockIdx.y == 0)
+        for (int j = n_kept + tid; j < F; j += TT) dst.feat_len[fb + j] = 0;
 }
 
 }  // namespace
@@ -292,7 +294,10 @@ cudaError_t launch_compact_tracks(const msckf_dims& d, int drop_lost, const unsi
                (double*)src[7], (double*)src[8], (int*)src[9], (int*)src[10]};
     TrackSet b{(int*)dst[0], (double*)dst[1], (double*)dst[2], (double*)dst[3], (int*)dst[4], (double*)dst[5], (int*)dst[6],
                (double*)dst[7], (double*)dst[8], (int*)dst[9], (int*)dst[10]};
-    compact_tracks_kernel<<<d.B, TT, (size_t)d.F * sizeof(int), s>>>(d, drop_lost, feat_status, a, b, active_out);
+    int slices = (d.F + 63) / 64;                       // ~64 tracks (8 per warp) per CTA
+    if (slices < 1) slices = 1;
+    if (slices > 16) slices = 16;
+    compact_tracks_kernel<<<dim3(d.B, slices), TT, (size_t)d.F * sizeof(int), s>>>(d, drop_lost, feat_status, a, b, active_out);
     msckf_count_launch(1);
     return cudaGetLastError();
 }
