@@ -231,14 +231,15 @@ int msckf_unobserved_cameras_batched(const msckf_dims* dims, const int* n_cams, 
  * order, to the front of a SECOND set of track arrays (the caller swaps the two sets); the rest of dst gets feat_len 0.
  * drop_lost = 0: only empty slots (feat_len 0) go.  drop_lost = 1: in filters whose last update had at least one valid
  * feature (feat_status ACCEPTED / GATED_OUT) the tracks flagged MSCKF_FEAT_LOST_FLAG go too (process_features,
- * MSCKF.py:450-456); active_out[b] (may be NULL) = 1 for those filters. */
+ * MSCKF.py:450-456); active_out[b] (may be NULL) = 1 for those filters.  dest_out[B][F] (may be NULL) receives the new
+ * slot of every old slot, -1 for a deleted track, so that a caller can keep its own per-track records aligned. */
 typedef struct msckf_track_arrays {
     int* feat_len; double* obs_uv; double* obs_dir; double* obs_conf; int* obs_slot; double* idp_base; int* idp_anchor_slot;
     double* idp_m; double* idp_rho; int* lost_cnt; int* tracked_cnt;
 } msckf_track_arrays;
 int msckf_compact_tracks_batched(const msckf_dims* dims, int drop_lost, const unsigned char* feat_status,
                                  const msckf_track_arrays* src, const msckf_track_arrays* dst, unsigned char* active_out,
-                                 void* stream);
+                                 int* dest_out, void* stream);
 int msckf_drop_observations_batched(const msckf_dims* dims, const unsigned char* remove_mask, const int* n_cams,
                                     const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
                                     int* obs_slot, double* idp_base, int* idp_anchor_slot, void* stream);

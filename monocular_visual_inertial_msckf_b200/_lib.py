@@ -123,7 +123,7 @@ def load_library():
     lib.msckf_unobserved_cameras_batched.restype = C.c_int
     lib.msckf_unobserved_cameras_batched.argtypes = [pd, ip, ip, ip, u8, u8, vp]
     lib.msckf_compact_tracks_batched.restype = C.c_int
-    lib.msckf_compact_tracks_batched.argtypes = [pd, C.c_int, u8, C.POINTER(TrackArrays), C.POINTER(TrackArrays), u8, vp]
+    lib.msckf_compact_tracks_batched.argtypes = [pd, C.c_int, u8, C.POINTER(TrackArrays), C.POINTER(TrackArrays), u8, ip, vp]
     lib.msckf_drop_observations_batched.restype = C.c_int
     lib.msckf_drop_observations_batched.argtypes = [pd, u8, ip, dp, ip, dp, dp, dp, ip, dp, ip, vp]
     lib.msckf_append_observations_batched.restype = C.c_int

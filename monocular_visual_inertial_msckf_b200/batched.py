@@ -296,22 +296,24 @@ class BatchedMSCKF:
             setattr(st, n, tensors[n].data_ptr())
         return st
 
-    def compact_tracks(self, drop_lost=False):
+    def compact_tracks(self, drop_lost=False, return_map=False):
         """Stable compaction of the track slots (MSCKF.remove_features / the track deletions of remove_cameras): the
         survivors move, in order, to the front of a second set of track arrays, which then becomes the current one.
-        Returns active [B] uint8 (drop_lost: filters that deleted their lost tracks)."""
+        Returns active [B] uint8 (drop_lost: filters that deleted their lost tracks); with return_map also dest [B, F]
+        int32: the new slot of every old slot, -1 for a deleted track."""
         cur = {n: getattr(self, n) for n in _lib.TRACK_FIELDS}
         if self._alt_tracks is None:
             self._alt_tracks = {n: torch.zeros_like(t) for n, t in cur.items()}
         active = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
+        dest = torch.empty((self.B, self.F), dtype=torch.int32, device=self.device) if return_map else None
         a, b = self._track_struct(cur), self._track_struct(self._alt_tracks)
         rc = self.lib.msckf_compact_tracks_batched(C.byref(self.dims), int(bool(drop_lost)), _ptr(self.feat_status), C.byref(a),
-                                                   C.byref(b), _ptr(active), self._stream())
+                                                   C.byref(b), _ptr(active), _ptr(dest), self._stream())
         _lib.check(rc, "msckf_compact_tracks_batched")
         for n in _lib.TRACK_FIELDS:
             setattr(self, n, self._alt_tracks[n])
         self._alt_tracks = cur
-        return active
+        return (active, dest) if return_map else active
 
     def unobserved_cameras(self, active=None):
         """MSCKF.get_cameras_without_features (MSCKF.py:739-749): [B, N] uint8 mask of the window slots no track observes."""
@@ -321,27 +323,33 @@ class BatchedMSCKF:
         _lib.check(rc, "msckf_unobserved_cameras_batched")
         return mask
 
-    def process_features(self):
+    def process_features(self, return_map=False):
         """MSCKF.process_features (MSCKF.py:450-456) on resident tracks: one update with every track; filters that had a
         valid feature then delete their lost tracks (remove_features) and the cameras nothing observes any more."""
         self.update()
-        active = self.compact_tracks(drop_lost=True)
+        active = self.compact_tracks(drop_lost=True, return_map=return_map)
+        dest = None
+        if return_map:
+            active, dest = active
         mask = self.unobserved_cameras(active)
         self.drop_observations(mask)          # renumbers the slots of the surviving observations
         self.remove_cameras(mask)
+        return dest
 
-    def frame_step(self, samples, R_I_C, t_I_C, action, new_uv, new_conf, max_cameras, use_null_state=False):
+    def frame_step(self, samples, R_I_C, t_I_C, action, new_uv, new_conf, max_cameras, use_null_state=False, return_maps=False):
         """One camera frame of every filter with everything resident (MSCKF.imu_callback x n + feature_callback,
         MSCKF.py:135-158): the IMU samples since the last frame, state_augmentation, the track bookkeeping of
         add_camera_measurements (the matcher's decisions come from the caller), process_features, and the pruning of the
-        two poorest cameras in the filters whose window exceeds max_cameras."""
+        two poorest cameras in the filters whose window exceeds max_cameras.  With return_maps: the two slot maps
+        ([B, F] int32, -1 = deleted) of the track deletions, for callers that keep per-track records of their own."""
         self.propagate(samples, use_null_state=use_null_state)
         self.augment(R_I_C, t_I_C)
         self.append_observations(action, new_uv, new_conf)
-        self.process_features()
-        self.prune_poorest_camera_states(prune_above=max_cameras)
+        m1 = self.process_features(return_map=return_maps)
+        m2 = self.prune_poorest_camera_states(prune_above=max_cameras, return_map=return_maps)
+        return (m1, m2) if return_maps else None
 
-    def prune_poorest_camera_states(self, max_select=2, prune_above=-1):
+    def prune_poorest_camera_states(self, max_select=2, prune_above=-1, return_map=False):
         """MSCKF.prune_poorest_camera_states (MSCKF.py:710-737) for every filter, everything resident: select the two
         cameras with the fewest observations, one last update with the tracks that observe them, then delete those
         cameras from the tracks, the window and the covariance.  Returns the (remove_mask, feat_touch) that were used."""
@@ -352,8 +360,8 @@ class BatchedMSCKF:
         self.feat_len.copy_(full_len)
         self.drop_observations(mask)
         self.remove_cameras(mask)
-        self.compact_tracks(drop_lost=False)               # tracks left without observations are deleted (MSCKF.py:768-772)
-        return mask, touch
+        out = self.compact_tracks(drop_lost=False, return_map=return_map)   # tracks left without observations are deleted (MSCKF.py:768-772)
+        return out[1] if return_map else (mask, touch)
 
     # ------------------------------------------------------------------------------------------------------------
     def load_cases(self, cases):

@@ -24,7 +24,7 @@ cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, int prune
 cudaError_t launch_unobserved_cameras(const msckf_dims& d, const int* n_cams, const int* feat_len, const int* obs_slot,
                                       const unsigned char* active, unsigned char* remove_mask, cudaStream_t s);
 cudaError_t launch_compact_tracks(const msckf_dims& d, int drop_lost, const unsigned char* feat_status, void* const* src,
-                                  void* const* dst, unsigned char* active_out, cudaStream_t s);
+                                  void* const* dst, unsigned char* active_out, int* dest_out, cudaStream_t s);
 cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_host, const int* n_cams, const double* cam_R,
                                        const double* cam_t, const unsigned char* action, const double* new_uv,
                                        const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
@@ -249,7 +249,7 @@ int msckf_unobserved_cameras_batched(const msckf_dims* dims, const int* n_cams, 
 
 int msckf_compact_tracks_batched(const msckf_dims* dims, int drop_lost, const unsigned char* feat_status,
                                  const msckf_track_arrays* src, const msckf_track_arrays* dst, unsigned char* active_out,
-                                 void* stream) {
+                                 int* dest_out, void* stream) {
     int rc = check_dims(dims);
     if (rc) return rc;
     if (!src || !dst || (drop_lost && !feat_status)) return MSCKF_EINVAL;
@@ -259,7 +259,7 @@ int msckf_compact_tracks_batched(const msckf_dims* dims, int drop_lost, const un
         if (!ps[k] || !pq[k] || ps[k] == pq[k]) return MSCKF_EINVAL;
     if ((size_t)dims->F * sizeof(int) > 48 * 1024) return MSCKF_ECAPACITY;
     return (int)launch_compact_tracks(*dims, drop_lost, feat_status, (void* const*)src, (void* const*)dst, active_out,
-                                      (cudaStream_t)stream);
+                                      dest_out, (cudaStream_t)stream);
 }
 
 int msckf_append_observations_batched(const msckf_dims* dims, const double* Kinv_host, const int* n_cams, const double* cam_R,

@@ -216,7 +216,8 @@ struct TrackSet {
     double* idp_m; double* idp_rho; int* lost_cnt; int* tracked_cnt;
 };
 __global__ void __launch_bounds__(TT) compact_tracks_kernel(msckf_dims dims, int drop_lost, const unsigned char* __restrict__ feat_status,
-                                                            TrackSet src, TrackSet dst, unsigned char* __restrict__ active_out) {
+                                                            TrackSet src, TrackSet dst, unsigned char* __restrict__ active_out,
+                                                            int* __restrict__ dest_out) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = dims.F, M = dims.M;
     extern __shared__ int s_dest[];            // [F] destination slot of each surviving track, -1 otherwise
@@ -252,6 +253,8 @@ __global__ void __launch_bounds__(TT) compact_tracks_kernel(msckf_dims dims, int
         __syncthreads();
     }
     const int n_kept = s_base;
+    if (dest_out && blockIdx.y == 0)
+        for (int j = tid; j < F; j += TT) dest_out[fb + j] = s_dest[j];
     // every CTA of the filter repeats the (cheap) scan above and moves its own slice of the tracks
     for (int j = blockIdx.y * (TT / 32) + warp; j < F; j += gridDim.y * (TT / 32)) {      // one warp per track
         const int d = s_dest[j];
@@ -289,7 +292,7 @@ cudaError_t launch_unobserved_cameras(const msckf_dims& d, const int* n_cams, co
 }
 
 cudaError_t launch_compact_tracks(const msckf_dims& d, int drop_lost, const unsigned char* feat_status, void* const* src,
-                                  void* const* dst, unsigned char* active_out, cudaStream_t s) {
+                                  void* const* dst, unsigned char* active_out, int* dest_out, cudaStream_t s) {
     TrackSet a{(int*)src[0], (double*)src[1], (double*)src[2], (double*)src[3], (int*)src[4], (double*)src[5], (int*)src[6],
                (double*)src[7], (double*)src[8], (int*)src[9], (int*)src[10]};
     TrackSet b{(int*)dst[0], (double*)dst[1], (double*)dst[2], (double*)dst[3], (int*)dst[4], (double*)dst[5], (int*)dst[6],
@@ -297,7 +300,7 @@ cudaError_t launch_compact_tracks(const msckf_dims& d, int drop_lost, const unsi
     int slices = (d.F + 63) / 64;                       // ~64 tracks (8 per warp) per CTA
     if (slices < 1) slices = 1;
     if (slices > 16) slices = 16;
-    compact_tracks_kernel<<<dim3(d.B, slices), TT, (size_t)d.F * sizeof(int), s>>>(d, drop_lost, feat_status, a, b, active_out);
+    compact_tracks_kernel<<<dim3(d.B, slices), TT, (size_t)d.F * sizeof(int), s>>>(d, drop_lost, feat_status, a, b, active_out, dest_out);
     msckf_count_launch(1);
     return cudaGetLastError();
 }

@@ -555,6 +555,20 @@ def test_whole_run_resident_frame_loop(golden_dir):
     print("resident frame loop, worst relative error over", len(tr["frames"]), "frames:", worst)
 
 
+def test_monte_carlo_sequences_resident():
+    """Six independent synthetic sequences (two seeds per IMU-noise level) run for 30 camera frames with everything
+    resident (monte_carlo.run_monte_carlo): the host's track records stay in step with the device through every
+    deletion (asserted inside), the windows respect their maximum, and the trajectories follow the ground truth."""
+    from monocular_visual_inertial_msckf_b200.monte_carlo import run_monte_carlo
+    res = run_monte_carlo(list(range(6)), n_frames=30, n_landmarks=40, window=8)
+    assert np.isfinite(res.positions).all()
+    assert (res.n_cams <= 9).all() and (res.n_cams[:, -1] >= 7).all()
+    assert (res.n_tracks[:, 5:] >= 20).all()
+    travelled = np.linalg.norm(np.diff(res.gt_positions, axis=1), axis=2).sum(axis=1)
+    print("ATE rmse [m]:", np.round(res.ate_rmse, 4), "path length [m]:", np.round(travelled, 2))
+    assert (res.ate_rmse < 0.05 * np.maximum(travelled, 1.0)).all()
+
+
 def test_prune_flow_vs_oracle(golden_dir):
     """prune_poorest_camera_states end to end on resident state (select -> update with the touched tracks -> drop ->
     remove) against the oracle's composition of the same reference steps."""
