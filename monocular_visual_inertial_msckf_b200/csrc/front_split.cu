@@ -73,9 +73,19 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
             const int ba = row / 6, r = row - 6 * ba;
             const double* Prow = P + (size_t)(15 + row) * ldp + 15;
             double* dst = sP + (size_t)tile_index(ba, 0) * PB + r * 6;
-            for (int col = lane; col < 6 * ba + 6; col += 32) {
+            // (all the loads of the row first: a load -> store pair per iteration leaves the global latency exposed)
+            constexpr int CU = (6 * 32 + 31) / 32;     // rows of the supported windows (N <= 32) span at most 6 x 32 columns
+            double pv[CU];
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
+                const int col = lane + 32 * u;
+                pv[u] = (col < 6 * ba + 6) ? Prow[col] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
+                const int col = lane + 32 * u;
                 const int bb = col / 6;
-                dst[bb * PB + (col - 6 * bb)] = Prow[col];
+                if (col < 6 * ba + 6) dst[bb * PB + (col - 6 * bb)] = pv[u];
             }
         }
         const double* camR = a.cam_R + (size_t)b * Ncap * 9;
