@@ -8,17 +8,23 @@
 // the camera block of P occupies the SM's shared memory: 255 registers x 8 warps, two warps per scheduler, and every
 // phase of it is latency-bound (profiles/r01n).  Here the two halves get the resources each one needs:
 //
-//   front_asm_kernel   CTA = (filter, feature chunk), 16 warps, <= 128 registers.  P's camera block (lower block triangle,
-//                      6x6 blocks padded to 38 doubles -> conflict-free 16-byte reads) + window poses staged once per CTA.
-//                      Per feature (one warp, lane = observation): geometry, factors for the compression stage, then the
-//                      M (M + 1) / 2 lower 2x2 blocks  A_i P[s_i, s_k] A_k^T  as a FLAT list, one block per lane per pass
-//                      (97 % lane use at M = 30), stored straight into the accumulator-fragment tile layout of the FP64
-//                      tensor instruction in a global (L2 / HBM) buffer: 20 KB per feature, written once, read once.
-//   front_chol_kernel  one warp per pending feature, 16 warps per SM, <= 128 registers: loads the 36 tiles (coalesced
-//                      16-byte loads), register-resident blocked Cholesky with the appended rows [r~; Q1^T]
-//                      (DMMA.8x8x4 panel solves / trailing updates, shuffles inside the 8x8 diagonal tiles), fully
-//                      unrolled over the block column with the matrix aligned to the bottom-right corner so that every
-//                      register index is static and no tile is ever moved;  gamma and the gate decision.
+//   front_asm_kernel   CTA = (filter, feature chunk: a whole filter when the batch fills the machine), 16 warps, <= 128
+//                      registers.  P's camera block (lower block triangle, 6x6 blocks padded to 38 doubles -> conflict-free
+//                      16-byte reads) + window poses staged once per CTA.  Per feature (one warp, lane = observation):
+//                      geometry (front_geom.cuh), factors for the compression stage, then the M (M + 1) / 2 lower 2x2
+//                      blocks  A_i P[s_i, s_k] A_k^T  as a FLAT list, one block per lane per pass (97 % lane use at
+//                      M = 30), stored straight into the accumulator-fragment tile layout of the FP64 tensor instruction
+//                      in a global (L2 / HBM) buffer.  The four appended rows [r~; Q1^T] are ordinary rows of the padded
+//                      matrix (they fill the padding rows of the last tile row at M = 30): 18 KB per feature, written
+//                      once, read once.  The warps of a CTA start staggered so that the geometry phases of some overlap
+//                      the shared-memory-bound pair loops of the others.
+//   front_chol_kernel  one warp per pending feature, 16 warps per SM, <= 128 registers: LEFT-looking blocked Cholesky
+//                      over 8x8 tiles in accumulator-fragment layout (DMMA.8x8x4 updates / panel solves, shuffles inside
+//                      the diagonal tiles); only the finished tiles still needed and the current block column are live,
+//                      the next block column's tiles are in flight (coalesced 16-byte loads); fully unrolled per tile
+//                      count with the matrix aligned to the bottom-right corner, so every register index is static and no
+//                      tile is ever moved.  The block under the appended rows ends up holding minus the Gram matrix of
+//                      [y; V]: gamma and the gate decision follow.
 //
 // gamma = y.y - (V^T y)^T (V^T V)^-1 (V^T y),  y = L^-1 r~,  V = L^-1 Q1  (basis-free form of the projected Mahalanobis
 // distance).
