@@ -261,13 +261,15 @@ __global__ void __launch_bounds__(TT) compact_tracks_kernel(msckf_dims dims, int
         if (d < 0) continue;
         const size_t sj = fb + j, dj = fb + d;
         const int n = min(src.feat_len[sj], M);
-        for (int i = lane; i < n; i += 32) {
-            const size_t se = sj * M + i, de = dj * M + i;
-            dst.obs_uv[de * 2] = src.obs_uv[se * 2]; dst.obs_uv[de * 2 + 1] = src.obs_uv[se * 2 + 1];
-            dst.obs_dir[de * 3] = src.obs_dir[se * 3]; dst.obs_dir[de * 3 + 1] = src.obs_dir[se * 3 + 1];
-            dst.obs_dir[de * 3 + 2] = src.obs_dir[se * 3 + 2];
-            dst.obs_conf[de] = src.obs_conf[se];
-            dst.obs_slot[de] = src.obs_slot[se];
+        // every array of a track is one contiguous range: linear, fully coalesced copies
+        {
+            const double* su = src.obs_uv + sj * M * 2; double* du = dst.obs_uv + dj * M * 2;
+            for (int x = lane; x < 2 * n; x += 32) du[x] = su[x];
+            const double* sd = src.obs_dir + sj * M * 3; double* dd = dst.obs_dir + dj * M * 3;
+            for (int x = lane; x < 3 * n; x += 32) dd[x] = sd[x];
+            const double* sc = src.obs_conf + sj * M; double* dc = dst.obs_conf + dj * M;
+            const int* ss = src.obs_slot + sj * M; int* ds = dst.obs_slot + dj * M;
+            for (int x = lane; x < n; x += 32) { dc[x] = sc[x]; ds[x] = ss[x]; }
         }
         if (lane == 0) {
             dst.feat_len[dj] = n;
