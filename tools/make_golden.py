@@ -516,6 +516,111 @@ def fixture_prune(ns):
     save_cases(os.path.join(GOLDEN, "small_track_append.npz"), cap.append_cases[::2], extra)
 
 
+class MatchCapture:
+    """add_camera_measurements with the geometric tests ENABLED (MSCKF.py:317-404): what the matcher was given and
+    returned (FeatureExtractor.match), which proposals survived the epipolar / homography walk, and the increments of the
+    reference's two discard counters."""
+
+    def __init__(self, f):
+        self.f = f
+        self.cases = []
+        self._orig_add = f.add_camera_measurements
+        self._orig_match = f.feature_extractor.match
+        f.add_camera_measurements = self.add
+        f.feature_extractor.match = self.match
+        self._m = None
+
+    def match(self, in1, in2, min_cossim=0.82):
+        out = self._orig_match(in1, in2, min_cossim)
+        matched, not_matched, (i1, i2, n1, n2) = out
+        self._m = dict(desc_tracks=np.array(in1.descriptors), desc_new=np.array(in2.descriptors),
+                       track_ids=np.array(in1.features_indices, np.int64), min_cossim=float(min_cossim),
+                       idxs1=np.asarray(i1, np.int64), idxs2=np.asarray(i2, np.int64),
+                       kp_new=np.array(in2.keypoints, float), sc_new=np.array(in2.scores, float))
+        return out
+
+    def add(self, image, extracted_features=None):
+        f = self.f
+        before = pack_tracks(f)
+        nh0, ne0 = f.number_of_features_discarder_for_homography_test, f.number_of_features_discarded_for_epipolar_test
+        self._m = None
+        out = self._orig_add(image, extracted_features)
+        m = self._m
+        if m is None:
+            return out
+        after = pack_tracks(f)
+        Fb = len(before["feat_ids"])
+        c = {k: before[k] for k in ("n_cams", "cam_R", "cam_t", "feat_ids", "feat_len", "obs_uv", "obs_slot", "lost_cnt")}
+        c["K"] = np.array(f.K, float)
+        c["Kinv"] = np.linalg.inv(f.K)
+        c["epipolar_rejection_threshold"] = float(f.epipolar_rejection_threshold)
+        c["homography_rejection_threshold"] = float(f.homography_rejection_threshold)
+        c["call_index"] = len(self.cases)
+        assert list(m["track_ids"]) == list(before["feat_ids"])          # matcher rows are the tracks in dict order
+        action = np.zeros(Fb, np.uint8)
+        new_uv = np.zeros((Fb, 2))
+        new_conf = np.zeros(Fb)
+        action[:] = 1                                                     # not matched: lost this frame (:437)
+        action[m["idxs1"]] = 2
+        new_uv[m["idxs1"]] = m["kp_new"][m["idxs2"]]
+        new_conf[m["idxs1"]] = m["sc_new"][m["idxs2"]]
+        passed = after["feat_len"][:Fb] > before["feat_len"]
+        assert not (passed & (action != 2)).any()
+        c.update(action=action, new_uv=new_uv, new_conf=new_conf, out_passed=passed,
+                 out_lost_cnt=after["lost_cnt"][:Fb],
+                 out_n_homography=f.number_of_features_discarder_for_homography_test - nh0,
+                 out_n_epipolar=f.number_of_features_discarded_for_epipolar_test - ne0)
+        for k in ("desc_tracks", "desc_new", "min_cossim", "idxs1", "idxs2"):
+            c["match_" + k] = m[k]
+        self.cases.append(c)
+        return out
+
+
+def fixture_match(ns):
+    """Geometric verification + matcher cases: the `small` stream with the reference's tests switched on (the other
+    fixtures run with both thresholds at 1e9), a slow start so that the homography branch (baseline < 1 cm) is taken, and
+    direct calls of the reference's XFeat.match on float32 64-dimensional descriptor sets."""
+    kw = dict(seed=42, n_frames=40, n_landmarks=40, noise_level="mid", p_drop=0.06, p_outlier=0.08, shuffle=True)
+    seq = synth.make_sequence(**kw)
+    fp = dict(min_parallax=2.0, max_number_of_camera_states=8, epipolar_rejection_threshold=0.002,
+              homography_rejection_threshold=0.15, min_number_of_frames_to_be_tracked=3)
+    params, pd = make_params(ns, seq, **fp)
+    f = ns.MSCKF(parameters=params, rr=None)
+    cap = MatchCapture(f)
+    image = np.zeros((seq.height, seq.width, 3), np.uint8)
+    frame_at = {fr.imu_index: fr for fr in seq.frames}
+    for i in range(len(seq.imu)):
+        row = seq.imu[i]
+        f.imu_callback(ns.IMUMeasurement(row[0], row[1:4].copy(), row[4:7].copy()))
+        fr = frame_at.get(i)
+        if fr is not None:
+            f.feature_callback(image, ns.CameraMeasurement(keypoints=fr.keypoints.copy(), descriptors=fr.descriptors.copy(),
+                                                           scores=fr.scores.copy()))
+    nh = sum(int(c["out_n_homography"]) for c in cap.cases)
+    ne = sum(int(c["out_n_epipolar"]) for c in cap.cases)
+    npass = sum(int(c["out_passed"].sum()) for c in cap.cases)
+    print(f"match fixture: {len(cap.cases)} frames, passed {npass}, homography rejections {nh}, epipolar rejections {ne}")
+    extra = seq_spec(**kw)
+    # the reference's matcher on XFeat-like inputs: float32, 64 dimensions, noisy re-detections, distractors, permutation
+    rng = np.random.default_rng(7)
+    xf = f.feature_extractor.xfeat
+    import torch
+    for t, (n1, n2, noise, thr) in enumerate([(40, 48, 0.05, 0.82), (256, 300, 0.6, 0.82), (300, 256, 0.45, 0.9),
+                                              (64, 64, 0.9, 0.82), (17, 5, 1.2, 0.0), (1, 9, 0.02, 0.82)]):
+        base = rng.standard_normal((max(n1, n2), 64))
+        base /= np.linalg.norm(base, axis=1, keepdims=True)
+        d1 = base[:n1].astype(np.float32)
+        perm = rng.permutation(max(n1, n2))[:n2]
+        d2 = base[perm] + noise * rng.standard_normal((n2, 64)) / 8.0
+        d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)
+        i0, i1 = xf.match(torch.from_numpy(d1), torch.from_numpy(d2), min_cossim=thr)
+        extra[f"xm{t}.d1"], extra[f"xm{t}.d2"], extra[f"xm{t}.thr"] = d1, d2, np.asarray(thr)
+        extra[f"xm{t}.idx0"], extra[f"xm{t}.idx1"] = i0.numpy().astype(np.int64), i1.numpy().astype(np.int64)
+        print(f"  xfeat.match set {t}: {n1} x {n2}, {len(i0)} matches")
+    extra["n_xm"] = np.asarray(6)
+    save_cases(os.path.join(GOLDEN, "small_match_verify.npz"), cap.cases, extra)
+
+
 def make_params(ns, seq, **kw):
     sa, sg, sba, sbg = synth.NOISE_LEVELS[seq.noise_level]
     p = dict(K=seq.K, width=seq.width, height=seq.height, sigma_image=0.1, only_imu=False,
@@ -621,6 +726,8 @@ if __name__ == "__main__":
         fixture_prune(ns)
     if args.only in (None, "trace"):
         fixture_trace(ns)
+    if args.only in (None, "match"):
+        fixture_match(ns)
     if args.only in (None, "mid"):
         # mid-size steady-state fixture (cheap to regenerate): F = 48, window 10
         KEEP_FROM[:] = [18, 14 * 9]
