@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 4
+#define MSCKF_B200_ABI_VERSION 5
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
@@ -215,6 +215,44 @@ int msckf_append_observations_batched(const msckf_dims* dims, const double* Kinv
                                       const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
                                       int* obs_slot, double* idp_base, int* idp_anchor_slot, double* idp_m, double* idp_rho,
                                       int* lost_cnt, int* tracked_cnt, int* overflow_count, void* stream);
+/* ---------------------------------------------------------------------------------------------------------------
+ * Matching front of add_camera_measurements, per filter and camera frame:
+ *
+ * msckf_match_descriptors_batched  <->  FeatureExtractor.match (src/msckf/FeatureExtractor.py:62-84) = XFeat.match
+ *   (src/accelerated_features/modules/xfeat.py:327-348): cossim = D1 D2^T in FP32, match12 = first row arg-max,
+ *   match21 = first row arg-max of D2 D1^T, kept where mutual and (min_cossim <= 0 or the row maximum > min_cossim).
+ *   desc_tracks[B][F_tracks][D] (rows 0 .. n_tracks[b]-1 are the filter's tracks in slot order = the reference's dict order;
+ *   the running weighted descriptor average of MSCKF.py:439 is supplied by the caller), desc_new[B][F_new][D] (the frame's
+ *   detections, rows 0 .. n_new[b]-1); n_tracks / n_new may be NULL (= full capacity).  D in {32, 64, 128}; both sets of
+ *   one filter must fit the shared memory of one SM ((F_tracks + F_new) (D + 4) 4 B + indices <= 227 KB), else
+ *   MSCKF_ECAPACITY.  Outputs: match12[B][F_tracks] = detection index or -1, match21[B][F_new] = track slot or -1.
+ *   With action != NULL the proposal list of MSCKF.py:317-318 / :400-434 is written as well, in the form
+ *   msckf_verify_matches_batched and msckf_append_observations_batched consume: action[B][F_tracks] = 2 + (new_uv,
+ *   new_conf) taken from kp_new[B][F_new][2] / score_new[B][F_new] for a matched track, 1 for an unmatched one (lost this
+ *   frame), 3 in the free slots n_tracks[b] ... for the unmatched detections in ascending detection order (the order of
+ *   np.setdiff1d, FeatureExtractor.py:73), 0 elsewhere; n_tracks_out[b] (may be NULL) = slots in use afterwards;
+ *   detections that find no free slot are counted in *overflow_count (device int, incremented; may be NULL).
+ *
+ * msckf_verify_matches_batched  <->  the epipolar / homography walk of MSCKF.add_camera_measurements (MSCKF.py:333-401):
+ *   for every track with action == 2 the proposal new_uv is tested against each past observation in order, relative
+ *   pose T_C1_C2 = T_W_C1^-1 T_W_Cnewest from the LIVE window poses: baseline < 0.01 -> mean symmetric transfer error
+ *   under H = K R K^-1 > homography threshold rejects; otherwise the SIGNED score x_new^T K^-T [t]x R K^-1 x_old >
+ *   epipolar threshold rejects (no absolute value, as in the reference); the first failing observation decides.
+ *   verdict[B][F] = 0 not proposed, 1 passed, 2 rejected by the homography test, 3 by the epipolar test; a rejected
+ *   proposal's action becomes 1 (the reference only bumps lost_for_n_frames, MSCKF.py:402-404); the per-filter counters
+ *   n_homography_rejected[B] / n_epipolar_rejected[B] (may be NULL) are incremented like the reference's
+ *   number_of_features_discarder_for_homography_test / number_of_features_discarded_for_epipolar_test.
+ *   K_host / Kinv_host: 9 doubles each on the HOST.
+ * ------------------------------------------------------------------------------------------------------------- */
+int msckf_match_descriptors_batched(int B, int F_tracks, int F_new, int D, double min_cossim, const int* n_tracks,
+                                    const int* n_new, const float* desc_tracks, const float* desc_new, int* match12,
+                                    int* match21, const double* kp_new, const double* score_new, unsigned char* action,
+                                    double* new_uv, double* new_conf, int* n_tracks_out, int* overflow_count, void* stream);
+int msckf_verify_matches_batched(const msckf_dims* dims, const double* K_host, const double* Kinv_host,
+                                 double epipolar_rejection_threshold, double homography_rejection_threshold,
+                                 const int* n_cams, const double* cam_R, const double* cam_t, const int* feat_len,
+                                 const double* obs_uv, const int* obs_slot, const double* new_uv, unsigned char* action,
+                                 unsigned char* verdict, int* n_homography_rejected, int* n_epipolar_rejected, void* stream);
 int msckf_select_poorest_cameras_batched(const msckf_dims* dims, int max_select, int prune_above, const int* n_cams,
                                          const int* feat_len, const int* obs_slot, unsigned char* remove_mask,
                                          unsigned char* feat_touch, void* stream);

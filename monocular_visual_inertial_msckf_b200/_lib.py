@@ -66,7 +66,7 @@ EXPORTS = [
     "msckf_remove_cameras_batched", "msckf_launch_count", "msckf_probe_fp64", "msckf_filter_step_host",
     "msckf_set_stage_timing", "msckf_front_stage_ms", "msckf_select_poorest_cameras_batched",
     "msckf_drop_observations_batched", "msckf_append_observations_batched", "msckf_unobserved_cameras_batched",
-    "msckf_compact_tracks_batched",
+    "msckf_compact_tracks_batched", "msckf_match_descriptors_batched", "msckf_verify_matches_batched",
 ]
 
 
@@ -129,11 +129,17 @@ def load_library():
     lib.msckf_append_observations_batched.restype = C.c_int
     lib.msckf_append_observations_batched.argtypes = [pd, C.POINTER(C.c_double), ip, dp, dp, u8, dp, dp, ip, dp, dp, dp, ip, dp, ip,
                                                       dp, dp, ip, ip, ip, vp]
+    lib.msckf_match_descriptors_batched.restype = C.c_int
+    lib.msckf_match_descriptors_batched.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, ip, ip, vp, vp, ip, ip,
+                                                    dp, dp, u8, dp, dp, ip, ip, vp]
+    lib.msckf_verify_matches_batched.restype = C.c_int
+    lib.msckf_verify_matches_batched.argtypes = [pd, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double,
+                                                 ip, dp, dp, ip, dp, ip, dp, u8, u8, ip, ip, vp]
     lib.msckf_set_stage_timing.restype = C.c_int
     lib.msckf_set_stage_timing.argtypes = [C.c_int]
     lib.msckf_front_stage_ms.restype = C.c_int
     lib.msckf_front_stage_ms.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    if lib.msckf_abi_version() != 4:
+    if lib.msckf_abi_version() != 5:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib
     return lib

@@ -270,6 +270,57 @@ class BatchedMSCKF:
         _lib.check(rc, "msckf_append_observations_batched")
         return self._overflow
 
+    def match_descriptors(self, desc_tracks, desc_new, min_cosine_similarity=0.82, n_tracks=None, n_new=None, kp_new=None,
+                          score_new=None):
+        """FeatureExtractor.match / XFeat.match (FeatureExtractor.py:62-84, xfeat.py:327-348) for every filter:
+        desc_tracks [B, F, D] float32 (rows = track slots), desc_new [B, F2, D] float32 (the frame's detections), optional
+        per-filter counts n_tracks / n_new [B] int32.  Returns (match12 [B, F] int32, match21 [B, F2] int32), -1 = no
+        match.  With kp_new [B, F2, 2] and score_new [B, F2] (float64) the proposal list of MSCKF.py:317-318 / :400-434
+        is produced too: returns (match12, match21, action, new_uv, new_conf, n_tracks_out) ready for verify_matches and
+        append_observations (new tracks in the free slots from n_tracks[b] on)."""
+        B, F1, D = desc_tracks.shape
+        F2 = desc_new.shape[1]
+        assert B == self.B and F1 == self.F and desc_new.shape[0] == B and desc_new.shape[2] == D
+        assert desc_tracks.dtype == torch.float32 and desc_new.dtype == torch.float32
+        assert desc_tracks.is_contiguous() and desc_new.is_contiguous()
+        m12 = torch.empty((B, F1), dtype=torch.int32, device=self.device)
+        m21 = torch.empty((B, F2), dtype=torch.int32, device=self.device)
+        prop = kp_new is not None
+        if prop:
+            action = torch.empty((B, F1), dtype=torch.uint8, device=self.device)
+            new_uv = torch.empty((B, F1, 2), dtype=torch.float64, device=self.device)
+            new_conf = torch.empty((B, F1), dtype=torch.float64, device=self.device)
+            n_out = torch.empty(B, dtype=torch.int32, device=self.device)
+            if self._overflow is None:
+                self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+            assert kp_new.dtype == torch.float64 and score_new.dtype == torch.float64
+        rc = self.lib.msckf_match_descriptors_batched(
+            B, F1, F2, D, float(min_cosine_similarity), _ptr(n_tracks) if n_tracks is not None else None,
+            _ptr(n_new) if n_new is not None else None, _ptr(desc_tracks), _ptr(desc_new), _ptr(m12), _ptr(m21),
+            _ptr(kp_new) if prop else None, _ptr(score_new) if prop else None, _ptr(action) if prop else None,
+            _ptr(new_uv) if prop else None, _ptr(new_conf) if prop else None, _ptr(n_out) if prop else None,
+            _ptr(self._overflow) if prop else None, self._stream())
+        _lib.check(rc, "msckf_match_descriptors_batched")
+        return (m12, m21, action, new_uv, new_conf, n_out) if prop else (m12, m21)
+
+    def verify_matches(self, action, new_uv, epipolar_rejection_threshold=5.0, homography_rejection_threshold=5.0,
+                       counters=None):
+        """The epipolar / homography walk of MSCKF.add_camera_measurements (MSCKF.py:333-401) over the resident tracks:
+        proposals (action == 2, new_uv) that fail against any past observation are demoted to action 1 IN PLACE.
+        Returns verdict [B, F] uint8 (0 none, 1 passed, 2 homography, 3 epipolar); counters = optional pair of [B] int32
+        device tensors incremented like the reference's two discard counters."""
+        verdict = torch.empty((self.B, self.F), dtype=torch.uint8, device=self.device)
+        k = (C.c_double * 9)(*[float(self.cpar.K[i]) for i in range(9)])
+        kinv = (C.c_double * 9)(*[float(self.cpar.Kinv[i]) for i in range(9)])
+        nh, ne = counters if counters is not None else (None, None)
+        rc = self.lib.msckf_verify_matches_batched(
+            C.byref(self.dims), k, kinv, float(epipolar_rejection_threshold), float(homography_rejection_threshold),
+            _ptr(self.n_cams), _ptr(self.cam_R), _ptr(self.cam_t), _ptr(self.feat_len), _ptr(self.obs_uv), _ptr(self.obs_slot),
+            _ptr(new_uv), _ptr(action), _ptr(verdict), _ptr(nh) if nh is not None else None,
+            _ptr(ne) if ne is not None else None, self._stream())
+        _lib.check(rc, "msckf_verify_matches_batched")
+        return verdict
+
     def select_poorest_cameras(self, max_select=2, prune_above=-1):
         """MSCKF.prune_poorest_camera_states' selection (MSCKF.py:712-733) for every filter: returns
         (remove_mask [B, N] uint8, feat_touch [B, F] uint8) on the device.  Filters whose window holds at most

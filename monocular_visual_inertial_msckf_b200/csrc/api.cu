@@ -33,6 +33,15 @@ cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_h
 cudaError_t launch_drop_observations(const msckf_dims& d, const unsigned char* remove_mask, const int* n_cams,
                                      const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
                                      int* obs_slot, double* idp_base, int* idp_anchor_slot, cudaStream_t s);
+cudaError_t launch_verify_matches(const msckf_dims& d, const double* K_host, const double* Kinv_host, double epipolar_thr,
+                                  double homography_thr, const int* n_cams, const double* cam_R, const double* cam_t,
+                                  const int* feat_len, const double* obs_uv, const int* obs_slot, const double* new_uv,
+                                  unsigned char* action, unsigned char* verdict, int* n_homography, int* n_epipolar,
+                                  cudaStream_t s);
+int launch_match_descriptors(int B, int F1, int F2, int D, double min_cossim, const int* n_tracks, const int* n_new,
+                             const float* desc_tracks, const float* desc_new, int* match12, int* match21,
+                             const double* kp_new, const double* score_new, unsigned char* action, double* new_uv,
+                             double* new_conf, int* n_tracks_out, int* overflow, cudaStream_t s);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -288,6 +297,33 @@ int msckf_drop_observations_batched(const msckf_dims* dims, const unsigned char*
         return MSCKF_EINVAL;
     return (int)launch_drop_observations(*dims, remove_mask, n_cams, cam_t, feat_len, obs_uv, obs_dir, obs_conf, obs_slot,
                                          idp_base, idp_anchor_slot, (cudaStream_t)stream);
+}
+
+int msckf_verify_matches_batched(const msckf_dims* dims, const double* K_host, const double* Kinv_host,
+                                 double epipolar_rejection_threshold, double homography_rejection_threshold,
+                                 const int* n_cams, const double* cam_R, const double* cam_t, const int* feat_len,
+                                 const double* obs_uv, const int* obs_slot, const double* new_uv, unsigned char* action,
+                                 unsigned char* verdict, int* n_homography_rejected, int* n_epipolar_rejected, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!K_host || !Kinv_host || !n_cams || !cam_R || !cam_t || !feat_len || !obs_uv || !obs_slot || !new_uv || !action ||
+        !verdict)
+        return MSCKF_EINVAL;
+    return (int)launch_verify_matches(*dims, K_host, Kinv_host, epipolar_rejection_threshold, homography_rejection_threshold,
+                                      n_cams, cam_R, cam_t, feat_len, obs_uv, obs_slot, new_uv, action, verdict,
+                                      n_homography_rejected, n_epipolar_rejected, (cudaStream_t)stream);
+}
+
+int msckf_match_descriptors_batched(int B, int F_tracks, int F_new, int D, double min_cossim, const int* n_tracks,
+                                    const int* n_new, const float* desc_tracks, const float* desc_new, int* match12,
+                                    int* match21, const double* kp_new, const double* score_new, unsigned char* action,
+                                    double* new_uv, double* new_conf, int* n_tracks_out, int* overflow_count, void* stream) {
+    if (B <= 0 || F_tracks <= 0 || F_new <= 0 || D <= 0 || !desc_tracks || !desc_new || !match12 || !match21) return MSCKF_EINVAL;
+    if (B > 2147483647 / 2) return MSCKF_ECAPACITY;
+    if (action && (!kp_new || !score_new || !new_uv || !new_conf)) return MSCKF_EINVAL;
+    return launch_match_descriptors(B, F_tracks, F_new, D, min_cossim, n_tracks, n_new, desc_tracks, desc_new, match12, match21,
+                                    kp_new, score_new, action, new_uv, new_conf, n_tracks_out, overflow_count,
+                                    (cudaStream_t)stream);
 }
 
 }  // extern "C"

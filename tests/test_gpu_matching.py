@@ -1,0 +1,236 @@
+"""GPU parity of the matching front of add_camera_measurements through the C ABI:
+msckf_match_descriptors_batched (XFeat.match + the proposal list) and msckf_verify_matches_batched (epipolar / homography
+walk), against the reference's own decisions (tests/golden/small_match_verify.npz) and the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+torch = pytest.importorskip("torch")
+from oracle import msckf_oracle as o                                   # noqa: E402  (checker only)
+from monocular_visual_inertial_msckf_b200.batched import BatchedMSCKF, UpdateParams   # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases(golden_dir):
+    return o.load_cases(os.path.join(golden_dir, "small_match_verify.npz"))
+
+
+def _verify_batch(cases, pad_F=3, pad_M=1):
+    F = max(len(c["feat_ids"]) for c in cases) + pad_F
+    M = max(c["obs_slot"].shape[1] for c in cases) + pad_M
+    N = max(int(c["n_cams"]) for c in cases)
+    flt = BatchedMSCKF(len(cases), F, M, N, UpdateParams(K=np.array(cases[0]["K"], float)))
+    action = torch.zeros((flt.B, F), dtype=torch.uint8, device="cuda")
+    new_uv = torch.zeros((flt.B, F, 2), dtype=torch.float64, device="cuda")
+    for b, c in enumerate(cases):
+        f, m, n = c["obs_slot"].shape[0], c["obs_slot"].shape[1], int(c["n_cams"])
+        flt.n_cams[b] = n
+        flt.feat_len[b].zero_()
+        flt.feat_len[b, :f] = torch.from_numpy(c["feat_len"])
+        flt.obs_slot[b, :f, :m] = torch.from_numpy(np.maximum(c["obs_slot"], 0))
+        flt.obs_uv[b, :f, :m] = torch.from_numpy(c["obs_uv"])
+        flt.cam_t[b, :n] = torch.from_numpy(c["cam_t"])
+        flt.cam_R[b, :n] = torch.from_numpy(np.asarray(c["cam_R"], float).reshape(n, 9))
+        flt.lost_cnt[b, :f] = torch.from_numpy(c["lost_cnt"])
+        action[b, :f] = torch.from_numpy(c["action"])
+        new_uv[b, :f] = torch.from_numpy(c["new_uv"])
+    return flt, action, new_uv
+
+
+def test_verify_matches_vs_golden(golden_dir):
+    """Every frame of a reference run with the geometric tests switched on (38 frames, 69 homography and 197 epipolar
+    rejections): the device keeps exactly the proposals the reference kept, demotes the others to `lost this frame`, and
+    its two counters move like the reference's; the verdict per track equals the oracle's (which names the failing test)."""
+    cases, _ = _cases(golden_dir)
+    flt, action, new_uv = _verify_batch(cases)
+    nh = torch.zeros(flt.B, dtype=torch.int32, device="cuda")
+    ne = torch.zeros(flt.B, dtype=torch.int32, device="cuda")
+    c0 = cases[0]
+    verdict = flt.verify_matches(action, new_uv, c0["epipolar_rejection_threshold"], c0["homography_rejection_threshold"],
+                                 counters=(nh, ne))
+    torch.cuda.synchronize()
+    verdict, act, nh, ne = verdict.cpu().numpy(), action.cpu().numpy(), nh.cpu().numpy(), ne.cpu().numpy()
+    n_rej = 0
+    for b, c in enumerate(cases):
+        f = len(c["feat_ids"])
+        ref = o.verify_matches(c)
+        assert np.array_equal(verdict[b, :f] == 1, c["out_passed"]), c["call_index"]
+        assert np.array_equal(verdict[b, :f], ref["verdict"]), c["call_index"]
+        assert np.array_equal(act[b, :f], ref["action"]) and (act[b, f:] == 0).all() and (verdict[b, f:] == 0).all()
+        assert nh[b] == c["out_n_homography"] and ne[b] == c["out_n_epipolar"], c["call_index"]
+        n_rej += int(nh[b] + ne[b])
+    assert n_rej > 200
+    # the bookkeeping kernel then reproduces the reference's lost counters (a rejected proposal is a lost frame)
+    zeros = torch.zeros((flt.B, flt.F), dtype=torch.float64, device="cuda")
+    flt.append_observations(action, new_uv, zeros)
+    torch.cuda.synchronize()
+    lost = flt.lost_cnt.cpu().numpy()
+    for b, c in enumerate(cases):
+        f = len(c["feat_ids"])
+        assert np.array_equal(lost[b, :f], c["out_lost_cnt"]), c["call_index"]
+
+
+def test_verify_matches_long_tracks_and_edges():
+    """Tracks longer than one warp (40 observations, 48-pose window): the first failing observation decides, wherever it
+    sits; empty tracks and filters without cameras pass every proposal; thresholds at +-inf."""
+    rng = np.random.default_rng(3)
+    B, F, M, N = 6, 9, 40, 36
+    K = np.array([[320.0, 0, 320], [0, 320, 240], [0, 0, 1]])
+    cases = []
+    for b in range(B):
+        cam_R = np.stack([np.linalg.qr(np.eye(3) + 0.02 * rng.standard_normal((3, 3)))[0] for _ in range(N)])
+        cam_R *= np.sign(np.linalg.det(cam_R))[:, None, None]
+        cam_t = 0.3 * rng.standard_normal((N, 3))
+        cam_t[5] = cam_t[N - 1] + 1e-3                      # one camera within 1 cm of the newest: homography branch
+        c = dict(K=K, Kinv=np.linalg.inv(K), n_cams=N, cam_R=cam_R, cam_t=cam_t, feat_len=rng.integers(0, M + 1, F).astype(np.int32),
+                 obs_uv=rng.uniform(0, 480, (F, M, 2)), obs_slot=rng.integers(0, N - 1, (F, M)).astype(np.int32),
+                 action=np.full(F, 2, np.uint8), new_uv=rng.uniform(0, 480, (F, 2)),
+                 epipolar_rejection_threshold=0.35, homography_rejection_threshold=5.0, feat_ids=np.arange(F))
+        c["feat_len"][0] = M
+        c["feat_len"][1] = 0
+        c["action"][2] = 1
+        c["feat_len"][3] = 35
+        c["obs_slot"][3] = 5                                # a track seen only from that camera: homography tests alone
+        cases.append(c)
+    flt = BatchedMSCKF(B, F, M, N, UpdateParams(K=K))
+    action = torch.zeros((B, F), dtype=torch.uint8, device="cuda")
+    new_uv = torch.zeros((B, F, 2), dtype=torch.float64, device="cuda")
+    for b, c in enumerate(cases):
+        flt.n_cams[b] = N
+        flt.feat_len[b] = torch.from_numpy(c["feat_len"])
+        flt.obs_slot[b] = torch.from_numpy(c["obs_slot"])
+        flt.obs_uv[b] = torch.from_numpy(c["obs_uv"])
+        flt.cam_t[b] = torch.from_numpy(c["cam_t"])
+        flt.cam_R[b] = torch.from_numpy(c["cam_R"].reshape(N, 9))
+        action[b] = torch.from_numpy(c["action"])
+        new_uv[b] = torch.from_numpy(c["new_uv"])
+    a0 = action.clone()
+    verdict = flt.verify_matches(action, new_uv, 0.35, 5.0).cpu().numpy()
+    seen = set()
+    for b, c in enumerate(cases):
+        ref = o.verify_matches(c)
+        far = np.abs(ref["score"] - np.where(ref["verdict"] == 2, 5.0, 0.35)) > 1e-9
+        assert np.array_equal(verdict[b][far], ref["verdict"][far])
+        seen.update(int(v) for v in verdict[b])
+        assert verdict[b, 1] == 1 and verdict[b, 2] == 0
+    assert seen == {0, 1, 2, 3}
+    act = a0.clone()
+    v_inf = flt.verify_matches(act, new_uv, float("inf"), float("inf")).cpu().numpy()
+    assert ((v_inf == 1) == (a0.cpu().numpy() == 2)).all() and torch.equal(act, a0)
+    flt.n_cams.zero_()
+    act = a0.clone()
+    v_none = flt.verify_matches(act, new_uv, -1e9, -1e9).cpu().numpy()
+    assert ((v_none == 1) == (a0.cpu().numpy() == 2)).all()
+
+
+def _run_matcher(d1_list, d2_list, thr, F1, F2, D, kp=None, sc=None):
+    B = len(d1_list)
+    flt = BatchedMSCKF(B, F1, 2, 2, UpdateParams())
+    dt = torch.zeros((B, F1, D), dtype=torch.float32, device="cuda")
+    dn = torch.zeros((B, F2, D), dtype=torch.float32, device="cuda")
+    n1 = torch.zeros(B, dtype=torch.int32, device="cuda")
+    n2 = torch.zeros(B, dtype=torch.int32, device="cuda")
+    for b, (d1, d2) in enumerate(zip(d1_list, d2_list)):
+        dt[b, :len(d1)] = torch.from_numpy(np.asarray(d1, np.float32))
+        dn[b, :len(d2)] = torch.from_numpy(np.asarray(d2, np.float32))
+        n1[b], n2[b] = len(d1), len(d2)
+    out = flt.match_descriptors(dt, dn, thr, n1, n2, kp, sc)
+    torch.cuda.synchronize()
+    return flt, [x.cpu().numpy() for x in out]
+
+
+def test_matcher_vs_reference_xfeat_sets(golden_dir):
+    """Direct XFeat.match calls of the reference on float32 64-dimensional descriptor sets (full, partial, almost empty
+    match sets, min_cossim = 0, a single track): identical index pairs."""
+    _, extra = _cases(golden_dir)
+    for t in range(int(extra["n_xm"])):
+        d1, d2, thr = extra[f"xm{t}.d1"], extra[f"xm{t}.d2"], float(extra[f"xm{t}.thr"])
+        _, (m12, m21) = _run_matcher([d1], [d2], thr, len(d1) + 3, len(d2) + 2, 64)
+        i1 = np.nonzero(m12[0] >= 0)[0]
+        assert np.array_equal(i1, extra[f"xm{t}.idx0"]) and np.array_equal(m12[0][i1], extra[f"xm{t}.idx1"]), t
+        o12, o21 = o.match_descriptors(d1, d2, thr)
+        assert np.array_equal(m12[0, :len(d1)], o12) and np.array_equal(m21[0, :len(d2)], o21)
+        assert (m12[0, len(d1):] == -1).all() and (m21[0, len(d2):] == -1).all()
+
+
+def test_matcher_proposals_vs_reference_frames(golden_dir):
+    """The matcher calls of the traced run, one filter per frame (32-dimensional synthetic descriptors): index pairs equal
+    to the reference's, and the proposal list (action / new_uv / new_conf, new tracks in ascending detection order in the
+    free slots) equal to what the reference derived from them; chained with verify_matches it gives the reference's
+    surviving proposals."""
+    cases, _ = _cases(golden_dir)
+    F1 = max(len(c["feat_ids"]) for c in cases) + 30
+    F2 = max(len(c["match_desc_new"]) for c in cases) + 1
+    B = len(cases)
+    kp = torch.zeros((B, F2, 2), dtype=torch.float64, device="cuda")
+    sc = torch.zeros((B, F2), dtype=torch.float64, device="cuda")
+    rng = np.random.default_rng(5)
+    kps, scs = [], []
+    for b, c in enumerate(cases):
+        n2 = len(c["match_desc_new"])
+        # the detections' keypoints / scores: those of the matched ones are in the fixture (new_uv / new_conf by track)
+        k_, s_ = rng.uniform(0, 400, (n2, 2)), rng.uniform(0.5, 1, n2)
+        k_[c["match_idxs2"]] = c["new_uv"][c["match_idxs1"]]
+        s_[c["match_idxs2"]] = c["new_conf"][c["match_idxs1"]]
+        kp[b, :n2], sc[b, :n2] = torch.from_numpy(k_), torch.from_numpy(s_)
+        kps.append(k_), scs.append(s_)
+    flt, (m12, m21, action, new_uv, new_conf, n_out) = _run_matcher(
+        [c["match_desc_tracks"] for c in cases], [c["match_desc_new"] for c in cases], float(cases[0]["match_min_cossim"]),
+        F1, F2, 32, kp, sc)
+    assert int(flt._overflow.item()) == 0
+    for b, c in enumerate(cases):
+        f, n2 = len(c["feat_ids"]), len(c["match_desc_new"])
+        i1 = np.nonzero(m12[b] >= 0)[0]
+        assert np.array_equal(i1, c["match_idxs1"]) and np.array_equal(m12[b][i1], c["match_idxs2"]), c["call_index"]
+        assert np.array_equal(action[b, :f], c["action"])
+        assert np.array_equal(new_uv[b, :f][c["action"] == 2], c["new_uv"][c["action"] == 2])
+        assert np.array_equal(new_conf[b, :f][c["action"] == 2], c["new_conf"][c["action"] == 2])
+        un = np.setdiff1d(np.arange(n2), c["match_idxs2"])               # FeatureExtractor.py:73
+        assert n_out[b] == f + len(un)
+        assert (action[b, f:f + len(un)] == 3).all() and (action[b, f + len(un):] == 0).all()
+        assert np.array_equal(new_uv[b, f:f + len(un)], kps[b][un]) and np.array_equal(new_conf[b, f:f + len(un)], scs[b][un])
+    # chained: proposals from the device matcher -> device verification == the reference's surviving proposals
+    vflt, act_ref, uv_ref = _verify_batch(cases, pad_F=F1 - max(len(c["feat_ids"]) for c in cases), pad_M=1)
+    act_dev = torch.from_numpy(np.where(action == 3, 0, action).astype(np.uint8)).cuda()
+    uv_dev = torch.from_numpy(new_uv).cuda()
+    v = vflt.verify_matches(act_dev, uv_dev, cases[0]["epipolar_rejection_threshold"],
+                            cases[0]["homography_rejection_threshold"]).cpu().numpy()
+    for b, c in enumerate(cases):
+        assert np.array_equal(v[b, :len(c["feat_ids"])] == 1, c["out_passed"]), c["call_index"]
+
+
+def test_matcher_capacity_and_overflow():
+    """Benchmark-shape sets (256 tracks x 300 detections x 64) against the oracle on noisy data away from ties; more new
+    detections than free slots are counted, not written out of bounds; unsupported descriptor lengths are refused."""
+    rng = np.random.default_rng(12)
+    d1s, d2s = [], []
+    for b in range(5):
+        base = rng.standard_normal((300, 64))
+        base /= np.linalg.norm(base, axis=1, keepdims=True)
+        d2 = base[rng.permutation(300)] + 0.7 * rng.standard_normal((300, 64)) / 8
+        d1s.append(base[:256].astype(np.float32))
+        d2s.append((d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32))
+    kp = torch.rand((5, 300, 2), dtype=torch.float64, device="cuda")
+    sc = torch.rand((5, 300), dtype=torch.float64, device="cuda")
+    flt, (m12, m21, action, new_uv, new_conf, n_out) = _run_matcher(d1s, d2s, 0.82, 256, 300, 64, kp, sc)
+    n_over = 0
+    for b in range(5):
+        o12, o21 = o.match_descriptors(d1s[b], d2s[b], 0.82)
+        cs = d1s[b] @ d2s[b].T
+        top2 = np.sort(cs, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0] > 1e-5) & (np.abs(top2[:, 1] - 0.82) > 1e-5)
+        col2 = np.sort(cs, axis=0)[-2:, :]
+        assert clear.all() and (col2[1] - col2[0] > 1e-5).all()          # the data keeps clear of ties / the threshold
+        assert np.array_equal(m12[b], o12) and np.array_equal(m21[b], o21)
+        assert 0 < (o12 >= 0).sum() < 256
+        n_over += int((o21 < 0).sum())                                   # all 256 slots are tracks: no room for new ones
+        assert n_out[b] == 256 and (action[b] != 3).all()
+    assert int(flt._overflow.item()) == n_over
+    with pytest.raises(RuntimeError):
+        _run_matcher([np.zeros((4, 48), np.float32)], [np.zeros((4, 48), np.float32)], 0.82, 4, 4, 48)
+    with pytest.raises(RuntimeError):
+        _run_matcher([np.zeros((4, 64), np.float32)], [np.zeros((4, 64), np.float32)], 0.82, 600, 600, 64)

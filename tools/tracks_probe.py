@@ -45,7 +45,33 @@ rows = [
     ("compact_tracks", lambda: flt.compact_tracks(False), None, 2.0 * obs_bytes),
     ("unobserved_cameras", lambda: flt.unobserved_cameras(), None, 4.0 * float(flt.feat_len.sum().item())),
 ]
+# matching front: proposals = every track re-detected near its last observation; 300 detections x 64-d
+F2, D = 300, 64
+gen = torch.Generator(device="cuda").manual_seed(1)
+desc_t = torch.nn.functional.normalize(torch.randn((B, F, D), device="cuda", generator=gen), dim=2).contiguous()
+desc_n = torch.zeros((B, F2, D), device="cuda")
+desc_n[:, :F] = desc_t
+desc_n[:, F:] = torch.nn.functional.normalize(torch.randn((B, F2 - F, D), device="cuda", generator=gen), dim=2)
+desc_n = torch.nn.functional.normalize(desc_n + 0.03 * torch.randn((B, F2, D), device="cuda", generator=gen), dim=2).contiguous()
+kp_n = torch.rand((B, F2, 2), dtype=torch.float64, device="cuda") * 400
+sc_n = torch.rand((B, F2), dtype=torch.float64, device="cuda")
+n_trk = torch.full((B,), F, dtype=torch.int32, device="cuda")
+last = (flt.feat_len - 1).clamp(min=0).long()
+uv_last = torch.gather(flt.obs_uv, 2, last[:, :, None, None].expand(B, F, 1, 2))[:, :, 0]
+prop_uv = (uv_last + 0.5 * torch.randn((B, F, 2), dtype=torch.float64, device="cuda")).contiguous()
+act_v = [None]
+def prep_verify():
+    act_v[0] = torch.full((B, F), 2, dtype=torch.uint8, device="cuda")
+match_flop = 2.0 * 2.0 * F * F2 * D * B
+rows += [
+    ("match_descriptors (256x300x64)", lambda: flt.match_descriptors(desc_t, desc_n, 0.82, n_trk, None, kp_n, sc_n), None,
+     4.0 * (F + F2) * D * B + 29.0 * F * B),
+    ("verify_matches (epipolar walk)", lambda: flt.verify_matches(act_v[0], prop_uv, 5.0, 5.0), prep_verify,
+     20.0 * float(flt.feat_len.sum().item()) + 18.0 * B * F),
+]
 print(f"{B} filters x {F} tracks x {M - 1} observations, window {N - 1} (capacity {N}); HBM peak 6550 GB/s")
 for name, fn, prep, nbytes in rows:
-    ms = timed(fn)
+    ms = timed(fn, prep or (lambda: None))
+    if name.startswith("match_descriptors"):
+        print(f"{name:34s} {ms:8.3f} ms   {match_flop / 1e9:7.2f} GFLOP fp32        {match_flop / (ms * 1e-3) / 1e12:8.2f} TFLOP/s")
     print(f"{name:34s} {ms:8.3f} ms   {nbytes / 1e9:7.2f} GB touched   {nbytes / (ms * 1e-3) / 1e9:8.1f} GB/s")
