@@ -129,6 +129,7 @@ class BatchedMSCKF:
         self._remove_ws = None
         self._overflow = None
         self._alt_tracks = None
+        self.desc_sum = self.desc_w = None       # per-track descriptor sums of frame_step_detections
         self._samples_dev = None
         self.Qc_diag = z(B, 4)
 
@@ -399,6 +400,62 @@ class BatchedMSCKF:
         m1 = self.process_features(return_map=return_maps)
         m2 = self.prune_poorest_camera_states(prune_above=max_cameras, return_map=return_maps)
         return (m1, m2) if return_maps else None
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _remap_descriptors(self, dest):
+        """Track descriptors follow a slot map of compact_tracks ([B, F] int32, -1 = deleted)."""
+        F, D = self.F, self.desc_sum.shape[2]
+        idx = torch.where(dest >= 0, dest, torch.full_like(dest, F)).long()
+        ds = torch.zeros((self.B, F + 1, D), dtype=self.desc_sum.dtype, device=self.device)
+        dw = torch.zeros((self.B, F + 1), dtype=self.desc_w.dtype, device=self.device)
+        ds.scatter_(1, idx[..., None].expand(-1, -1, D), self.desc_sum)
+        dw.scatter_(1, idx, self.desc_w)
+        self.desc_sum, self.desc_w = ds[:, :F].contiguous(), dw[:, :F].contiguous()
+
+    def frame_step_detections(self, samples, R_I_C, t_I_C, desc_new, kp_new, score_new, n_new, max_cameras,
+                              min_cosine_similarity=0.82, epipolar_rejection_threshold=5.0,
+                              homography_rejection_threshold=5.0, use_null_state=False, counters=None):
+        """One camera frame of every filter from the frame's DETECTIONS (MSCKF.imu_callback x n + feature_callback,
+        MSCKF.py:135-158, with add_camera_measurements :284-448 on the device): propagation, state_augmentation, the
+        mutual-NN descriptor matcher against the tracks' score-weighted mean descriptors (:317, :439), the epipolar /
+        homography walk (:333-401), the track bookkeeping (:400-438), process_features and the pruning.
+        desc_new [B, F2, D] float32, kp_new [B, F2, 2] / score_new [B, F2] float64, n_new [B] int32 (detections that passed
+        the caller's score filter, MSCKF.py:279-282).  The per-track descriptor sums are kept here with torch index
+        operations (plumbing; they follow the slot maps of the track compactions).  Returns (action, verdict)."""
+        B, F2, D = desc_new.shape
+        if getattr(self, "desc_sum", None) is None:
+            self.desc_sum = torch.zeros((self.B, self.F, D), dtype=torch.float32, device=self.device)
+            self.desc_w = torch.zeros((self.B, self.F), dtype=torch.float32, device=self.device)
+        self.propagate(samples, use_null_state=use_null_state)
+        self.augment(R_I_C, t_I_C)
+        n_tracks = (self.feat_len > 0).sum(1).to(torch.int32)            # the slots in use are 0 .. n-1 (tracks stay compacted)
+        desc_tracks = (self.desc_sum / self.desc_w.clamp_min(1e-30)[..., None]).contiguous()
+        m12, m21, action, new_uv, new_conf, _ = self.match_descriptors(desc_tracks, desc_new, min_cosine_similarity, n_tracks,
+                                                                      n_new, kp_new, score_new)
+        # `if len(matched.keypoints) == 0: return` (MSCKF.py:320): a filter with tracks but no match skips the frame
+        skip = (n_tracks > 0) & ((m12 >= 0).sum(1) == 0)
+        action.masked_fill_(skip[:, None], 0)
+        verdict = self.verify_matches(action, new_uv, epipolar_rejection_threshold, homography_rejection_threshold, counters)
+        # descriptors: an accepted match adds (score, descriptor) to its track (MSCKF.py:407-408), a new track starts its list
+        acc = action == 2
+        idx = m12.clamp(min=0).long()
+        w = torch.gather(score_new, 1, idx).to(torch.float32) * acc
+        self.desc_sum += w[..., None] * torch.gather(desc_new, 1, idx[..., None].expand(-1, -1, D))
+        self.desc_w += w
+        un = (m21 < 0) & (torch.arange(F2, device=self.device)[None, :] < n_new[:, None]) & ~skip[:, None]
+        slot = n_tracks[:, None].long() + torch.cumsum(un, 1) - 1
+        ok = un & (slot < self.F)
+        slot = torch.where(ok, slot, torch.full_like(slot, self.F))
+        wn = score_new.to(torch.float32) * ok
+        ds = torch.cat([self.desc_sum, torch.zeros((self.B, 1, D), dtype=torch.float32, device=self.device)], 1)
+        dw = torch.cat([self.desc_w, torch.zeros((self.B, 1), dtype=torch.float32, device=self.device)], 1)
+        ds.scatter_add_(1, slot[..., None].expand(-1, -1, D), wn[..., None] * desc_new)
+        dw.scatter_add_(1, slot, wn)
+        self.desc_sum, self.desc_w = ds[:, :self.F].contiguous(), dw[:, :self.F].contiguous()
+        self.append_observations(action, new_uv, new_conf)
+        self._remap_descriptors(self.process_features(return_map=True))
+        self._remap_descriptors(self.prune_poorest_camera_states(prune_above=max_cameras, return_map=True))
+        return action, verdict
 
     def prune_poorest_camera_states(self, max_select=2, prune_above=-1, return_map=False):
         """MSCKF.prune_poorest_camera_states (MSCKF.py:710-737) for every filter, everything resident: select the two

@@ -18,12 +18,14 @@ constexpr int MM = 512;      // threads of a matcher CTA (thread grid 16 x 32, 1
 struct Intrinsics { double k[9], ki[9]; };
 
 // ---- geometric verification -----------------------------------------------------------------------------------------
-// CTA = (filter, 64 tracks).  First the relative geometry of every window camera against the newest one is put into shared
-// memory once (thread = camera): R = R_s^T R_new, the branch flag |t| < 0.01 and the fundamental matrix in pixel
-// coordinates F = K^-T [t]x R K^-1 (MSCKF.py:360-362, :387).  Then one warp per track, lane = past observation (tracks
-// longer than 32 observations: chunks of 32 in order): every lane evaluates the test of its observation -- 11 multiply-adds
-// on the epipolar branch -- and the FIRST failing observation decides the verdict, which is what the reference's sequential
-// walk with `break` yields (MSCKF.py:381, :398).  HBM: 20 B per past observation (uv + slot) + 18 B per proposal.
+// CTA = (filter, 64 consecutive tracks).  Two warps stage the proposals of those tracks, two others put the relative
+// geometry of every window camera against the newest one into shared memory (thread = camera): R = R_s^T R_new, the branch
+// flag |t| < 0.01 and the fundamental matrix in pixel coordinates F = K^-T [t]x R K^-1 (MSCKF.py:360-362, :387).  Then the
+// CTA walks the 64 x M observation slots of its tracks as ONE flat, contiguous range (coalesced 16-byte uv and 4-byte slot
+// loads, all independent): every valid observation is tested -- 11 multiply-adds on the epipolar branch -- and a failure
+// enters a shared-memory atomicMin over (observation index, test); the minimum is the FIRST failing observation, which is
+// what the reference's sequential walk with `break` reports (MSCKF.py:381, :398).
+// HBM: 20 B per past observation (uv + slot) + 18 B per proposal.
 constexpr int V_TRACKS = 64;
 
 __global__ void __launch_bounds__(MT) verify_matches_kernel(msckf_dims dims, Intrinsics Km, double epipolar_thr,
@@ -36,14 +38,25 @@ __global__ void __launch_bounds__(MT) verify_matches_kernel(msckf_dims dims, Int
     __shared__ double s_F[MSCKF_MAX_CAMS][9];
     __shared__ double s_R[MSCKF_MAX_CAMS][9];
     __shared__ unsigned char s_h[MSCKF_MAX_CAMS];
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    __shared__ double s_uv[V_TRACKS][2];
+    __shared__ int s_len[V_TRACKS], s_first[V_TRACKS];
+    const int b = blockIdx.y, tid = threadIdx.x;
     const int F = dims.F, M = dims.M, N = dims.N;
     const int nc = min(n_cams[b], N), s2 = nc - 1;
+    const int j0 = blockIdx.x * V_TRACKS, nt = min(V_TRACKS, F - j0);
     const double* Ki = Km.ki;
     const double* K = Km.k;
-    if (tid < nc) {
-        const double* R1 = cam_R + ((size_t)b * N + tid) * 9;
-        const double* t1 = cam_t + ((size_t)b * N + tid) * 3;
+    if (tid < nt) {
+        const size_t fj = (size_t)b * F + j0 + tid;
+        const bool proposed = action[fj] == 2;
+        s_len[tid] = proposed ? (s2 >= 0 ? min(feat_len[fj], M) : 0) : -1;          // -1: not proposed
+        s_uv[tid][0] = new_uv[fj * 2];
+        s_uv[tid][1] = new_uv[fj * 2 + 1];
+        s_first[tid] = 0x7fffffff;
+    } else if (tid >= V_TRACKS && tid - V_TRACKS < nc) {
+        const int s1 = tid - V_TRACKS;
+        const double* R1 = cam_R + ((size_t)b * N + s1) * 9;
+        const double* t1 = cam_t + ((size_t)b * N + s1) * 3;
         const double* R2 = cam_R + ((size_t)b * N + s2) * 9;
         const double* t2 = cam_t + ((size_t)b * N + s2) * 3;
         // T_C1_C2 = T_W_C1^-1 T_W_C2 (MSCKF.py:360): R = R1^T R2, t = R1^T (t2 - t1)
@@ -68,77 +81,76 @@ __global__ void __launch_bounds__(MT) verify_matches_kernel(msckf_dims dims, Int
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) s_F[tid][r * 3 + c] = Ki[r] * G[c] + Ki[3 + r] * G[3 + c] + Ki[6 + r] * G[6 + c];
+            for (int c = 0; c < 3; ++c) s_F[s1][r * 3 + c] = Ki[r] * G[c] + Ki[3 + r] * G[3 + c] + Ki[6 + r] * G[6 + c];
+        const bool near = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]) < 0.01;
+        s_h[s1] = near ? 1 : 0;
+        if (near) {
+            // homography branch (MSCKF.py:362-363): H = K R K^-1 into s_R, H^-1 = K R^T K^-1 into s_F (F is not needed)
+            double A[9], Bt[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) s_R[tid][k] = R[k];
-        s_h[tid] = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]) < 0.01 ? 1 : 0;
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    A[r * 3 + c] = R[r * 3] * Ki[c] + R[r * 3 + 1] * Ki[3 + c] + R[r * 3 + 2] * Ki[6 + c];      // R K^-1
+                    Bt[r * 3 + c] = R[r] * Ki[c] + R[3 + r] * Ki[3 + c] + R[6 + r] * Ki[6 + c];                 // R^T K^-1
+                }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    s_R[s1][r * 3 + c] = K[r * 3] * A[c] + K[r * 3 + 1] * A[3 + c] + K[r * 3 + 2] * A[6 + c];
+                    s_F[s1][r * 3 + c] = K[r * 3] * Bt[c] + K[r * 3 + 1] * Bt[3 + c] + K[r * 3 + 2] * Bt[6 + c];
+                }
+        }
     }
     __syncthreads();
-    for (int q = 0; q < V_TRACKS / (MT / 32); ++q) {
-        const int j = blockIdx.x * V_TRACKS + q * (MT / 32) + w;
-        if (j >= F) break;
-        const size_t fj = (size_t)b * F + j;
-        if (action[fj] != 2) {
-            if (lane == 0) verdict[fj] = 0;
-            continue;
+    const size_t base = ((size_t)b * F + j0) * M;
+    const double2* uv2 = reinterpret_cast<const double2*>(obs_uv) + base;
+    for (int e = tid; e < nt * M; e += MT) {
+        const int jl = e / M, i = e - jl * M;
+        if (i >= s_len[jl]) continue;
+        const int s1 = obs_slot[base + e];
+        const double2 f = uv2[e];
+        if (s1 < 0 || s1 > s2) continue;
+        const double fu = f.x, fv = f.y, mu = s_uv[jl][0], mv = s_uv[jl][1];
+        int fail = 0;
+        if (s_h[s1]) {
+            // homography H = K R K^-1 (MSCKF.py:363), H^-1 = K R^T K^-1.  Literal reference form (:364-368): the new
+            // detection is compared with ITS OWN image under H^-1, the old observation with its own image under H (not
+            // with each other); mean of the two distances
+            const double* H = s_R[s1];
+            const double* Hi = s_F[s1];
+            const double p0 = H[0] * fu + H[1] * fv + H[2], p1 = H[3] * fu + H[4] * fv + H[5], p2 = H[6] * fu + H[7] * fv + H[8];
+            const double q0 = Hi[0] * mu + Hi[1] * mv + Hi[2], q1 = Hi[3] * mu + Hi[4] * mv + Hi[5],
+                         q2 = Hi[6] * mu + Hi[7] * mv + Hi[8];
+            const double e1x = mu - q0 / q2, e1y = mv - q1 / q2;       // matched_keypoint - x1_pred
+            const double e2x = fu - p0 / p2, e2y = fv - p1 / p2;       // feature_keypoint - x2_pred
+            const double score = 0.5 * (sqrt(e1x * e1x + e1y * e1y) + sqrt(e2x * e2x + e2y * e2y));
+            if (score > homography_thr) fail = 2;
+        } else {
+            // SIGNED score [x_new, 1]^T F [x_old, 1] > threshold rejects (MSCKF.py:388-390)
+            const double* Fm = s_F[s1];
+            const double v0 = Fm[0] * fu + Fm[1] * fv + Fm[2], v1 = Fm[3] * fu + Fm[4] * fv + Fm[5],
+                         v2 = Fm[6] * fu + Fm[7] * fv + Fm[8];
+            const double score = mu * v0 + mv * v1 + v2;
+            if (score > epipolar_thr) fail = 3;
         }
-        int code = 1;
-        if (s2 >= 0) {
-            const double mu = new_uv[fj * 2], mv = new_uv[fj * 2 + 1];
-            const int n = min(feat_len[fj], M);
-            for (int base = 0; base < n; base += 32) {
-                const int i = base + lane;
-                int fail = 0;
-                if (i < n) {
-                    const int s1 = obs_slot[fj * M + i];
-                    const double fu = obs_uv[(fj * M + i) * 2], fv = obs_uv[(fj * M + i) * 2 + 1];
-                    if (s1 >= 0 && s1 <= s2) {
-                        if (s_h[s1]) {
-                            // homography H = K R K^-1 (MSCKF.py:363), H^-1 = K R^T K^-1.  Literal reference form (:364-368):
-                            // the new detection is compared with ITS OWN image under H^-1, the old observation with its own
-                            // image under H (not with each other); mean of the two distances
-                            const double* R = s_R[s1];
-                            const double xm0 = Ki[0] * mu + Ki[1] * mv + Ki[2], xm1 = Ki[3] * mu + Ki[4] * mv + Ki[5],
-                                         xm2 = Ki[6] * mu + Ki[7] * mv + Ki[8];
-                            const double xf0 = Ki[0] * fu + Ki[1] * fv + Ki[2], xf1 = Ki[3] * fu + Ki[4] * fv + Ki[5],
-                                         xf2 = Ki[6] * fu + Ki[7] * fv + Ki[8];
-                            const double a0 = R[0] * xf0 + R[1] * xf1 + R[2] * xf2, a1 = R[3] * xf0 + R[4] * xf1 + R[5] * xf2,
-                                         a2 = R[6] * xf0 + R[7] * xf1 + R[8] * xf2;
-                            const double p0 = K[0] * a0 + K[1] * a1 + K[2] * a2, p1 = K[3] * a0 + K[4] * a1 + K[5] * a2,
-                                         p2 = K[6] * a0 + K[7] * a1 + K[8] * a2;
-                            const double c0 = R[0] * xm0 + R[3] * xm1 + R[6] * xm2, c1 = R[1] * xm0 + R[4] * xm1 + R[7] * xm2,
-                                         c2 = R[2] * xm0 + R[5] * xm1 + R[8] * xm2;
-                            const double q0 = K[0] * c0 + K[1] * c1 + K[2] * c2, q1 = K[3] * c0 + K[4] * c1 + K[5] * c2,
-                                         q2 = K[6] * c0 + K[7] * c1 + K[8] * c2;
-                            const double e1x = mu - q0 / q2, e1y = mv - q1 / q2;       // matched_keypoint - x1_pred
-                            const double e2x = fu - p0 / p2, e2y = fv - p1 / p2;       // feature_keypoint - x2_pred
-                            const double score = 0.5 * (sqrt(e1x * e1x + e1y * e1y) + sqrt(e2x * e2x + e2y * e2y));
-                            if (score > homography_thr) fail = 2;
-                        } else {
-                            // SIGNED score [x_new, 1]^T F [x_old, 1] > threshold rejects (MSCKF.py:388-390)
-                            const double* Fm = s_F[s1];
-                            const double v0 = Fm[0] * fu + Fm[1] * fv + Fm[2], v1 = Fm[3] * fu + Fm[4] * fv + Fm[5],
-                                         v2 = Fm[6] * fu + Fm[7] * fv + Fm[8];
-                            const double score = mu * v0 + mv * v1 + v2;
-                            if (score > epipolar_thr) fail = 3;
-                        }
-                    }
-                }
-                const unsigned ball = __ballot_sync(0xffffffffu, fail != 0);
-                if (ball) {
-                    code = __shfl_sync(0xffffffffu, fail, __ffs(ball) - 1);
-                    break;
-                }
-            }
-        }
-        if (lane == 0) {
-            verdict[fj] = (unsigned char)code;
+        if (fail) atomicMin(&s_first[jl], i * 4 + fail);
+    }
+    __syncthreads();
+    if (tid < nt) {
+        const size_t fj = (size_t)b * F + j0 + tid;
+        int code = 0;
+        if (s_len[tid] >= 0) {
+            const int first = s_first[tid];
+            code = first == 0x7fffffff ? 1 : (first & 3);
             if (code != 1) {
                 action[fj] = 1;               // rejected proposal: the track is only marked lost this frame (MSCKF.py:402-404)
                 if (code == 2 && n_homography) atomicAdd(n_homography + b, 1);
                 if (code == 3 && n_epipolar) atomicAdd(n_epipolar + b, 1);
             }
         }
+        verdict[fj] = (unsigned char)code;
     }
 }
 

@@ -234,3 +234,80 @@ def test_matcher_capacity_and_overflow():
         _run_matcher([np.zeros((4, 48), np.float32)], [np.zeros((4, 48), np.float32)], 0.82, 4, 4, 48)
     with pytest.raises(RuntimeError):
         _run_matcher([np.zeros((4, 64), np.float32)], [np.zeros((4, 64), np.float32)], 0.82, 600, 600, 64)
+
+
+def test_whole_run_from_detections(golden_dir):
+    """The camera-frame loop of a whole reference run driven by nothing but the IMU samples and each frame's DETECTIONS
+    (keypoints, descriptors, scores of the synthetic stream the reference was run on): matcher, geometric verification,
+    track bookkeeping, updates and pruning all on the device (BatchedMSCKF.frame_step_detections).  After every camera
+    frame the proposals equal the reference matcher's, and the filter state and the tracks equal the reference's."""
+    from monocular_visual_inertial_msckf_b200 import synth, _lib
+    from helpers import rel_err
+    tr = o.load_trace(os.path.join(golden_dir, "small_trace.npz"))
+    seq = synth.make_sequence(seed=42, n_frames=60, n_landmarks=40, noise_level="mid", p_drop=0.06, p_outlier=0.03, shuffle=True)
+    ini, cases, apps = tr["init"], tr["cases"], tr["appends"]
+    assert len(apps) == len(seq.frames) - 1
+    F = max(len(a["action"]) for a in apps) + 1
+    M = max(c["obs_uv"].shape[1] for c in cases) + 1
+    N = tr["max_cams"] + 1
+    F2 = max(len(fr.keypoints) for fr in seq.frames) + 2
+    D = seq.frames[0].descriptors.shape[1]
+    par = UpdateParams.from_case(cases[0], _lib.COMPRESS_GRAM)
+    par.gravity = np.array(ini["gravity"], float)
+    B = 2
+    flt = BatchedMSCKF(B, F, M, N, par)
+    flt.P.zero_()
+    flt.P[:, :15, :15] = torch.from_numpy(np.asarray(ini["P"], float))
+    flt.imu_state[:] = torch.from_numpy(np.concatenate([np.asarray(ini["imu_R"], float).flatten(), ini["imu_t"], ini["imu_v"],
+                                                        ini["imu_bg"], ini["imu_ba"]]))
+    flt.imu_null[:] = torch.from_numpy(np.concatenate([np.asarray(ini["null_R"], float).flatten(), ini["null_t"], ini["null_v"]]))
+    flt.imu_time[:] = float(ini["timestamp"])
+    flt.Qc_diag[:] = torch.from_numpy(np.asarray(ini["Qc_diag"], float)[[0, 3, 6, 9]].copy())
+    flt.n_cams.zero_()
+    flt.feat_len.zero_()
+    ops = tr["ops"]
+    first, worst, start = True, 0.0, 0
+    for i, fr in enumerate(tr["frames"]):
+        seg = ops[start:int(fr["op_index"])]
+        start = int(fr["op_index"])
+        smp = np.array([tr["samples"][idx] for kind, idx in seg if kind == 0], float)
+        a = apps[[idx for kind, idx in seg if kind == 4][0]]
+        det = seq.frames[i + 1]
+        keep = det.scores >= 0.5 * det.scores.mean()                     # the score filter of MSCKF.py:279-282 (host side)
+        n2 = int(keep.sum())
+        desc = torch.zeros((B, F2, D), dtype=torch.float32, device="cuda")
+        kp = torch.zeros((B, F2, 2), dtype=torch.float64, device="cuda")
+        sc = torch.zeros((B, F2), dtype=torch.float64, device="cuda")
+        desc[:, :n2] = torch.from_numpy(det.descriptors[keep].astype(np.float32)).cuda()
+        kp[:, :n2] = torch.from_numpy(det.keypoints[keep]).cuda()
+        sc[:, :n2] = torch.from_numpy(det.scores[keep]).cuda()
+        n_new = torch.full((B,), n2, dtype=torch.int32, device="cuda")
+        samples = torch.from_numpy(smp).reshape(1, -1, 7).repeat(B, 1, 1).cuda()
+        action, verdict = flt.frame_step_detections(samples, ini["R_I_C"], ini["t_I_C"], desc, kp, sc, n_new, tr["max_cams"],
+                                                    min_cosine_similarity=0.95, epipolar_rejection_threshold=1e9,
+                                                    homography_rejection_threshold=1e9, use_null_state=first)
+        first = False
+        torch.cuda.synchronize()
+        fa = len(a["action"])
+        act = action.cpu().numpy()
+        assert (act[:, :fa] == a["action"]).all() and (act[:, fa:] == 0).all(), i
+        d = fr["P"].shape[0]
+        nc = (d - 15) // 6
+        nf = len(fr["feat_len"])
+        for b in range(B):
+            assert int(flt.n_cams[b]) == nc, (i, int(flt.n_cams[b]), nc)
+            ln = flt.feat_len[b].cpu().numpy()
+            assert (ln[:nf] == fr["feat_len"]).all() and (ln[nf:] == 0).all(), i
+            sl = flt.obs_slot[b].cpu().numpy()
+            for j in range(nf):
+                assert (sl[j, :ln[j]] == fr["obs_slot"][j, :ln[j]]).all(), (i, j)
+            assert (flt.lost_cnt[b, :nf].cpu().numpy() == fr["lost_cnt"]).all(), i
+            assert (flt.tracked_cnt[b, :nf].cpu().numpy() == fr["tracked_cnt"]).all(), i
+            st = flt.imu_state[b].cpu().numpy()
+            errs = [rel_err(flt.P[b, :d, :d].cpu().numpy(), fr["P"]), rel_err(st[:9].reshape(3, 3), fr["imu_R"]),
+                    rel_err(st[9:12], fr["imu_t"]), rel_err(st[12:15], fr["imu_v"]),
+                    rel_err(flt.cam_t[b, :nc].cpu().numpy(), fr["cam_t"])]
+            worst = max(worst, max(errs))
+            assert worst < 1e-9, (i, errs)
+    assert len(tr["frames"]) >= 50
+    print("frame loop from detections, worst relative error over", len(tr["frames"]), "frames:", worst)

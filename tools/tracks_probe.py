@@ -62,6 +62,8 @@ prop_uv = (uv_last + 0.5 * torch.randn((B, F, 2), dtype=torch.float64, device="c
 act_v = [None]
 def prep_verify():
     act_v[0] = torch.full((B, F), 2, dtype=torch.uint8, device="cuda")
+    flt.imu_state[:, 9:12] += 0.05     # the platform moved 5 cm since the last frame (at rest every walk would end in the homography branch)
+    flt.augment(R_I_C, t_I_C)          # the frame's own pose enters the window before add_camera_measurements (MSCKF.py:150-153)
 match_flop = 2.0 * 2.0 * F * F2 * D * B
 rows += [
     ("match_descriptors (256x300x64)", lambda: flt.match_descriptors(desc_t, desc_n, 0.82, n_trk, None, kp_n, sc_n), None,
