@@ -106,36 +106,57 @@ __global__ void __launch_bounds__(MT) verify_matches_kernel(msckf_dims dims, Int
     __syncthreads();
     const size_t base = ((size_t)b * F + j0) * M;
     const double2* uv2 = reinterpret_cast<const double2*>(obs_uv) + base;
-    for (int e = tid; e < nt * M; e += MT) {
-        const int jl = e / M, i = e - jl * M;
-        if (i >= s_len[jl]) continue;
-        const int s1 = obs_slot[base + e];
-        const double2 f = uv2[e];
-        if (s1 < 0 || s1 > s2) continue;
-        const double fu = f.x, fv = f.y, mu = s_uv[jl][0], mv = s_uv[jl][1];
-        int fail = 0;
-        if (s_h[s1]) {
-            // homography H = K R K^-1 (MSCKF.py:363), H^-1 = K R^T K^-1.  Literal reference form (:364-368): the new
-            // detection is compared with ITS OWN image under H^-1, the old observation with its own image under H (not
-            // with each other); mean of the two distances
-            const double* H = s_R[s1];
-            const double* Hi = s_F[s1];
-            const double p0 = H[0] * fu + H[1] * fv + H[2], p1 = H[3] * fu + H[4] * fv + H[5], p2 = H[6] * fu + H[7] * fv + H[8];
-            const double q0 = Hi[0] * mu + Hi[1] * mv + Hi[2], q1 = Hi[3] * mu + Hi[4] * mv + Hi[5],
-                         q2 = Hi[6] * mu + Hi[7] * mv + Hi[8];
-            const double e1x = mu - q0 / q2, e1y = mv - q1 / q2;       // matched_keypoint - x1_pred
-            const double e2x = fu - p0 / p2, e2y = fv - p1 / p2;       // feature_keypoint - x2_pred
-            const double score = 0.5 * (sqrt(e1x * e1x + e1y * e1y) + sqrt(e2x * e2x + e2y * e2y));
-            if (score > homography_thr) fail = 2;
-        } else {
-            // SIGNED score [x_new, 1]^T F [x_old, 1] > threshold rejects (MSCKF.py:388-390)
-            const double* Fm = s_F[s1];
-            const double v0 = Fm[0] * fu + Fm[1] * fv + Fm[2], v1 = Fm[3] * fu + Fm[4] * fv + Fm[5],
-                         v2 = Fm[6] * fu + Fm[7] * fv + Fm[8];
-            const double score = mu * v0 + mv * v1 + v2;
-            if (score > epipolar_thr) fail = 3;
+    // four slots per thread and pass: all eight loads are issued before the first test (the walk is bound by load latency)
+    constexpr int VU = 4;
+    for (int e0 = tid; e0 < nt * M; e0 += VU * MT) {
+        int jl_[VU], i_[VU], s_[VU];
+        double2 f_[VU];
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+            const int e = e0 + u * MT;
+            s_[u] = -1;
+            jl_[u] = 0;
+            i_[u] = 0;
+            f_[u] = make_double2(0.0, 0.0);
+            if (e < nt * M) {
+                jl_[u] = e / M;
+                i_[u] = e - jl_[u] * M;
+                if (i_[u] < s_len[jl_[u]]) {
+                    s_[u] = obs_slot[base + e];
+                    f_[u] = uv2[e];
+                }
+            }
         }
-        if (fail) atomicMin(&s_first[jl], i * 4 + fail);
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+            const int s1 = s_[u], jl = jl_[u], i = i_[u];
+            const double2 f = f_[u];
+            if (s1 < 0 || s1 > s2) continue;
+            const double fu = f.x, fv = f.y, mu = s_uv[jl][0], mv = s_uv[jl][1];
+            int fail = 0;
+            if (s_h[s1]) {
+                // homography H = K R K^-1 (MSCKF.py:363), H^-1 = K R^T K^-1.  Literal reference form (:364-368): the new
+                // detection is compared with ITS OWN image under H^-1, the old observation with its own image under H (not
+                // with each other); mean of the two distances
+                const double* H = s_R[s1];
+                const double* Hi = s_F[s1];
+                const double p0 = H[0] * fu + H[1] * fv + H[2], p1 = H[3] * fu + H[4] * fv + H[5], p2 = H[6] * fu + H[7] * fv + H[8];
+                const double q0 = Hi[0] * mu + Hi[1] * mv + Hi[2], q1 = Hi[3] * mu + Hi[4] * mv + Hi[5],
+                             q2 = Hi[6] * mu + Hi[7] * mv + Hi[8];
+                const double e1x = mu - q0 / q2, e1y = mv - q1 / q2;       // matched_keypoint - x1_pred
+                const double e2x = fu - p0 / p2, e2y = fv - p1 / p2;       // feature_keypoint - x2_pred
+                const double score = 0.5 * (sqrt(e1x * e1x + e1y * e1y) + sqrt(e2x * e2x + e2y * e2y));
+                if (score > homography_thr) fail = 2;
+            } else {
+                // SIGNED score [x_new, 1]^T F [x_old, 1] > threshold rejects (MSCKF.py:388-390)
+                const double* Fm = s_F[s1];
+                const double v0 = Fm[0] * fu + Fm[1] * fv + Fm[2], v1 = Fm[3] * fu + Fm[4] * fv + Fm[5],
+                             v2 = Fm[6] * fu + Fm[7] * fv + Fm[8];
+                const double score = mu * v0 + mv * v1 + v2;
+                if (score > epipolar_thr) fail = 3;
+            }
+            if (fail) atomicMin(&s_first[jl], i * 4 + fail);
+        }
     }
     __syncthreads();
     if (tid < nt) {
