@@ -28,7 +28,7 @@ struct Intrinsics { double k[9], ki[9]; };
 // HBM: 20 B per past observation (uv + slot) + 18 B per proposal.
 constexpr int V_TRACKS = 64;
 
-__global__ void __launch_bounds__(MT) verify_matches_kernel(msckf_dims dims, Intrinsics Km, double epipolar_thr,
+__global__ void __launch_bounds__(MT, 4) verify_matches_kernel(msckf_dims dims, Intrinsics Km, double epipolar_thr,
                                                             double homography_thr, const int* __restrict__ n_cams,
                                                             const double* __restrict__ cam_R, const double* __restrict__ cam_t,
                                                             const int* __restrict__ feat_len, const double* __restrict__ obs_uv,
