@@ -78,9 +78,14 @@ class MonteCarloResult:
 
 
 def run_monte_carlo(filter_indices, n_frames=30, n_landmarks=48, window=8, device="cuda", imu_per_frame=9,
-                    min_parallax=2.0, p_drop=0.05, p_outlier=0.02):
+                    min_parallax=2.0, p_drop=0.05, p_outlier=0.02, matcher="host", min_cosine_similarity=0.95,
+                    epipolar_rejection_threshold=1e9, homography_rejection_threshold=1e9):
     """Run the filters `filter_indices` (global indices: seed 42 + index, IMU-noise level index mod 3) for n_frames camera
-    frames, all of them resident on `device`."""
+    frames, all of them resident on `device`.  matcher = "host": the association of detections with tracks comes from the
+    streams' ground-truth landmark ids (TrackAssociator); "device": the host only uploads each frame's detections
+    (descriptors, keypoints, scores) and the mutual-NN matcher, the epipolar / homography tests and the bookkeeping run
+    on the device (BatchedMSCKF.frame_step_detections, MSCKF.add_camera_measurements :284-448)."""
+    assert matcher in ("host", "device")
     levels = list(synth.NOISE_LEVELS.keys())
     seqs = [synth.make_sequence(seed=42 + int(i), n_frames=n_frames, n_landmarks=n_landmarks, imu_per_frame=imu_per_frame,
                                 noise_level=levels[int(i) % len(levels)], p_drop=p_drop, p_outlier=p_outlier, shuffle=True)
@@ -128,6 +133,28 @@ def run_monte_carlo(filter_indices, n_frames=30, n_landmarks=48, window=8, devic
             assert len(a) <= F, "track capacity exceeded"
             action[b, :len(a)], new_uv[b, :len(a)], new_conf[b, :len(a)] = a, uv, cf
             gtp[b, f] = sq.gt_p[fr.imu_index + 1]
+        if matcher == "device":
+            F2 = max(len(sq.frames[f].keypoints) for sq in seqs)
+            D = seqs[0].frames[f].descriptors.shape[1]
+            desc = np.zeros((B, F2, D), np.float32)
+            kp = np.zeros((B, F2, 2))
+            sc = np.zeros((B, F2))
+            n_new = np.zeros(B, np.int32)
+            for b, sq in enumerate(seqs):
+                fr = sq.frames[f]
+                keep = fr.scores >= 0.5 * np.mean(fr.scores)              # score filter of MSCKF.py:279-282
+                n = int(keep.sum())
+                desc[b, :n], kp[b, :n], sc[b, :n], n_new[b] = fr.descriptors[keep], fr.keypoints[keep], fr.scores[keep], n
+            dv = flt.device
+            flt.frame_step_detections(torch.from_numpy(samples).to(dv), R_I_C, t_I_C, torch.from_numpy(desc).to(dv),
+                                      torch.from_numpy(kp).to(dv), torch.from_numpy(sc).to(dv), torch.from_numpy(n_new).to(dv),
+                                      window, min_cosine_similarity=min_cosine_similarity,
+                                      epipolar_rejection_threshold=epipolar_rejection_threshold,
+                                      homography_rejection_threshold=homography_rejection_threshold)
+            pos[:, f] = flt.imu_state[:, 9:12].cpu().numpy()
+            ntr[:, f] = (flt.feat_len > 0).sum(dim=1).cpu().numpy()
+            ncm[:, f] = flt.n_cams.cpu().numpy()
+            continue
         m1, m2 = flt.frame_step(torch.from_numpy(samples).to(flt.device), R_I_C, t_I_C, torch.from_numpy(action).to(flt.device),
                                 torch.from_numpy(new_uv).to(flt.device), torch.from_numpy(new_conf).to(flt.device), window,
                                 use_null_state=False, return_maps=True)

@@ -311,3 +311,15 @@ def test_whole_run_from_detections(golden_dir):
             assert worst < 1e-9, (i, errs)
     assert len(tr["frames"]) >= 50
     print("frame loop from detections, worst relative error over", len(tr["frames"]), "frames:", worst)
+
+
+def test_monte_carlo_device_matcher_equals_host_association():
+    """Monte-Carlo driver with the association done on the device from the detections (matcher = "device") against the
+    same sequences associated on the host from the ground-truth landmark ids: same tracks, same windows, same
+    trajectories, for six filters (three IMU-noise levels) over 24 frames."""
+    from monocular_visual_inertial_msckf_b200.monte_carlo import run_monte_carlo
+    host = run_monte_carlo(list(range(6)), n_frames=24, n_landmarks=40, window=8)
+    dev = run_monte_carlo(list(range(6)), n_frames=24, n_landmarks=40, window=8, matcher="device")
+    assert np.array_equal(host.n_tracks, dev.n_tracks) and np.array_equal(host.n_cams, dev.n_cams)
+    assert np.max(np.abs(host.positions - dev.positions)) < 1e-9
+    assert np.isfinite(dev.ate_rmse).all()

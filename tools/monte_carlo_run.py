@@ -28,6 +28,8 @@ if __name__ == "__main__":
     ap.add_argument("--frames", type=int, default=40)
     ap.add_argument("--landmarks", type=int, default=48)
     ap.add_argument("--window", type=int, default=8)
+    ap.add_argument("--matcher", choices=("host", "device"), default="host",
+                    help="device: the descriptor matcher / geometric tests of add_camera_measurements run on the GPU")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
@@ -36,7 +38,7 @@ if __name__ == "__main__":
     lo, hi = shard_range(args.filters, rank, world)
     t0 = time.time()
     res = run_monte_carlo(list(range(lo, hi)), n_frames=args.frames, n_landmarks=args.landmarks, window=args.window,
-                          device=f"cuda:{local}")
+                          device=f"cuda:{local}", matcher=args.matcher)
     torch.cuda.synchronize()
     wall = time.time() - t0
     stats = torch.from_numpy(np.concatenate([res.ate_rmse[:, None], res.positions[:, -1], res.gt_positions[:, -1]], axis=1)).to(f"cuda:{local}")
@@ -44,7 +46,7 @@ if __name__ == "__main__":
     if rank == 0:
         a = allstats.cpu().numpy()
         levels = list(synth.NOISE_LEVELS.keys())
-        out = dict(filters=args.filters, frames=args.frames, n_gpus=world, wall_s_rank0=wall, ate_rmse_m={})
+        out = dict(filters=args.filters, frames=args.frames, n_gpus=world, matcher=args.matcher, wall_s_rank0=wall, ate_rmse_m={})
         for k, name in enumerate(levels):
             sel = a[k::len(levels), 0]
             out["ate_rmse_m"][name] = dict(mean=float(sel.mean()), p50=float(np.median(sel)), max=float(sel.max()), n=int(len(sel)))
