@@ -18,15 +18,15 @@ constexpr int MM = 512;      // threads of a matcher CTA (thread grid 16 x 32, 1
 struct Intrinsics { double k[9], ki[9]; };
 
 // ---- geometric verification -----------------------------------------------------------------------------------------
-// CTA = (filter, 64 consecutive tracks).  Two warps stage the proposals of those tracks, two others put the relative
+// CTA = (filter, 128 consecutive tracks).  Four warps stage the proposals of those tracks, two others put the relative
 // geometry of every window camera against the newest one into shared memory (thread = camera): R = R_s^T R_new, the branch
 // flag |t| < 0.01 and the fundamental matrix in pixel coordinates F = K^-T [t]x R K^-1 (MSCKF.py:360-362, :387).  Then the
-// CTA walks the 64 x M observation slots of its tracks as ONE flat, contiguous range (coalesced 16-byte uv and 4-byte slot
+// CTA walks the 128 x M observation slots of its tracks as ONE flat, contiguous range (coalesced 16-byte uv and 4-byte slot
 // loads, all independent): every valid observation is tested -- 11 multiply-adds on the epipolar branch -- and a failure
 // enters a shared-memory atomicMin over (observation index, test); the minimum is the FIRST failing observation, which is
 // what the reference's sequential walk with `break` reports (MSCKF.py:381, :398).
 // HBM: 20 B per past observation (uv + slot) + 18 B per proposal.
-constexpr int V_TRACKS = 64;
+constexpr int V_TRACKS = 128;
 
 __global__ void __launch_bounds__(MT, 4) verify_matches_kernel(msckf_dims dims, Intrinsics Km, double epipolar_thr,
                                                             double homography_thr, const int* __restrict__ n_cams,
