@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 5
+#define MSCKF_B200_ABI_VERSION 6
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
@@ -42,6 +42,11 @@ extern "C" {
 #define MSCKF_FEAT_LOST_FLAG 0x10  /* OR-ed in when the feature is in the reference's `lost_features` dict */
 #define MSCKF_FEAT_GAMMA_BOUND 0x20 /* OR-ed in when the gate was decided by the exact bounds below (gate_mode 1):
                                       gamma[] then holds the bound that decided it, not the Mahalanobis distance */
+
+#define MSCKF_FEAT_TRIANGULATED 0x40 /* OR-ed in when the re-triangulated point projected inside the first observing
+                                       camera's image, i.e. idp_m / idp_rho were rewritten (MSCKF.py:484-490: the features
+                                       whose W_p_hat the reference appends to its debug lists estimated_world_points /
+                                       currently_processed_world_points) */
 
 /* how the chi-square gate (MSCKF.gating_test, MSCKF.py:561-568) is evaluated */
 #define MSCKF_GATE_EXACT 0     /* gamma = r_o^T (H_o P H_o^T + sigma^2 I)^-1 r_o for every selected feature */
@@ -174,12 +179,16 @@ int msckf_propagate_batched(const msckf_dims* dims, int n_samples, const double*
  * Next rows (window surgery kept on the device so P never leaves HBM between calls):
  * msckf_augment_batched  <-> MSCKF.state_augmentation (MSCKF.py:250-265): appends camera pose slot n_cams[b]
  *   (T_W_C = T_W_I * T_I_C), P <- [I; J] P [I; J]^T symmetrised, n_cams[b] += 1.   T_I_C: host R (9) + t (3).
+ *   A filter whose window already holds dims->N poses is left untouched and counted in *overflow_count (device int,
+ *   incremented; may be NULL): the reference's dict has no capacity, so the caller must size N for the longest window
+ *   (max_number_of_camera_states + 1 + the frames that can pass without a valid feature) and treat a non-zero count as
+ *   an error.
  * msckf_remove_cameras_batched <-> MSCKF.remove_cameras (MSCKF.py:751-758): deletes the poses flagged in
  *   remove_mask[B][N] (and their covariance rows/columns), compacting slots; n_cams updated.
  * ------------------------------------------------------------------------------------------------------------- */
 int msckf_augment_batched(const msckf_dims* dims, const double* T_I_C_host, const double* imu_state,
                           double* cam_R, double* cam_t, double* P, int* n_cams, const unsigned char* active,
-                          void* stream);
+                          int* overflow_count, void* stream);
 
 size_t msckf_remove_workspace_bytes(const msckf_dims* dims);
 int msckf_remove_cameras_batched(const msckf_dims* dims, const unsigned char* remove_mask,

@@ -10,6 +10,8 @@ COMPRESS_GRAM = 1
 
 FEAT_SKIPPED, FEAT_ACCEPTED, FEAT_GATED_OUT, FEAT_LOST_DISCARD, FEAT_LOST_FLAG = 0, 1, 2, 3, 0x10
 FEAT_GAMMA_BOUND = 0x20
+FEAT_TRIANGULATED = 0x40
+ABI_VERSION = 6
 GATE_EXACT, GATE_BOUNDS = 0, 1
 
 
@@ -110,7 +112,7 @@ def load_library():
     lib.msckf_propagate_batched.restype = C.c_int
     lib.msckf_propagate_batched.argtypes = [pd, C.c_int, dp, dp, dp, C.POINTER(C.c_double), dp, dp, dp, ip, vp]
     lib.msckf_augment_batched.restype = C.c_int
-    lib.msckf_augment_batched.argtypes = [pd, C.POINTER(C.c_double), dp, dp, dp, dp, ip, u8, vp]
+    lib.msckf_augment_batched.argtypes = [pd, C.POINTER(C.c_double), dp, dp, dp, dp, ip, u8, ip, vp]
     lib.msckf_remove_cameras_batched.restype = C.c_int
     lib.msckf_remove_cameras_batched.argtypes = [pd, u8, dp, dp, dp, ip, vp, C.c_size_t, vp]
     lib.msckf_probe_fp64.restype = C.c_int
@@ -139,7 +141,7 @@ def load_library():
     lib.msckf_set_stage_timing.argtypes = [C.c_int]
     lib.msckf_front_stage_ms.restype = C.c_int
     lib.msckf_front_stage_ms.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    if lib.msckf_abi_version() != 5:
+    if lib.msckf_abi_version() != ABI_VERSION:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib
     return lib

@@ -67,6 +67,9 @@ class UpdateParams:
                             compress_mode=compress_mode, gate_mode=gate_mode)
 
 
+SAMPLES_STAGE = 16      # IMU samples the small-state slab can stage per filter (the reference delivers ~10 per frame)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -89,15 +92,23 @@ class BatchedMSCKF:
                              f"N={self.N} (max {self.lib.msckf_max_cameras(params.compress_mode)} in this mode)")
         dv, f64, i32 = self.device, torch.float64, torch.int32
         z = lambda *s, dtype=f64: torch.zeros(*s, dtype=dtype, device=dv)  # noqa: E731
-        # filter state
+        # filter state.  Everything except P lives in ONE slab (imu_state, imu_null, imu_time, Qc_diag, cam_R, cam_t and a
+        # staging area for IMU samples are views of it, each padded to 256 B), so that a host-side owner of a single
+        # filter moves the whole small state with one copy in each direction (push_small / pull_small).
         self.P = z(B, self.ldp, self.ldp)
-        self.imu_state = z(B, 21)
+        layout, off = {}, 0
+        for name, shape in (("imu_state", (B, 21)), ("imu_null", (B, 15)), ("imu_time", (B,)), ("Qc_diag", (B, 4)),
+                            ("cam_R", (B, N, 9)), ("cam_t", (B, N, 3)), ("samples_stage", (B, SAMPLES_STAGE, 7))):
+            n = int(np.prod(shape))
+            layout[name] = (off, n, shape)
+            off += (n + 31) // 32 * 32
+        self.small_layout = layout
+        self.small_slab = z(off)
+        for name, (o, n, shape) in layout.items():
+            setattr(self, name, self.small_slab[o:o + n].view(shape))
+        self.small_host = None                   # pinned host mirror of the slab, created on first use
         self.imu_state[:, [0, 4, 8]] = 1.0
-        self.imu_null = z(B, 15)
         self.imu_null[:, [0, 4, 8]] = 1.0
-        self.imu_time = z(B)
-        self.cam_R = z(B, N, 9)
-        self.cam_t = z(B, N, 3)
         self.n_cams = z(B, dtype=i32)
         # tracks
         self.feat_len = z(B, F, dtype=i32)
@@ -128,14 +139,32 @@ class BatchedMSCKF:
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dv)
         self._remove_ws = None
         self._overflow = None
+        self.window_overflow = None
         self._alt_tracks = None
         self.desc_sum = self.desc_w = None       # per-track descriptor sums of frame_step_detections
         self._samples_dev = None
-        self.Qc_diag = z(B, 4)
 
     # ------------------------------------------------------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def small_host_views(self):
+        """numpy views (name -> array of the field's shape) of the pinned host mirror of the small-state slab."""
+        if self.small_host is None:
+            self.small_host = torch.zeros(self.small_slab.numel(), dtype=torch.float64).pin_memory()
+            self.small_host.copy_(self.small_slab)
+            a = self.small_host.numpy()
+            self._small_np = {name: a[o:o + n].reshape(shape) for name, (o, n, shape) in self.small_layout.items()}
+        return self._small_np
+
+    def push_small(self):
+        """host mirror -> device: IMU state, null state, time, noise densities, window poses, staged samples (one H2D)."""
+        self.small_slab.copy_(self.small_host, non_blocking=True)
+
+    def pull_small(self):
+        """device -> host mirror (one D2H) and wait for it."""
+        self.small_host.copy_(self.small_slab, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
 
     def _front_tail(self):
         return [_ptr(self.cam_R), _ptr(self.cam_t), _ptr(self.n_cams), _ptr(self.feat_len), _ptr(self.obs_uv),
@@ -239,12 +268,26 @@ class BatchedMSCKF:
         _lib.check(rc, "msckf_filter_step_host")
 
     def augment(self, R_I_C, t_I_C, active=None):
+        """state_augmentation (MSCKF.py:250-265) for every (active) filter.  A filter whose window is already full is left
+        untouched and counted in self.window_overflow (device int32; the reference's dict has no capacity, so size N for
+        max_number_of_camera_states + 1 + the frames that may pass without a valid feature); check_window_overflow() raises."""
         T = (C.c_double * 12)(*[float(x) for x in np.asarray(R_I_C, float).flatten()],
                               *[float(x) for x in np.asarray(t_I_C, float).flatten()])
+        if self.window_overflow is None:
+            self.window_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         rc = self.lib.msckf_augment_batched(C.byref(self.dims), T, _ptr(self.imu_state), _ptr(self.cam_R),
                                             _ptr(self.cam_t), _ptr(self.P), _ptr(self.n_cams), _ptr(active),
-                                            self._stream())
+                                            _ptr(self.window_overflow), self._stream())
         _lib.check(rc, "msckf_augment_batched")
+
+    def check_window_overflow(self):
+        """Raises if any state_augmentation found its filter's window full since the last check (synchronises)."""
+        if self.window_overflow is not None:
+            n = int(self.window_overflow.item())
+            if n:
+                self.window_overflow.zero_()
+                raise OverflowError(f"{n} state augmentation(s) found the camera window full (N = {self.N}): the new pose was "
+                                    "NOT appended; allocate a larger N")
 
     def remove_cameras(self, mask):
         """mask: [B, N] uint8 device tensor, 1 = delete that window slot."""

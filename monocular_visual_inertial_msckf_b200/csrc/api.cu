@@ -8,8 +8,6 @@ static std::atomic<long long> g_launches{0};
 void msckf_count_launch(int n) { g_launches += n; }
 int tsqr_max_cams();
 bool gram_supported(const msckf_dims& d);
-bool front_warp_supported(const msckf_dims& d);
-cudaError_t launch_front_warp(const FrontArgs& a, cudaStream_t s);
 bool front_split_supported(const msckf_dims& d);
 int front_split_sub_filters(const msckf_dims& d);
 size_t front_split_tile_bytes(const msckf_dims& d);
@@ -127,12 +125,11 @@ int msckf_front_batched(const msckf_dims* dims, const msckf_update_params* param
     FrontArgs a = make_front(dims, params, chi2_table, chi2_len, P, cam_R, cam_t, n_cams, feat_len, obs_uv, obs_dir,
                              obs_conf, obs_slot, idp_base, idp_anchor_slot, idp_m, idp_rho, lost_cnt, tracked_cnt,
                              feat_status, gamma, dof, (char*)workspace, w);
-    // warp-per-feature kernel when the track length / window fit its tile budget, CTA-per-feature kernel otherwise
-    // split front end (assembly kernel + factorisation kernel) by default; MSCKF_FRONT_FUSED=1 selects the fused kernel
-    if (front_split_supported(*dims) && !getenv("MSCKF_FRONT_FUSED"))
+    // warp-per-feature pair (assembly kernel + factorisation kernel) when the track length / window fit its tile budget,
+    // CTA-per-feature kernel otherwise
+    if (front_split_supported(*dims))
         return (int)launch_front_split(a, (double2*)((char*)workspace + w.k_tiles), (int*)((char*)workspace + w.pend_list),
                                        (int*)((char*)workspace + w.pend_count), (cudaStream_t)stream);
-    if (front_warp_supported(*dims)) return (int)launch_front_warp(a, (cudaStream_t)stream);
     return (int)launch_front(a, (cudaStream_t)stream);
 }
 
@@ -174,7 +171,7 @@ int msckf_apply_update_batched(const msckf_dims* dims, const msckf_update_params
     a.scratch = (double*)((char*)workspace + w.scratch);
     a.scratch_per_cta = w.scratch_per_cta / sizeof(double);
     if (params->compress_mode == MSCKF_COMPRESS_QR) return (int)launch_apply(a, w.n_update_ctas, (cudaStream_t)stream);
-    if (update_smem_supported(*dims) && !getenv("MSCKF_UPDATE_L2")) return (int)launch_update_smem(a, w.n_update_ctas, (cudaStream_t)stream);
+    if (update_smem_supported(*dims)) return (int)launch_update_smem(a, w.n_update_ctas, (cudaStream_t)stream);
     return (int)launch_update_info(a, w.n_update_ctas, (cudaStream_t)stream);
 }
 
@@ -214,12 +211,14 @@ int msckf_propagate_batched(const msckf_dims* dims, int n_samples, const double*
 }
 
 int msckf_augment_batched(const msckf_dims* dims, const double* T_I_C_host, const double* imu_state, double* cam_R,
-                          double* cam_t, double* P, int* n_cams, const unsigned char* active, void* stream) {
+                          double* cam_t, double* P, int* n_cams, const unsigned char* active, int* overflow_count,
+                          void* stream) {
     int rc = check_dims(dims);
     if (rc) return rc;
     if (!T_I_C_host || !imu_state || !cam_R || !cam_t || !P || !n_cams) return MSCKF_EINVAL;
     if (15 + 6 * dims->N > 512) return MSCKF_ECAPACITY;
-    return (int)launch_augment(*dims, T_I_C_host, imu_state, cam_R, cam_t, P, n_cams, active, (cudaStream_t)stream);
+    return (int)launch_augment(*dims, T_I_C_host, imu_state, cam_R, cam_t, P, n_cams, active, overflow_count,
+                               (cudaStream_t)stream);
 }
 
 size_t msckf_remove_workspace_bytes(const msckf_dims* dims) {
@@ -335,8 +334,9 @@ struct HostStepCtx {
     int device = -1;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_entry = nullptr, ev_out_done = nullptr;
-    cudaEvent_t ev_in[HS_MAX_CHUNKS] = {}, ev_done[HS_MAX_CHUNKS] = {};
+    cudaEvent_t ev_in[HS_MAX_CHUNKS] = {}, ev_done[HS_MAX_CHUNKS] = {}, ev_out[HS_MAX_CHUNKS] = {};
     int n_events = 0;
+    int last_chunk_filters = -1, last_B = -1;   // chunk geometry of the previous call (the per-chunk events refer to it)
 };
 HostStepCtx g_hs[16];
 
@@ -356,6 +356,7 @@ cudaError_t hs_ctx(HostStepCtx** out, int n_chunks) {
     for (; c.n_events < n_chunks; ++c.n_events) {
         if ((e = cudaEventCreateWithFlags(&c.ev_in[c.n_events], cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&c.ev_done[c.n_events], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&c.ev_out[c.n_events], cudaEventDisableTiming)) != cudaSuccess) return e;
     }
     *out = &c;
     return cudaSuccess;
@@ -387,14 +388,21 @@ extern "C" int msckf_filter_step_host(const msckf_dims* dims, const msckf_update
     cudaStream_t sc = (cudaStream_t)stream;
     const size_t FM = (size_t)F * M;
 #define HS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
-    if (!overlap_previous) {
+    // The per-chunk events order this call's uploads after the previous call's kernels AND downloads of the same chunk;
+    // they mean that only while the chunk geometry is unchanged -- otherwise fall back to "after everything enqueued".
+    const bool same_chunks = cx->last_chunk_filters == chunk_filters && cx->last_B == B;
+    if (!overlap_previous || !same_chunks) {
         HS_TRY(cudaEventRecord(cx->ev_entry, sc));
         HS_TRY(cudaStreamWaitEvent(cx->s_in, cx->ev_entry, 0));
+        HS_TRY(cudaStreamWaitEvent(cx->s_in, cx->ev_out_done, 0));   // (a never-recorded event is complete)
     }
+    cx->last_chunk_filters = chunk_filters;
+    cx->last_B = B;
     for (int k = 0; k < n_chunks; ++k) {
         const int b0 = k * chunk_filters, nb = (b0 + chunk_filters <= B) ? chunk_filters : B - b0;
         // ---- uploads of this chunk (after the previous call's kernels of the same chunk released the buffers) ----
         HS_TRY(cudaStreamWaitEvent(cx->s_in, cx->ev_done[k], 0));
+        HS_TRY(cudaStreamWaitEvent(cx->s_in, cx->ev_out[k], 0));   // idp_m / idp_rho are upload targets AND download sources
         const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
         HS_TRY(hs_copy(dev->feat_len, io->feat_len, F, b0, nb, H2D, cx->s_in));
         HS_TRY(hs_copy(dev->obs_uv, io->obs_uv, FM * 2, b0, nb, H2D, cx->s_in));
@@ -444,6 +452,7 @@ extern "C" int msckf_filter_step_host(const msckf_dims* dims, const msckf_update
         HS_TRY(hs_copy(io->delta_x, (const double*)dev->delta_x, ldp, b0, nb, D2H, cx->s_out));
         HS_TRY(hs_copy(io->n_accepted, (const int*)dev->n_accepted, 1, b0, nb, D2H, cx->s_out));
         HS_TRY(hs_copy(io->n_rejected, (const int*)dev->n_rejected, 1, b0, nb, D2H, cx->s_out));
+        HS_TRY(cudaEventRecord(cx->ev_out[k], cx->s_out));
     }
     HS_TRY(cudaEventRecord(cx->ev_out_done, cx->s_out));
     HS_TRY(cudaStreamWaitEvent(sc, cx->ev_out_done, 0));

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
     double* sm = sS + nS;                   // [64] small scratch
     int* sslot = (int*)(sm + 64);           // [Mcap]
     unsigned char* s_trow = (unsigned char*)(sslot + Mcap);   // [tri(n2cap + 1)] packed index -> row lookup
-    __shared__ int s_flag[4];               // 0: selection code, 1: rank
+    __shared__ int s_flag[4];               // 0: selection code, 1: rank, 2: MSCKF_FEAT_TRIANGULATED or 0
     __shared__ double s_red[FRONT_THREADS / 32];
 
     double* facA = a.fac_A + fj * (size_t)Mcap * 12;
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
             code = (lost || enough) ? (MSCKF_FEAT_ACCEPTED | (lost ? MSCKF_FEAT_LOST_FLAG : 0)) : MSCKF_FEAT_SKIPPED;
         }
         s_flag[0] = code;
+        s_flag[2] = 0;
     }
     for (int i = tid; i < M; i += nth) sslot[i] = slot[i];
     for (int e = tid; e < tri(n2 + 1); e += nth) s_trow[e] = (unsigned char)tri_row(e);
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
                 m0 = wx / wn; m1 = wy / wn; m2 = wz / wn;
                 a.idp_rho[fj] = rho;
                 a.idp_m[fj * 3] = m0; a.idp_m[fj * 3 + 1] = m1; a.idp_m[fj * 3 + 2] = m2;
+                s_flag[2] = MSCKF_FEAT_TRIANGULATED;
             }
         }
         const int as = a.idp_anchor_slot[fj];
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
         if (tid == 0) {
             const double crit = a.chi2_table[0];
             const bool pass = 0.0 <= crit;
-            a.feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (code & MSCKF_FEAT_LOST_FLAG));
+            a.feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (code & MSCKF_FEAT_LOST_FLAG) | s_flag[2]);
             a.gamma[fj] = 0.0;
             a.dof[fj] = 0;
             a.fac_rank[fj] = rank;
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
         for (int w = 0; w < (nth + 31) / 32; ++w) g += s_red[w];
         const double crit = (dofv < a.chi2_len) ? a.chi2_table[dofv] : nan("");
         const bool pass = g <= crit;
-        a.feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (code & MSCKF_FEAT_LOST_FLAG));
+        a.feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (code & MSCKF_FEAT_LOST_FLAG) | s_flag[2]);
         a.gamma[fj] = g;
         a.dof[fj] = dofv;
         a.fac_rank[fj] = rank;

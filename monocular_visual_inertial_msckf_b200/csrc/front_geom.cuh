@@ -1,5 +1,5 @@
-// Lane-per-observation geometry of one feature track shared by the warp-per-feature front-end kernels
-// (front_warp.cu: fused gate; front_split.cu: assembly + factorisation as two kernels):
+// Lane-per-observation geometry of one feature track for the warp-per-feature front-end kernels
+// (front_split.cu: assembly + factorisation as two kernels):
 //   selection + closed-form triangulation     reference src/msckf/MSCKF.py:458-495, src/utils/geometry.py:274-303
 //   residual + Jacobian blocks                MSCKF.py:497-548, src/msckf/Camera.py:54-67
 //   orthonormal basis Q1 of range(H_f), rank by SciPy's null_space rule, r~ = (I - Q1 Q1^T) r   MSCKF.py:554-559
@@ -211,7 +211,7 @@ __device__ __forceinline__ GeoConsts make_geo_consts(const FrontArgs& a) {
 }
 
 // Rows 3-7 for the feature fj of M observations held one per lane in `o` (sR / sT: the staged window poses).
-// Returns the selection code (MSCKF_FEAT_*); when it is MSCKF_FEAT_ACCEPTED (| LOST_FLAG) the outputs hold the
+// Returns the selection code (MSCKF_FEAT_*); when it is MSCKF_FEAT_ACCEPTED (| LOST_FLAG | TRIANGULATED) the outputs hold the
 // observability-projected 2x6 block Hx, the lane's two rows of Q1 (zero columns beyond `rank`) and r~.  Re-triangulated
 // (rho, m) are written back by lane 0 (MSCKF.py:485-488).
 __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoConsts& gc, size_t fj, int M, int lane,
@@ -322,6 +322,7 @@ __device__ __forceinline__ int feature_geometry(const FrontArgs& a, const GeoCon
                 rho = 1.0 / cz;                      // InverseDepthPoint.update, geometry.py:61-71
                 const double iwn = fast_rsqrt(wx * wx + wy * wy + wz * wz);
                 m0 = wx * iwn; m1 = wy * iwn; m2 = wz * iwn;
+                code |= MSCKF_FEAT_TRIANGULATED;
                 if (lane == 0) {
                     a.idp_rho[fj] = rho;
                     a.idp_m[fj * 3] = m0; a.idp_m[fj * 3 + 1] = m1; a.idp_m[fj * 3 + 2] = m2;

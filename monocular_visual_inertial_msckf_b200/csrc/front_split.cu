@@ -4,9 +4,10 @@
 //   left-null-space projection of H_f         MSCKF.py:554-559
 //   chi-square Mahalanobis gate               MSCKF.py:561-568
 //
-// The fused kernel (front_warp.cu) keeps the 2M x 2M matrix K = H_x P H_x^T + sigma^2 I of a feature in registers while
+// A single fused kernel would have to keep the 2M x 2M matrix K = H_x P H_x^T + sigma^2 I of a feature in registers while
 // the camera block of P occupies the SM's shared memory: 255 registers x 8 warps, two warps per scheduler, and every
-// phase of it is latency-bound (profiles/r01n).  Here the two halves get the resources each one needs:
+// phase of it is latency-bound (measured in round 1: 42.6 ms against 18.6 ms, profiles/r01n; that kernel was removed).
+// Here the two halves get the resources each one needs:
 //
 //   front_asm_kernel   CTA = (filter, feature chunk: a whole filter when the batch fills the machine), 16 warps, <= 128
 //                      registers.  P's camera block (lower block triangle, 6x6 blocks padded to 38 doubles -> conflict-free
@@ -28,7 +29,6 @@
 //
 // gamma = y.y - (V^T y)^T (V^T V)^-1 (V^T y),  y = L^-1 r~,  V = L^-1 Q1  (basis-free form of the projected Mahalanobis
 // distance).
-#include <cstdlib>
 #include "msckf_common.cuh"
 #include "dense.cuh"
 #include "front_geom.cuh"
@@ -41,6 +41,7 @@ constexpr int FA_THREADS = 512;
 constexpr int FA_WARPS = FA_THREADS / 32;
 constexpr int FC_THREADS = 128;
 constexpr int FC_WARPS = FC_THREADS / 32;
+constexpr int FLAG_KEEP = MSCKF_FEAT_LOST_FLAG | MSCKF_FEAT_TRIANGULATED;   // selection flags carried into the final status
 constexpr int TC = 9;                          // 8x8 tile columns: up to 64 measurement rows (32 observations) + 4 appended rows
 constexpr int NTILE = TC * (TC + 1) / 2;
 constexpr int PB = 38;                         // doubles per staged 6x6 block of P (stride 76 words = 12 mod 32)
@@ -179,7 +180,7 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                 if (lane == 0) {
                     const double crit = a.chi2_table[0];
                     const bool pass = 0.0 <= crit;
-                    a.feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (code & MSCKF_FEAT_LOST_FLAG));
+                    a.feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (code & FLAG_KEEP));
                     a.gamma[fj] = 0.0;
                     a.dof[fj] = 0;
                     a.fac_rank[fj] = rank;
@@ -209,7 +210,7 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                 if (acc || rej) {
                     if (lane == 0) {
                         a.feat_status[fj] = (unsigned char)((acc ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) |
-                                                            (code & MSCKF_FEAT_LOST_FLAG) | MSCKF_FEAT_GAMMA_BOUND);
+                                                            (code & FLAG_KEEP) | MSCKF_FEAT_GAMMA_BOUND);
                         a.gamma[fj] = acc ? gub : glb;
                         a.dof[fj] = dofv;
                         a.fac_rank[fj] = rank;
@@ -222,7 +223,7 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
             const int fl = bl * F + j;
             int pend_pos = 0;     // (the list position is consumed after the pair loop: the atomic's latency stays hidden)
             if (lane == 0) {
-                a.feat_status[fj] = (unsigned char)(MSCKF_FEAT_PENDING | (code & MSCKF_FEAT_LOST_FLAG));
+                a.feat_status[fj] = (unsigned char)(MSCKF_FEAT_PENDING | (code & FLAG_KEEP));
                 a.dof[fj] = dofv;
                 a.fac_rank[fj] = rank;
                 pend_pos = atomicAdd(pend_count, 1);
@@ -565,7 +566,7 @@ front_chol_kernel(const double2* __restrict__ Kbuf, const int* __restrict__ pend
         if (lane == 0) {
             const double crit = (dofv < chi2_len) ? chi2_table[dofv] : nan("");
             const bool pass = gam <= crit;
-            feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (st & MSCKF_FEAT_LOST_FLAG));
+            feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (st & FLAG_KEEP));
             gamma[fj] = gam;
         }
     }
@@ -650,8 +651,8 @@ cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list
         }
         // feature chunks per filter so that the CTAs come in >= ~6 waves of 148 (each warp keeps >= 2 features): long CTAs
         // amortise the staggered start of their warps (measured: 13.3 ms -> 12.0 ms per 4096 filters with both)
-        static const int waves = getenv("MSCKF_ASM_WAVES") ? atoi(getenv("MSCKF_ASM_WAVES")) : 6;
-        static const unsigned stagger_ns = getenv("MSCKF_ASM_STAGGER_NS") ? (unsigned)atoi(getenv("MSCKF_ASM_STAGGER_NS")) : 1500u;
+        constexpr int waves = 6;
+        constexpr unsigned stagger_ns = 1500u;
         int chunks = (waves * 148 + nb - 1) / nb;
         int fpc = (F + chunks - 1) / chunks;
         if (fpc < 2 * FA_WARPS) fpc = 2 * FA_WARPS;

@@ -103,7 +103,8 @@ cudaError_t launch_propagate(const msckf_dims& d, int n_samples, const double* s
                              const double* Qc_diag, const double* g, double* imu_state, double* imu_null, double* P,
                              const int* n_cams, cudaStream_t s);
 cudaError_t launch_augment(const msckf_dims& d, const double* T_I_C, const double* imu_state, double* cam_R,
-                           double* cam_t, double* P, int* n_cams, const unsigned char* active, cudaStream_t s);
+                           double* cam_t, double* P, int* n_cams, const unsigned char* active, int* overflow,
+                           cudaStream_t s);
 cudaError_t launch_remove(const msckf_dims& d, const unsigned char* mask, double* cam_R, double* cam_t, double* P,
                           int* n_cams, double* scratch, cudaStream_t s);
 

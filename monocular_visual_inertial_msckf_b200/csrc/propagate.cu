@@ -1,232 +1,17 @@
 // Row 11 of SURVEY.md section 8a: MSCKF.process_imu (reference src/msckf/MSCKF.py:160-248) + IMU.integrate
 // (src/msckf/IMU.py:78-100), n_samples per launch, one CTA per filter.
 //
-// The 15x15 IMU block, the transition matrix and the 15 x 6N cross-covariance strip stay in shared memory across all
-// the samples between two camera frames; HBM is touched once: read P[0:15, :] (15 d doubles), write P[0:15, :] and its
-// transpose P[:, 0:15].  The camera block of P is not touched: the reference's global (P + P^T)/2 (MSCKF.py:244) is the
+// The 15x15 IMU block and the composed transition matrix stay in shared memory across all the samples between two camera
+// frames; HBM is touched once: read P[0:15, :] (15 d doubles), write P[0:15, :] and its transpose P[:, 0:15].  The camera block of P is not touched: the reference's global (P + P^T)/2 (MSCKF.py:244) is the
 // identity on it because every producer of P leaves it exactly symmetric.
-#include <cstdlib>
 #include "msckf_common.cuh"
 
 namespace {
 
 constexpr int PT = 128;
 
-// C (n x m) = A (n x k) B (k x m), all row-major with the given leading dimensions, summed in k order
-__device__ __forceinline__ void mm_small(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int n,
-                                         int m, int k) {
-    for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
-        const int i = e / m, j = e - i * m;
-        double acc = 0.0;
-        for (int l = 0; l < k; ++l) acc += A[i * lda + l] * B[l * ldb + j];
-        C[i * ldc + j] = acc;
-    }
-}
-
-__global__ void __launch_bounds__(PT) propagate_kernel(msckf_dims dims, int n_samples, const double* __restrict__ samples,
-                                                       double* imu_time, const double* __restrict__ Qc_diag, double g0,
-                                                       double g1, double g2, double* imu_state, double* imu_null,
-                                                       double* Pall, const int* __restrict__ n_cams) {
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int ldp = dims.ldp;
-    const int nc = n_cams[b];
-    const int c = 6 * nc;
-    double* P = Pall + (size_t)b * ldp * ldp;
-
-    extern __shared__ double sm[];
-    double* sPic = sm;                       // [15][c]
-    double* sPic2 = sPic + 15 * 6 * dims.N;  // [15][c]
-    double* sF = sPic2 + 15 * 6 * dims.N;    // Fdt
-    double* sF2 = sF + 225;
-    double* sF3 = sF2 + 225;
-    double* sPhi = sF3 + 225;
-    double* sT1 = sPhi + 225;
-    double* sT2 = sT1 + 225;
-    double* sPii = sT2 + 225;
-    double* sQ = sPii + 225;
-    double* st = sQ + 225;                   // [21] state  R t v bg ba
-    double* sn = st + 21;                    // [15] null   R t v
-    double* sc = sn + 15;                    // scalars: dt, time, w(3), a(3)
-    const double g[3] = {g0, g1, g2};
-
-    for (int e = tid; e < 15 * c; e += PT) sPic[e] = P[(size_t)(e / c) * ldp + 15 + (e % c)];
-    for (int e = tid; e < 225; e += PT) sPii[e] = P[(size_t)(e / 15) * ldp + (e % 15)];
-    if (tid < 21) st[tid] = imu_state[(size_t)b * 21 + tid];
-    if (tid < 15) sn[tid] = imu_null ? imu_null[(size_t)b * 15 + tid] : imu_state[(size_t)b * 21 + tid];
-    if (tid == 0) sc[1] = imu_time[b];
-    __syncthreads();
-
-    for (int smp = 0; smp < n_samples; ++smp) {
-        const double* z = samples + ((size_t)b * n_samples + smp) * 7;
-        for (int e = tid; e < 225; e += PT) sF[e] = 0.0;
-        __syncthreads();
-        if (tid == 0) {
-            const double dt = z[0] - sc[1];
-            sc[0] = dt;
-            sc[1] = z[0];
-            double w[3], a[3];
-            for (int k = 0; k < 3; ++k) {
-                w[k] = z[1 + k] - st[15 + k];
-                a[k] = z[4 + k] - st[18 + k];
-            }
-            double* R = st;
-            double* p = st + 9;
-            double* v = st + 12;
-            // IMU.integrate
-            const double wn = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-            const double theta = wn * dt;
-            double dR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-            if (theta > 0.0) {
-                const double x = w[0] / wn, y = w[1] / wn, zz = w[2] / wn;
-                const double K[9] = {0, -zz, y, zz, 0, -x, -y, x, 0};
-                double K2[9];
-                for (int r = 0; r < 3; ++r)
-                    for (int cc = 0; cc < 3; ++cc) K2[r * 3 + cc] = K[r * 3] * K[cc] + K[r * 3 + 1] * K[3 + cc] + K[r * 3 + 2] * K[6 + cc];
-                const double sn_ = sin(theta), cs = 1.0 - cos(theta);
-                for (int k = 0; k < 9; ++k) dR[k] = dR[k] + sn_ * K[k] + cs * K2[k];
-            }
-            double Rn[9];
-            for (int r = 0; r < 3; ++r)
-                for (int cc = 0; cc < 3; ++cc) Rn[r * 3 + cc] = R[r * 3] * dR[cc] + R[r * 3 + 1] * dR[3 + cc] + R[r * 3 + 2] * dR[6 + cc];
-            double aw[3];
-            for (int r = 0; r < 3; ++r) aw[r] = (R[r * 3] * a[0] + R[r * 3 + 1] * a[1] + R[r * 3 + 2] * a[2]) - g[r];
-            for (int r = 0; r < 3; ++r) {
-                p[r] = p[r] + v[r] * dt + 0.5 * aw[r] * (dt * dt);
-                v[r] = v[r] + aw[r] * dt;
-            }
-            for (int k = 0; k < 9; ++k) R[k] = Rn[k];
-            // F dt (MSCKF.py:179-192, 215) with the post-integration rotation
-            const double sw[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
-            const double sa[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
-            for (int r = 0; r < 3; ++r)
-                for (int cc = 0; cc < 3; ++cc) {
-                    sF[r * 15 + cc] = (-sw[r * 3 + cc]) * dt;
-                    sF[r * 15 + 3 + cc] = (r == cc ? -1.0 : -0.0) * dt;
-                    const double ra = Rn[r * 3] * sa[cc] + Rn[r * 3 + 1] * sa[3 + cc] + Rn[r * 3 + 2] * sa[6 + cc];
-                    sF[(6 + r) * 15 + cc] = (-ra) * dt;
-                    sF[(6 + r) * 15 + 9 + cc] = (-Rn[r * 3 + cc]) * dt;
-                    sF[(12 + r) * 15 + 6 + cc] = (r == cc ? 1.0 : 0.0) * dt;
-                }
-            for (int k = 0; k < 3; ++k) { sc[2 + k] = w[k]; sc[5 + k] = a[k]; }
-        }
-        __syncthreads();
-        mm_small(sF2, 15, sF, 15, sF, 15, 15, 15, 15);
-        __syncthreads();
-        mm_small(sF3, 15, sF2, 15, sF, 15, 15, 15, 15);
-        __syncthreads();
-        for (int e = tid; e < 225; e += PT) {
-            const double eye = ((e / 15) == (e % 15)) ? 1.0 : 0.0;
-            sPhi[e] = ((eye + sF[e]) + 0.5 * sF2[e]) + (1.0 / 6.0) * sF3[e];
-        }
-        __syncthreads();
-        if (tid == 0) {   // observability fix-up (MSCKF.py:221-233); null state = state before this integration
-            const double dt = sc[0];
-            const double* R = st;
-            const double* p = st + 9;
-            const double* v = st + 12;
-            const double* Rn = sn;
-            const double* tn = sn + 9;
-            const double* vn = sn + 12;
-            for (int r = 0; r < 3; ++r)
-                for (int cc = 0; cc < 3; ++cc)
-                    sPhi[r * 15 + cc] = R[r * 3] * Rn[cc * 3] + R[r * 3 + 1] * Rn[cc * 3 + 1] + R[r * 3 + 2] * Rn[cc * 3 + 2];
-            double u[3], s[3];
-            for (int r = 0; r < 3; ++r) u[r] = Rn[r * 3] * g[0] + Rn[r * 3 + 1] * g[1] + Rn[r * 3 + 2] * g[2];
-            const double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
-            for (int r = 0; r < 3; ++r) s[r] = u[r] / uu;
-            const double d1[3] = {vn[0] - v[0], vn[1] - v[1], vn[2] - v[2]};
-            const double d2[3] = {dt * vn[0] + tn[0] - p[0], dt * vn[1] + tn[1] - p[1], dt * vn[2] + tn[2] - p[2]};
-            const double w1[3] = {d1[1] * g[2] - d1[2] * g[1], d1[2] * g[0] - d1[0] * g[2], d1[0] * g[1] - d1[1] * g[0]};
-            const double w2[3] = {d2[1] * g[2] - d2[2] * g[1], d2[2] * g[0] - d2[0] * g[2], d2[0] * g[1] - d2[1] * g[0]};
-            for (int r = 0; r < 3; ++r) {
-                double* av = sPhi + (6 + r) * 15;
-                double* ap = sPhi + (12 + r) * 15;
-                const double ev = (av[0] * u[0] + av[1] * u[1] + av[2] * u[2]) - w1[r];
-                const double ep = (ap[0] * u[0] + ap[1] * u[1] + ap[2] * u[2]) - w2[r];
-                for (int cc = 0; cc < 3; ++cc) {
-                    av[cc] = av[cc] - ev * s[cc];
-                    ap[cc] = ap[cc] - ep * s[cc];
-                }
-            }
-            // null state <- current (MSCKF.py:247-248); used from the next sample on
-        }
-        __syncthreads();
-        // Q = Phi G Qc G^T Phi^T dt, evaluated left to right like the reference (MSCKF.py:237)
-        {
-            const double* R = st;
-            const double* qc = Qc_diag + (size_t)b * 4;
-            // T1 = (Phi G) Qc : 15 x 12
-            for (int e = tid; e < 15 * 12; e += PT) {
-                const int i = e / 12, j = e % 12;
-                const int blk = j / 3, jj = j % 3;
-                double v;
-                if (blk == 0) v = -sPhi[i * 15 + jj];
-                else if (blk == 1) v = sPhi[i * 15 + 3 + jj];
-                else if (blk == 2) v = sPhi[i * 15 + 6] * (-R[jj]) + sPhi[i * 15 + 7] * (-R[3 + jj]) + sPhi[i * 15 + 8] * (-R[6 + jj]);
-                else v = sPhi[i * 15 + 9 + jj];
-                sT1[i * 12 + j] = v * qc[blk];
-            }
-            __syncthreads();
-            // T2 = T1 G^T : 15 x 15
-            for (int e = tid; e < 225; e += PT) {
-                const int i = e / 15, j = e % 15;
-                const int blk = j / 3, jj = j % 3;
-                double v;
-                if (blk == 0) v = -sT1[i * 12 + jj];
-                else if (blk == 1) v = sT1[i * 12 + 3 + jj];
-                else if (blk == 2) v = sT1[i * 12 + 6] * (-R[jj * 3]) + sT1[i * 12 + 7] * (-R[jj * 3 + 1]) + sT1[i * 12 + 8] * (-R[jj * 3 + 2]);
-                else if (blk == 3) v = sT1[i * 12 + 9 + jj];
-                else v = 0.0;
-                sT2[e] = v;
-            }
-            __syncthreads();
-            // Q = (T2 Phi^T) dt
-            const double dt = sc[0];
-            for (int e = tid; e < 225; e += PT) {
-                const int i = e / 15, j = e % 15;
-                double acc = 0.0;
-                for (int l = 0; l < 15; ++l) acc += sT2[i * 15 + l] * sPhi[j * 15 + l];
-                sQ[e] = acc * dt;
-            }
-            __syncthreads();
-        }
-        // P_II <- (Phi P_II) Phi^T + Q ; P_IC <- Phi P_IC
-        mm_small(sT1, 15, sPhi, 15, sPii, 15, 15, 15, 15);
-        mm_small(sPic2, c, sPhi, 15, sPic, c, 15, c, 15);
-        __syncthreads();
-        for (int e = tid; e < 225; e += PT) {
-            const int i = e / 15, j = e % 15;
-            double acc = 0.0;
-            for (int l = 0; l < 15; ++l) acc += sT1[i * 15 + l] * sPhi[j * 15 + l];
-            sT2[e] = acc + sQ[e];
-        }
-        __syncthreads();
-        for (int e = tid; e < 225; e += PT) {
-            const int i = e / 15, j = e % 15;
-            sPii[e] = (sT2[i * 15 + j] + sT2[j * 15 + i]) / 2;
-        }
-        for (int e = tid; e < 15 * c; e += PT) sPic[e] = sPic2[e];
-        if (tid < 15) sn[tid] = st[tid];
-        __syncthreads();
-    }
-
-    for (int e = tid; e < 15 * c; e += PT) {
-        const int i = e / c, j = e % c;
-        P[(size_t)i * ldp + 15 + j] = sPic[e];
-    }
-    for (int e = tid; e < 15 * c; e += PT) {   // transpose strip, 15 contiguous doubles per row
-        const int j = e / 15, i = e % 15;
-        P[(size_t)(15 + j) * ldp + i] = sPic[i * c + j];
-    }
-    for (int e = tid; e < 225; e += PT) P[(size_t)(e / 15) * ldp + (e % 15)] = sPii[e];
-    if (tid < 21) imu_state[(size_t)b * 21 + tid] = st[tid];
-    if (tid < 15 && imu_null) imu_null[(size_t)b * 15 + tid] = sn[tid];
-    if (tid == 0) imu_time[b] = sc[1];
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------------
-// v2: the same arithmetic reorganised so that nothing but a 3x3 recurrence is serial.
+// The arithmetic is organised so that nothing but a 3x3 recurrence is serial.
 //   A  thread k: sample k's dt, bias-corrected w / a and its rotation increment exp(w dt) (the sin / cos / sqrt)
 //   B  thread 0: the state recurrence R <- R dR, p, v over the chunk (the only sequential part: ~60 flops per sample)
 //   C  warp w, samples w, w + 4, ...: F dt, Phi = I + F + F^2/2 + F^3/6, the observability fix-up and Q_k, all from the
@@ -526,29 +311,16 @@ __global__ void __launch_bounds__(PT, 4) propagate_kernel_v2(msckf_dims dims, in
 cudaError_t launch_propagate(const msckf_dims& d, int n_samples, const double* samples, double* imu_time,
                              const double* Qc_diag, const double* g, double* imu_state, double* imu_null, double* P,
                              const int* n_cams, cudaStream_t s) {
-    if (!getenv("MSCKF_PROPAGATE_V1")) {
-        const int cap = n_samples < PCH ? n_samples : PCH;
-        const size_t smem = ((size_t)cap * 450 + 4 * 450 + 4 * 225 + 21 + 15 + 1) * sizeof(double) + (size_t)cap * sizeof(SampleState);
-        static size_t configured2 = 0;
-        if (smem > 48 * 1024 && smem > configured2) {
-            cudaError_t e = cudaFuncSetAttribute(propagate_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured2 = smem;
-        }
-        propagate_kernel_v2<<<d.B, PT, smem, s>>>(d, n_samples, samples, imu_time, Qc_diag, g[0], g[1], g[2], imu_state,
-                                                   imu_null, P, n_cams, cap);
-        msckf_count_launch(1);
-        return cudaGetLastError();
-    }
-    const size_t smem = ((size_t)2 * 15 * 6 * d.N + 8 * 225 + 21 + 15 + 16) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int cap = n_samples < PCH ? n_samples : PCH;
+    const size_t smem = ((size_t)cap * 450 + 4 * 450 + 4 * 225 + 21 + 15 + 1) * sizeof(double) + (size_t)cap * sizeof(SampleState);
+    static size_t configured2 = 0;
+    if (smem > 48 * 1024 && smem > configured2) {
+        cudaError_t e = cudaFuncSetAttribute(propagate_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured2 = smem;
     }
-    propagate_kernel<<<d.B, PT, smem, s>>>(d, n_samples, samples, imu_time, Qc_diag, g[0], g[1], g[2], imu_state,
-                                            imu_null, P, n_cams);
+    propagate_kernel_v2<<<d.B, PT, smem, s>>>(d, n_samples, samples, imu_time, Qc_diag, g[0], g[1], g[2], imu_state,
+                                               imu_null, P, n_cams, cap);
     msckf_count_launch(1);
     return cudaGetLastError();
 }

@@ -13,7 +13,7 @@
 // lower triangle (325 tiles = 166 KB at d = 195, XOR-swizzled so that every FP64 tensor-instruction fragment load is
 // bank-conflict free); P' -> L' is spilled to the CTA's L2-resident scratch while B is factored in the same tiles, and
 // comes back for the in-place triangular solve.  All O(n^3) work is DMMA.8x8x4 (mma.sync.m8n8k4.f64); the 8x8 diagonal
-// tiles are factored by one warp with shuffles (same routine as the gate in front_warp.cu).
+// tiles are factored by one warp with shuffles (same routine as the gate's factorisation kernel in front_split.cu).
 #include "msckf_common.cuh"
 #include "dense.cuh"
 

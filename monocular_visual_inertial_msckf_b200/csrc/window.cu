@@ -10,13 +10,16 @@ constexpr int WT = 256;
 // P <- [I; J] P [I; J]^T, symmetrised; J (6 x d) has non-zero columns 0:3 and 12:15 only (MSCKF.py:258-261).
 __global__ void __launch_bounds__(WT) augment_kernel(msckf_dims dims, const double* __restrict__ imu_state, double* cam_R,
                                                      double* cam_t, double* Pall, int* n_cams,
-                                                     const unsigned char* __restrict__ active, double r0, double r1,
+                                                     const unsigned char* __restrict__ active, int* overflow, double r0, double r1,
                                                      double r2, double r3, double r4, double r5, double r6, double r7,
                                                      double r8, double t0, double t1, double t2) {
     const int b = blockIdx.x, tid = threadIdx.x;
     if (active && !active[b]) return;
     const int n = n_cams[b];
-    if (n >= dims.N) return;
+    if (n >= dims.N) {   // window full: nothing is appended; the caller must not go on as if the pose existed
+        if (tid == 0 && overflow) atomicAdd(overflow, 1);
+        return;
+    }
     const int ldp = dims.ldp, d = 15 + 6 * n;
     double* P = Pall + (size_t)b * ldp * ldp;
     const double* st = imu_state + (size_t)b * 21;
@@ -129,8 +132,8 @@ __global__ void __launch_bounds__(WT) remove_kernel(msckf_dims dims, const unsig
 }  // namespace
 
 cudaError_t launch_augment(const msckf_dims& d, const double* T, const double* imu_state, double* cam_R, double* cam_t,
-                           double* P, int* n_cams, const unsigned char* active, cudaStream_t s) {
-    augment_kernel<<<d.B, WT, 0, s>>>(d, imu_state, cam_R, cam_t, P, n_cams, active, T[0], T[1], T[2], T[3], T[4], T[5],
+                           double* P, int* n_cams, const unsigned char* active, int* overflow, cudaStream_t s) {
+    augment_kernel<<<d.B, WT, 0, s>>>(d, imu_state, cam_R, cam_t, P, n_cams, active, overflow, T[0], T[1], T[2], T[3], T[4], T[5],
                                       T[6], T[7], T[8], T[9], T[10], T[11]);
     msckf_count_launch(1);
     return cudaGetLastError();

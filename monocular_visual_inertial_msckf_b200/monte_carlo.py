@@ -79,12 +79,15 @@ class MonteCarloResult:
 
 def run_monte_carlo(filter_indices, n_frames=30, n_landmarks=48, window=8, device="cuda", imu_per_frame=9,
                     min_parallax=2.0, p_drop=0.05, p_outlier=0.02, matcher="host", min_cosine_similarity=0.95,
-                    epipolar_rejection_threshold=1e9, homography_rejection_threshold=1e9):
+                    epipolar_rejection_threshold=1e9, homography_rejection_threshold=1e9, window_slack=2):
     """Run the filters `filter_indices` (global indices: seed 42 + index, IMU-noise level index mod 3) for n_frames camera
     frames, all of them resident on `device`.  matcher = "host": the association of detections with tracks comes from the
     streams' ground-truth landmark ids (TrackAssociator); "device": the host only uploads each frame's detections
     (descriptors, keypoints, scores) and the mutual-NN matcher, the epipolar / homography tests and the bookkeeping run
-    on the device (BatchedMSCKF.frame_step_detections, MSCKF.add_camera_measurements :284-448)."""
+    on the device (BatchedMSCKF.frame_step_detections, MSCKF.add_camera_measurements :284-448).
+    The window capacity is window + 1 (the frame's own pose before pruning) + window_slack: a camera added on a frame that
+    produced no valid feature stays in the reference's window too (it only prunes cameras some track observes), so a run
+    of such frames needs the slack; an augmentation that finds the window full is an error (check_window_overflow)."""
     assert matcher in ("host", "device")
     levels = list(synth.NOISE_LEVELS.keys())
     seqs = [synth.make_sequence(seed=42 + int(i), n_frames=n_frames, n_landmarks=n_landmarks, imu_per_frame=imu_per_frame,
@@ -96,7 +99,7 @@ def run_monte_carlo(filter_indices, n_frames=30, n_landmarks=48, window=8, devic
                        min_parallax=min_parallax)
     from . import _lib
     par.compress_mode = _lib.COMPRESS_GRAM
-    F, M, N = n_landmarks + 8, window + 2, window + 1
+    F, M, N = n_landmarks + 8, window + 2 + window_slack, window + 1 + window_slack
     flt = BatchedMSCKF(B, F, M, N, par, device=device)
     # initial state as the reference's IMU.initialize leaves it for a stream that starts at rest, level (IMU.py:43-60)
     flt.P.zero_()
@@ -167,5 +170,6 @@ def run_monte_carlo(filter_indices, n_frames=30, n_landmarks=48, window=8, devic
         ncm[:, f] = flt.n_cams.cpu().numpy()
         for b in range(B):
             assert ntr[b, f] == len(assoc[b].slots), "host track records out of step with the device"
+    flt.check_window_overflow()
     ate = np.sqrt(np.mean(np.sum((pos - gtp) ** 2, axis=2), axis=1))
     return MonteCarloResult(pos, gtp, ate, ntr, ncm, [42 + int(i) for i in filter_indices])

@@ -125,14 +125,14 @@ def test_window_surgery_like_the_reference(golden_dir):
     f.features = feats
     n = int(c["n_cams"])
     # --- augmentation: a new pose under the key imu.id, P grows by one 6x6 block (MSCKF.py:250-265) ---
-    f.state.imu.id = 4242
     f.state.imu.T_W_I = Isometry3D(np.eye(3), np.zeros(3))
+    key = f.state.imu.id                      # the camera is filed under the IMU's running id (MSCKF.py:164, 255)
     P0 = f.state.covariance.copy()
     T_I_C = f.state.imu.T_W_I.inv() * f.T_W_C
     f.state_augmentation()
-    assert list(f.state.cameras.keys())[-1] == 4242 and len(f.state.cameras) == n + 1
+    assert list(f.state.cameras.keys())[-1] == key and len(f.state.cameras) == n + 1
     assert rel_err(f.state.covariance, o.augment_covariance(P0, T_I_C.R, T_I_C.t, f.state.imu.T_W_Ii.R)) < 1e-12
-    new_cam = f.state.cameras[4242].T_W_Ci
+    new_cam = f.state.cameras[key].T_W_Ci
     ref_pose = f.state.imu.T_W_Ii * T_I_C
     assert rel_err(new_cam.R, ref_pose.R) < 1e-13 and rel_err(new_cam.t, ref_pose.t) < 1e-13
     # --- prune: selection as the reference's dict + stable sort, one last update, removal ---
@@ -152,3 +152,14 @@ def test_window_surgery_like_the_reference(golden_dir):
     first = list(f.state.cameras.keys())[0]
     f.remove_cameras({first: f.state.cameras[first]})
     assert rel_err(f.state.covariance, o.remove_camera_covariance(P2, 0)) == 0.0
+
+
+def test_whole_reference_run_through_the_drop_in_class(golden_dir):
+    """Sequence level, through the reference's OWN method names on the reference's object model: the operation trace of a
+    whole reference run (540 process_imu, 59 state_augmentation, 85 get_valid_features + update, 79 remove_cameras) is
+    replayed call by call on the drop-in class.  Camera keys come from imu.id as it advances with every process_imu
+    (MSCKF.py:164, 255) -- nothing is set by hand -- the covariance is uploaded ONCE and stays resident on the device, and
+    after every camera frame the state equals the reference's to 1e-9."""
+    from dropin_replay import replay_trace_through_drop_in
+    f, worst = replay_trace_through_drop_in(lambda p: MSCKF(p), golden_dir)
+    print("drop-in class over the whole reference run: worst relative error", worst)

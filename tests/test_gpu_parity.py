@@ -55,15 +55,12 @@ def test_update_vs_golden(golden_dir, name, mode):
     print(name, "gram" if mode else "qr", _summarise(errs))
 
 
-@pytest.mark.parametrize("pad_M,fused", [pytest.param(2, False, id="split-assembly+factorisation"),
-                                         pytest.param(2, True, id="fused-warp-per-feature"),
-                                         pytest.param(30, False, id="cta-per-feature")])
-def test_front_stage_vs_golden(golden_dir, pad_M, fused, monkeypatch):
+@pytest.mark.parametrize("pad_M", [pytest.param(2, id="split-assembly+factorisation"),
+                                   pytest.param(30, id="cta-per-feature")])
+def test_front_stage_vs_golden(golden_dir, pad_M):
     """rows 3-8 alone: selection, triangulation, gamma/dof/gate per feature, state untouched.  The observation capacity
-    picks the kernel: <= 32 observations per track -> warp-per-feature kernels (assembly + factorisation pair by default,
-    the fused kernel with MSCKF_FRONT_FUSED=1), more -> CTA-per-feature kernel."""
-    if fused:
-        monkeypatch.setenv("MSCKF_FRONT_FUSED", "1")
+    picks the kernel: <= 32 observations per track -> warp-per-feature kernels (assembly + factorisation pair), more ->
+    CTA-per-feature kernel."""
     cases, _ = _load(golden_dir, "small_updates.npz")
     flt = _batch_from_cases(cases, pad_F=3, pad_M=pad_M, pad_N=1)
     assert (flt.M <= 32) == (pad_M == 2)
@@ -665,18 +662,13 @@ def test_large_windows_vs_oracle(mode, F, M, N):
         assert ref["out_updated"]
 
 
-@pytest.mark.parametrize("fused", [pytest.param(False, id="split"), pytest.param(True, id="fused")])
 @pytest.mark.parametrize("F,M,N", [(40, 32, 32), (24, 31, 31), (24, 29, 32), (48, 30, 30)])
-def test_warp_front_end_capacity_edges(F, M, N, fused, monkeypatch):
+def test_warp_front_end_capacity_edges(F, M, N):
     """The warp-per-feature front ends at the edges of their tile budget (M = 32: no padding rows in the last tile row;
     N = 32: the staged covariance block fills the shared memory), with RAGGED track lengths 1..M in one batch (every
     tile count of the factorisation kernel) and tracks whose observations are stored newest-first (slots decreasing with
     the observation index: the transposed-block path of the assembly) -- against the oracle."""
     from helpers import make_case
-    if fused:
-        monkeypatch.setenv("MSCKF_FRONT_FUSED", "1")
-        if N > 31:
-            pytest.skip("the fused kernel's staged window stops at 31 poses")
     cases = []
     for seed in (3, 4):
         c = make_case(F, M, N, seed=seed)
