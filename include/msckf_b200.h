@@ -349,12 +349,12 @@ int msckf_probe_fp64(int n_ctas, int iters, double* sink, double* flops_out_host
 long long msckf_launch_count(void);
 
 /* Optional per-kernel timing of the split front end (measurement aid for bench.py; not part of the reference's surface):
- * with timing on, msckf_front_batched / msckf_update_batched record CUDA events on the caller's stream around the assembly
- * and the factorisation kernel of every sub-batch; msckf_front_stage_ms waits for the last recorded call and returns the
- * summed durations in milliseconds.  Returns the number of sub-batches timed (0: timing off, or the fused / general
+ * with timing on, msckf_front_batched / msckf_update_batched record CUDA events on the caller's stream around the geometry,
+ * the assembly and the factorisation kernel of every sub-batch; msckf_front_stage_ms waits for the last recorded call and
+ * returns the summed durations in milliseconds.  Returns the number of sub-batches timed (0: timing off, or the general
  * front-end kernel ran instead). */
 int msckf_set_stage_timing(int on);
-int msckf_front_stage_ms(double* asm_ms, double* chol_ms);
+int msckf_front_stage_ms(double* geo_ms, double* asm_ms, double* chol_ms);
 
 #ifdef __cplusplus
 }

@@ -140,7 +140,7 @@ def load_library():
     lib.msckf_set_stage_timing.restype = C.c_int
     lib.msckf_set_stage_timing.argtypes = [C.c_int]
     lib.msckf_front_stage_ms.restype = C.c_int
-    lib.msckf_front_stage_ms.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.msckf_front_stage_ms.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     if lib.msckf_abi_version() != ABI_VERSION:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib

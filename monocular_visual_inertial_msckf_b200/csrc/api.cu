@@ -11,7 +11,8 @@ bool gram_supported(const msckf_dims& d);
 bool front_split_supported(const msckf_dims& d);
 int front_split_sub_filters(const msckf_dims& d);
 size_t front_split_tile_bytes(const msckf_dims& d);
-cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, cudaStream_t s);
+cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, int* pend_key,
+                               unsigned char* slot_map, cudaStream_t s);
 size_t info_scratch_doubles(const msckf_dims& d);
 cudaError_t launch_update_info(const ApplyArgs& a, int n_ctas, cudaStream_t s);
 bool update_smem_supported(const msckf_dims& d);
@@ -64,6 +65,8 @@ WsLayout msckf_ws_layout(const msckf_dims& d, int mode) {
         w.k_tiles = off;    off = align256(off + front_split_tile_bytes(d));
         w.pend_list = off;  off = align256(off + (size_t)front_split_sub_filters(d) * d.F * sizeof(int));
         w.pend_count = off; off = align256(off + sizeof(int));
+        w.pend_key = off;   off = align256(off + (size_t)front_split_sub_filters(d) * d.F * sizeof(int));
+        w.slot_map = off;   off = align256(off + (size_t)front_split_sub_filters(d) * d.F * 32);
     }
     w.total = off;
     (void)mode;
@@ -129,7 +132,8 @@ int msckf_front_batched(const msckf_dims* dims, const msckf_update_params* param
     // CTA-per-feature kernel otherwise
     if (front_split_supported(*dims))
         return (int)launch_front_split(a, (double2*)((char*)workspace + w.k_tiles), (int*)((char*)workspace + w.pend_list),
-                                       (int*)((char*)workspace + w.pend_count), (cudaStream_t)stream);
+                                       (int*)((char*)workspace + w.pend_count), (int*)((char*)workspace + w.pend_key),
+                                       (unsigned char*)workspace + w.slot_map, (cudaStream_t)stream);
     return (int)launch_front(a, (cudaStream_t)stream);
 }
 

@@ -1,4 +1,4 @@
-// Per-feature front end as TWO kernels (rows 3-8 of SURVEY.md section 8a) for tracks of up to 32 observations:
+// Per-feature front end as THREE kernels (rows 3-8 of SURVEY.md section 8a) for tracks of up to 32 observations:
 //   selection + closed-form triangulation     reference src/msckf/MSCKF.py:458-495, src/utils/geometry.py:274-303
 //   residual + Jacobian blocks                MSCKF.py:497-548, src/msckf/Camera.py:54-67
 //   left-null-space projection of H_f         MSCKF.py:554-559
@@ -7,18 +7,24 @@
 // A single fused kernel would have to keep the 2M x 2M matrix K = H_x P H_x^T + sigma^2 I of a feature in registers while
 // the camera block of P occupies the SM's shared memory: 255 registers x 8 warps, two warps per scheduler, and every
 // phase of it is latency-bound (measured in round 1: 42.6 ms against 18.6 ms, profiles/r01n; that kernel was removed).
-// Here the two halves get the resources each one needs:
+// Round 1 ran geometry + assembly in one kernel: the geometry is a chain of warp reductions whose every shuffle then waits
+// in the same memory-input queue as the shared-memory-bound pair loops of the other warps (~9 us per feature and warp).
+// Here every phase gets the resources it needs:
 //
-//   front_asm_kernel   CTA = (filter, feature chunk: a whole filter when the batch fills the machine), 16 warps, <= 128
-//                      registers.  P's camera block (lower block triangle, 6x6 blocks padded to 38 doubles -> conflict-free
-//                      16-byte reads) + window poses staged once per CTA.  Per feature (one warp, lane = observation):
-//                      geometry (front_geom.cuh), factors for the compression stage, then the M (M + 1) / 2 lower 2x2
-//                      blocks  A_i P[s_i, s_k] A_k^T  as a FLAT list, one block per lane per pass (97 % lane use at
-//                      M = 30), stored straight into the accumulator-fragment tile layout of the FP64 tensor instruction
-//                      in a global (L2 / HBM) buffer.  The four appended rows [r~; Q1^T] are ordinary rows of the padded
-//                      matrix (they fill the padding rows of the last tile row at M = 30): 18 KB per feature, written
-//                      once, read once.  The warps of a CTA start staggered so that the geometry phases of some overlap
-//                      the shared-memory-bound pair loops of the others.
+//   front_geo_kernel   one warp per feature, lane = observation, many warps per SM (no covariance staged, the window
+//                      poses are the only shared memory): geometry (front_geom.cuh), the factors A_i / Q1 / r~ written to
+//                      the workspace (the compression stage needs them anyway), the exact gate bounds when requested, and
+//                      a key per pending feature (first window slot, length, "slots are consecutive"), its slot ->
+//                      observation map, and every part of the padded K that is not a measurement block.
+//   front_asm_kernel   CTA = filter, 12 warps.  P's camera block (lower block triangle, 6x6 blocks padded to 38 doubles ->
+//                      conflict-free 16-byte reads) staged once per CTA; the filter's pending features are bucketed by
+//                      key in shared memory and taken in PAIRS: two features with the same slot pattern share every
+//                      staged 6x6 block of P (one 16-byte shared-memory read feeds the multiply-adds of both), which is
+//                      what bounds this kernel (shared-memory wavefronts).  The M (M + 1) / 2 lower 2x2 blocks
+//                      A_i P[s_i, s_k] A_k^T are a FLAT list, one block per lane per pass (97 % lane use at M = 30), stored
+//                      straight into the accumulator-fragment tile layout of the FP64 tensor instruction in a global
+//                      (L2 / HBM) buffer.  The four appended rows [r~; Q1^T] are ordinary rows of the padded matrix (they
+//                      fill the padding rows of the last tile row at M = 30): 18 KB per feature, written once, read once.
 //   front_chol_kernel  one warp per pending feature, 16 warps per SM, <= 128 registers: LEFT-looking blocked Cholesky
 //                      over 8x8 tiles in accumulator-fragment layout (DMMA.8x8x4 updates / panel solves, shuffles inside
 //                      the diagonal tiles); only the finished tiles still needed and the current block column are live,
@@ -37,8 +43,10 @@ namespace {
 
 using namespace fgeom;
 
-constexpr int FA_THREADS = 512;
-constexpr int FA_WARPS = FA_THREADS / 32;
+constexpr int FG_THREADS = 256;                // geometry kernel: 8 warps per CTA, 2+ CTAs per SM
+constexpr int FG_WARPS = FG_THREADS / 32;
+constexpr int FA_WARPS_MAX = 12;               // assembly kernel: up to 12 warps (170 registers each), 2 features per warp
+constexpr int FA_THREADS_MAX = FA_WARPS_MAX * 32;
 constexpr int FC_THREADS = 128;
 constexpr int FC_WARPS = FC_THREADS / 32;
 constexpr int FLAG_KEEP = MSCKF_FEAT_LOST_FLAG | MSCKF_FEAT_TRIANGULATED;   // selection flags carried into the final status
@@ -47,32 +55,437 @@ constexpr int NTILE = TC * (TC + 1) / 2;
 constexpr int PB = 38;                         // doubles per staged 6x6 block of P (stride 76 words = 12 mod 32)
 constexpr int AR = 14;                         // doubles per observation's 2x6 block in the warp scratch (28 words)
 constexpr int KT_D2 = NTILE * 32;               // double2 per feature slot in the tile buffer (45 tiles; M = 30 uses 36)
+constexpr int KEY_BINS = 32 * 33 + 1;          // (first slot, length) of a consecutive-slot track; last bin: anything else
 
 __device__ __forceinline__ int tile_index(int I, int J) { return I * (I + 1) / 2 + J; }
 
+// key of a pending feature: bin of the assembly kernel's bucketing, or -1 (not pending)
+__device__ __forceinline__ int make_key(bool affine, int s0, int M) { return affine ? (s0 * 33 + M) : (KEY_BINS - 1); }
+
+// rows [0, n2) measurement rows, [n2, a4) identity (a4 = n2 rounded up to a multiple of 4), [a4, a4 + 4) the appended rows
+// [r~; Q1^T] (they never straddle a tile row and their diagonal block is zero: after the factorisation of the columns < a4
+// it holds minus their Gram matrix), rest zero.  At M = 30 the appended rows fill the four padding rows of the eighth tile row.
+__device__ __forceinline__ void write_appended_rows(double2* Kt, const int M, const int lane, const double rt0, const double rt1,
+                                                    const double (&Hf)[2][3]) {
+    const int n2 = 2 * M, a4 = (n2 + 3) & ~3;
+    const int Tn = (a4 + 4 + 7) >> 3;
+    const int rr = a4 - 8 * (Tn - 1);          // local row of the first appended row in the last tile row: 0 or 4
+    const int ia = a4 >> 1;                     // the appended rows as two observation-sized row pairs ia, ia + 1
+    if (lane < M) {   // columns (2 lane, 2 lane + 1) of the four appended rows
+        double2* Gt = Kt + tile_index(Tn - 1, lane >> 2) * 32 + 4 * rr + (lane & 3);
+        Gt[0] = make_double2(rt0, rt1);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) Gt[4 * (q + 1)] = make_double2(Hf[0][q], Hf[1][q]);
+        if ((lane >> 2) == Tn - 1) {   // measurement rows of the same (diagonal) tile: define the mirrored blocks
+            double2* Tm = Kt + tile_index(Tn - 1, Tn - 1) * 32 + 8 * (lane & 3) + (ia & 3);
+            Tm[0] = Tm[1] = Tm[4] = Tm[5] = make_double2(0.0, 0.0);
+        }
+    }
+}
+
+// the padding row pairs i = M .. Mp-1 (at most 7): identity before the appended rows, zero after; the blocks (appended
+// rows x measurement columns) were written by write_appended_rows
+__device__ __forceinline__ void write_padding_rows(double2* Kt, const int M, const int lane) {
+    const int n2 = 2 * M, a4 = (n2 + 3) & ~3;
+    const int Tn = (a4 + 4 + 7) >> 3, Mp = 4 * Tn;
+    const int ia = a4 >> 1;
+    for (int i = M; i < Mp; ++i) {
+        const bool appended = i >= ia && i < ia + 2;
+        for (int k = (appended ? M : 0) + lane; k <= i; k += 32) {
+            const double dg = (i == k && i < ia) ? 1.0 : 0.0;
+            const int I = i >> 2, J = k >> 2;
+            double2* T = Kt + tile_index(I, J) * 32;
+            const int l0 = 8 * (i & 3) + (k & 3);
+            T[l0] = make_double2(dg, 0.0);
+            T[l0 + 4] = make_double2(0.0, dg);
+            if (I == J && i != k) {
+                const int l1 = 8 * (k & 3) + (i & 3);
+                T[l1] = make_double2(0.0, 0.0);
+                T[l1 + 4] = make_double2(0.0, 0.0);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
-// kernel A: geometry + assembly of K into the tile buffer
+// kernel G: geometry, factors, gate bounds, keys
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FA_THREADS, 1)
-front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict__ pend_list, int* __restrict__ pend_count,
-                 const int b0, const int feats_per_cta, const unsigned stagger_ns) {
+__global__ void __launch_bounds__(FG_THREADS, 2)
+front_geo_kernel(const FrontArgs a, int* __restrict__ pend_key, unsigned char* __restrict__ slot_map, double2* __restrict__ Kbuf,
+                 int* __restrict__ pend_list, int* __restrict__ pend_count, const int b0, const int feats_per_cta) {
     const int bl = blockIdx.y, b = b0 + bl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = a.dims.F, Mcap = a.dims.M, Ncap = a.dims.N, ldp = a.dims.ldp;
     const int nc = min(a.n_cams[b], Ncap);
 
     extern __shared__ double smem[];
-    double* sP = smem;                                              // [nblk(Ncap)][PB] lower block triangle of P_CC
-    double* sR = sP + (size_t)(Ncap * (Ncap + 1) / 2) * PB;         // [Ncap][9]
-    double* sT = sR + (size_t)Ncap * 9;                             // [Ncap][3]
-    double* wsA = sT + (size_t)Ncap * 3 + (size_t)warp * (FW_MAX_OBS * AR);   // 16-byte aligned (12 Ncap doubles of poses)
-    const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
+    double* sR = smem;                       // [Ncap][9]
+    double* sT = sR + (size_t)Ncap * 9;      // [Ncap][3]
 
     const int f_begin = blockIdx.x * feats_per_cta;
     const int f_end = min(F, f_begin + feats_per_cta);
     if (f_begin >= f_end) return;
+    {
+        const double* camR = a.cam_R + (size_t)b * Ncap * 9;
+        const double* camt = a.cam_t + (size_t)b * Ncap * 3;
+        for (int e = tid; e < nc * 9; e += FG_THREADS) sR[e] = camR[e];
+        for (int e = tid; e < nc * 3; e += FG_THREADS) sT[e] = camt[e];
+    }
+    __syncthreads();
 
-    // ---- stage the window once per CTA ----
+    const GeoConsts gc = make_geo_consts(a);
+    const double s2 = gc.s2;
+
+    ObsRegs nxt;
+    int Mn = 0;
+    {
+        const int j0 = f_begin + warp;
+        if (j0 < f_end) {
+            Mn = a.feat_len[(size_t)b * F + j0];
+            load_obs(nxt, a, (size_t)b * F + j0, min(max(Mn, 0), FW_MAX_OBS), lane);
+        }
+    }
+    for (int j = f_begin + warp; j < f_end; j += FG_WARPS) {
+        const size_t fj = (size_t)b * F + j;
+        int* key_out = pend_key + (size_t)bl * F + j;
+        ObsRegs o = nxt;
+        const int M = Mn;
+        mask_obs(o, M, lane);
+        {   // prefetch the next feature of this warp
+            const int jn = j + FG_WARPS;
+            if (jn < f_end) {
+                Mn = a.feat_len[(size_t)b * F + jn];
+                load_obs(nxt, a, (size_t)b * F + jn, min(max(Mn, 0), FW_MAX_OBS), lane);
+            }
+        }
+        if (M <= 0 || M > Mcap || M > FW_MAX_OBS) {
+            if (lane == 0) {
+                a.feat_status[fj] = MSCKF_FEAT_SKIPPED;
+                a.gamma[fj] = nan("");
+                a.dof[fj] = 0;
+                a.fac_rank[fj] = 0;
+                *key_out = -1;
+            }
+            continue;
+        }
+        const int n2 = 2 * M;
+        const bool live = lane < M;
+
+        int rank, code;
+        double rt0, rt1;
+        double Hx[2][6], Hf[2][3];
+        code = feature_geometry(a, gc, fj, M, lane, o, sR, sT, Hx, Hf, rt0, rt1, rank);
+        if ((code & 0xF) != MSCKF_FEAT_ACCEPTED) {
+            if (lane == 0) {
+                a.feat_status[fj] = (unsigned char)code;
+                a.gamma[fj] = nan("");
+                a.dof[fj] = 0;
+                a.fac_rank[fj] = 0;
+                *key_out = -1;
+            }
+            continue;
+        }
+        // ---- factors for the assembly kernel and the compression stage ----
+        if (live) {
+            double2* fA = reinterpret_cast<double2*>(a.fac_A + (fj * Mcap + lane) * 12);
+            double2* fQ = reinterpret_cast<double2*>(a.fac_Q + (fj * Mcap + lane) * 6);
+#pragma unroll
+            for (int c2 = 0; c2 < 6; ++c2) fA[c2] = make_double2(Hx[c2 / 3][2 * (c2 % 3)], Hx[c2 / 3][2 * (c2 % 3) + 1]);
+            fQ[0] = make_double2(Hf[0][0], Hf[0][1]);
+            fQ[1] = make_double2(Hf[0][2], Hf[1][0]);
+            fQ[2] = make_double2(Hf[1][1], Hf[1][2]);
+            *reinterpret_cast<double2*>(a.fac_rt + (fj * Mcap + lane) * 2) = make_double2(rt0, rt1);
+        }
+        const int dofv = n2 - rank;
+        if (dofv <= 0) {   // empty null space: gamma = 0 against chi2.ppf(0.95, 0) = NaN -> rejected (MSCKF.py:566-568)
+            if (lane == 0) {
+                const double crit = a.chi2_table[0];
+                const bool pass = 0.0 <= crit;
+                a.feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (code & FLAG_KEEP));
+                a.gamma[fj] = 0.0;
+                a.dof[fj] = 0;
+                a.fac_rank[fj] = rank;
+                *key_out = -1;
+            }
+            continue;
+        }
+
+        // ---- exact early-out (MSCKF_GATE_BOUNDS): |r~|^2 / (s^2 + tr S_x) <= gamma <= |r~|^2 / s^2 ----
+        if (a.par.gate_mode == MSCKF_GATE_BOUNDS) {
+            double trs = 0.0;
+            if (live) {
+                const double* Pd = a.P + (size_t)b * ldp * ldp + (size_t)(15 + 6 * o.slot) * ldp + 15 + 6 * o.slot;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        // (lower triangle of the symmetric block, as the assembly kernel stages it)
+                        const double pv = (c <= r) ? Pd[(size_t)r * ldp + c] : Pd[(size_t)c * ldp + r];
+                        v0 += pv * Hx[0][c];
+                        v1 += pv * Hx[1][c];
+                    }
+                    trs += Hx[0][r] * v0 + Hx[1][r] * v1;
+                }
+            }
+            trs = warp_sum_all(trs);
+            const double rr = warp_sum_all(rt0 * rt0 + rt1 * rt1);
+            const double crit = (dofv < a.chi2_len) ? a.chi2_table[dofv] : nan("");
+            const double gub = rr / s2, glb = rr / (s2 + trs);
+            const bool acc = gub <= crit, rej = glb > crit;
+            if (acc || rej) {
+                if (lane == 0) {
+                    a.feat_status[fj] = (unsigned char)((acc ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) |
+                                                        (code & FLAG_KEEP) | MSCKF_FEAT_GAMMA_BOUND);
+                    a.gamma[fj] = acc ? gub : glb;
+                    a.dof[fj] = dofv;
+                    a.fac_rank[fj] = rank;
+                    *key_out = -1;
+                }
+                continue;
+            }
+        }
+
+        // ---- pending: the assembly + factorisation kernels finish this feature ----
+        const int s0 = __shfl_sync(0xffffffffu, o.slot, 0);
+        const bool affine = __all_sync(0xffffffffu, !live || o.slot == s0 + lane) && s0 >= 0 && s0 < 32;
+        const int fl = bl * F + j;
+        if (lane == 0) {
+            a.feat_status[fj] = (unsigned char)(MSCKF_FEAT_PENDING | (code & FLAG_KEEP));
+            a.dof[fj] = dofv;
+            a.fac_rank[fj] = rank;
+            *key_out = make_key(affine, s0, M);
+            pend_list[atomicAdd(pend_count, 1)] = fl;
+        }
+        // everything of the padded matrix that is not a measurement block: appended rows [r~; Q1^T], identity / zero padding
+        double2* Kt = Kbuf + (size_t)fl * KT_D2;
+        write_appended_rows(Kt, M, lane, rt0, rt1, Hf);
+        write_padding_rows(Kt, M, lane);
+        // window slot -> observation index of this track (0xFF: not observed from that slot)
+        unsigned char* mp = slot_map + (size_t)fl * 32;
+        mp[lane] = 0xFF;
+        __syncwarp();
+        if (live && o.slot >= 0 && o.slot < 32) mp[o.slot] = (unsigned char)lane;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel A: assembly of K into the tile buffer, two features of equal slot pattern per warp
+// ---------------------------------------------------------------------------------------------------------------------
+struct AsmFeature {
+    int j;            // feature index in the filter (-1: none)
+    int M, s0;
+    bool affine;
+    int slot;         // this lane's observation slot
+    double2* Kt;      // its tile buffer
+    const double* wsA;
+};
+
+__device__ __forceinline__ void store_block(double2* Kt, const int i, const int k, const double o00, const double o01,
+                                            const double o10, const double o11) {
+    // rows 2 i, 2 i + 1 / columns 2 k, 2 k + 1  ->  tile (i / 4, k / 4), lanes 4 (2 (i & 3) + row) + (k & 3)
+    const int I = i >> 2, J = k >> 2;
+    double2* T = Kt + tile_index(I, J) * 32;
+    const int l0 = 8 * (i & 3) + (k & 3);
+    T[l0] = make_double2(o00, o01);
+    T[l0 + 4] = make_double2(o10, o11);
+    if (I == J && i != k) {   // the mirrored block of a diagonal tile is never read as data: keep it defined
+        const int l1 = 8 * (k & 3) + (i & 3);
+        T[l1] = make_double2(0.0, 0.0);
+        T[l1 + 4] = make_double2(0.0, 0.0);
+    }
+}
+
+// pair p = i (i + 1) / 2 + k of the flat lower-triangle list
+__device__ __forceinline__ void pair_of(const int p, int& i, int& k) {
+    i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+    i -= (i * (i + 1) / 2 > p) ? 1 : 0;
+    i += ((i + 1) * (i + 2) / 2 <= p) ? 1 : 0;
+    k = p - i * (i + 1) / 2;
+}
+
+// K = H_x P H_x^T + sigma^2 I of NF features with the SAME consecutive slot pattern (s0, M): one lower 2x2 block per lane
+// per pass and feature; every 16-byte read of a staged block of P feeds the multiply-adds of all NF features.  The
+// arithmetic of a feature does not depend on NF (same operations in the same order).
+template <int NF>
+__device__ __forceinline__ void pair_loop_affine(const double* __restrict__ sP, const AsmFeature (&f)[NF], const int lane,
+                                                 const double s2) {
+    const int M = f[0].M, s0 = f[0].s0;
+    const int npairs = M * (M + 1) / 2;
+#pragma unroll 1
+    for (int p0 = 0; p0 < npairs; p0 += 32) {
+        const int p = p0 + lane;
+        if (p >= npairs) continue;
+        int i, k;
+        pair_of(p, i, k);
+        double ai[NF][2][6];
+#pragma unroll
+        for (int q = 0; q < NF; ++q) {
+            const double2* Ai = reinterpret_cast<const double2*>(f[q].wsA + i * AR);
+#pragma unroll
+            for (int c2 = 0; c2 < 6; ++c2) {
+                const double2 x = Ai[c2];
+                ai[q][c2 / 3][2 * (c2 % 3)] = x.x;
+                ai[q][c2 / 3][2 * (c2 % 3) + 1] = x.y;
+            }
+        }
+        double v0[NF][6], v1[NF][6];
+#pragma unroll
+        for (int q = 0; q < NF; ++q)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { v0[q][c] = 0.0; v1[q][c] = 0.0; }
+        const double2* Pb = reinterpret_cast<const double2*>(sP + (size_t)tile_index(s0 + i, s0 + k) * PB);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+            for (int c2 = 0; c2 < 3; ++c2) {
+                const double2 pv = Pb[r * 3 + c2];
+#pragma unroll
+                for (int q = 0; q < NF; ++q) {
+                    v0[q][2 * c2] += ai[q][0][r] * pv.x;
+                    v0[q][2 * c2 + 1] += ai[q][0][r] * pv.y;
+                    v1[q][2 * c2] += ai[q][1][r] * pv.x;
+                    v1[q][2 * c2 + 1] += ai[q][1][r] * pv.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NF; ++q) {
+            double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
+            const double2* Ak = reinterpret_cast<const double2*>(f[q].wsA + k * AR);
+#pragma unroll
+            for (int c2 = 0; c2 < 3; ++c2) {
+                const double2 x0 = Ak[c2], x1 = Ak[3 + c2];
+                o00 = fma(v0[q][2 * c2 + 1], x0.y, fma(v0[q][2 * c2], x0.x, o00));
+                o01 = fma(v0[q][2 * c2 + 1], x1.y, fma(v0[q][2 * c2], x1.x, o01));
+                o10 = fma(v1[q][2 * c2 + 1], x0.y, fma(v1[q][2 * c2], x0.x, o10));
+                o11 = fma(v1[q][2 * c2 + 1], x1.y, fma(v1[q][2 * c2], x1.x, o11));
+            }
+            if (i == k) { o00 += s2; o11 += s2; }
+            store_block(f[q].Kt, i, k, o00, o01, o10, o11);
+        }
+    }
+}
+
+// the same for ONE feature whose slots are arbitrary (gaps, or stored newest-first): slots from the lanes that hold them,
+// transposed block when the slots do not increase with the observation index
+__device__ __forceinline__ void pair_loop_general(const double* __restrict__ sP, const AsmFeature& f, const int lane,
+                                                  const double s2) {
+    const int M = f.M;
+    const int npairs = M * (M + 1) / 2;
+#pragma unroll 1
+    for (int p0 = 0; p0 < npairs; p0 += 32) {
+        const int p = p0 + lane;
+        const bool act = p < npairs;
+        int i, k;
+        pair_of(p, i, k);
+        const int si = __shfl_sync(0xffffffffu, f.slot, i & 31);
+        const int sk = __shfl_sync(0xffffffffu, f.slot, k & 31);
+        if (!act) continue;
+        double ai[2][6];
+        {
+            const double2* Ai = reinterpret_cast<const double2*>(f.wsA + i * AR);
+#pragma unroll
+            for (int c2 = 0; c2 < 6; ++c2) {
+                const double2 x = Ai[c2];
+                ai[c2 / 3][2 * (c2 % 3)] = x.x;
+                ai[c2 / 3][2 * (c2 % 3) + 1] = x.y;
+            }
+        }
+        double v0[6], v1[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { v0[c] = 0.0; v1[c] = 0.0; }
+        if (si >= sk) {
+            const double2* Pb = reinterpret_cast<const double2*>(sP + (size_t)tile_index(si, sk) * PB);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                for (int c2 = 0; c2 < 3; ++c2) {
+                    const double2 pv = Pb[r * 3 + c2];
+                    v0[2 * c2] += ai[0][r] * pv.x;
+                    v0[2 * c2 + 1] += ai[0][r] * pv.y;
+                    v1[2 * c2] += ai[1][r] * pv.x;
+                    v1[2 * c2 + 1] += ai[1][r] * pv.y;
+                }
+            }
+        } else {   // transposed block
+            const double2* Pb = reinterpret_cast<const double2*>(sP + (size_t)tile_index(sk, si) * PB);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+#pragma unroll
+                for (int r2 = 0; r2 < 3; ++r2) {
+                    const double2 pv = Pb[c * 3 + r2];
+                    v0[c] = fma(ai[0][2 * r2 + 1], pv.y, fma(ai[0][2 * r2], pv.x, v0[c]));
+                    v1[c] = fma(ai[1][2 * r2 + 1], pv.y, fma(ai[1][2 * r2], pv.x, v1[c]));
+                }
+            }
+        }
+        double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
+        const double2* Ak = reinterpret_cast<const double2*>(f.wsA + k * AR);
+#pragma unroll
+        for (int c2 = 0; c2 < 3; ++c2) {
+            const double2 x0 = Ak[c2], x1 = Ak[3 + c2];
+            o00 = fma(v0[2 * c2 + 1], x0.y, fma(v0[2 * c2], x0.x, o00));
+            o01 = fma(v0[2 * c2 + 1], x1.y, fma(v0[2 * c2], x1.x, o01));
+            o10 = fma(v1[2 * c2 + 1], x0.y, fma(v1[2 * c2], x0.x, o10));
+            o11 = fma(v1[2 * c2 + 1], x1.y, fma(v1[2 * c2], x1.x, o11));
+        }
+        if (i == k) { o00 += s2; o11 += s2; }
+        store_block(f.Kt, i, k, o00, o01, o10, o11);
+    }
+}
+
+__global__ void __launch_bounds__(FA_THREADS_MAX, 1)
+front_asm_kernel(const FrontArgs a, const int* __restrict__ pend_key, double2* __restrict__ Kbuf, const int b0) {
+    const int bl = blockIdx.x, b = b0 + bl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = a.dims.F, Mcap = a.dims.M, Ncap = a.dims.N, ldp = a.dims.ldp;
+    const int nc = min(a.n_cams[b], Ncap);
+    const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
+
+    extern __shared__ double smem[];
+    double* sP = smem;                                                        // [nblk(Ncap)][PB] lower block triangle of P_CC
+    double* wsAll = sP + (size_t)(Ncap * (Ncap + 1) / 2) * PB;                // [nwarps][2][FW_MAX_OBS * AR]
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(wsAll + (size_t)nwarps * 2 * FW_MAX_OBS * AR);   // [F] bucketed
+    int* s_hist = reinterpret_cast<int*>(wsAll);                              // [KEY_BINS] (aliases the scratch: start-up only)
+    int* s_cur = s_hist + KEY_BINS;                                           // [KEY_BINS]
+    __shared__ int s_npend, s_next;
+
+    const int* keys = pend_key + (size_t)bl * F;
+
+    // ---- bucket the filter's pending features by slot pattern ----
+    for (int e = tid; e < 2 * KEY_BINS; e += nthreads) s_hist[e] = 0;
+    if (tid == 0) { s_npend = 0; s_next = 0; }
+    __syncthreads();
+    for (int j = tid; j < F; j += nthreads) {
+        const int key = keys[j];
+        if (key >= 0) atomicAdd(&s_hist[key], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the bins, 34 per lane
+        constexpr int PER = (KEY_BINS + 31) / 32;
+        int sum = 0;
+        for (int q = 0; q < PER; ++q) { const int e = lane * PER + q; sum += (e < KEY_BINS) ? s_hist[e] : 0; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        int run = incl - sum;
+        for (int q = 0; q < PER; ++q) {
+            const int e = lane * PER + q;
+            if (e < KEY_BINS) { s_cur[e] = run; run += s_hist[e]; }
+        }
+        if (lane == 31) s_npend = incl;
+    }
+    __syncthreads();
+    for (int j = tid; j < F; j += nthreads) {
+        const int key = keys[j];
+        if (key >= 0) s_list[atomicAdd(&s_cur[key], 1)] = (unsigned short)j;
+    }
+    __syncthreads();
+    const int npend = s_npend;
+    if (npend == 0) return;
+
+    // ---- stage the camera block of P (the scratch aliasing ends here: barrier above) ----
     {
         const double* P = a.P + (size_t)b * ldp * ldp;
         const int c = 6 * nc;
@@ -95,267 +508,239 @@ front_asm_kernel(const FrontArgs a, double2* __restrict__ Kbuf, int* __restrict_
                 if (col < 6 * ba + 6) dst[bb * PB + (col - 6 * bb)] = pv[u];
             }
         }
-        const double* camR = a.cam_R + (size_t)b * Ncap * 9;
-        const double* camt = a.cam_t + (size_t)b * Ncap * 3;
-        for (int e = tid; e < nc * 9; e += nthreads) sR[e] = camR[e];
-        for (int e = tid; e < nc * 3; e += nthreads) sT[e] = camt[e];
     }
     __syncthreads();
 
-    const GeoConsts gc = make_geo_consts(a);
-    const double s2 = gc.s2;
+    const double s2 = a.par.sigma_image * a.par.sigma_image;
+    double* ws0 = wsAll + (size_t)warp * 2 * FW_MAX_OBS * AR;
+    double* ws1 = ws0 + FW_MAX_OBS * AR;
+    const int n_units = (npend + 1) >> 1;
 
-    ObsRegs nxt;
-    int Mn = 0;
-    {
-        const int j0 = f_begin + warp;
-        if (j0 < f_end) {
-            Mn = a.feat_len[(size_t)b * F + j0];
-            load_obs(nxt, a, (size_t)b * F + j0, min(max(Mn, 0), FW_MAX_OBS), lane);
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(&s_next, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        AsmFeature f[2];
+        int key[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int e = 2 * u + q;
+            AsmFeature& g = f[q];
+            g.j = (e < npend) ? (int)s_list[e] : -1;
+            g.wsA = q ? ws1 : ws0;
+            g.M = 0; g.s0 = 0; g.affine = false; g.slot = 0; g.Kt = nullptr;
+            key[q] = -1;
+            if (g.j < 0) continue;
+            const size_t fj = (size_t)b * F + g.j;
+            key[q] = keys[g.j];
+            g.M = a.feat_len[fj];
+            g.affine = key[q] != KEY_BINS - 1;
+            g.Kt = Kbuf + ((size_t)bl * F + g.j) * KT_D2;
+            const size_t e0 = fj * Mcap + (lane < g.M ? lane : 0);
+            g.slot = a.obs_slot[e0];
+            const double2* fA = reinterpret_cast<const double2*>(a.fac_A + e0 * 12);
+            double2 av[6];
+#pragma unroll
+            for (int c2 = 0; c2 < 6; ++c2) av[c2] = fA[c2];
+            g.s0 = __shfl_sync(0xffffffffu, g.slot, 0);
+            __syncwarp();      // the previous unit's pair loop no longer reads this scratch
+            if (lane < g.M) {
+                double2* sA = reinterpret_cast<double2*>(const_cast<double*>(g.wsA) + lane * AR);
+#pragma unroll
+                for (int c2 = 0; c2 < 6; ++c2) sA[c2] = av[c2];
+            }
+        }
+        __syncwarp();
+        if (f[1].j >= 0 && key[0] == key[1] && f[0].affine) {
+            pair_loop_affine<2>(sP, f, lane, s2);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (f[q].j < 0) continue;
+                if (f[q].affine) {
+                    const AsmFeature one[1] = {f[q]};
+                    pair_loop_affine<1>(sP, one, lane, s2);
+                } else {
+                    pair_loop_general(sP, f[q], lane, s2);
+                }
+            }
         }
     }
-    // Every warp alternates between the geometry (no shared-memory traffic) and the pair loop (shared-memory bound), and
-    // all the warps of the CTA leave the barrier above in the same phase: staggering their start spreads the phases, so
-    // that the pair loops of some warps run under the geometry of the others instead of all of them queueing on the
-    // shared-memory pipe at once.
-    if (stagger_ns) __nanosleep(warp * stagger_ns);
+}
 
-    for (int j = f_begin + warp; j < f_end; j += nwarps) {
-        const size_t fj = (size_t)b * F + j;
-        ObsRegs o = nxt;
-        const int M = Mn;
-        mask_obs(o, M, lane);
-        {   // prefetch the next feature of this warp
-            const int jn = j + nwarps;
-            if (jn < f_end) {
-                Mn = a.feat_len[(size_t)b * F + jn];
-                load_obs(nxt, a, (size_t)b * F + jn, min(max(Mn, 0), FW_MAX_OBS), lane);
-            }
-        }
-        if (M <= 0 || M > Mcap || M > FW_MAX_OBS) {
-            if (lane == 0) {
-                a.feat_status[fj] = MSCKF_FEAT_SKIPPED;
-                a.gamma[fj] = nan("");
-                a.dof[fj] = 0;
-                a.fac_rank[fj] = 0;
-            }
-            continue;
-        }
-        const int n2 = 2 * M;
-        const bool live = lane < M;
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel A (windows of up to 30 / 31 poses): P-STATIONARY assembly.  The lower block triangle of P's camera block lives in
+// the REGISTER FILE of the CTA: thread p owns the 6x6 block P[s, t] of the slot pair (s, t), p = s (s + 1) / 2 + t, for the
+// whole life of the CTA (465 blocks = 15 warps at a 30-pose window), and the filter's pending features stream through
+// shared memory (cp.async, double-buffered batches of their 2x6 Jacobian blocks + slot maps).  For every feature each
+// thread computes the one 2x2 block of K that involves its block of P: A_i P[s, t] A_k^T with (i, k) the track's
+// observations from the slots (s, t).  Per block that is 12 shared-memory reads (the two Jacobian blocks) instead of 30
+// (Jacobians + the staged block of P), the shared memory holds ~56 features in flight instead of 24, and tracks with
+// gaps or stored newest-first need no special path (the slot map says which observation, if any, a slot holds; a block
+// above the diagonal is stored transposed).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int NLEFT>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NLEFT) : "memory"); }
 
-        int rank, code;
-        double rt0, rt1;
-        {
-            double Hx[2][6], Hf[2][3];
-            code = feature_geometry(a, gc, fj, M, lane, o, sR, sT, Hx, Hf, rt0, rt1, rank);
-            if ((code & 0xF) != MSCKF_FEAT_ACCEPTED) {
-                if (lane == 0) {
-                    a.feat_status[fj] = (unsigned char)code;
-                    a.gamma[fj] = nan("");
-                    a.dof[fj] = 0;
-                    a.fac_rank[fj] = 0;
+constexpr int PS_FEAT_BYTES = FW_MAX_OBS * AR * 8 + 32;   // one feature in a batch buffer: Jacobian blocks + slot map
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_map, double2* __restrict__ Kbuf, const int b0,
+                    const int batch) {
+    constexpr int NT = NWARPS * 32;
+    const int bl = blockIdx.x, b = b0 + bl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = a.dims.F, Mcap = a.dims.M, Ncap = a.dims.N, ldp = a.dims.ldp;
+    const int nc = min(a.n_cams[b], Ncap);
+    const int nblk = nc * (nc + 1) / 2;
+
+    extern __shared__ double smem[];
+    unsigned char* sbuf = reinterpret_cast<unsigned char*>(smem);                        // [2][batch][PS_FEAT_BYTES]
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(sbuf + (size_t)2 * batch * PS_FEAT_BYTES);   // [F] pending, in order
+    unsigned char* s_len = reinterpret_cast<unsigned char*>(s_list + ((F + 7) & ~7));    // [F] their lengths
+    __shared__ int s_warp_cnt[NWARPS + 1];
+
+    // ---- the filter's pending features, in feature order (ballot scan) ----
+    int npend = 0;
+    for (int base = 0; base < F; base += NT) {
+        const int j = base + tid;
+        const bool pend = j < F && (a.feat_status[(size_t)b * F + j] & 0xF) == MSCKF_FEAT_PENDING;
+        const unsigned bal = __ballot_sync(0xffffffffu, pend);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = npend;
+        for (int w = 0; w < warp; ++w) off += s_warp_cnt[w];
+        if (pend) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            s_list[pos] = (unsigned short)j;
+            s_len[pos] = (unsigned char)a.feat_len[(size_t)b * F + j];
+        }
+        int tot = 0;
+        for (int w = 0; w < NWARPS; ++w) tot += s_warp_cnt[w];
+        npend += tot;
+        __syncthreads();
+    }
+    if (npend == 0) return;
+
+    // ---- teams: ceil(nblk / 32) warps cover the block triangle once; several teams work on different features ----
+    const int team_warps = (nblk + 31) >> 5;
+    const int n_teams = NWARPS / team_warps;           // >= 1 (the launcher guarantees nblk <= NT)
+    const int team = warp / team_warps;
+    const int p = (warp - team * team_warps) * 32 + lane;
+    const bool has_block = team < n_teams && p < nblk;
+    int s = 0, t = 0;
+    if (has_block) pair_of(p, s, t);
+    double Pb[6][6];
+    {
+        const double* P = a.P + (size_t)b * ldp * ldp + (size_t)(15 + 6 * s) * ldp + 15 + 6 * t;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) Pb[r][c] = has_block ? P[(size_t)r * ldp + c] : 0.0;
+    }
+    const double s2 = a.par.sigma_image * a.par.sigma_image;
+    const int n_batches = (npend + batch - 1) / batch;
+
+    auto issue_batch = [&](int bt) {
+        unsigned char* dst = sbuf + (size_t)(bt & 1) * batch * PS_FEAT_BYTES;
+        const int e_end = min(batch, npend - bt * batch);
+        // 16-byte chunks: 6 per observation of Jacobian blocks (AR = 14 doubles per observation in shared memory) + 2 of map
+        for (int e = warp; e < e_end; e += NWARPS) {
+            const int pos = bt * batch + e;
+            const int j = s_list[pos], M = s_len[pos];
+            const size_t fj = (size_t)b * F + j;
+            const double* gA = a.fac_A + fj * Mcap * 12;
+            unsigned char* d = dst + (size_t)e * PS_FEAT_BYTES;
+            for (int it = lane; it < 6 * M; it += 32) {
+                const int ob = it / 6, c2 = it - 6 * ob;
+                cp_async16(d + (size_t)(ob * AR + 2 * c2) * 8, gA + (size_t)it * 2);
+            }
+            if (lane < 2) cp_async16(d + FW_MAX_OBS * AR * 8 + 16 * lane, slot_map + ((size_t)bl * F + j) * 32 + 16 * lane);
+        }
+        cp_async_commit();
+    };
+
+    issue_batch(0);
+    for (int bt = 0; bt < n_batches; ++bt) {
+        if (bt + 1 < n_batches) {
+            issue_batch(bt + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const unsigned char* src = sbuf + (size_t)(bt & 1) * batch * PS_FEAT_BYTES;
+        const int e_end = min(batch, npend - bt * batch);
+        if (has_block) {
+            // (the slot map of the NEXT feature is read one iteration ahead: its latency is off the dependency chain)
+            int i_n = 0xFF, k_n = 0xFF;
+            if (team < e_end) {
+                const unsigned char* mp = src + (size_t)team * PS_FEAT_BYTES + FW_MAX_OBS * AR * 8;
+                i_n = mp[s];
+                k_n = mp[t];
+            }
+#pragma unroll 1
+            for (int e = team; e < e_end; e += n_teams) {
+                const unsigned char* fb = src + (size_t)e * PS_FEAT_BYTES;
+                const int i = i_n, k = k_n;
+                if (e + n_teams < e_end) {
+                    const unsigned char* mp = fb + (size_t)n_teams * PS_FEAT_BYTES + FW_MAX_OBS * AR * 8;
+                    i_n = mp[s];
+                    k_n = mp[t];
                 }
-                continue;
-            }
-            // ---- factors for the compression stage + the warp's shared scratch ----
-            __syncwarp();
-            if (live) {
-                double2* fA = reinterpret_cast<double2*>(a.fac_A + (fj * Mcap + lane) * 12);
-                double2* fQ = reinterpret_cast<double2*>(a.fac_Q + (fj * Mcap + lane) * 6);
-                double2* sA = reinterpret_cast<double2*>(wsA + lane * AR);
+                if (i == 0xFF || k == 0xFF) continue;
+                const double* sA = reinterpret_cast<const double*>(fb);
+                const double2* Ai = reinterpret_cast<const double2*>(sA + i * AR);
+                const double2* Ak = reinterpret_cast<const double2*>(sA + k * AR);
+                double ak[2][6];
 #pragma unroll
                 for (int c2 = 0; c2 < 6; ++c2) {
-                    const double2 v = make_double2(Hx[c2 / 3][2 * (c2 % 3)], Hx[c2 / 3][2 * (c2 % 3) + 1]);
-                    fA[c2] = v;
-                    sA[c2] = v;
+                    const double2 x = Ak[c2];
+                    ak[c2 / 3][2 * (c2 % 3)] = x.x;
+                    ak[c2 / 3][2 * (c2 % 3) + 1] = x.y;
                 }
-                fQ[0] = make_double2(Hf[0][0], Hf[0][1]);
-                fQ[1] = make_double2(Hf[0][2], Hf[1][0]);
-                fQ[2] = make_double2(Hf[1][1], Hf[1][2]);
-                *reinterpret_cast<double2*>(a.fac_rt + (fj * Mcap + lane) * 2) = make_double2(rt0, rt1);
-            }
-            const int dofv = n2 - rank;
-            if (dofv <= 0) {   // empty null space: gamma = 0 against chi2.ppf(0.95, 0) = NaN -> rejected (MSCKF.py:566-568)
-                if (lane == 0) {
-                    const double crit = a.chi2_table[0];
-                    const bool pass = 0.0 <= crit;
-                    a.feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (code & FLAG_KEEP));
-                    a.gamma[fj] = 0.0;
-                    a.dof[fj] = 0;
-                    a.fac_rank[fj] = rank;
-                }
-                continue;
-            }
-            __syncwarp();
-
-            // ---- exact early-out (MSCKF_GATE_BOUNDS): |r~|^2 / (s^2 + tr S_x) <= gamma <= |r~|^2 / s^2 ----
-            if (a.par.gate_mode == MSCKF_GATE_BOUNDS) {
-                double trs = 0.0;
-                if (live) {
-                    const double* Pd = sP + (size_t)tile_index(o.slot, o.slot) * PB;
+                double o[2][2];
+                // one row of A_i at a time: six independent accumulation chains over the rows of the block of P (the same
+                // operations in the same order as the shared-memory kernel: identical bits)
 #pragma unroll
-                    for (int r = 0; r < 6; ++r) {
-                        double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) { v0 += Pd[r * 6 + c] * Hx[0][c]; v1 += Pd[r * 6 + c] * Hx[1][c]; }
-                        trs += Hx[0][r] * v0 + Hx[1][r] * v1;
-                    }
-                }
-                trs = warp_sum_all(trs);
-                const double rr = warp_sum_all(rt0 * rt0 + rt1 * rt1);
-                const double crit = (dofv < a.chi2_len) ? a.chi2_table[dofv] : nan("");
-                const double gub = rr / s2, glb = rr / (s2 + trs);
-                const bool acc = gub <= crit, rej = glb > crit;
-                if (acc || rej) {
-                    if (lane == 0) {
-                        a.feat_status[fj] = (unsigned char)((acc ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) |
-                                                            (code & FLAG_KEEP) | MSCKF_FEAT_GAMMA_BOUND);
-                        a.gamma[fj] = acc ? gub : glb;
-                        a.dof[fj] = dofv;
-                        a.fac_rank[fj] = rank;
-                    }
-                    continue;
-                }
-            }
-
-            // ---- pending: the factorisation kernel finishes this feature ----
-            const int fl = bl * F + j;
-            int pend_pos = 0;     // (the list position is consumed after the pair loop: the atomic's latency stays hidden)
-            if (lane == 0) {
-                a.feat_status[fj] = (unsigned char)(MSCKF_FEAT_PENDING | (code & FLAG_KEEP));
-                a.dof[fj] = dofv;
-                a.fac_rank[fj] = rank;
-                pend_pos = atomicAdd(pend_count, 1);
-            }
-            double2* Kt = Kbuf + (size_t)fl * KT_D2;
-            // Padded matrix of the factorisation kernel: rows [0, n2) measurement rows, [n2, a4) identity (a4 = n2 rounded up
-            // to a multiple of 4), [a4, a4 + 4) the appended rows [r~; Q1^T] (they never straddle a tile row and their
-            // diagonal block is zero: after the factorisation of the columns < a4 it holds minus their Gram matrix), rest
-            // zero.  At M = 30 the appended rows fill the four padding rows of the eighth tile row.
-            const int a4 = (n2 + 3) & ~3;
-            const int Tn = (a4 + 4 + 7) >> 3, Mp = 4 * Tn;
-            const int rr = a4 - 8 * (Tn - 1);          // local row of the first appended row in the last tile row: 0 or 4
-            const int ia = a4 >> 1;                     // the appended rows as two observation-sized row pairs ia, ia + 1
-            if (live) {   // columns (2 lane, 2 lane + 1) of the four appended rows
-                double2* Gt = Kt + tile_index(Tn - 1, lane >> 2) * 32 + 4 * rr + (lane & 3);
-                Gt[0] = make_double2(rt0, rt1);
-#pragma unroll
-                for (int q = 0; q < 3; ++q) Gt[4 * (q + 1)] = make_double2(Hf[0][q], Hf[1][q]);
-                if ((lane >> 2) == Tn - 1) {   // measurement rows of the same (diagonal) tile: define the mirrored blocks
-                    double2* Tm = Kt + tile_index(Tn - 1, Tn - 1) * 32 + 8 * (lane & 3) + (ia & 3);
-                    Tm[0] = Tm[1] = Tm[4] = Tm[5] = make_double2(0.0, 0.0);
-                }
-            }
-
-            // ---- K = H_x P H_x^T + sigma^2 I, one lower 2x2 block per lane per pass ----
-            const int npairs = M * (M + 1) / 2;     // measurement rows only; the few padding blocks follow below
-            // Pair p = i (i + 1) / 2 + k and its window slots.  Under load every dependent shared-memory / shuffle access
-            // costs a full trip through the saturated memory-input queue, so the descriptor is pure arithmetic whenever
-            // the track's slots are consecutive (slot[i] = slot[0] + i: the normal case, a track is observed from every
-            // camera since its first one); otherwise the slots come from the lanes that hold them.
-            const int s0 = __shfl_sync(0xffffffffu, o.slot, 0);
-            const bool affine = __all_sync(0xffffffffu, !live || o.slot == s0 + lane);
-#pragma unroll 1
-            for (int p0 = 0; p0 < npairs; p0 += 32) {
-                const int p = p0 + lane;
-                const bool act = p < npairs;
-                int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-                i -= (i * (i + 1) / 2 > p) ? 1 : 0;
-                i += ((i + 1) * (i + 2) / 2 <= p) ? 1 : 0;
-                const int k = p - i * (i + 1) / 2;
-                int si, sk;
-                if (affine) {
-                    si = s0 + i;
-                    sk = s0 + k;
-                } else {
-                    si = __shfl_sync(0xffffffffu, o.slot, i & 31);
-                    sk = __shfl_sync(0xffffffffu, o.slot, k & 31);
-                }
-                if (!act) continue;
-                double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
-                {
-                    double ai[2][6];
-                    {
-                        const double2* Ai = reinterpret_cast<const double2*>(wsA + i * AR);
-#pragma unroll
-                        for (int c2 = 0; c2 < 6; ++c2) {
-                            const double2 x = Ai[c2];
-                            ai[c2 / 3][2 * (c2 % 3)] = x.x;
-                            ai[c2 / 3][2 * (c2 % 3) + 1] = x.y;
-                        }
-                    }
-                    double v0[6], v1[6];
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) { v0[c] = 0.0; v1[c] = 0.0; }
-                    if (si >= sk) {
-                        const double2* Pb = reinterpret_cast<const double2*>(sP + (size_t)tile_index(si, sk) * PB);
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                            for (int c2 = 0; c2 < 3; ++c2) {
-                                const double2 pv = Pb[r * 3 + c2];
-                                v0[2 * c2] += ai[0][r] * pv.x;
-                                v0[2 * c2 + 1] += ai[0][r] * pv.y;
-                                v1[2 * c2] += ai[1][r] * pv.x;
-                                v1[2 * c2 + 1] += ai[1][r] * pv.y;
-                            }
-                        }
-                    } else {   // transposed block (slots not increasing with the observation index)
-                        const double2* Pb = reinterpret_cast<const double2*>(sP + (size_t)tile_index(sk, si) * PB);
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) {
-#pragma unroll
-                            for (int r2 = 0; r2 < 3; ++r2) {
-                                const double2 pv = Pb[c * 3 + r2];
-                                v0[c] = fma(ai[0][2 * r2 + 1], pv.y, fma(ai[0][2 * r2], pv.x, v0[c]));
-                                v1[c] = fma(ai[1][2 * r2 + 1], pv.y, fma(ai[1][2 * r2], pv.x, v1[c]));
-                            }
-                        }
-                    }
-                    const double2* Ak = reinterpret_cast<const double2*>(wsA + k * AR);
+                for (int row = 0; row < 2; ++row) {
+                    double ar[6];
 #pragma unroll
                     for (int c2 = 0; c2 < 3; ++c2) {
-                        const double2 x0 = Ak[c2], x1 = Ak[3 + c2];
-                        o00 = fma(v0[2 * c2 + 1], x0.y, fma(v0[2 * c2], x0.x, o00));
-                        o01 = fma(v0[2 * c2 + 1], x1.y, fma(v0[2 * c2], x1.x, o01));
-                        o10 = fma(v1[2 * c2 + 1], x0.y, fma(v1[2 * c2], x0.x, o10));
-                        o11 = fma(v1[2 * c2 + 1], x1.y, fma(v1[2 * c2], x1.x, o11));
+                        const double2 x = Ai[3 * row + c2];
+                        ar[2 * c2] = x.x;
+                        ar[2 * c2 + 1] = x.y;
                     }
-                    if (i == k) { o00 += s2; o11 += s2; }
-                }
-                // rows 2 i, 2 i + 1 / columns 2 k, 2 k + 1  ->  tile (i / 4, k / 4), lanes 4 (2 (i & 3) + row) + (k & 3)
-                const int I = i >> 2, J = k >> 2;
-                double2* T = Kt + tile_index(I, J) * 32;
-                const int l0 = 8 * (i & 3) + (k & 3);
-                T[l0] = make_double2(o00, o01);
-                T[l0 + 4] = make_double2(o10, o11);
-                if (I == J && i != k) {   // the mirrored block of a diagonal tile is never read as data: keep it defined
-                    const int l1 = 8 * (k & 3) + (i & 3);
-                    T[l1] = make_double2(0.0, 0.0);
-                    T[l1 + 4] = make_double2(0.0, 0.0);
-                }
-            }
-            // ---- the padding row pairs i = M .. Mp-1 (at most 7): identity before the appended rows, zero after; the
-            //      blocks (appended rows x measurement columns) were written above ----
-            for (int i = M; i < Mp; ++i) {
-                const bool appended = i >= ia && i < ia + 2;
-                for (int k = (appended ? M : 0) + lane; k <= i; k += 32) {
-                    const double dg = (i == k && i < ia) ? 1.0 : 0.0;
-                    const int I = i >> 2, J = k >> 2;
-                    double2* T = Kt + tile_index(I, J) * 32;
-                    const int l0 = 8 * (i & 3) + (k & 3);
-                    T[l0] = make_double2(dg, 0.0);
-                    T[l0 + 4] = make_double2(0.0, dg);
-                    if (I == J && i != k) {
-                        const int l1 = 8 * (k & 3) + (i & 3);
-                        T[l1] = make_double2(0.0, 0.0);
-                        T[l1 + 4] = make_double2(0.0, 0.0);
+                    double v[6];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) v[c] = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) v[c] += ar[r] * Pb[r][c];
+                    double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        q0 = fma(v[c], ak[0][c], q0);
+                        q1 = fma(v[c], ak[1][c], q1);
                     }
+                    o[row][0] = q0;
+                    o[row][1] = q1;
                 }
+                double2* Kt = Kbuf + ((size_t)bl * F + s_list[bt * batch + e]) * KT_D2;
+                if (i == k) { o[0][0] += s2; o[1][1] += s2; }
+                if (i >= k) store_block(Kt, i, k, o[0][0], o[0][1], o[1][0], o[1][1]);
+                else store_block(Kt, k, i, o[0][0], o[1][0], o[0][1], o[1][1]);      // block above the diagonal: its transpose below it
             }
-            if (lane == 0) pend_list[pend_pos] = fl;
         }
+        __syncthreads();      // the buffer is free for batch bt + 2
     }
 }
 
@@ -572,15 +957,29 @@ front_chol_kernel(const double2* __restrict__ Kbuf, const int* __restrict__ pend
     }
 }
 
-size_t front_asm_smem(const msckf_dims& d, int warps = FA_WARPS) {
-    return ((size_t)(d.N * (d.N + 1) / 2) * PB + (size_t)d.N * 12 + (size_t)warps * FW_MAX_OBS * AR) * sizeof(double);
+int front_asm_warps(const msckf_dims& d) {
+    const size_t p_bytes = (size_t)(d.N * (d.N + 1) / 2) * PB * sizeof(double);
+    const size_t list_bytes = ((size_t)d.F * sizeof(unsigned short) + 15) & ~(size_t)15;
+    const size_t per_warp = (size_t)2 * FW_MAX_OBS * AR * sizeof(double);
+    const size_t cap = 227 * 1024;
+    if (p_bytes + list_bytes + 2 * per_warp > cap) return 0;
+    size_t w = (cap - p_bytes - list_bytes) / per_warp;
+    return (int)(w > (size_t)FA_WARPS_MAX ? FA_WARPS_MAX : w);
+}
+
+size_t front_asm_smem(const msckf_dims& d, int warps) {
+    return (size_t)(d.N * (d.N + 1) / 2) * PB * sizeof(double) + (size_t)warps * 2 * FW_MAX_OBS * AR * sizeof(double) +
+           (((size_t)d.F * sizeof(unsigned short) + 15) & ~(size_t)15);
 }
 
 }  // namespace
 
-bool front_split_supported(const msckf_dims& d) { return d.M <= fgeom::FW_MAX_OBS && front_asm_smem(d) <= 227 * 1024; }
+bool front_split_supported(const msckf_dims& d) {
+    // (the start-up histogram of the assembly kernel aliases two warps' scratch; the bucketed list holds 16-bit indices)
+    return d.M <= fgeom::FW_MAX_OBS && d.N <= 32 && d.F <= 65535 && front_asm_warps(d) >= 2;
+}
 
-// filters handled per assembly / factorisation kernel pair: bounds the tile buffer (20 KB per feature)
+// filters handled per kernel triple: bounds the tile buffer (20 KB per feature)
 int front_split_sub_filters(const msckf_dims& d) {
     const size_t budget = (size_t)6 << 30;
     const size_t per_filter = (size_t)(d.F > 0 ? d.F : 1) * KT_D2 * sizeof(double2);
@@ -596,11 +995,11 @@ size_t front_split_tile_bytes(const msckf_dims& d) {
 }
 
 // optional per-kernel timing (msckf_set_stage_timing / msckf_front_stage_ms): CUDA events on the launching stream around
-// the two kernels of every sub-batch
+// the three kernels of every sub-batch
 namespace {
 constexpr int MAX_SUB = 64;
 bool g_timing = false;
-cudaEvent_t g_ev[MAX_SUB][3];
+cudaEvent_t g_ev[MAX_SUB][4];
 int g_ev_created = 0, g_ev_used = 0;
 }  // namespace
 
@@ -610,26 +1009,58 @@ extern "C" int msckf_set_stage_timing(int on) {
     return 0;
 }
 
-extern "C" int msckf_front_stage_ms(double* asm_ms, double* chol_ms) {
-    double a = 0.0, c = 0.0;
+extern "C" int msckf_front_stage_ms(double* geo_ms, double* asm_ms, double* chol_ms) {
+    double g = 0.0, a = 0.0, c = 0.0;
     for (int k = 0; k < g_ev_used; ++k) {
-        float t0 = 0.f, t1 = 0.f;
-        cudaError_t e = cudaEventSynchronize(g_ev[k][2]);
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        cudaError_t e = cudaEventSynchronize(g_ev[k][3]);
         if (e == cudaSuccess) e = cudaEventElapsedTime(&t0, g_ev[k][0], g_ev[k][1]);
         if (e == cudaSuccess) e = cudaEventElapsedTime(&t1, g_ev[k][1], g_ev[k][2]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t2, g_ev[k][2], g_ev[k][3]);
         if (e != cudaSuccess) return (int)e;
-        a += t0;
-        c += t1;
+        g += t0;
+        a += t1;
+        c += t2;
     }
+    if (geo_ms) *geo_ms = g;
     if (asm_ms) *asm_ms = a;
     if (chol_ms) *chol_ms = c;
     return g_ev_used;
 }
 
-cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, cudaStream_t s) {
-    const size_t smem = front_asm_smem(a.dims);
+int front_ps_batch(const msckf_dims& d) {
+    const size_t cap = 227 * 1024;
+    const size_t lists = (((size_t)d.F + 7) & ~(size_t)7) * 2 + (((size_t)d.F + 15) & ~(size_t)15) + 1024;
+    if (lists + 2 * 2 * (size_t)PS_FEAT_BYTES > cap) return 0;
+    size_t nb = (cap - lists) / (2 * (size_t)PS_FEAT_BYTES);
+    return (int)(nb > 32 ? 32 : nb);
+}
+
+template <int NWARPS>
+cudaError_t launch_asm_ps(const FrontArgs& a, const unsigned char* slot_map, double2* Kbuf, int b0, int nb, cudaStream_t s) {
+    const int batch = front_ps_batch(a.dims);
+    const size_t smem = (size_t)2 * batch * PS_FEAT_BYTES + (((size_t)a.dims.F + 7) & ~(size_t)7) * 2 +
+                        (((size_t)a.dims.F + 15) & ~(size_t)15);
     static size_t configured = 0;
     if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(front_asm_ps_kernel<NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    front_asm_ps_kernel<NWARPS><<<nb, NWARPS * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, int* pend_key,
+                               unsigned char* slot_map, cudaStream_t s) {
+    // P-stationary assembly when the block triangle of the window fits one CTA's threads and the batch buffers fit its
+    // shared memory; P staged in shared memory otherwise
+    const int nblk = a.dims.N * (a.dims.N + 1) / 2;
+    const int ps_warps = (front_ps_batch(a.dims) >= 2) ? (nblk <= 15 * 32 ? 15 : (nblk <= 16 * 32 ? 16 : 0)) : 0;
+    const int warps = front_asm_warps(a.dims);
+    const size_t smem = front_asm_smem(a.dims, warps);
+    static size_t configured = 0;
+    if (!ps_warps && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(front_asm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
@@ -645,30 +1076,34 @@ cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list
         const int slot = g_ev_used;
         if (timed) {
             for (; g_ev_created <= slot; ++g_ev_created)
-                for (int q = 0; q < 3; ++q)
+                for (int q = 0; q < 4; ++q)
                     if ((e = cudaEventCreate(&g_ev[g_ev_created][q])) != cudaSuccess) return e;
             cudaEventRecord(g_ev[slot][0], s);
         }
-        // feature chunks per filter so that the CTAs come in >= ~6 waves of 148 (each warp keeps >= 2 features): long CTAs
-        // amortise the staggered start of their warps (measured: 13.3 ms -> 12.0 ms per 4096 filters with both)
-        constexpr int waves = 6;
-        constexpr unsigned stagger_ns = 1500u;
-        int chunks = (waves * 148 + nb - 1) / nb;
-        int fpc = (F + chunks - 1) / chunks;
-        if (fpc < 2 * FA_WARPS) fpc = 2 * FA_WARPS;
-        chunks = (F + fpc - 1) / fpc;
-        dim3 grid(chunks, nb);
-        front_asm_kernel<<<grid, FA_THREADS, smem, s>>>(a, Kbuf, pend_list, pend_count, b0, fpc, stagger_ns);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+        {   // geometry: 8 features per warp and CTA keep the prefetch chain going; small CTAs fill the machine at any B
+            const int fpc = 8 * FG_WARPS;
+            dim3 grid((F + fpc - 1) / fpc, nb);
+            const size_t gsm = (size_t)a.dims.N * 12 * sizeof(double);
+            front_geo_kernel<<<grid, FG_THREADS, gsm, s>>>(a, pend_key, slot_map, Kbuf, pend_list, pend_count, b0, fpc);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
         if (timed) cudaEventRecord(g_ev[slot][1], s);
+        if (ps_warps == 15) e = launch_asm_ps<15>(a, slot_map, Kbuf, b0, nb, s);
+        else if (ps_warps == 16) e = launch_asm_ps<16>(a, slot_map, Kbuf, b0, nb, s);
+        else {
+            front_asm_kernel<<<nb, warps * 32, smem, s>>>(a, pend_key, Kbuf, b0);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) return e;
+        if (timed) cudaEventRecord(g_ev[slot][2], s);
         front_chol_kernel<<<148 * 4, FC_THREADS, 0, s>>>(Kbuf, pend_list, pend_count, a.feat_len, a.fac_rank, a.dof,
                                                         a.chi2_table, a.chi2_len, a.feat_status, a.gamma, (size_t)b0 * F);
-        msckf_count_launch(2);
+        msckf_count_launch(3);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (timed) {
-            cudaEventRecord(g_ev[slot][2], s);
+            cudaEventRecord(g_ev[slot][3], s);
             ++g_ev_used;
         }
     }

@@ -8,7 +8,7 @@
 
 #define MSCKF_MAX_OBS 64          // observation capacity per feature supported by the front-end kernel
 #define MSCKF_TSQR_MAX_COLS 256   // 6 N + 1 columns (R | rhs) handled by one TSQR CTA  -> N <= 42
-#define MSCKF_FEAT_PENDING 0x40   // internal feat_status value between the two kernels of the split front end
+#define MSCKF_FEAT_PENDING 0x04   // internal feat_status CODE (low nibble) between the kernels of the split front end
 #define MSCKF_MAX_CAMS 64         // pose capacity of the dense-update kernels (d <= 399)
 
 // Workspace carve-up shared by msckf_*_workspace_bytes and the launches.  All offsets in bytes, 256-aligned.
@@ -27,6 +27,8 @@ struct WsLayout {
     size_t k_tiles;   // [sub][F][1280] double2: per-feature K tiles of the split front end (front_split.cu); 0 bytes if unused
     size_t pend_list; // [sub][F] int   features waiting for the factorisation kernel
     size_t pend_count;// int
+    size_t pend_key;  // [sub][F] int   slot-pattern key of every pending feature (-1: not pending)
+    size_t slot_map;  // [sub][F][32] u8 window slot -> observation index of every pending feature (0xFF: none)
     size_t total;
 };
 
