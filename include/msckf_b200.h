@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 6
+#define MSCKF_B200_ABI_VERSION 7
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
@@ -339,6 +339,51 @@ int msckf_filter_step_host(const msckf_dims* dims, const msckf_update_params* pa
                            const msckf_device_buffers* dev, const msckf_host_step* io,
                            int chunk_filters, int overlap_previous,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Data synthesis and metrics on the device: a Monte-Carlo run builds its streams and reduces
+ * its errors where the filters live; the final gather carries statistics only.
+ *
+ * msckf_synth_imu_batched  <->  IMU synthesis from ground-truth poses:
+ *   PhotorealisticGenerator.process_data, dataset/tools/dataset_generators/photorealistic_generator.py:145-216 (interp = 10:
+ *   every key interval is sampled at np.linspace(0, 1, 10) -- linear position, Slerp rotation -- and differentiated:
+ *   v = dp/dt, a = R_prev^T (dv/dt + g), w = (2/dt) vec(q_prev^* q_cur) with the sign of q_cur fixed; noisy = gt + white
+ *   noise + random-walk INCREMENT) and MeasurementsGenerator.generate, synthetic_generator.py:145-186 (interp = 1: the poses
+ *   are at IMU rate; sign_fix = 0; accumulate_bias = 1: noisy = gt + white noise + ACCUMULATED walk).
+ *   key_poses[B][K][12] (R row-major, t), key_times[B][K]; T = (interp > 1 ? interp - 1 : 1) (K - 1) samples.
+ *   noise[B][T][12] (may be NULL): acc white (3), acc walk increment (3), gyro white (3), gyro walk increment (3), already
+ *   scaled; with noise == NULL and sigmas[B][4] (acc, gyro, acc walk, gyro walk) != NULL the draws come from a
+ *   counter-based generator (Philox4x32-10 + Box-Muller, keyed by seed / filter / sample); both NULL: noisy = gt.
+ *   Outputs: poses_out[B][T+1][12] / times_out[B][T+1] (may be NULL), imu_gt / imu_noisy[B][T+1][7] = (timestamp, w, a) in
+ *   the sample layout of msckf_propagate_batched; row 0 is the reference's zero row at the first timestamp.
+ *
+ * msckf_project_landmarks_batched  <->  the camera-measurement loop of MeasurementsGenerator.generate,
+ *   synthetic_generator.py:189-223 (Camera.W2Ci / project_point, src/msckf/Camera.py:13-52): body_poses[B][n_frames][12],
+ *   T_I_C_host (R 9 + t 3) and K_host (9) on the HOST, landmarks[B][L][3].  Per (filter, frame) the landmarks in front of
+ *   the camera and inside the image are listed in id order: kp_out[B][n_frames][L][2] (pixel + noise), id_out[B][n_frames][L],
+ *   count_out[B][n_frames], score_out (may be NULL) = 1 / (1 + 2 sigma_px^2).  noise_uv[B][n_frames][L][2] indexed by
+ *   landmark id (may be NULL: drawn on the device with sigma_px, or none when sigma_px == 0).
+ *
+ * msckf_metrics_step_batched / msckf_metrics_finalize_batched  <->  the error block of the reference driver, main.py:312-391
+ *   and 436-437, and its summary, main.py:440-445.  One call per step with the step's ground-truth body pose gt_pose[B][12];
+ *   the estimate is read from imu_state / P.  metrics_state[B][msckf_metrics_state_doubles()] is the running state (zero it
+ *   before the first step): previous poses, the two 10-sample deques of the smoothing (:352-361), running sums.
+ *   record_out[B][14] (may be NULL) = rte_smoothed, roe_smoothed, ATE x y z, AOE roll pitch yaw (intrinsic XYZ Euler angles of
+ *   the absolute rotation error, R2euler), the six 3-sigma bounds (:337-345).  summary_out[B][8] = rmse_position,
+ *   rmse_orientation, mean_rte, std_rte, mean_roe, std_roe (unrounded; the reference rounds to 8 decimals), rmse of |ATE|, n.
+ * ------------------------------------------------------------------------------------------------------------- */
+int msckf_synth_imu_batched(int B, int K, int interp, const double* key_poses, const double* key_times,
+                            const double* gravity_host, const double* noise, const double* sigmas, unsigned long long seed,
+                            int accumulate_bias, int sign_fix, double* poses_out, double* times_out, double* imu_gt,
+                            double* imu_noisy, void* stream);
+int msckf_project_landmarks_batched(int B, int L, int n_frames, const double* body_poses, const double* T_I_C_host,
+                                    const double* K_host, int width, int height, const double* landmarks,
+                                    const double* noise_uv, double sigma_px, unsigned long long seed, double* kp_out,
+                                    int* id_out, int* count_out, double* score_out, void* stream);
+int msckf_metrics_state_doubles(void);
+int msckf_metrics_step_batched(const msckf_dims* dims, const double* gt_pose, const double* imu_state, const double* P,
+                               double* metrics_state, double* record_out, void* stream);
+int msckf_metrics_finalize_batched(int B, const double* metrics_state, double* summary_out, void* stream);
 
 /* Diagnostic: launches n_ctas x 256 threads, every warp running 8 independent FP64 tensor-instruction (DMMA.8x8x4) chains
  * of length iters (the measured FP64-pipe roofline denominator; MEASURED_PEAKS.json has no FP64 figure).

@@ -11,7 +11,7 @@ COMPRESS_GRAM = 1
 FEAT_SKIPPED, FEAT_ACCEPTED, FEAT_GATED_OUT, FEAT_LOST_DISCARD, FEAT_LOST_FLAG = 0, 1, 2, 3, 0x10
 FEAT_GAMMA_BOUND = 0x20
 FEAT_TRIANGULATED = 0x40
-ABI_VERSION = 6
+ABI_VERSION = 7
 GATE_EXACT, GATE_BOUNDS = 0, 1
 
 
@@ -69,6 +69,8 @@ EXPORTS = [
     "msckf_set_stage_timing", "msckf_front_stage_ms", "msckf_select_poorest_cameras_batched",
     "msckf_drop_observations_batched", "msckf_append_observations_batched", "msckf_unobserved_cameras_batched",
     "msckf_compact_tracks_batched", "msckf_match_descriptors_batched", "msckf_verify_matches_batched",
+    "msckf_synth_imu_batched", "msckf_project_landmarks_batched", "msckf_metrics_state_doubles",
+    "msckf_metrics_step_batched", "msckf_metrics_finalize_batched",
 ]
 
 
@@ -141,6 +143,17 @@ def load_library():
     lib.msckf_set_stage_timing.argtypes = [C.c_int]
     lib.msckf_front_stage_ms.restype = C.c_int
     lib.msckf_front_stage_ms.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.msckf_synth_imu_batched.restype = C.c_int
+    lib.msckf_synth_imu_batched.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_double), dp, dp, C.c_ulonglong, C.c_int,
+                                            C.c_int, dp, dp, dp, dp, vp]
+    lib.msckf_project_landmarks_batched.restype = C.c_int
+    lib.msckf_project_landmarks_batched.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                    C.c_int, C.c_int, dp, dp, C.c_double, C.c_ulonglong, dp, ip, ip, dp, vp]
+    lib.msckf_metrics_state_doubles.restype = C.c_int
+    lib.msckf_metrics_step_batched.restype = C.c_int
+    lib.msckf_metrics_step_batched.argtypes = [pd, dp, dp, dp, dp, dp, vp]
+    lib.msckf_metrics_finalize_batched.restype = C.c_int
+    lib.msckf_metrics_finalize_batched.argtypes = [C.c_int, dp, dp, vp]
     if lib.msckf_abi_version() != ABI_VERSION:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib
