@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 7
+#define MSCKF_B200_ABI_VERSION 8
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
@@ -339,6 +339,47 @@ int msckf_filter_step_host(const msckf_dims* dims, const msckf_update_params* pa
                            const msckf_device_buffers* dev, const msckf_host_step* io,
                            int chunk_filters, int overlap_previous,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Track descriptors of the matching front with the reference's list semantics.
+ * obs_desc[B][F][M][D] float32 holds Feature.descriptors (one row per observation, aligned with obs_uv / obs_conf; obs_conf
+ * IS Feature.scores: Line.confidence is the same number, MSCKF.py:408-410).  D a multiple of 4, <= 128.
+ *
+ * msckf_score_filter_batched  <->  MSCKF.add_camera_measurements' score filter (MSCKF.py:279-284): per filter the detections
+ *   with score >= 0.5 mean(score) are kept, in order: (scores, kp[.][2], desc[.][D]) of n_in[b] detections (NULL = F_new) ->
+ *   compacted copies + n_out[b].  Source and destination must not alias.
+ * msckf_append_descriptors_batched  <->  feature.descriptors.append(...) of MSCKF.py:407 (accepted match, action 2: the
+ *   detection match12[slot]) and :425 (new track, action 3: the r-th unmatched detection in ascending order feeds slot
+ *   n_tracks[b] + r, as msckf_match_descriptors_batched assigns them).  Call it with the FINAL actions (after
+ *   msckf_verify_matches_batched) and BEFORE msckf_append_observations_batched: feat_len must still hold the lengths before
+ *   the frame.
+ * msckf_drop_descriptors_batched  <->  del feature.descriptors[i] / del feature.scores[i] of MSCKF.remove_cameras
+ *   (MSCKF.py:764-765).  Same remove_mask as msckf_drop_observations_batched, called BEFORE it (obs_slot / feat_len still
+ *   describe the window before the deletion).
+ * msckf_compact_descriptors_batched  <->  the track deletions (MSCKF.py:739-741, 768-772) for the descriptor lists: every
+ *   track moves to the slot dest[B][F] that msckf_compact_tracks_batched returned (-1: deleted); feat_len_dst = the lengths
+ *   AFTER the compaction.  src and dst are two different buffers (the caller swaps them like the track arrays).
+ * msckf_track_descriptors_batched  <->  np.average(feature.descriptors, axis=0, weights=feature.scores) for every track
+ *   (MSCKF.py:436-441): desc_tracks[B][F][D], the rows msckf_match_descriptors_batched matches against (accumulated in FP64,
+ *   NOT re-normalised, zero rows for empty slots).  The reference rebuilds these rows at the END of add_camera_measurements
+ *   (after the frame's appends, before process_features / pruning) and matches the NEXT frame against them, so a pruned
+ *   camera's descriptors leave a track's mean one frame after they left its list; a filter that returned early from
+ *   add_camera_measurements (no detections / no match, MSCKF.py:286, 320) keeps its old rows: keep_old[B] (may be NULL)
+ *   marks those filters.  Rows of deleted tracks follow msckf_compact_descriptors_batched (called with dims->M = 1).
+ * ------------------------------------------------------------------------------------------------------------- */
+int msckf_score_filter_batched(int B, int F_new, int D, const int* n_in, const double* scores, const double* kp,
+                               const float* desc, double* scores_out, double* kp_out, float* desc_out, int* n_out,
+                               void* stream);
+int msckf_append_descriptors_batched(const msckf_dims* dims, int D, int F_new, const unsigned char* action,
+                                     const int* match12, const int* match21, const int* n_tracks, const int* n_new,
+                                     const float* desc_new, const int* feat_len, float* obs_desc, void* stream);
+int msckf_drop_descriptors_batched(const msckf_dims* dims, int D, const unsigned char* remove_mask, const int* feat_len,
+                                   const int* obs_slot, float* obs_desc, void* stream);
+int msckf_compact_descriptors_batched(const msckf_dims* dims, int D, const int* dest, const int* feat_len_dst,
+                                      const float* src, float* dst, void* stream);
+int msckf_track_descriptors_batched(const msckf_dims* dims, int D, const int* feat_len, const double* obs_conf,
+                                    const float* obs_desc, const unsigned char* keep_old, float* desc_tracks,
+                                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Data synthesis and metrics on the device: a Monte-Carlo run builds its streams and reduces

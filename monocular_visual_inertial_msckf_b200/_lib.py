@@ -11,7 +11,7 @@ COMPRESS_GRAM = 1
 FEAT_SKIPPED, FEAT_ACCEPTED, FEAT_GATED_OUT, FEAT_LOST_DISCARD, FEAT_LOST_FLAG = 0, 1, 2, 3, 0x10
 FEAT_GAMMA_BOUND = 0x20
 FEAT_TRIANGULATED = 0x40
-ABI_VERSION = 7
+ABI_VERSION = 8
 GATE_EXACT, GATE_BOUNDS = 0, 1
 
 
@@ -71,6 +71,8 @@ EXPORTS = [
     "msckf_compact_tracks_batched", "msckf_match_descriptors_batched", "msckf_verify_matches_batched",
     "msckf_synth_imu_batched", "msckf_project_landmarks_batched", "msckf_metrics_state_doubles",
     "msckf_metrics_step_batched", "msckf_metrics_finalize_batched",
+    "msckf_score_filter_batched", "msckf_append_descriptors_batched", "msckf_drop_descriptors_batched",
+    "msckf_compact_descriptors_batched", "msckf_track_descriptors_batched",
 ]
 
 
@@ -154,6 +156,16 @@ def load_library():
     lib.msckf_metrics_step_batched.argtypes = [pd, dp, dp, dp, dp, dp, vp]
     lib.msckf_metrics_finalize_batched.restype = C.c_int
     lib.msckf_metrics_finalize_batched.argtypes = [C.c_int, dp, dp, vp]
+    lib.msckf_score_filter_batched.restype = C.c_int
+    lib.msckf_score_filter_batched.argtypes = [C.c_int, C.c_int, C.c_int, ip, dp, dp, dp, dp, dp, dp, ip, vp]
+    lib.msckf_append_descriptors_batched.restype = C.c_int
+    lib.msckf_append_descriptors_batched.argtypes = [pd, C.c_int, C.c_int, u8, ip, ip, ip, ip, dp, ip, dp, vp]
+    lib.msckf_drop_descriptors_batched.restype = C.c_int
+    lib.msckf_drop_descriptors_batched.argtypes = [pd, C.c_int, u8, ip, ip, dp, vp]
+    lib.msckf_compact_descriptors_batched.restype = C.c_int
+    lib.msckf_compact_descriptors_batched.argtypes = [pd, C.c_int, ip, ip, dp, dp, vp]
+    lib.msckf_track_descriptors_batched.restype = C.c_int
+    lib.msckf_track_descriptors_batched.argtypes = [pd, C.c_int, ip, dp, dp, u8, dp, vp]
     if lib.msckf_abi_version() != ABI_VERSION:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib

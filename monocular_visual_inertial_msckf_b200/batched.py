@@ -141,7 +141,13 @@ class BatchedMSCKF:
         self._overflow = None
         self.window_overflow = None
         self._alt_tracks = None
-        self.desc_sum = self.desc_w = None       # per-track descriptor sums of frame_step_detections
+        self.obs_desc = None                     # [B, F, M, D] float32: Feature.descriptors, one row per observation
+        self._alt_desc = None
+        self.lcm_desc = None                     # [B, F, D] float32: last_camera_measurement.descriptors (the matcher's view)
+        self._alt_lcm = None
+        self.desc_dim = 0
+        self.feature_updates = None              # device int64: features that went through rows 3-8 (set count_feature_updates)
+        self.count_feature_updates = False
         self._samples_dev = None
 
     # ------------------------------------------------------------------------------------------------------------
@@ -179,6 +185,11 @@ class BatchedMSCKF:
                                            _ptr(self.delta_x), _ptr(self.n_accepted), _ptr(self.n_rejected),
                                            _ptr(self.workspace), self.workspace.numel(), self._stream())
         _lib.check(rc, "msckf_update_batched")
+        if self.count_feature_updates:
+            if self.feature_updates is None:
+                self.feature_updates = torch.zeros((), dtype=torch.int64, device=self.device)
+            code = self.feat_status & 0xF
+            self.feature_updates += ((code == _lib.FEAT_ACCEPTED) | (code == _lib.FEAT_GATED_OUT)).sum()
 
     def front(self):
         rc = self.lib.msckf_front_batched(C.byref(self.dims), C.byref(self.cpar), _ptr(self.chi2), self.chi2_len,
@@ -378,7 +389,12 @@ class BatchedMSCKF:
         return mask, touch
 
     def drop_observations(self, mask):
-        """Track part of MSCKF.remove_cameras (MSCKF.py:760-770); call before remove_cameras(mask)."""
+        """Track part of MSCKF.remove_cameras (MSCKF.py:760-770); call before remove_cameras(mask).  The per-observation
+        descriptors (if this batch keeps them) lose the same rows (:764-765)."""
+        if self.obs_desc is not None:
+            rc = self.lib.msckf_drop_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(mask), _ptr(self.feat_len),
+                                                         _ptr(self.obs_slot), _ptr(self.obs_desc), self._stream())
+            _lib.check(rc, "msckf_drop_descriptors_batched")
         rc = self.lib.msckf_drop_observations_batched(C.byref(self.dims), _ptr(mask), _ptr(self.n_cams), _ptr(self.cam_t),
                                                       _ptr(self.feat_len), _ptr(self.obs_uv), _ptr(self.obs_dir),
                                                       _ptr(self.obs_conf), _ptr(self.obs_slot), _ptr(self.idp_base),
@@ -400,7 +416,8 @@ class BatchedMSCKF:
         if self._alt_tracks is None:
             self._alt_tracks = {n: torch.zeros_like(t) for n, t in cur.items()}
         active = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
-        dest = torch.empty((self.B, self.F), dtype=torch.int32, device=self.device) if return_map else None
+        want_map = return_map or self.obs_desc is not None
+        dest = torch.empty((self.B, self.F), dtype=torch.int32, device=self.device) if want_map else None
         a, b = self._track_struct(cur), self._track_struct(self._alt_tracks)
         rc = self.lib.msckf_compact_tracks_batched(C.byref(self.dims), int(bool(drop_lost)), _ptr(self.feat_status), C.byref(a),
                                                    C.byref(b), _ptr(active), _ptr(dest), self._stream())
@@ -408,6 +425,22 @@ class BatchedMSCKF:
         for n in _lib.TRACK_FIELDS:
             setattr(self, n, self._alt_tracks[n])
         self._alt_tracks = cur
+        if self.obs_desc is not None:            # the descriptor lists move with their tracks
+            if self._alt_desc is None:
+                self._alt_desc = torch.zeros_like(self.obs_desc)
+            rc = self.lib.msckf_compact_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
+                                                            _ptr(self.obs_desc), _ptr(self._alt_desc), self._stream())
+            _lib.check(rc, "msckf_compact_descriptors_batched")
+            self.obs_desc, self._alt_desc = self._alt_desc, self.obs_desc
+            # ... and so do their rows of last_camera_measurement (MSCKF.py:742-747, 774-778): one row per track
+            if self._alt_lcm is None:
+                self._alt_lcm = torch.zeros_like(self.lcm_desc)
+            d1 = _lib.Dims(self.B, self.F, 1, self.N, self.ldp)
+            self._alt_lcm.zero_()
+            rc = self.lib.msckf_compact_descriptors_batched(C.byref(d1), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
+                                                            _ptr(self.lcm_desc), _ptr(self._alt_lcm), self._stream())
+            _lib.check(rc, "msckf_compact_descriptors_batched")
+            self.lcm_desc, self._alt_lcm = self._alt_lcm, self.lcm_desc
         return (active, dest) if return_map else active
 
     def unobserved_cameras(self, active=None):
@@ -445,60 +478,94 @@ class BatchedMSCKF:
         return (m1, m2) if return_maps else None
 
     # ------------------------------------------------------------------------------------------------------------
-    def _remap_descriptors(self, dest):
-        """Track descriptors follow a slot map of compact_tracks ([B, F] int32, -1 = deleted)."""
-        F, D = self.F, self.desc_sum.shape[2]
-        idx = torch.where(dest >= 0, dest, torch.full_like(dest, F)).long()
-        ds = torch.zeros((self.B, F + 1, D), dtype=self.desc_sum.dtype, device=self.device)
-        dw = torch.zeros((self.B, F + 1), dtype=self.desc_w.dtype, device=self.device)
-        ds.scatter_(1, idx[..., None].expand(-1, -1, D), self.desc_sum)
-        dw.scatter_(1, idx, self.desc_w)
-        self.desc_sum, self.desc_w = ds[:, :F].contiguous(), dw[:, :F].contiguous()
+    def _ensure_descriptors(self, D):
+        if self.obs_desc is None or self.desc_dim != D:
+            self.desc_dim = int(D)
+            self.obs_desc = torch.zeros((self.B, self.F, self.M, D), dtype=torch.float32, device=self.device)
+            self.lcm_desc = torch.zeros((self.B, self.F, D), dtype=torch.float32, device=self.device)
+            self._alt_desc = self._alt_lcm = None
+
+    def score_filter(self, desc_new, kp_new, score_new, n_new=None):
+        """The score filter of MSCKF.add_camera_measurements (MSCKF.py:279-284) on the device: detections with
+        score >= 0.5 mean(score) survive, in order.  Returns (desc, kp, score, n) compacted copies."""
+        B, F2, D = desc_new.shape
+        do, ko, so = torch.zeros_like(desc_new), torch.zeros_like(kp_new), torch.zeros_like(score_new)
+        no = torch.empty(B, dtype=torch.int32, device=self.device)
+        rc = self.lib.msckf_score_filter_batched(B, F2, D, _ptr(n_new), _ptr(score_new), _ptr(kp_new), _ptr(desc_new), _ptr(so),
+                                                 _ptr(ko), _ptr(do), _ptr(no), self._stream())
+        _lib.check(rc, "msckf_score_filter_batched")
+        return do, ko, so, no
+
+    def track_descriptors(self, out=None, keep_old=None):
+        """[B, F, D] float32: the score-weighted mean descriptor of every track over its current descriptor list
+        (np.average(..., weights=scores), MSCKF.py:436-441).  keep_old [B] uint8: filters whose rows of `out` stay."""
+        if out is None:
+            out = torch.empty((self.B, self.F, self.desc_dim), dtype=torch.float32, device=self.device)
+        rc = self.lib.msckf_track_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(self.feat_len), _ptr(self.obs_conf),
+                                                      _ptr(self.obs_desc), _ptr(keep_old), _ptr(out), self._stream())
+        _lib.check(rc, "msckf_track_descriptors_batched")
+        return out
+
+    def append_descriptors(self, action, match12, match21, n_tracks, n_new, desc_new):
+        """feature.descriptors.append(...) for the accepted matches and the new tracks (MSCKF.py:407, 425); call with the
+        final actions and before append_observations."""
+        rc = self.lib.msckf_append_descriptors_batched(C.byref(self.dims), self.desc_dim, int(desc_new.shape[1]), _ptr(action),
+                                                       _ptr(match12), _ptr(match21), _ptr(n_tracks), _ptr(n_new), _ptr(desc_new),
+                                                       _ptr(self.feat_len), _ptr(self.obs_desc), self._stream())
+        _lib.check(rc, "msckf_append_descriptors_batched")
 
     def frame_step_detections(self, samples, R_I_C, t_I_C, desc_new, kp_new, score_new, n_new, max_cameras,
                               min_cosine_similarity=0.82, epipolar_rejection_threshold=5.0,
-                              homography_rejection_threshold=5.0, use_null_state=False, counters=None):
+                              homography_rejection_threshold=5.0, use_null_state=False, counters=None, score_filter=False):
         """One camera frame of every filter from the frame's DETECTIONS (MSCKF.imu_callback x n + feature_callback,
-        MSCKF.py:135-158, with add_camera_measurements :284-448 on the device): propagation, state_augmentation, the
-        mutual-NN descriptor matcher against the tracks' score-weighted mean descriptors (:317, :439), the epipolar /
-        homography walk (:333-401), the track bookkeeping (:400-438), process_features and the pruning.
-        desc_new [B, F2, D] float32, kp_new [B, F2, 2] / score_new [B, F2] float64, n_new [B] int32 (detections that passed
-        the caller's score filter, MSCKF.py:279-282).  The per-track descriptor sums are kept here with torch index
-        operations (plumbing; they follow the slot maps of the track compactions).  Returns (action, verdict)."""
+        MSCKF.py:135-158, with add_camera_measurements :267-448 on the device): propagation, state_augmentation, the
+        score filter (:279-284, score_filter=True; otherwise the caller filtered), the tracks' score-weighted mean
+        descriptors (:436-441) over their per-observation lists, the mutual-NN matcher (:317), the epipolar / homography
+        walk (:333-401), the track bookkeeping with the descriptor lists (:400-438), process_features and the pruning --
+        the descriptor rows of a pruned camera leave their tracks (:764-765) before the next mean.
+        desc_new [B, F2, D] float32, kp_new [B, F2, 2] / score_new [B, F2] float64, n_new [B] int32.
+        Returns (action, verdict)."""
         B, F2, D = desc_new.shape
-        if getattr(self, "desc_sum", None) is None:
-            self.desc_sum = torch.zeros((self.B, self.F, D), dtype=torch.float32, device=self.device)
-            self.desc_w = torch.zeros((self.B, self.F), dtype=torch.float32, device=self.device)
+        self._ensure_descriptors(D)
         self.propagate(samples, use_null_state=use_null_state)
         self.augment(R_I_C, t_I_C)
+        if score_filter:
+            desc_new, kp_new, score_new, n_new = self.score_filter(desc_new, kp_new, score_new, n_new)
         n_tracks = (self.feat_len > 0).sum(1).to(torch.int32)            # the slots in use are 0 .. n-1 (tracks stay compacted)
-        desc_tracks = (self.desc_sum / self.desc_w.clamp_min(1e-30)[..., None]).contiguous()
-        m12, m21, action, new_uv, new_conf, _ = self.match_descriptors(desc_tracks, desc_new, min_cosine_similarity, n_tracks,
+        # the matcher sees last_camera_measurement: the means built at the end of the PREVIOUS frame's bookkeeping
+        m12, m21, action, new_uv, new_conf, _ = self.match_descriptors(self.lcm_desc, desc_new, min_cosine_similarity, n_tracks,
                                                                       n_new, kp_new, score_new)
-        # `if len(matched.keypoints) == 0: return` (MSCKF.py:320): a filter with tracks but no match skips the frame
-        skip = (n_tracks > 0) & ((m12 >= 0).sum(1) == 0)
+        # `if len(keypoints) == 0: return` / `if len(matched.keypoints) == 0: return` (MSCKF.py:286, 320): such a filter
+        # skips the frame's bookkeeping and keeps its old last_camera_measurement
+        skip = (n_new <= 0) | ((n_tracks > 0) & ((m12 >= 0).sum(1) == 0))
         action.masked_fill_(skip[:, None], 0)
         verdict = self.verify_matches(action, new_uv, epipolar_rejection_threshold, homography_rejection_threshold, counters)
-        # descriptors: an accepted match adds (score, descriptor) to its track (MSCKF.py:407-408), a new track starts its list
-        acc = action == 2
-        idx = m12.clamp(min=0).long()
-        w = torch.gather(score_new, 1, idx).to(torch.float32) * acc
-        self.desc_sum += w[..., None] * torch.gather(desc_new, 1, idx[..., None].expand(-1, -1, D))
-        self.desc_w += w
-        un = (m21 < 0) & (torch.arange(F2, device=self.device)[None, :] < n_new[:, None]) & ~skip[:, None]
-        slot = n_tracks[:, None].long() + torch.cumsum(un, 1) - 1
-        ok = un & (slot < self.F)
-        slot = torch.where(ok, slot, torch.full_like(slot, self.F))
-        wn = score_new.to(torch.float32) * ok
-        ds = torch.cat([self.desc_sum, torch.zeros((self.B, 1, D), dtype=torch.float32, device=self.device)], 1)
-        dw = torch.cat([self.desc_w, torch.zeros((self.B, 1), dtype=torch.float32, device=self.device)], 1)
-        ds.scatter_add_(1, slot[..., None].expand(-1, -1, D), wn[..., None] * desc_new)
-        dw.scatter_add_(1, slot, wn)
-        self.desc_sum, self.desc_w = ds[:, :self.F].contiguous(), dw[:, :self.F].contiguous()
+        self.append_descriptors(action, m12, m21, n_tracks, n_new, desc_new)
         self.append_observations(action, new_uv, new_conf)
-        self._remap_descriptors(self.process_features(return_map=True))
-        self._remap_descriptors(self.prune_poorest_camera_states(prune_above=max_cameras, return_map=True))
+        self.track_descriptors(out=self.lcm_desc, keep_old=skip.to(torch.uint8))      # MSCKF.py:436-441
+        self.process_features()
+        self.prune_poorest_camera_states(prune_above=max_cameras)
         return action, verdict
+
+    # ------------------------------------------------------------------------------------------------------------
+    def snapshot(self):
+        """Every state tensor of the batch (filter state, window, tracks, descriptor lists) cloned: restore() brings the
+        batch back to this point (benchmarks and A/B comparisons re-run the same frames from it)."""
+        snap = dict(P=self.P.clone(), small_slab=self.small_slab.clone(), n_cams=self.n_cams.clone(),
+                    tracks={n: getattr(self, n).clone() for n in _lib.TRACK_FIELDS},
+                    obs_desc=None if self.obs_desc is None else self.obs_desc.clone(),
+                    lcm_desc=None if self.lcm_desc is None else self.lcm_desc.clone())
+        return snap
+
+    def restore(self, snap):
+        self.P.copy_(snap["P"])
+        self.small_slab.copy_(snap["small_slab"])
+        self.n_cams.copy_(snap["n_cams"])
+        for n in _lib.TRACK_FIELDS:
+            getattr(self, n).copy_(snap["tracks"][n])
+        if snap["obs_desc"] is not None:
+            self.obs_desc.copy_(snap["obs_desc"])
+            self.lcm_desc.copy_(snap["lcm_desc"])
 
     def prune_poorest_camera_states(self, max_select=2, prune_above=-1, return_map=False):
         """MSCKF.prune_poorest_camera_states (MSCKF.py:710-737) for every filter, everything resident: select the two

@@ -1,0 +1,262 @@
+// Track descriptors of the matching front with the reference's semantics:
+//   score filter of the frame's detections                 reference src/msckf/MSCKF.py:279-284
+//   per-observation descriptor / score lists of a track    Feature.descriptors / Feature.scores, MSCKF.py:407-408, 425-427
+//   their deletion when a camera leaves the window          MSCKF.py:764-765
+//   the score-weighted mean descriptor the matcher sees     np.average(feature.descriptors, axis=0, weights=feature.scores),
+//                                                           MSCKF.py:436-441 (NOT re-normalised)
+// Descriptors are float32 as XFeat delivers them; the per-observation scores are the tracks' obs_conf (Line.confidence is
+// the same number, MSCKF.py:410).  The mean is accumulated in FP64 and rounded once.  All kernels are one pass over the
+// arrays they touch (HBM-bound by construction).
+#include "msckf_common.cuh"
+
+namespace {
+
+constexpr int DT = 256;
+
+// ---- score filter: keep detections with score >= 0.5 mean(score), in order (MSCKF.py:279-284) ----
+__global__ void __launch_bounds__(DT) score_filter_kernel(int F2, int D, const int* __restrict__ n_in,
+                                                          const double* __restrict__ scores, const double* __restrict__ kp,
+                                                          const float* __restrict__ desc, double* __restrict__ scores_out,
+                                                          double* __restrict__ kp_out, float* __restrict__ desc_out,
+                                                          int* __restrict__ n_out) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = n_in ? min(max(n_in[b], 0), F2) : F2;
+    __shared__ double s_part[DT / 32];
+    __shared__ int s_cnt[DT / 32], s_base;
+    __shared__ double s_thr;
+    // np.mean: pairwise summation in NumPy; a tree reduction in FP64 differs from it by rounding only, and the comparison
+    // below is >= against half of it: detections within an ulp of the threshold are the caller's tie to break
+    double acc = 0.0;
+    for (int j = tid; j < n; j += DT) acc += scores[(size_t)b * F2 + j];
+    acc = warp_sum(acc);
+    if (lane == 0) s_part[warp] = acc;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < DT / 32; ++w) t += s_part[w];
+        s_thr = n > 0 ? 0.5 * (t / (double)n) : 0.0;
+    }
+    __syncthreads();
+    const double thr = s_thr;
+    for (int j0 = 0; j0 < n; j0 += DT) {
+        const int j = j0 + tid;
+        const bool keep = j < n && scores[(size_t)b * F2 + j] >= thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_cnt[w];
+        const int pos = off + __popc(bal & ((1u << lane) - 1u));
+        // (the descriptor rows are moved by the whole warp below: positions through shared memory would cost more than this)
+        if (keep) {
+            scores_out[(size_t)b * F2 + pos] = scores[(size_t)b * F2 + j];
+            kp_out[((size_t)b * F2 + pos) * 2] = kp[((size_t)b * F2 + j) * 2];
+            kp_out[((size_t)b * F2 + pos) * 2 + 1] = kp[((size_t)b * F2 + j) * 2 + 1];
+            const float* s = desc + ((size_t)b * F2 + j) * D;
+            float* d = desc_out + ((size_t)b * F2 + pos) * D;
+            for (int e = 0; e < D; e += 4) *reinterpret_cast<float4*>(d + e) = *reinterpret_cast<const float4*>(s + e);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < DT / 32; ++w) tot += s_cnt[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_out[b] = s_base;
+}
+
+// ---- append: the accepted match / the new track stores the detection's descriptor as its newest / first observation ----
+// Runs BEFORE msckf_append_observations_batched (feat_len still holds the lengths before the frame) with the FINAL actions.
+__global__ void __launch_bounds__(DT) append_descriptors_kernel(msckf_dims dims, int D, int F2, const unsigned char* __restrict__ action,
+                                                                const int* __restrict__ match12, const int* __restrict__ match21,
+                                                                const int* __restrict__ n_tracks, const int* __restrict__ n_new,
+                                                                const float* __restrict__ desc_new, const int* __restrict__ feat_len,
+                                                                float* __restrict__ obs_desc) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = dims.F, M = dims.M;
+    const int n1 = n_tracks ? min(max(n_tracks[b], 0), F) : F;
+    const int n2 = n_new ? min(max(n_new[b], 0), F2) : F2;
+    const int q4 = D / 4;
+    // matched tracks: warp per track, 16-byte pieces per lane
+    for (int j = warp; j < n1; j += DT / 32) {
+        const size_t fj = (size_t)b * F + j;
+        if (action[fj] != 2) continue;
+        const int src = match12[fj], len = feat_len[fj];
+        if (src < 0 || len >= M) continue;
+        const float4* s = reinterpret_cast<const float4*>(desc_new + ((size_t)b * F2 + src) * D);
+        float4* d = reinterpret_cast<float4*>(obs_desc + ((fj * M) + len) * D);
+        for (int e = lane; e < q4; e += 32) d[e] = s[e];
+    }
+    // new tracks: the r-th unmatched detection (ascending) went to slot n1 + r (np.setdiff1d order, FeatureExtractor.py:73)
+    __shared__ int s_cnt[DT / 32], s_base;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < n2; j0 += DT) {
+        const int j = j0 + tid;
+        const bool un = j < n2 && match21[(size_t)b * F2 + j] < 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, un);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_cnt[w];
+        if (un) {
+            const int slot = n1 + off + __popc(bal & ((1u << lane) - 1u));
+            if (slot < F && action[(size_t)b * F + slot] == 3) {
+                const float4* s = reinterpret_cast<const float4*>(desc_new + ((size_t)b * F2 + j) * D);
+                float4* d = reinterpret_cast<float4*>(obs_desc + (((size_t)b * F + slot) * M) * D);
+                for (int e = 0; e < q4; ++e) d[e] = s[e];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < DT / 32; ++w) tot += s_cnt[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- deletion: the descriptors observed from the cameras flagged in remove_mask leave their tracks (MSCKF.py:764-765) ----
+// Runs BEFORE msckf_drop_observations_batched (same mask; obs_slot / feat_len still describe the window before the deletion).
+__global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, int D, const unsigned char* __restrict__ remove_mask,
+                                                              const int* __restrict__ feat_len, const int* __restrict__ obs_slot,
+                                                              float* __restrict__ obs_desc) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
+    const int F = dims.F, M = dims.M, N = dims.N;
+    if (j >= F) return;
+    const size_t fj = (size_t)b * F + j;
+    const int len = min(feat_len[fj], M);
+    if (len <= 0) return;
+    const int q4 = D / 4;
+    int w = 0;
+    bool moved = false;
+    for (int i = 0; i < len; ++i) {      // (uniform per warp: the track's observations in order)
+        const int s = obs_slot[fj * M + i];
+        const bool gone = s >= 0 && s < N && remove_mask[(size_t)b * N + s] != 0;
+        if (gone) { moved = true; continue; }
+        if (moved) {
+            const float4* src = reinterpret_cast<const float4*>(obs_desc + (fj * M + i) * D);
+            float4* dst = reinterpret_cast<float4*>(obs_desc + (fj * M + w) * D);
+            for (int e = lane; e < q4; e += 32) dst[e] = src[e];
+            __syncwarp();
+        }
+        ++w;
+    }
+}
+
+// ---- whole tracks follow the slot map of msckf_compact_tracks_batched ----
+__global__ void __launch_bounds__(DT) compact_descriptors_kernel(msckf_dims dims, int D, const int* __restrict__ dest,
+                                                                 const int* __restrict__ feat_len_dst, const float* __restrict__ src,
+                                                                 float* __restrict__ dst) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
+    const int F = dims.F, M = dims.M;
+    if (j >= F) return;
+    const int to = dest[(size_t)b * F + j];
+    if (to < 0 || to >= F) return;
+    const int len = min(feat_len_dst[(size_t)b * F + to], M);
+    const size_t n4 = (size_t)len * D / 4;
+    const float4* s = reinterpret_cast<const float4*>(src + ((size_t)b * F + j) * M * D);
+    float4* d = reinterpret_cast<float4*>(dst + ((size_t)b * F + to) * M * D);
+    for (size_t e = lane; e < n4; e += 32) d[e] = s[e];
+}
+
+// ---- the matcher's view: score-weighted mean descriptor of every track (MSCKF.py:439), zero rows for empty slots ----
+__global__ void __launch_bounds__(DT) track_descriptors_kernel(msckf_dims dims, int D, const int* __restrict__ feat_len,
+                                                               const double* __restrict__ obs_conf, const float* __restrict__ obs_desc,
+                                                               const unsigned char* __restrict__ keep_old,
+                                                               float* __restrict__ desc_tracks) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
+    const int F = dims.F, M = dims.M;
+    if (j >= F || (keep_old && keep_old[b])) return;
+    const size_t fj = (size_t)b * F + j;
+    const int len = min(feat_len[fj], M);
+    // lane e holds components e, e + 32, ... (D <= 128: four accumulators)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double wsum = 0.0;
+    for (int i = 0; i < len; ++i) {
+        const double w = obs_conf[fj * M + i];
+        wsum += w;
+        const float* d = obs_desc + (fj * M + i) * D;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lane + 32 * q < D) acc[q] += w * (double)d[lane + 32 * q];
+    }
+    const double inv = (len > 0 && wsum != 0.0) ? 1.0 / wsum : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (lane + 32 * q < D) desc_tracks[fj * D + lane + 32 * q] = (float)(acc[q] * inv);
+}
+
+}  // namespace
+
+static int check_desc(const msckf_dims* d, int D) {
+    if (!d || d->B <= 0 || d->F <= 0 || d->M <= 0 || d->N <= 0) return MSCKF_EINVAL;
+    if (D <= 0 || D > 128 || (D & 3)) return MSCKF_ECAPACITY;
+    if (d->B > 65535) return MSCKF_ECAPACITY;
+    return 0;
+}
+
+extern "C" {
+
+int msckf_score_filter_batched(int B, int F2, int D, const int* n_in, const double* scores, const double* kp, const float* desc,
+                               double* scores_out, double* kp_out, float* desc_out, int* n_out, void* stream) {
+    if (B <= 0 || F2 <= 0 || !scores || !kp || !desc || !scores_out || !kp_out || !desc_out || !n_out) return MSCKF_EINVAL;
+    if (D <= 0 || (D & 3)) return MSCKF_ECAPACITY;
+    score_filter_kernel<<<B, DT, 0, (cudaStream_t)stream>>>(F2, D, n_in, scores, kp, desc, scores_out, kp_out, desc_out, n_out);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+int msckf_append_descriptors_batched(const msckf_dims* dims, int D, int F_new, const unsigned char* action, const int* match12,
+                                     const int* match21, const int* n_tracks, const int* n_new, const float* desc_new,
+                                     const int* feat_len, float* obs_desc, void* stream) {
+    int rc = check_desc(dims, D);
+    if (rc) return rc;
+    if (F_new <= 0 || !action || !match12 || !match21 || !desc_new || !feat_len || !obs_desc) return MSCKF_EINVAL;
+    append_descriptors_kernel<<<dims->B, DT, 0, (cudaStream_t)stream>>>(*dims, D, F_new, action, match12, match21, n_tracks, n_new,
+                                                                       desc_new, feat_len, obs_desc);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+int msckf_drop_descriptors_batched(const msckf_dims* dims, int D, const unsigned char* remove_mask, const int* feat_len,
+                                   const int* obs_slot, float* obs_desc, void* stream) {
+    int rc = check_desc(dims, D);
+    if (rc) return rc;
+    if (!remove_mask || !feat_len || !obs_slot || !obs_desc) return MSCKF_EINVAL;
+    dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
+    drop_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, remove_mask, feat_len, obs_slot, obs_desc);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+int msckf_compact_descriptors_batched(const msckf_dims* dims, int D, const int* dest, const int* feat_len_dst, const float* src,
+                                      float* dst, void* stream) {
+    int rc = check_desc(dims, D);
+    if (rc) return rc;
+    if (!dest || !feat_len_dst || !src || !dst || src == dst) return MSCKF_EINVAL;
+    dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
+    compact_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, dest, feat_len_dst, src, dst);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+int msckf_track_descriptors_batched(const msckf_dims* dims, int D, const int* feat_len, const double* obs_conf,
+                                    const float* obs_desc, const unsigned char* keep_old, float* desc_tracks, void* stream) {
+    int rc = check_desc(dims, D);
+    if (rc) return rc;
+    if (!feat_len || !obs_conf || !obs_desc || !desc_tracks) return MSCKF_EINVAL;
+    dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
+    track_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, feat_len, obs_conf, obs_desc, keep_old, desc_tracks);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

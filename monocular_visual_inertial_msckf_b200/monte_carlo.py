@@ -145,15 +145,14 @@ def run_monte_carlo(filter_indices, n_frames=30, n_landmarks=48, window=8, devic
             n_new = np.zeros(B, np.int32)
             for b, sq in enumerate(seqs):
                 fr = sq.frames[f]
-                keep = fr.scores >= 0.5 * np.mean(fr.scores)              # score filter of MSCKF.py:279-282
-                n = int(keep.sum())
-                desc[b, :n], kp[b, :n], sc[b, :n], n_new[b] = fr.descriptors[keep], fr.keypoints[keep], fr.scores[keep], n
+                n = len(fr.scores)                        # RAW detections: the score filter of MSCKF.py:279-284 runs on the device
+                desc[b, :n], kp[b, :n], sc[b, :n], n_new[b] = fr.descriptors, fr.keypoints, fr.scores, n
             dv = flt.device
             flt.frame_step_detections(torch.from_numpy(samples).to(dv), R_I_C, t_I_C, torch.from_numpy(desc).to(dv),
                                       torch.from_numpy(kp).to(dv), torch.from_numpy(sc).to(dv), torch.from_numpy(n_new).to(dv),
                                       window, min_cosine_similarity=min_cosine_similarity,
                                       epipolar_rejection_threshold=epipolar_rejection_threshold,
-                                      homography_rejection_threshold=homography_rejection_threshold)
+                                      homography_rejection_threshold=homography_rejection_threshold, score_filter=True)
             pos[:, f] = flt.imu_state[:, 9:12].cpu().numpy()
             ntr[:, f] = (flt.feat_len > 0).sum(dim=1).cpu().numpy()
             ncm[:, f] = flt.n_cams.cpu().numpy()

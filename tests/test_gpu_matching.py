@@ -323,3 +323,159 @@ def test_monte_carlo_device_matcher_equals_host_association():
     assert np.array_equal(host.n_tracks, dev.n_tracks) and np.array_equal(host.n_cams, dev.n_cams)
     assert np.max(np.abs(host.positions - dev.positions)) < 1e-9
     assert np.isfinite(dev.ate_rmse).all()
+
+
+def test_descriptor_kernels_vs_oracle():
+    """Score filter (MSCKF.py:279-284), per-observation descriptor lists with the deletion of a pruned camera's rows
+    (:764-765), the move of whole tracks on compaction, and the score-weighted mean the matcher sees (:439), on random
+    tracks against the oracle's restatements."""
+    import ctypes as C
+    from monocular_visual_inertial_msckf_b200 import _lib
+    rng = np.random.default_rng(3)
+    B, F, M, N, D, F2 = 3, 20, 8, 8, 32, 26
+    flt = BatchedMSCKF(B, F, M, N, UpdateParams())
+    flt._ensure_descriptors(D)
+    # --- score filter ---
+    sc = rng.uniform(0.05, 1.0, (B, F2))
+    kp = rng.uniform(0, 400, (B, F2, 2))
+    de = rng.standard_normal((B, F2, D)).astype(np.float32)
+    n_in = np.array([F2, 17, 0], np.int32)
+    do, ko, so, no = flt.score_filter(torch.from_numpy(de).cuda(), torch.from_numpy(kp).cuda(), torch.from_numpy(sc).cuda(),
+                                      torch.from_numpy(n_in).cuda())
+    for b in range(B):
+        keep = o.score_filter(sc[b, :n_in[b]])
+        n = int(keep.sum())
+        assert int(no[b]) == n
+        assert np.array_equal(so[b, :n].cpu().numpy(), sc[b, :n_in[b]][keep]) and np.array_equal(ko[b, :n].cpu().numpy(), kp[b, :n_in[b]][keep])
+        assert np.array_equal(do[b, :n].cpu().numpy(), de[b, :n_in[b]][keep])
+    # --- lists: random tracks, mean, drop two cameras, mean again ---
+    lens = rng.integers(0, M + 1, (B, F)).astype(np.int32)
+    slots = np.zeros((B, F, M), np.int32)
+    for b in range(B):
+        for j in range(F):
+            slots[b, j, :lens[b, j]] = np.sort(rng.choice(N, lens[b, j], replace=False))
+    conf = rng.uniform(0.1, 1.0, (B, F, M))
+    od = rng.standard_normal((B, F, M, D)).astype(np.float32)
+    flt.feat_len.copy_(torch.from_numpy(lens))
+    flt.obs_slot.copy_(torch.from_numpy(slots))
+    flt.obs_conf.copy_(torch.from_numpy(conf))
+    flt.obs_desc.copy_(torch.from_numpy(od))
+    flt.n_cams.fill_(N)
+
+    def check_means(lens_now, conf_now, od_now):
+        got = flt.track_descriptors().cpu().numpy()
+        for b in range(B):
+            for j in range(F):
+                n = int(lens_now[b, j])
+                want = o.track_mean_descriptor(od_now[b, j, :n], conf_now[b, j, :n]).astype(np.float32) if n else np.zeros(D, np.float32)
+                assert np.max(np.abs(got[b, j] - want)) <= 2e-7 * max(1.0, np.max(np.abs(want))), (b, j)
+
+    check_means(lens, conf, od)
+    mask = np.zeros((B, N), np.uint8)
+    mask[:, [1, 4]] = 1
+    mask[2, 6] = 1
+    flt.drop_observations(torch.from_numpy(mask).cuda())
+    lens2, conf2, od2 = lens.copy(), conf.copy(), od.copy()
+    for b in range(B):
+        for j in range(F):
+            keep = [i for i in range(lens[b, j]) if not mask[b, slots[b, j, i]]]
+            lens2[b, j] = len(keep)
+            conf2[b, j, :len(keep)] = conf[b, j, keep]
+            od2[b, j, :len(keep)] = od[b, j, keep]
+    assert np.array_equal(flt.feat_len.cpu().numpy(), lens2)
+    check_means(lens2, conf2, od2)
+    # --- compaction: emptied tracks leave, the lists follow their tracks ---
+    active, dest = flt.compact_tracks(drop_lost=False, return_map=True)
+    dest = dest.cpu().numpy()
+    lens3, conf3, od3 = np.zeros_like(lens2), np.zeros_like(conf2), np.zeros_like(od2)
+    for b in range(B):
+        for j in range(F):
+            if dest[b, j] >= 0:
+                lens3[b, dest[b, j]], conf3[b, dest[b, j]], od3[b, dest[b, j]] = lens2[b, j], conf2[b, j], od2[b, j]
+    assert np.array_equal(flt.feat_len.cpu().numpy(), lens3)
+    check_means(lens3, conf3, od3)
+
+
+def test_whole_run_from_detections_with_moving_descriptors(golden_dir):
+    """A whole reference run whose detections carry per-frame descriptor noise and widely spread scores
+    (tests/golden/small_desc_trace.npz): the score filter drops detections, the tracks' score-weighted mean descriptors
+    move every frame and lose the rows of every pruned camera.  The device loop gets the RAW detections
+    (frame_step_detections(score_filter=True)); after every frame its proposals equal what the reference's matcher led to,
+    the matcher's view of the tracks equals the reference's last_camera_measurement.descriptors (the means of MSCKF.py:436-441
+    built after the frame's appends, minus the rows of the tracks deleted by :742-747 / :774-778; a pruned camera's
+    descriptors leave a track's list at once, :764-765, and its mean at the next rebuild), and the state equals the reference's."""
+    from monocular_visual_inertial_msckf_b200 import _lib
+    from helpers import rel_err
+    path = os.path.join(golden_dir, "small_desc_trace.npz")
+    tr = o.load_trace(path)
+    z = np.load(path)
+    ini, cases, apps = tr["init"], tr["cases"], tr["appends"]
+    nfr = len(tr["frames"])
+    F = max(len(a["action"]) for a in apps) + 1
+    M = max(c["obs_uv"].shape[1] for c in cases) + 1
+    N = tr["max_cams"] + 1
+    F2 = max(len(z[f"x{i}.scores"]) for i in range(nfr)) + 2
+    D = z["x0.desc"].shape[1]
+    par = UpdateParams.from_case(cases[0], _lib.COMPRESS_GRAM)
+    par.gravity = np.array(ini["gravity"], float)
+    B = 2
+    flt = BatchedMSCKF(B, F, M, N, par)
+    flt.P.zero_()
+    flt.P[:, :15, :15] = torch.from_numpy(np.asarray(ini["P"], float))
+    flt.imu_state[:] = torch.from_numpy(np.concatenate([np.asarray(ini["imu_R"], float).flatten(), ini["imu_t"], ini["imu_v"],
+                                                        ini["imu_bg"], ini["imu_ba"]]))
+    flt.imu_null[:] = torch.from_numpy(np.concatenate([np.asarray(ini["null_R"], float).flatten(), ini["null_t"], ini["null_v"]]))
+    flt.imu_time[:] = float(ini["timestamp"])
+    flt.Qc_diag[:] = torch.from_numpy(np.asarray(ini["Qc_diag"], float)[[0, 3, 6, 9]].copy())
+    flt.n_cams.zero_()
+    flt.feat_len.zero_()
+    thr = float(z["min_cosine_similarity"])
+    ops = tr["ops"]
+    first, worst, worst_desc, start, n_filtered, n_moved = True, 0.0, 0.0, 0, 0, 0
+    for i, fr in enumerate(tr["frames"]):
+        seg = ops[start:int(fr["op_index"])]
+        start = int(fr["op_index"])
+        smp = np.array([tr["samples"][idx] for kind, idx in seg if kind == 0], float)
+        a = apps[[idx for kind, idx in seg if kind == 4][0]]
+        kp_raw, de_raw, sc_raw = z[f"x{i}.kp"], z[f"x{i}.desc"], z[f"x{i}.scores"]
+        n2 = len(sc_raw)
+        n_filtered += n2 - int(o.score_filter(sc_raw).sum())
+        desc = torch.zeros((B, F2, D), dtype=torch.float32, device="cuda")
+        kp = torch.zeros((B, F2, 2), dtype=torch.float64, device="cuda")
+        sc = torch.zeros((B, F2), dtype=torch.float64, device="cuda")
+        desc[:, :n2] = torch.from_numpy(de_raw.astype(np.float32)).cuda()
+        kp[:, :n2] = torch.from_numpy(kp_raw).cuda()
+        sc[:, :n2] = torch.from_numpy(sc_raw).cuda()
+        n_new = torch.full((B,), n2, dtype=torch.int32, device="cuda")
+        samples = torch.from_numpy(smp).reshape(1, -1, 7).repeat(B, 1, 1).cuda()
+        action, verdict = flt.frame_step_detections(samples, ini["R_I_C"], ini["t_I_C"], desc, kp, sc, n_new, tr["max_cams"],
+                                                    min_cosine_similarity=thr, epipolar_rejection_threshold=1e9,
+                                                    homography_rejection_threshold=1e9, use_null_state=first, score_filter=True)
+        first = False
+        torch.cuda.synchronize()
+        fa = len(a["action"])
+        act = action.cpu().numpy()
+        assert (act[:, :fa] == a["action"]).all() and (act[:, fa:] == 0).all(), i
+        d = fr["P"].shape[0]
+        nc = (d - 15) // 6
+        nf = len(fr["feat_len"])
+        lcm_desc, lcm_idx = z[f"x{i}.lcm_desc"], z[f"x{i}.lcm_idx"]
+        assert np.array_equal(lcm_idx, fr["feat_ids"])            # the matcher's view lists exactly the live tracks, in order
+        got = flt.lcm_desc.cpu().numpy()
+        for b in range(B):
+            assert int(flt.n_cams[b]) == nc, (i, int(flt.n_cams[b]), nc)
+            ln = flt.feat_len[b].cpu().numpy()
+            assert (ln[:nf] == fr["feat_len"]).all() and (ln[nf:] == 0).all(), i
+            e = np.max(np.abs(got[b, :nf] - lcm_desc))
+            worst_desc = max(worst_desc, e)
+            assert e < 5e-7, (i, e)                               # float32 descriptors against the reference's float64 means
+            assert (flt.lost_cnt[b, :nf].cpu().numpy() == fr["lost_cnt"]).all(), i
+            st = flt.imu_state[b].cpu().numpy()
+            errs = [rel_err(flt.P[b, :d, :d].cpu().numpy(), fr["P"]), rel_err(st[9:12], fr["imu_t"]),
+                    rel_err(flt.cam_t[b, :nc].cpu().numpy(), fr["cam_t"])]
+            worst = max(worst, max(errs))
+            assert worst < 1e-9, (i, errs)
+        n_moved += int(np.sum(np.abs(np.linalg.norm(lcm_desc, axis=1) - 1.0) > 1e-4))
+    assert nfr >= 50 and n_filtered > 100 and n_moved > 500       # the filter fired and the means were not unit vectors
+    print(f"frame loop from raw detections with moving descriptors: state {worst:.2e}, mean descriptors {worst_desc:.2e}, "
+          f"{n_filtered} detections filtered by score")

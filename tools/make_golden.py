@@ -448,10 +448,26 @@ class TraceCapture:
                                 idp_anchor_slot=trk["idp_anchor_slot"], **st))
 
 
-def fixture_trace(ns):
-    """Whole-run operation trace of the small configuration (window 8, 40 landmarks, 60 frames)."""
+def noisy_detections(seq, seed=2024, desc_sigma=0.03, score_range=(0.1, 1.0)):
+    """Per-frame descriptor noise and widely spread scores on a synthetic stream: the tracks' score-weighted mean
+    descriptors then MOVE from frame to frame and the score filter of MSCKF.py:279-282 drops detections."""
+    rng = np.random.default_rng(seed)
+    for fr in seq.frames:
+        d = fr.descriptors + desc_sigma * rng.standard_normal(fr.descriptors.shape)
+        fr.descriptors = d / np.linalg.norm(d, axis=1, keepdims=True)
+        fr.scores = rng.uniform(score_range[0], score_range[1], len(fr.scores))
+    return seq
+
+
+def fixture_trace(ns, desc_noise=False):
+    """Whole-run operation trace of the small configuration (window 8, 40 landmarks, 60 frames).  desc_noise: the variant
+    with per-frame descriptor noise / spread scores (small_desc_trace.npz), which also records every frame's raw
+    detections and the matcher's view of the tracks afterwards (last_camera_measurement: the score-weighted mean
+    descriptor of every track, MSCKF.py:436-441, after the deletions of :742-747 / :772-778)."""
     kw = dict(seed=42, n_frames=60, n_landmarks=40, noise_level="mid", p_drop=0.06, p_outlier=0.03, shuffle=True)
     seq = synth.make_sequence(**kw)
+    if desc_noise:
+        noisy_detections(seq)
     fp = dict(min_parallax=2.0, max_number_of_camera_states=8, epipolar_rejection_threshold=1e9,
               homography_rejection_threshold=1e9, min_number_of_frames_to_be_tracked=3)
     params, pd = make_params(ns, seq, **fp)
@@ -459,6 +475,7 @@ def fixture_trace(ns):
     cap = TraceCapture(ns, f)
     image = np.zeros((seq.height, seq.width, 3), np.uint8)
     frame_at = {fr.imu_index: fr for fr in seq.frames}
+    extra_frames = []
     for i in range(len(seq.imu)):
         row = seq.imu[i]
         f.imu_callback(ns.IMUMeasurement(row[0], row[1:4].copy(), row[4:7].copy()))
@@ -468,6 +485,12 @@ def fixture_trace(ns):
                                                            scores=fr.scores.copy()))
             if cap.init is not None:
                 cap.frame_done()
+                if desc_noise:
+                    lcm = f.last_camera_measurement
+                    extra_frames.append(dict(kp=fr.keypoints, desc=fr.descriptors, scores=fr.scores,
+                                             lcm_desc=np.array(lcm.descriptors, float), lcm_idx=np.array(lcm.features_indices, np.int64),
+                                             n_hom=f.number_of_features_discarder_for_homography_test,
+                                             n_epi=f.number_of_features_discarded_for_epipolar_test))
     flat = {"ops": np.array(cap.ops, np.int32), "samples": np.array(cap.samples), "n_cases": np.asarray(len(cap.cases)),
             "n_masks": np.asarray(len(cap.masks)), "n_frames": np.asarray(len(cap.frames))}
     for k, v in cap.init.items():
@@ -485,7 +508,11 @@ def fixture_trace(ns):
     for i, fr in enumerate(cap.frames):
         for k, v in fr.items():
             flat[f"f{i}.{k}"] = np.asarray(v)
-    path = os.path.join(GOLDEN, "small_trace.npz")
+    for i, x in enumerate(extra_frames):
+        for k, v in x.items():
+            flat[f"x{i}.{k}"] = np.asarray(v)
+    flat["min_cosine_similarity"] = np.asarray(float(f.min_cosine_similarity))
+    path = os.path.join(GOLDEN, "small_desc_trace.npz" if desc_noise else "small_trace.npz")
     np.savez_compressed(path, **flat)
     kinds = np.bincount(np.array(cap.ops)[:, 0], minlength=5)
     print(f"wrote {path}: {len(cap.ops)} ops (imu {kinds[0]}, augment {kinds[1]}, update {kinds[2]}, remove {kinds[3]}), "
@@ -726,6 +753,8 @@ if __name__ == "__main__":
         fixture_prune(ns)
     if args.only in (None, "trace"):
         fixture_trace(ns)
+    if args.only in (None, "desc"):
+        fixture_trace(ns, desc_noise=True)
     if args.only in (None, "match"):
         fixture_match(ns)
     if args.only in (None, "mid"):
