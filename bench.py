@@ -39,7 +39,17 @@ NOISE = [(1e-3, 1e-4, 1e-4, 1e-5), (5e-3, 5e-4, 5e-4, 5e-5), (1e-2, 1e-3, 1e-3, 
 # ----------------------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------------------
-def load_base_case(n_cams=30):
+def stress_case():
+    """BASELINE.json configs[4] shape (1024 features x 60 observations, 60-pose window, d = 375): no reference run exists at
+    this size (its update() would need 115 GB), so the snapshot is the self-consistent synthetic case the parity tests use."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_case
+    return make_case(1024, 60, 60, seed=7)
+
+
+def load_base_case(n_cams=30, config=4):
+    if config == 5:
+        return stress_case()
     z = np.load(FIXTURE)
     n = int(z["n_cases"])
     best = None
@@ -123,10 +133,10 @@ def algorithmic_info_update_flops_per_filter(N):
 # CPU arm (oracle port on the host cores)
 # ----------------------------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    index, n_steps = args
+    index, n_steps, config = args
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     from oracle import msckf_oracle as o
-    base = load_base_case()
+    base = load_base_case(config=config)
     uv, samples, qc, t0 = filter_inputs(base, index)
     c = dict(base)
     c["obs_uv"] = uv
@@ -149,7 +159,7 @@ def _cpu_worker(args):
     return time.perf_counter() - t_start, nfeat
 
 
-def run_cpu(n_workers, steps_per_worker):
+def run_cpu(n_workers, steps_per_worker, config=4):
     """Each of n_workers processes (1 BLAS thread each) runs `steps_per_worker` filter-steps of its own filter."""
     import multiprocessing as mp
     for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
@@ -157,7 +167,7 @@ def run_cpu(n_workers, steps_per_worker):
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(n_workers) as pool:
-        res = pool.map(_cpu_worker, [(i, steps_per_worker) for i in range(n_workers)])
+        res = pool.map(_cpu_worker, [(i, steps_per_worker, config) for i in range(n_workers)])
     wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)          # exclude interpreter start-up / imports: the slowest worker's compute time
     feats = sum(r[1] for r in res)
@@ -247,7 +257,7 @@ def pin_near_gpu(gpu_index):
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
-def run_gpu(args):
+def run_gpu_snapshot(args):
     import torch
     import torch.distributed as dist
     from monocular_visual_inertial_msckf_b200 import BatchedMSCKF, UpdateParams, _lib
@@ -262,7 +272,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
     numa = pin_near_gpu(local_rank) if world > 1 else None   # host buffers of a rank live on its GPU's NUMA node
 
-    base = load_base_case(args.window)
+    base = load_base_case(args.window, args.config)
     B = args.filters
     F = len(base["feat_len"])
     M = base["obs_uv"].shape[1]
@@ -667,10 +677,10 @@ def run_gpu(args):
         if _ORIG_AFFINITY:
             os.sched_setaffinity(0, _ORIG_AFFINITY[0])      # the CPU arm uses every host core again
         nw = min(ncpu, 64)
-        r = run_cpu(nw, 1)
+        r = run_cpu(nw, 1, args.config)
         cpu = dict(value=r["feature_updates_per_s"], unit="feature-updates/s", cores=nw, kind="port",
                    filter_steps_per_s=r["filter_steps_per_s"],
-                   sample=f"{nw} filters x 1 filter-step (9 propagations + 256-feature update) of the same workload, "
+                   sample=f"{nw} filters x 1 filter-step (9 propagations + {F}-feature update) of the same workload, "
                           f"one single-threaded process per core, slowest worker {r['busy_s']:.1f} s")
 
     e2e_sec = ms_e2e * 1e-3
@@ -679,9 +689,9 @@ def run_gpu(args):
         warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f64", data="synthetic",
         filter_steps_per_s=fsteps,
-        config=dict(workload=f"BASELINE.json configs[3] shape: {B} filters/GPU x {F} features x {N}-pose window "
+        config=dict(workload=f"BASELINE.json {CONFIGS[args.config]['name']}: {B} filters/GPU x {F} features x {N}-pose window "
                              f"(d={15 + 6 * N}), {N_IMU} IMU samples/frame, FP64; steady-state snapshot replicated with "
-                             f"per-filter pixel noise", filters_per_gpu=B, features=F, obs_per_feature=M, window=N,
+                             f"per-filter pixel noise; step = 9 propagations + one update", config=args.config, filters_per_gpu=B, features=F, obs_per_feature=M, window=N,
                     compress=args.mode, gate=args.gate, l2="inputs larger than L2 (%.1f GB touched per step)" % (
                         (step_bytes + 2 * flt.P.numel() * 8) / 1e9),
                     accepted_features=n_acc, gated_out=n_rej),
@@ -704,6 +714,341 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm, stream workload (default): heterogeneous filters on device-built streams, whole camera frames
+# ----------------------------------------------------------------------------------------------------------------------
+CONFIGS = {
+    2: dict(filters=1, name="configs[1]: single filter, TartanAir-shaped synthetic sequence, 256 tracked features/frame, 30-pose window"),
+    3: dict(filters=64, name="configs[2]: 64 concurrent filters (IMU noise low/mid/high x sequences), 30-pose window, 256 features/update"),
+    4: dict(filters=4096, name="configs[3]: 4096 Monte-Carlo filter instances per GPU, 30-pose window, 256 features/update"),
+    5: dict(filters=128, name="configs[4] stress: 1024 filters (128 per GPU of 8) x 1024 features/update x 60-pose window (state 375)"),
+}
+
+
+def run_gpu_stream(args):
+    """One step = one camera frame of every filter, everything resident: the 9 IMU samples since the last frame
+    (propagation), state_augmentation, the frame's detections matched against the tracks (matcher, geometric
+    verification, bookkeeping), process_features (get_valid_features + update + correct over every track, deletion of lost
+    tracks / unobserved cameras) and, when the window exceeds 30 poses, prune_poorest_camera_states with its own update
+    (BatchedMSCKF.frame_step_detections = MSCKF.imu_callback x 9 + feature_callback, MSCKF.py:135-158).  Every filter
+    runs its own stream (trajectory seed 42 + global index, IMU-noise level index mod 3, 2 % outliers, 3 % drop-outs), built on
+    the device and warmed up until the window cycles between 30 and 31 poses."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    from monocular_visual_inertial_msckf_b200 import BatchedMSCKF, UpdateParams, _lib
+    from monocular_visual_inertial_msckf_b200.sharding import gather_filter_results, max_over_ranks, shard_range
+    from monocular_visual_inertial_msckf_b200.streams import DeviceStreams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    numa = pin_near_gpu(local_rank) if world > 1 else None
+
+    B, K, W = args.filters, args.steps, max(args.warmup, 3)
+    L, WINDOW, N_WARM, DESC = 256, 30, 34, 32
+    F, M, N = L + 32, 32, WINDOW + 1
+    mode = _lib.COMPRESS_QR if args.mode == "qr" else _lib.COMPRESS_GRAM
+    gate = _lib.GATE_BOUNDS if args.gate == "bounds" else _lib.GATE_EXACT
+    first_filter, _ = shard_range(B * world, rank, world)
+    t0h = time.time()
+    n_frames = N_WARM + W + K + 1
+    st = DeviceStreams(range(first_filter, first_filter + B), n_frames, n_landmarks=L, imu_per_frame=N_IMU, frame_dt=FRAME_DT,
+                       device=dev, sigma_px=0.1, p_drop=0.03, p_outlier=0.02, desc_dim=DESC, seed=42)
+    par = UpdateParams(K=st.K, width=st.width, height=st.height, sigma_image=0.1, min_lost=2, min_tracked=3, use_parallax=True,
+                       min_parallax=0.0, compress_mode=mode, gate_mode=gate)
+    flt = BatchedMSCKF(B, F, M, N, par, device=dev)
+    flt.P.zero_()
+    flt.n_cams.zero_()
+    flt.feat_len.zero_()
+    flt.Qc_diag.copy_(st.Qc_diag)
+
+    def frame(inp):
+        smp, desc, kp, sc, cnt = inp
+        flt.frame_step_detections(smp, st.R_I_C, st.t_I_C, desc, kp, sc, cnt, WINDOW, min_cosine_similarity=0.82,
+                                  epipolar_rejection_threshold=1e9, homography_rejection_threshold=1e9)
+
+    for f in range(N_WARM):                       # fill the window (untimed)
+        frame(st.frame_inputs(f))
+    f0 = N_WARM + W
+    inputs = [st.frame_inputs(f0 + k) for k in range(K)]
+    for w in range(W):                            # warm-up steps
+        frame(st.frame_inputs(N_WARM + w))
+    flt.check_window_overflow()
+    snap = flt.snapshot()
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0h
+    n_cams0 = int(flt.n_cams.max().item())
+    len_stats = flt.feat_len[flt.feat_len > 0].double()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for k in range(steps):
+            fn(k)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), device=dev)
+
+    # ---- the timed K steps (inputs resident in HBM) ----
+    flt.count_feature_updates = True
+    flt.feature_updates = torch.zeros((), dtype=torch.int64, device=dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = flt.lib.msckf_launch_count()
+    ms_total = timed(lambda k: frame(inputs[k]), K)
+    launches = flt.lib.msckf_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    fu = int(flt.feature_updates.item())
+    state_exact = flt.imu_state.clone()
+    flt.check_window_overflow()
+
+    # ---- the same K frames with the gate's exact early-out (identical decisions => identical states) ----
+    gate_bounds = None
+    if args.gate == "exact" and mode == _lib.COMPRESS_GRAM:
+        flt.restore(snap)
+        flt.cpar.gate_mode = _lib.GATE_BOUNDS
+        flt.feature_updates.zero_()
+        ms_b = timed(lambda k: frame(inputs[k]), K)
+        same = bool(torch.equal(flt.imu_state, state_exact))
+        worst = float((flt.imu_state - state_exact).abs().max().item())
+        fu_b = int(flt.feature_updates.item())
+        flt.cpar.gate_mode = _lib.GATE_EXACT
+        gate_bounds = dict(ms_per_step=ms_b / K, identical_states=same, max_state_difference=worst, feature_updates_rank0=fu_b)
+
+    # ---- end to end: every step's inputs come from pinned host memory (uploaded on a copy stream, double-buffered, inside
+    #      the timed region), every step's result goes back to the host ----
+    Ke = max(2, min(K, 6))
+    host_in = [[t.cpu().pin_memory() for t in inputs[k]] for k in range(Ke)]
+    dev_in = [[torch.empty_like(t) for t in inputs[0]] for _ in range(2)]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_in[0])
+    h_state = torch.empty((B, 21), dtype=torch.float64).pin_memory()
+    h_ncams = torch.empty((B,), dtype=torch.int32).pin_memory()
+    d2h_bytes = h_state.numel() * 8 + h_ncams.numel() * 4
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(k):
+        slot = k & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[slot])
+            for d, h in zip(dev_in[slot], host_in[k]):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def step_e2e(k):
+        cur = torch.cuda.current_stream(dev)
+        if k == 0:
+            free[0].record(cur)
+            free[1].record(cur)
+            upload(0)
+        if k + 1 < Ke:
+            upload(k + 1)
+        cur.wait_event(ready[k & 1])
+        frame(dev_in[k & 1])
+        free[k & 1].record(cur)
+        h_state.copy_(flt.imu_state, non_blocking=True)
+        h_ncams.copy_(flt.n_cams, non_blocking=True)
+
+    flt.restore(snap)
+    flt.feature_updates.zero_()
+    ms_e2e = timed(step_e2e, Ke)
+    fu_e2e = int(flt.feature_updates.item())
+    flt.count_feature_updates = False
+
+    # ---- per-kernel durations on the state of the first timed frame (one update of every track) ----
+    flt.restore(snap)
+    smp, desc, kp, sc, cnt = inputs[0]
+    flt.propagate(smp)
+    flt.augment(st.R_I_C, st.t_I_C)
+    n_tracks = (flt.feat_len > 0).sum(1).to(torch.int32)
+    m12, m21, action, new_uv, new_conf, _ = flt.match_descriptors(flt.lcm_desc, desc, 0.82, n_tracks, cnt, kp, sc)
+    flt.verify_matches(action, new_uv, 1e9, 1e9)
+    flt.append_descriptors(action, m12, m21, n_tracks, cnt, desc)
+    flt.append_observations(action, new_uv, new_conf)
+    sub = dict(P=flt.P.clone(), slab=flt.small_slab.clone(), m=flt.idp_m.clone(), rho=flt.idp_rho.clone())
+    Nw = int(flt.n_cams.max().item())
+    Mw = float(flt.feat_len[flt.feat_len > 0].double().mean().item())
+
+    def sub_restore():
+        flt.P.copy_(sub["P"])
+        flt.small_slab.copy_(sub["slab"])
+        flt.idp_m.copy_(sub["m"])
+        flt.idp_rho.copy_(sub["rho"])
+
+    def time_stage(fn, prep=lambda: None):
+        best = 1e30
+        for _ in range(3):
+            sub_restore()
+            prep()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    stage_ms = dict(front=time_stage(flt.front))
+    flt.lib.msckf_set_stage_timing(1)
+    best3, front_launches = (1e30, 1e30, 1e30), 1
+    for _ in range(3):
+        sub_restore()
+        flt.front()
+        g_ms, a_ms, c_ms = C.c_double(0), C.c_double(0), C.c_double(0)
+        n_sub = flt.lib.msckf_front_stage_ms(C.byref(g_ms), C.byref(a_ms), C.byref(c_ms))
+        if n_sub > 0 and g_ms.value + a_ms.value + c_ms.value < sum(best3):
+            best3, front_launches = (g_ms.value, a_ms.value, c_ms.value), n_sub
+    flt.lib.msckf_set_stage_timing(0)
+    split_front = best3[0] < 1e29
+    if split_front:
+        stage_ms["front_geo"], stage_ms["front_asm"], stage_ms["front_chol"] = best3
+    stage_ms["compress"] = time_stage(flt.compress, flt.front)
+    stage_ms["apply"] = time_stage(flt.apply_update, lambda: (flt.front(), flt.compress()))
+    sub_restore()
+    flt.front()
+    code = flt.feat_status & 0xF
+    n_valid = int(((code == 1) | (code == 2)).sum().item())
+    n_acc1 = int((code == 1).sum().item())
+    lens = flt.feat_len.double()
+    valid_mask = ((code == 1) | (code == 2)).double()
+    pair_flops = float((192.0 * lens * (lens + 1) / 2 * valid_mask).sum().item())
+    chol_flops = float((((2 * lens) ** 3 / 3.0 + 4.0 * (2 * lens) ** 2) * valid_mask).sum().item())
+    geo_flops = float((300.0 * lens * (lens > 0)).sum().item())
+    flt.restore(snap)
+    stage_ms["propagate"] = time_stage(lambda: flt.propagate(smp))
+    stage_ms["match_descriptors"] = time_stage(lambda: flt.match_descriptors(flt.lcm_desc, desc, 0.82, n_tracks, cnt, kp, sc))
+
+    # ---- FP64 pipe peak (measured here: MEASURED_PEAKS.json has no FP64 figure) ----
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    flops = C.c_double(0)
+    fp64_peak = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        flt.lib.msckf_probe_fp64(148 * 8, 20000, C.c_void_p(sink.data_ptr()), C.byref(flops),
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        e1.record()
+        torch.cuda.synchronize()
+        fp64_peak = max(fp64_peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+
+    tot = torch.tensor([fu, fu_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = gather_filter_results(flt.imu_state, B * world, dst=0)      # the final gather (SURVEY.md section 8e)
+        assert rank != 0 or gathered.shape[0] == B * world
+        dist.all_reduce(tot)
+    fu_all, fu_e2e_all = [float(x) for x in tot.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    sec = ms_total * 1e-3
+    value = fu_all / sec
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    stage_flops = dict(compress=algorithmic_gram_flops_per_filter(n_acc1 / B, Nw) * B if mode == _lib.COMPRESS_GRAM
+                       else algorithmic_qr_flops_per_filter(2.0 * Mw * n_acc1 / B, Nw) * B,
+                       apply=(algorithmic_info_update_flops_per_filter(Nw) if mode == _lib.COMPRESS_GRAM else 8.0 * (15 + 6 * Nw) ** 3) * B)
+    names = dict(front_geo="front_geo_kernel", front_asm="front_asm_ps_kernel", front_chol="front_chol_kernel",
+                 compress="gram_kernel" if mode == _lib.COMPRESS_GRAM else "tsqr_kernel",
+                 apply="update_smem_kernel" if mode == _lib.COMPRESS_GRAM else "apply_kernel")
+    if split_front:
+        stage_flops.update(front_geo=geo_flops, front_asm=pair_flops, front_chol=chol_flops)
+    else:
+        stage_flops["front"] = geo_flops + pair_flops + chol_flops
+        names["front"] = "front_kernel"
+    dom = max(stage_flops, key=lambda k: stage_ms[k])
+    dom_ms, dom_flops = stage_ms[dom], stage_flops[dom]
+    is_front = dom.startswith("front_")
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(names[dom])
+    except Exception:
+        pass
+    update_flops = sum(stage_flops.values())
+    step_bytes = algorithmic_bytes_per_filter_step(L, int(round(Mw)), Nw, N_IMU) * B
+    roofline = dict(bound="tensor", pipe="fp64 (DFMA/DMMA share one nominal peak on B200; tcgen05 has no f64 kind)",
+                    kernel=names[dom], achieved=dom_flops / (dom_ms * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s",
+                    frac=dom_flops / (dom_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None, traffic=traffic,
+                    peak_source="measured in this run by msckf_probe_fp64 (8 independent DMMA.8x8x4 chains per warp; DFMA "
+                                "chains give the same 36-37 TFLOP/s, profiles/fp64_probe.txt)",
+                    kernel_ms=dom_ms / (front_launches if is_front else 1), kernel_ms_per_update=dom_ms,
+                    flops_per_launch=dom_flops / (front_launches if is_front else 1),
+                    launches_per_update=(front_launches if is_front else 1),
+                    measured_on=f"one update of every track at the first timed frame's state (window {Nw} poses, mean track "
+                                f"length {Mw:.1f}, {n_valid} valid / {n_acc1} accepted features on rank 0); a frame runs one such "
+                                f"update, plus a second one over the tracks of the two pruned cameras when the window exceeds 30",
+                    stage_ms=stage_ms, stage_tflops={names[k]: stage_flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in stage_flops},
+                    update_flops=dict(achieved=update_flops / (sum(stage_ms[k] for k in stage_flops) * 1e-3) / 1e12, unit="TFLOP/s",
+                                      flops_per_filter_update=update_flops / B),
+                    step_hbm=dict(bound="hbm", achieved=step_bytes / (sec / K) / 1e9, peak=hbm_peak, unit="GB/s",
+                                  frac=step_bytes / (sec / K) / 1e9 / hbm_peak, peak_source=hbm_src,
+                                  bytes_per_filter_step=algorithmic_bytes_per_filter_step(L, int(round(Mw)), Nw, N_IMU),
+                                  note="SURVEY.md section 8d: the path is FP64-bound, not HBM-bound, at these shapes"))
+
+    ncpu = os.cpu_count() or 1
+    cpu = dict(value=None)
+    if not args.no_cpu:
+        if _ORIG_AFFINITY:
+            os.sched_setaffinity(0, _ORIG_AFFINITY[0])
+        nw = min(ncpu, 64)
+        r = run_cpu(nw, 1)
+        cpu = dict(value=r["feature_updates_per_s"], unit="feature-updates/s", cores=nw, kind="port",
+                   filter_steps_per_s=r["filter_steps_per_s"],
+                   sample=f"{nw} filters x 1 filter-step (9 propagations + one 256-feature update at a 30-pose window, the "
+                          f"steady-state snapshot captured from the reference at this shape), one single-threaded process per "
+                          f"core, slowest worker {r['busy_s']:.1f} s")
+
+    e2e_sec = ms_e2e * 1e-3
+    line = dict(
+        metric="msckf_feature_updates_per_s", value=value, unit="feature-updates/s", n_gpus=world, steps=K, warmup=W,
+        ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+        filter_steps_per_s=B * world * K / sec, feature_updates_per_filter_step=fu_all / (B * world * K),
+        config=dict(workload=f"BASELINE.json {CONFIGS[args.config]['name']}: {B} filters/GPU, each on its own device-built stream "
+                             f"(trajectory seed 42 + index, IMU noise low/mid/high by index mod 3, 0.1 px pixel noise, 2 % outliers, "
+                             f"3 % drop-outs), {L} landmarks, window cycling {WINDOW}/{WINDOW + 1} poses, {N_IMU} IMU samples/frame, FP64; "
+                             f"step = one whole camera frame (propagation, augmentation, matching, update(s), pruning)",
+                    config=args.config, filters_per_gpu=B, landmarks=L, track_capacity=F, window=WINDOW, window_at_start=n_cams0,
+                    mean_track_length=float(len_stats.mean().item()), min_track_length=float(len_stats.min().item()),
+                    compress=args.mode, gate=args.gate, descriptor_dim=DESC,
+                    l2="inputs larger than L2 (state + tracks of a rank: %.1f GB)" % (
+                        (flt.P.numel() * 8 + flt.obs_uv.numel() * 8 * 3.5 + flt.obs_desc.numel() * 4) / 1e9)),
+        roofline=roofline, cpu_baseline=cpu, gate_bounds=gate_bounds,
+        e2e=dict(value=fu_e2e_all / e2e_sec, unit="feature-updates/s", h2d_bytes_per_step=h2d_bytes * world,
+                 d2h_bytes_per_step=d2h_bytes * world, ms_per_step=ms_e2e / Ke, steps=Ke,
+                 call="BatchedMSCKF.frame_step_detections (msckf_propagate / augment / match_descriptors / verify_matches / "
+                      "append_* / update / select_poorest / drop_* / remove_cameras / compact_* _batched)",
+                 inputs="per step and filter: 9 IMU samples + the frame's detections (256 x (keypoint, score, 32-d float32 "
+                        "descriptor)) from pinned host memory, uploaded on a copy stream while the previous frame computes; "
+                        "result: IMU state + window size back to pinned host memory",
+                 filter_steps_per_s=B * world * Ke / e2e_sec),
+        gpu_launches=int(launches), clocks=clocks, setup_s=setup_s, cpu_affinity_rank0=numa)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -714,18 +1059,21 @@ def run_reference(args):
         pass
     t0 = time.perf_counter()
     steps = max(1, min(args.steps, 3))
-    run_cpu(min(nw, 4), 1)                        # warm-up: imports, page cache
-    r = run_cpu(nw, steps)
-    base = load_base_case()
+    if args.config == 5:
+        steps = 1
+    run_cpu(min(nw, 4), 1, args.config if args.config != 5 else 4)    # warm-up: imports, page cache
+    r = run_cpu(nw, steps, args.config)
+    base = load_base_case(config=args.config)
     F, M, N = len(base["feat_len"]), base["obs_uv"].shape[1], int(base["n_cams"])
-    sample = (f"{nw} filters x {steps} filter-step(s) each (9 propagations + 256-feature update), one single-threaded "
+    sample = (f"{nw} filters x {steps} filter-step(s) each (9 propagations + {F}-feature update), one single-threaded "
               f"process per core; NumPy port of the reference update (the Python reference is not on the GPU box)")
     line = dict(impl="reference", metric="msckf_feature_updates_per_s", value=r["feature_updates_per_s"],
                 unit="feature-updates/s", n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=steps, warmup=1,
                 ms_per_step=r["busy_s"] * 1e3 / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic", filter_steps_per_s=r["filter_steps_per_s"],
-                config=dict(workload=f"bounded sample of BASELINE.json configs[3] shape: {F} features x {N}-pose window, "
-                                     f"{N_IMU} IMU samples/frame, FP64", features=F, obs_per_feature=M, window=N),
+                config=dict(workload=f"bounded sample of BASELINE.json {CONFIGS[args.config]['name']}: {F} features x {N}-pose window, "
+                                     f"{N_IMU} IMU samples/frame, FP64; steady-state snapshot, step = 9 propagations + one update",
+                            config=args.config, features=F, obs_per_feature=M, window=N),
                 cpu_baseline=dict(value=r["feature_updates_per_s"], unit="feature-updates/s", cores=nw, kind="port",
                                   sample=sample),
                 e2e=dict(value=r["feature_updates_per_s"], unit="feature-updates/s", h2d_bytes_per_step=0,
@@ -752,9 +1100,22 @@ if __name__ == "__main__":
     ap.add_argument("--chunk", type=int, default=592,
                     help="filters per upload/compute/download chunk of the end-to-end (host-buffer) step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5],
+                    help="BASELINE.json workload (1-based): 2 single filter, 3 = 64 filters, 4 = 4096 Monte-Carlo filters per GPU "
+                         "(default, the configuration the metric is quoted on), 5 = stress 1024 x 1024 x 60 (128 filters per GPU)")
+    ap.add_argument("--workload", default=None, choices=["stream", "snapshot"],
+                    help="stream (default for configs 2-4): every filter on its own device-built stream, a step is a whole "
+                         "camera frame; snapshot (config 5, and round 1's benchmark): one steady-state snapshot replicated with "
+                         "per-filter noise, a step is 9 propagations + one update")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if "--filters" not in " ".join(sys.argv):
+        args.filters = CONFIGS[args.config]["filters"]
+    if args.workload is None:
+        args.workload = "snapshot" if args.config == 5 else "stream"
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "stream":
+        run_gpu_stream(args)
     else:
-        run_gpu(args)
+        run_gpu_snapshot(args)

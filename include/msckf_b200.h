@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 8
+#define MSCKF_B200_ABI_VERSION 9
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
@@ -287,6 +287,12 @@ typedef struct msckf_track_arrays {
 int msckf_compact_tracks_batched(const msckf_dims* dims, int drop_lost, const unsigned char* feat_status,
                                  const msckf_track_arrays* src, const msckf_track_arrays* dst, unsigned char* active_out,
                                  int* dest_out, void* stream);
+/* The same compaction IN PLACE: `tracks` is compacted where it lies, `scratch` (a second set of track arrays of the same
+ * shapes) only stages the tracks that move.  A filter in which nothing moves costs one scan of its F lengths, so the frame
+ * loop pays for deletions only where they happen; nothing is swapped by the caller. */
+int msckf_compact_tracks_inplace_batched(const msckf_dims* dims, int drop_lost, const unsigned char* feat_status,
+                                         const msckf_track_arrays* tracks, const msckf_track_arrays* scratch,
+                                         unsigned char* active_out, int* dest_out, void* stream);
 int msckf_drop_observations_batched(const msckf_dims* dims, const unsigned char* remove_mask, const int* n_cams,
                                     const double* cam_t, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
                                     int* obs_slot, double* idp_base, int* idp_anchor_slot, void* stream);
@@ -377,6 +383,10 @@ int msckf_drop_descriptors_batched(const msckf_dims* dims, int D, const unsigned
                                    const int* obs_slot, float* obs_desc, void* stream);
 int msckf_compact_descriptors_batched(const msckf_dims* dims, int D, const int* dest, const int* feat_len_dst,
                                       const float* src, float* dst, void* stream);
+/* in-place variant for msckf_compact_tracks_inplace_batched: desc is compacted where it lies, scratch stages the rows that
+ * move; zero_deleted != 0 clears the rows behind the survivors (the rows of last_camera_measurement). */
+int msckf_compact_descriptors_inplace_batched(const msckf_dims* dims, int D, const int* dest, const int* feat_len_new,
+                                              float* desc, float* scratch, int zero_deleted, void* stream);
 int msckf_track_descriptors_batched(const msckf_dims* dims, int D, const int* feat_len, const double* obs_conf,
                                     const float* obs_desc, const unsigned char* keep_old, float* desc_tracks,
                                     void* stream);

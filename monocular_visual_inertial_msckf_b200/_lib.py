@@ -11,7 +11,7 @@ COMPRESS_GRAM = 1
 FEAT_SKIPPED, FEAT_ACCEPTED, FEAT_GATED_OUT, FEAT_LOST_DISCARD, FEAT_LOST_FLAG = 0, 1, 2, 3, 0x10
 FEAT_GAMMA_BOUND = 0x20
 FEAT_TRIANGULATED = 0x40
-ABI_VERSION = 8
+ABI_VERSION = 9
 GATE_EXACT, GATE_BOUNDS = 0, 1
 
 
@@ -73,6 +73,7 @@ EXPORTS = [
     "msckf_metrics_step_batched", "msckf_metrics_finalize_batched",
     "msckf_score_filter_batched", "msckf_append_descriptors_batched", "msckf_drop_descriptors_batched",
     "msckf_compact_descriptors_batched", "msckf_track_descriptors_batched",
+    "msckf_compact_tracks_inplace_batched", "msckf_compact_descriptors_inplace_batched",
 ]
 
 
@@ -130,6 +131,8 @@ def load_library():
     lib.msckf_unobserved_cameras_batched.argtypes = [pd, ip, ip, ip, u8, u8, vp]
     lib.msckf_compact_tracks_batched.restype = C.c_int
     lib.msckf_compact_tracks_batched.argtypes = [pd, C.c_int, u8, C.POINTER(TrackArrays), C.POINTER(TrackArrays), u8, ip, vp]
+    lib.msckf_compact_tracks_inplace_batched.restype = C.c_int
+    lib.msckf_compact_tracks_inplace_batched.argtypes = [pd, C.c_int, u8, C.POINTER(TrackArrays), C.POINTER(TrackArrays), u8, ip, vp]
     lib.msckf_drop_observations_batched.restype = C.c_int
     lib.msckf_drop_observations_batched.argtypes = [pd, u8, ip, dp, ip, dp, dp, dp, ip, dp, ip, vp]
     lib.msckf_append_observations_batched.restype = C.c_int
@@ -164,6 +167,8 @@ def load_library():
     lib.msckf_drop_descriptors_batched.argtypes = [pd, C.c_int, u8, ip, ip, dp, vp]
     lib.msckf_compact_descriptors_batched.restype = C.c_int
     lib.msckf_compact_descriptors_batched.argtypes = [pd, C.c_int, ip, ip, dp, dp, vp]
+    lib.msckf_compact_descriptors_inplace_batched.restype = C.c_int
+    lib.msckf_compact_descriptors_inplace_batched.argtypes = [pd, C.c_int, ip, ip, dp, dp, C.c_int, vp]
     lib.msckf_track_descriptors_batched.restype = C.c_int
     lib.msckf_track_descriptors_batched.argtypes = [pd, C.c_int, ip, dp, dp, u8, dp, vp]
     if lib.msckf_abi_version() != ABI_VERSION:

@@ -408,39 +408,32 @@ class BatchedMSCKF:
         return st
 
     def compact_tracks(self, drop_lost=False, return_map=False):
-        """Stable compaction of the track slots (MSCKF.remove_features / the track deletions of remove_cameras): the
-        survivors move, in order, to the front of a second set of track arrays, which then becomes the current one.
+        """Stable compaction of the track slots (MSCKF.remove_features / the track deletions of remove_cameras), in place:
+        the survivors move, in order, to the front; a filter in which nothing moves costs one scan of its lengths.
         Returns active [B] uint8 (drop_lost: filters that deleted their lost tracks); with return_map also dest [B, F]
         int32: the new slot of every old slot, -1 for a deleted track."""
         cur = {n: getattr(self, n) for n in _lib.TRACK_FIELDS}
         if self._alt_tracks is None:
-            self._alt_tracks = {n: torch.zeros_like(t) for n, t in cur.items()}
+            self._alt_tracks = {n: torch.zeros_like(t) for n, t in cur.items()}      # scratch: stages the tracks that move
         active = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
         want_map = return_map or self.obs_desc is not None
         dest = torch.empty((self.B, self.F), dtype=torch.int32, device=self.device) if want_map else None
         a, b = self._track_struct(cur), self._track_struct(self._alt_tracks)
-        rc = self.lib.msckf_compact_tracks_batched(C.byref(self.dims), int(bool(drop_lost)), _ptr(self.feat_status), C.byref(a),
-                                                   C.byref(b), _ptr(active), _ptr(dest), self._stream())
-        _lib.check(rc, "msckf_compact_tracks_batched")
-        for n in _lib.TRACK_FIELDS:
-            setattr(self, n, self._alt_tracks[n])
-        self._alt_tracks = cur
-        if self.obs_desc is not None:            # the descriptor lists move with their tracks
+        rc = self.lib.msckf_compact_tracks_inplace_batched(C.byref(self.dims), int(bool(drop_lost)), _ptr(self.feat_status),
+                                                           C.byref(a), C.byref(b), _ptr(active), _ptr(dest), self._stream())
+        _lib.check(rc, "msckf_compact_tracks_inplace_batched")
+        if self.obs_desc is not None:            # the descriptor lists move with their tracks ...
             if self._alt_desc is None:
                 self._alt_desc = torch.zeros_like(self.obs_desc)
-            rc = self.lib.msckf_compact_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
-                                                            _ptr(self.obs_desc), _ptr(self._alt_desc), self._stream())
-            _lib.check(rc, "msckf_compact_descriptors_batched")
-            self.obs_desc, self._alt_desc = self._alt_desc, self.obs_desc
-            # ... and so do their rows of last_camera_measurement (MSCKF.py:742-747, 774-778): one row per track
-            if self._alt_lcm is None:
                 self._alt_lcm = torch.zeros_like(self.lcm_desc)
+            rc = self.lib.msckf_compact_descriptors_inplace_batched(C.byref(self.dims), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
+                                                                    _ptr(self.obs_desc), _ptr(self._alt_desc), 0, self._stream())
+            _lib.check(rc, "msckf_compact_descriptors_inplace_batched")
+            # ... and so do their rows of last_camera_measurement (MSCKF.py:742-747, 774-778): one row per track
             d1 = _lib.Dims(self.B, self.F, 1, self.N, self.ldp)
-            self._alt_lcm.zero_()
-            rc = self.lib.msckf_compact_descriptors_batched(C.byref(d1), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
-                                                            _ptr(self.lcm_desc), _ptr(self._alt_lcm), self._stream())
-            _lib.check(rc, "msckf_compact_descriptors_batched")
-            self.lcm_desc, self._alt_lcm = self._alt_lcm, self.lcm_desc
+            rc = self.lib.msckf_compact_descriptors_inplace_batched(C.byref(d1), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
+                                                                    _ptr(self.lcm_desc), _ptr(self._alt_lcm), 1, self._stream())
+            _lib.check(rc, "msckf_compact_descriptors_inplace_batched")
         return (active, dest) if return_map else active
 
     def unobserved_cameras(self, active=None):

@@ -24,6 +24,8 @@ cudaError_t launch_unobserved_cameras(const msckf_dims& d, const int* n_cams, co
                                       const unsigned char* active, unsigned char* remove_mask, cudaStream_t s);
 cudaError_t launch_compact_tracks(const msckf_dims& d, int drop_lost, const unsigned char* feat_status, void* const* src,
                                   void* const* dst, unsigned char* active_out, int* dest_out, cudaStream_t s);
+cudaError_t launch_compact_tracks_inplace(const msckf_dims& d, int drop_lost, const unsigned char* feat_status, void* const* trk,
+                                          void* const* tmp, unsigned char* active_out, int* dest_out, cudaStream_t s);
 cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_host, const int* n_cams, const double* cam_R,
                                        const double* cam_t, const unsigned char* action, const double* new_uv,
                                        const double* new_conf, int* feat_len, double* obs_uv, double* obs_dir, double* obs_conf,
@@ -272,6 +274,21 @@ int msckf_compact_tracks_batched(const msckf_dims* dims, int drop_lost, const un
     if ((size_t)dims->F * sizeof(int) > 48 * 1024) return MSCKF_ECAPACITY;
     return (int)launch_compact_tracks(*dims, drop_lost, feat_status, (void* const*)src, (void* const*)dst, active_out,
                                       dest_out, (cudaStream_t)stream);
+}
+
+int msckf_compact_tracks_inplace_batched(const msckf_dims* dims, int drop_lost, const unsigned char* feat_status,
+                                         const msckf_track_arrays* tracks, const msckf_track_arrays* scratch,
+                                         unsigned char* active_out, int* dest_out, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!tracks || !scratch || (drop_lost && !feat_status)) return MSCKF_EINVAL;
+    const void* const* ps = (const void* const*)tracks;
+    const void* const* pq = (const void* const*)scratch;
+    for (int k = 0; k < 11; ++k)
+        if (!ps[k] || !pq[k] || ps[k] == pq[k]) return MSCKF_EINVAL;
+    if ((size_t)dims->F * sizeof(int) > 48 * 1024) return MSCKF_ECAPACITY;
+    return (int)launch_compact_tracks_inplace(*dims, drop_lost, feat_status, (void* const*)tracks, (void* const*)scratch, active_out,
+                                              dest_out, (cudaStream_t)stream);
 }
 
 int msckf_append_observations_batched(const msckf_dims* dims, const double* Kinv_host, const int* n_cams, const double* cam_R,

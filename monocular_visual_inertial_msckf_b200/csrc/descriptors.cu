@@ -129,6 +129,12 @@ __global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, i
     const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
     const int F = dims.F, M = dims.M, N = dims.N;
     if (j >= F) return;
+    {   // nothing leaves this filter's window: its lists stay as they are (the usual case)
+        const unsigned char* mk = remove_mask + (size_t)b * N;
+        int any = 0;
+        for (int s = lane; s < N; s += 32) any |= mk[s];
+        if (!__any_sync(0xffffffffu, any != 0)) return;
+    }
     const size_t fj = (size_t)b * F + j;
     const int len = min(feat_len[fj], M);
     if (len <= 0) return;
@@ -166,6 +172,51 @@ __global__ void __launch_bounds__(DT) compact_descriptors_kernel(msckf_dims dims
     for (size_t e = lane; e < n4; e += 32) d[e] = s[e];
 }
 
+// the same IN PLACE, one CTA per filter, staged through a scratch buffer (rows of M observations x D floats; M = 1 for the
+// rows of last_camera_measurement); a filter whose map moves nothing returns after reading its map
+__global__ void __launch_bounds__(DT) compact_descriptors_inplace_kernel(msckf_dims dims, int D, const int* __restrict__ dest,
+                                                                         const int* __restrict__ feat_len_new, float* __restrict__ desc,
+                                                                         float* __restrict__ tmp, int zero_deleted) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = dims.F, M = dims.M;
+    __shared__ int s_moves, s_kept;
+    if (tid == 0) { s_moves = 0; s_kept = 0; }
+    __syncthreads();
+    int moves = 0, kept = 0;
+    for (int j = tid; j < F; j += DT) {
+        const int d = dest[(size_t)b * F + j];
+        if (d >= 0) { ++kept; if (d != j) moves = 1; }
+    }
+    if (moves) atomicOr(&s_moves, 1);
+    if (kept) atomicAdd(&s_kept, kept);
+    __syncthreads();
+    if (s_moves) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const float* from = pass == 0 ? desc : tmp;
+            float* to = pass == 0 ? tmp : desc;
+            for (int j = warp; j < F; j += DT / 32) {
+                const int d = dest[(size_t)b * F + j];
+                if (d < 0 || d == j || d >= F) continue;
+                const int len = min(feat_len_new[(size_t)b * F + d], M);
+                const size_t n4 = (size_t)len * D / 4;
+                const float4* s4 = reinterpret_cast<const float4*>(from + ((size_t)b * F + (pass == 0 ? j : d)) * M * D);
+                float4* d4 = reinterpret_cast<float4*>(to + ((size_t)b * F + d) * M * D);
+                for (size_t e = lane; e < n4; e += 32) d4[e] = s4[e];
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
+    }
+    if (zero_deleted) {   // rows behind the survivors hold no track any more
+        const int n_kept = s_kept;
+        const size_t row4 = (size_t)M * D / 4;
+        for (int j = n_kept + warp; j < F; j += DT / 32) {
+            float4* d4 = reinterpret_cast<float4*>(desc + ((size_t)b * F + j) * M * D);
+            for (size_t e = lane; e < row4; e += 32) d4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 // ---- the matcher's view: score-weighted mean descriptor of every track (MSCKF.py:439), zero rows for empty slots ----
 __global__ void __launch_bounds__(DT) track_descriptors_kernel(msckf_dims dims, int D, const int* __restrict__ feat_len,
                                                                const double* __restrict__ obs_conf, const float* __restrict__ obs_desc,
@@ -177,21 +228,33 @@ __global__ void __launch_bounds__(DT) track_descriptors_kernel(msckf_dims dims, 
     if (j >= F || (keep_old && keep_old[b])) return;
     const size_t fj = (size_t)b * F + j;
     const int len = min(feat_len[fj], M);
-    // lane e holds components e, e + 32, ... (D <= 128: four accumulators)
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    double wsum = 0.0;
-    for (int i = 0; i < len; ++i) {
-        const double w = obs_conf[fj * M + i];
-        wsum += w;
-        const float* d = obs_desc + (fj * M + i) * D;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (lane + 32 * q < D) acc[q] += w * (double)d[lane + 32 * q];
+    // a descriptor row is D / 4 float4 pieces: lane l handles piece l % q4 of the rows l / q4, l / q4 + 32 / q4, ... (D = 32:
+    // four rows per 512-byte warp load); the partial sums of the lanes that share a piece are combined by shuffles
+    const int q4 = D / 4;                     // 8, 16 or 32 for D = 32, 64, 128 (other D: one row per pass, lanes beyond q4 idle)
+    const int rows_per_pass = q4 <= 32 && (32 % q4) == 0 ? 32 / q4 : 1;
+    const int piece = lane % q4, sub = lane / q4;
+    const bool lane_on = (rows_per_pass > 1) || lane < q4;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, wsum = 0.0;
+    if (lane_on) {
+        for (int i = sub; i < len; i += rows_per_pass) {
+            const double w = obs_conf[fj * M + i];
+            const float4 v = *reinterpret_cast<const float4*>(obs_desc + (fj * M + i) * D + 4 * piece);
+            wsum += w;
+            a0 += w * (double)v.x; a1 += w * (double)v.y; a2 += w * (double)v.z; a3 += w * (double)v.w;
+        }
     }
-    const double inv = (len > 0 && wsum != 0.0) ? 1.0 / wsum : 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (lane + 32 * q < D) desc_tracks[fj * D + lane + 32 * q] = (float)(acc[q] * inv);
+    for (int o = q4; o < 32; o <<= 1) {       // lanes with the same piece: l, l + q4, l + 2 q4, ...
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
+    if (lane < q4) {
+        const double inv = (len > 0 && wsum != 0.0) ? 1.0 / wsum : 0.0;
+        *reinterpret_cast<float4*>(desc_tracks + fj * D + 4 * lane) =
+            make_float4((float)(a0 * inv), (float)(a1 * inv), (float)(a2 * inv), (float)(a3 * inv));
+    }
 }
 
 }  // namespace
@@ -244,6 +307,16 @@ int msckf_compact_descriptors_batched(const msckf_dims* dims, int D, const int* 
     if (!dest || !feat_len_dst || !src || !dst || src == dst) return MSCKF_EINVAL;
     dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
     compact_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, dest, feat_len_dst, src, dst);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+int msckf_compact_descriptors_inplace_batched(const msckf_dims* dims, int D, const int* dest, const int* feat_len_new, float* desc,
+                                              float* scratch, int zero_deleted, void* stream) {
+    int rc = check_desc(dims, D);
+    if (rc) return rc;
+    if (!dest || !feat_len_new || !desc || !scratch || desc == scratch) return MSCKF_EINVAL;
+    compact_descriptors_inplace_kernel<<<dims->B, DT, 0, (cudaStream_t)stream>>>(*dims, D, dest, feat_len_new, desc, scratch, zero_deleted);
     msckf_count_launch(1);
     return (int)cudaGetLastError();
 }

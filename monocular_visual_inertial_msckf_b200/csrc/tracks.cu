@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(TT) drop_observations_kernel(msckf_dims dims, 
         s_shift[tid] = (unsigned char)c;
     }
     __syncthreads();
+    if (nc == 0 || s_shift[nc - 1] == 0) return;     // nothing leaves this filter's window: its tracks stay as they are
     const int j = blockIdx.x * (TT / 32) + (tid >> 5);
     if (j >= F) return;
     const size_t fj = (size_t)b * F + j;
@@ -284,6 +285,91 @@ __global__ void __launch_bounds__(TT) compact_tracks_kernel(msckf_dims dims, int
         for (int j = n_kept + tid; j < F; j += TT) dst.feat_len[fb + j] = 0;
 }
 
+// The same compaction IN PLACE, one CTA per filter: a filter in which no track moves (the usual case: nothing was
+// deleted, or only tracks at the end) costs one scan of its F lengths; otherwise only the tracks behind the first
+// deleted slot are moved, staged through a scratch set of track arrays (pass 1: track -> scratch at its new slot;
+// barrier; pass 2: scratch -> the live arrays), so no second full copy of the tracks exists and the caller swaps nothing.
+__global__ void __launch_bounds__(TT) compact_tracks_inplace_kernel(msckf_dims dims, int drop_lost,
+                                                                    const unsigned char* __restrict__ feat_status, TrackSet trk,
+                                                                    TrackSet tmp, unsigned char* __restrict__ active_out,
+                                                                    int* __restrict__ dest_out) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = dims.F, M = dims.M;
+    extern __shared__ int s_dest[];
+    __shared__ int s_wsum[TT / 32];
+    __shared__ int s_base, s_any, s_moves;
+    const size_t fb = (size_t)b * F;
+    if (tid == 0) { s_base = 0; s_any = 0; s_moves = 0; }
+    __syncthreads();
+    bool lost_rule = false;
+    if (drop_lost) {
+        int any = 0;
+        for (int j = tid; j < F; j += TT) {
+            const int code = feat_status[fb + j] & 0xF;
+            if (trk.feat_len[fb + j] > 0 && (code == MSCKF_FEAT_ACCEPTED || code == MSCKF_FEAT_GATED_OUT)) any = 1;
+        }
+        if (any) atomicOr(&s_any, 1);
+        __syncthreads();
+        lost_rule = s_any != 0;
+    }
+    if (tid == 0 && active_out) active_out[b] = lost_rule ? 1 : 0;
+    int moves = 0;
+    for (int j0 = 0; j0 < F; j0 += TT) {
+        const int j = j0 + tid;
+        int keep = 0;
+        if (j < F) keep = (trk.feat_len[fb + j] > 0 && !(lost_rule && (feat_status[fb + j] & MSCKF_FEAT_LOST_FLAG))) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_wsum[w];
+        if (j < F) {
+            const int d = keep ? off + __popc(bal & ((1u << lane) - 1u)) : -1;
+            s_dest[j] = d;
+            if (d >= 0 && d != j) moves = 1;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < TT / 32; ++w) t += s_wsum[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (moves) atomicOr(&s_moves, 1);
+    __syncthreads();
+    const int n_kept = s_base;
+    if (dest_out)
+        for (int j = tid; j < F; j += TT) dest_out[fb + j] = s_dest[j];
+    if (s_moves) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const TrackSet& from = pass == 0 ? trk : tmp;
+            const TrackSet& to = pass == 0 ? tmp : trk;
+            for (int j = warp; j < F; j += TT / 32) {
+                const int d = s_dest[j];
+                if (d < 0 || d == j) continue;
+                const size_t sj = fb + (pass == 0 ? j : d), dj = fb + d;
+                const int n = min(from.feat_len[sj], M);
+                const double* su = from.obs_uv + sj * M * 2; double* du = to.obs_uv + dj * M * 2;
+                for (int x = lane; x < 2 * n; x += 32) du[x] = su[x];
+                const double* sd = from.obs_dir + sj * M * 3; double* dd = to.obs_dir + dj * M * 3;
+                for (int x = lane; x < 3 * n; x += 32) dd[x] = sd[x];
+                const double* sc = from.obs_conf + sj * M; double* dc = to.obs_conf + dj * M;
+                const int* ss = from.obs_slot + sj * M; int* ds = to.obs_slot + dj * M;
+                for (int x = lane; x < n; x += 32) { dc[x] = sc[x]; ds[x] = ss[x]; }
+                if (lane == 0) {
+                    to.idp_anchor_slot[dj] = from.idp_anchor_slot[sj];
+                    to.idp_rho[dj] = from.idp_rho[sj];
+                    to.lost_cnt[dj] = from.lost_cnt[sj];
+                    to.tracked_cnt[dj] = from.tracked_cnt[sj];
+                }
+                if (lane < 3) { to.idp_base[dj * 3 + lane] = from.idp_base[sj * 3 + lane]; to.idp_m[dj * 3 + lane] = from.idp_m[sj * 3 + lane]; }
+                __syncwarp();
+                if (lane == 0) to.feat_len[dj] = n;       // (pass 0 reads from.feat_len[sj] of OTHER tracks only through tmp: trk untouched)
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
+    }
+    for (int j = n_kept + tid; j < F; j += TT) trk.feat_len[fb + j] = 0;
+}
+
 }  // namespace
 
 cudaError_t launch_unobserved_cameras(const msckf_dims& d, const int* n_cams, const int* feat_len, const int* obs_slot,
@@ -337,6 +423,17 @@ cudaError_t launch_drop_observations(const msckf_dims& d, const unsigned char* r
     dim3 grid((d.F + TT / 32 - 1) / (TT / 32), d.B);
     drop_observations_kernel<<<grid, TT, 0, s>>>(d, remove_mask, n_cams, cam_t, feat_len, obs_uv, obs_dir, obs_conf, obs_slot,
                                                  idp_base, idp_anchor_slot);
+    msckf_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_tracks_inplace(const msckf_dims& d, int drop_lost, const unsigned char* feat_status, void* const* trk,
+                                          void* const* tmp, unsigned char* active_out, int* dest_out, cudaStream_t s) {
+    TrackSet a{(int*)trk[0], (double*)trk[1], (double*)trk[2], (double*)trk[3], (int*)trk[4], (double*)trk[5], (int*)trk[6],
+               (double*)trk[7], (double*)trk[8], (int*)trk[9], (int*)trk[10]};
+    TrackSet b{(int*)tmp[0], (double*)tmp[1], (double*)tmp[2], (double*)tmp[3], (int*)tmp[4], (double*)tmp[5], (int*)tmp[6],
+               (double*)tmp[7], (double*)tmp[8], (int*)tmp[9], (int*)tmp[10]};
+    compact_tracks_inplace_kernel<<<d.B, TT, (size_t)d.F * sizeof(int), s>>>(d, drop_lost, feat_status, a, b, active_out, dest_out);
     msckf_count_launch(1);
     return cudaGetLastError();
 }
