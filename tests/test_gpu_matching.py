@@ -479,3 +479,79 @@ def test_whole_run_from_detections_with_moving_descriptors(golden_dir):
     assert nfr >= 50 and n_filtered > 100 and n_moved > 500       # the filter fired and the means were not unit vectors
     print(f"frame loop from raw detections with moving descriptors: state {worst:.2e}, mean descriptors {worst_desc:.2e}, "
           f"{n_filtered} detections filtered by score")
+
+
+def test_sixty_four_distinct_filters_vs_their_reference_runs(golden_dir):
+    """BASELINE.json configs[2] as a parity test: 64 DISTINCT filters (IMU noise low / mid / high x 22 stream seeds, each with
+    its own trajectory, landmarks, drop-outs, outliers, descriptor noise and scores) run as ONE batch through the resident
+    frame loop from their raw detections; after every camera frame every filter's IMU state, window poses, track lengths and
+    covariance diagonal -- and after the last frame its whole covariance -- equal what the unmodified reference produced when
+    it ran that filter's stream alone (tests/golden/multi_64.npz, tools/make_golden.py --only multi)."""
+    from monocular_visual_inertial_msckf_b200 import _lib
+    from helpers import rel_err
+    z = np.load(os.path.join(golden_dir, "multi_64.npz"))
+    B = int(z["n_filters"])
+    nfr = int(z["t0.n_frames"])
+    assert all(int(z[f"t{i}.n_frames"]) == nfr for i in range(B))
+    F, M, N, F2, D = 64, 8, int(z["par.max_cams"]) + 1, 32, z["t0.f0.desc"].shape[1]
+    par = UpdateParams(K=z["K"], width=640, height=480, sigma_image=float(z["t0.sigma"]), gravity=np.array(z["t0.init.gravity"], float),
+                       min_lost=int(z["par.min_lost"]), min_tracked=int(z["par.min_tracked"]), use_parallax=True,
+                       min_parallax=float(z["par.min_parallax"]), compress_mode=_lib.COMPRESS_GRAM)
+    flt = BatchedMSCKF(B, F, M, N, par)
+    flt.P.zero_()
+    flt.n_cams.zero_()
+    flt.feat_len.zero_()
+    for i in range(B):
+        g = lambda k: np.asarray(z[f"t{i}.init.{k}"], float)  # noqa: E731
+        flt.P[i, :15, :15] = torch.from_numpy(g("P"))
+        flt.imu_state[i] = torch.from_numpy(np.concatenate([g("imu_R").flatten(), g("imu_t"), g("imu_v"), g("imu_bg"), g("imu_ba")]))
+        flt.imu_null[i] = torch.from_numpy(np.concatenate([g("null_R").flatten(), g("null_t"), g("null_v")]))
+        flt.imu_time[i] = float(z[f"t{i}.init.timestamp"])
+        flt.Qc_diag[i] = torch.from_numpy(g("Qc_diag")[[0, 3, 6, 9]].copy())
+    R_I_C, t_I_C = np.asarray(z["t0.init.R_I_C"], float), np.asarray(z["t0.init.t_I_C"], float)
+    thr = float(z["par.min_cosine_similarity"])
+    prev = [0] * B
+    worst, levels_seen, n_updates_like = 0.0, set(), 0
+    for k in range(nfr):
+        ns = [int(z[f"t{i}.f{k}.n_samples"]) for i in range(B)]
+        n = ns[0] - prev[0]
+        assert all(ns[i] - prev[i] == n for i in range(B)), "every stream delivers the same number of IMU samples per frame"
+        smp = np.stack([z[f"t{i}.samples"][prev[i]:ns[i]] for i in range(B)])
+        prev = ns
+        desc = torch.zeros((B, F2, D), dtype=torch.float32, device="cuda")
+        kp = torch.zeros((B, F2, 2), dtype=torch.float64, device="cuda")
+        sc = torch.zeros((B, F2), dtype=torch.float64, device="cuda")
+        n_new = torch.zeros(B, dtype=torch.int32, device="cuda")
+        for i in range(B):
+            m = len(z[f"t{i}.f{k}.scores"])
+            desc[i, :m] = torch.from_numpy(z[f"t{i}.f{k}.desc"]).cuda()
+            kp[i, :m] = torch.from_numpy(z[f"t{i}.f{k}.kp"]).cuda()
+            sc[i, :m] = torch.from_numpy(z[f"t{i}.f{k}.scores"]).cuda()
+            n_new[i] = m
+        flt.frame_step_detections(torch.from_numpy(smp).cuda(), R_I_C, t_I_C, desc, kp, sc, n_new, int(z["par.max_cams"]),
+                                  min_cosine_similarity=thr, epipolar_rejection_threshold=1e9, homography_rejection_threshold=1e9,
+                                  use_null_state=(k == 0), score_filter=True)
+        torch.cuda.synchronize()
+        st = flt.imu_state.cpu().numpy()
+        nc = flt.n_cams.cpu().numpy()
+        ln = flt.feat_len.cpu().numpy()
+        ct = flt.cam_t.cpu().numpy()
+        Pd = torch.diagonal(flt.P, dim1=1, dim2=2).cpu().numpy()
+        for i in range(B):
+            pre = f"t{i}.f{k}."
+            ref_ct, ref_len = z[pre + "cam_t"], z[pre + "feat_len"]
+            assert nc[i] == len(ref_ct), (k, i, nc[i], len(ref_ct))
+            assert (ln[i, :len(ref_len)] == ref_len).all() and (ln[i, len(ref_len):] == 0).all(), (k, i)
+            d = 15 + 6 * nc[i]
+            errs = [rel_err(st[i], z[pre + "imu"]), rel_err(ct[i, :nc[i]], ref_ct) if nc[i] else 0.0, rel_err(Pd[i, :d], z[pre + "P_diag"])]
+            worst = max(worst, max(errs))
+            assert worst < 1e-9, (k, i, errs)
+    assert int(flt._overflow.item()) == 0
+    flt.check_window_overflow()
+    for i in range(B):
+        Pl = z[f"t{i}.P_last"]
+        assert rel_err(flt.P[i, :Pl.shape[0], :Pl.shape[0]].cpu().numpy(), Pl) < 1e-9, i
+    gates = [int(z[f"t{i}.f{nfr - 1}.n_gate"]) for i in range(B)]
+    assert sum(gates) > 50 and len(set(tuple(z[f"t{i}.f{nfr - 1}.feat_len"]) for i in range(B))) > 32      # distinct, with rejections
+    print(f"64 distinct filters x {nfr} frames as one batch vs their reference runs: worst relative error {worst:.2e}, "
+          f"{sum(gates)} gate rejections in the reference runs")

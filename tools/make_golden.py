@@ -648,6 +648,62 @@ def fixture_match(ns):
     save_cases(os.path.join(GOLDEN, "small_match_verify.npz"), cap.cases, extra)
 
 
+def fixture_multi(ns, n_filters=64):
+    """BASELINE.json configs[2] as a parity fixture: 64 DISTINCT filters (IMU noise low / mid / high x 22 stream seeds), each
+    run through the unmodified reference on its own stream (30 landmarks, window 6, 16 frames, drop-outs, outliers, moving
+    descriptors, spread scores).  Stored per filter: the state the reference held when its first process_imu began, every IMU
+    sample, every frame's raw detections, and after every frame the IMU state, the window poses, the track lengths and the
+    covariance's diagonal (the full covariance after the last frame)."""
+    levels = list(synth.NOISE_LEVELS.keys())
+    flat = {"n_filters": np.asarray(n_filters)}
+    t0 = time.time()
+    for i in range(n_filters):
+        kw = dict(seed=42 + i, n_frames=16, n_landmarks=30, noise_level=levels[i % 3], p_drop=0.06, p_outlier=0.03, shuffle=True)
+        seq = noisy_detections(synth.make_sequence(**kw), seed=7000 + i)
+        fp = dict(min_parallax=2.0, max_number_of_camera_states=6, epipolar_rejection_threshold=1e9,
+                  homography_rejection_threshold=1e9, min_number_of_frames_to_be_tracked=3)
+        params, pd = make_params(ns, seq, **fp)
+        f = ns.MSCKF(parameters=params, rr=None)
+        cap = TraceCapture(ns, f)
+        image = np.zeros((seq.height, seq.width, 3), np.uint8)
+        frame_at = {fr.imu_index: fr for fr in seq.frames}
+        k = 0
+        for j in range(len(seq.imu)):
+            row = seq.imu[j]
+            f.imu_callback(ns.IMUMeasurement(row[0], row[1:4].copy(), row[4:7].copy()))
+            fr = frame_at.get(j)
+            if fr is not None:
+                f.feature_callback(image, ns.CameraMeasurement(keypoints=fr.keypoints.copy(), descriptors=fr.descriptors.copy(),
+                                                               scores=fr.scores.copy()))
+                if cap.init is not None:
+                    st = cap._state()
+                    trk = pack_tracks(f)
+                    pre = f"t{i}.f{k}."
+                    flat[pre + "kp"], flat[pre + "desc"], flat[pre + "scores"] = fr.keypoints, fr.descriptors.astype(np.float32), fr.scores
+                    flat[pre + "n_samples"] = np.asarray(len(cap.samples))
+                    flat[pre + "imu"] = np.concatenate([st["imu_R"].flatten(), st["imu_t"], st["imu_v"], st["imu_bg"], st["imu_ba"]])
+                    flat[pre + "cam_t"] = st["cam_t"]
+                    flat[pre + "feat_len"] = trk["feat_len"]
+                    flat[pre + "P_diag"] = np.diag(st["P"]).copy()
+                    flat[pre + "n_gate"] = np.asarray(f.number_of_residuals_discarded_for_gasting_test)
+                    k += 1
+        for key, v in cap.init.items():
+            flat[f"t{i}.init.{key}"] = np.asarray(v)
+        flat[f"t{i}.samples"] = np.array(cap.samples)
+        flat[f"t{i}.n_frames"] = np.asarray(k)
+        flat[f"t{i}.P_last"] = cap._state()["P"]
+        flat[f"t{i}.sigma"] = np.asarray(float(f.sigma_image))
+        if i % 8 == 0:
+            print(f"  filter {i}: {k} frames, {len(f.features)} tracks, {len(f.state.cameras)} cameras, {time.time() - t0:.0f} s", flush=True)
+    flat["par.min_parallax"], flat["par.max_cams"], flat["par.min_tracked"], flat["par.min_lost"] = (np.asarray(2.0), np.asarray(6),
+                                                                                                   np.asarray(3), np.asarray(2))
+    flat["par.min_cosine_similarity"] = np.asarray(float(f.min_cosine_similarity))
+    flat["K"] = np.asarray(seq.K, float)
+    path = os.path.join(GOLDEN, "multi_64.npz")
+    np.savez_compressed(path, **flat)
+    print(f"wrote {path}: {n_filters} filters, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def make_params(ns, seq, **kw):
     sa, sg, sba, sbg = synth.NOISE_LEVELS[seq.noise_level]
     p = dict(K=seq.K, width=seq.width, height=seq.height, sigma_image=0.1, only_imu=False,
@@ -755,6 +811,8 @@ if __name__ == "__main__":
         fixture_trace(ns)
     if args.only in (None, "desc"):
         fixture_trace(ns, desc_noise=True)
+    if args.only in (None, "multi"):
+        fixture_multi(ns)
     if args.only in (None, "match"):
         fixture_match(ns)
     if args.only in (None, "mid"):
