@@ -11,6 +11,7 @@ bool gram_supported(const msckf_dims& d);
 bool front_split_supported(const msckf_dims& d);
 int front_split_sub_filters(const msckf_dims& d);
 size_t front_split_tile_bytes(const msckf_dims& d);
+int front_split_map_bytes(const msckf_dims& d);
 cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, int* pend_key,
                                unsigned char* slot_map, cudaStream_t s);
 size_t info_scratch_doubles(const msckf_dims& d);
@@ -68,7 +69,7 @@ WsLayout msckf_ws_layout(const msckf_dims& d, int mode) {
         w.pend_list = off;  off = align256(off + (size_t)front_split_sub_filters(d) * d.F * sizeof(int));
         w.pend_count = off; off = align256(off + sizeof(int));
         w.pend_key = off;   off = align256(off + (size_t)front_split_sub_filters(d) * d.F * sizeof(int));
-        w.slot_map = off;   off = align256(off + (size_t)front_split_sub_filters(d) * d.F * 32);
+        w.slot_map = off;   off = align256(off + (size_t)front_split_sub_filters(d) * d.F * front_split_map_bytes(d));
     }
     w.total = off;
     (void)mode;

@@ -13,10 +13,22 @@
 // LDL^T on the packed lower triangle in shared memory with the projected residual appended as an extra row, which yields
 // gamma without a separate triangular solve.  The factors (A_i, Q1, PI r) go to HBM for the compression stage.
 #include "msckf_common.cuh"
+#include "front_geom.cuh"
+#include "front_tiles.cuh"
 
 namespace {
 
 constexpr int FRONT_THREADS = 128;
+
+// what the geometry-only mode hands to the assembly / factorisation kernels of the split front end (long tracks)
+struct GeoOut {
+    double2* Kbuf;            // tile buffer of the sub-batch, kt_d2 double2 per feature slot
+    int kt_d2;
+    unsigned char* slot_map;  // [sub][F][64]
+    int* pend_list;
+    int* pend_count;
+    int b0;                   // first filter of the sub-batch
+};
 
 // cyclic Jacobi eigen-decomposition of a symmetric 3x3 (a = [xx, xy, xz, yy, yz, zz]); V columns = eigenvectors
 __device__ void sym3_eig(const double* a, double* lam, double* V) {
@@ -83,8 +95,12 @@ __device__ void svals3(double* G, double* sv) {
     for (int c = 0; c < 3; ++c) sv[c] = sqrt(G[c] * G[c] + G[3 + c] * G[3 + c] + G[6 + c] * G[6 + c]);
 }
 
-__global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a) {
-    const int j = blockIdx.x, b = blockIdx.y;
+// GEO_ONLY: stop after the factors -- write the appended / padding rows of the padded K, the slot map and the pending list
+// (what front_geo_kernel does for short tracks) and leave K's measurement blocks and its factorisation to the P-stationary
+// assembly kernel and front_chol_smem_kernel.
+template <bool GEO_ONLY>
+__global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a, const GeoOut go) {
+    const int j = blockIdx.x, b = blockIdx.y + (GEO_ONLY ? go.b0 : 0);
     const int tid = threadIdx.x, nth = blockDim.x;
     const int F = a.dims.F, Mcap = a.dims.M, Ncap = a.dims.N, ldp = a.dims.ldp;
     const size_t fj = (size_t)b * F + j;
@@ -99,7 +115,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
     double* srt = sr + n2cap;               // [n2cap]      projected residual
     double* sU = srt + n2cap;               // [n2cap][3]
     double* sS = sU + n2cap * 3;            // packed lower (n2cap+1)(n2cap+2)/2, aliased by the triangulation terms
-    const int nS = max(((n2cap + 1) * (n2cap + 2)) / 2, Mcap * 9);
+    const int nS = GEO_ONLY ? Mcap * 9 : max(((n2cap + 1) * (n2cap + 2)) / 2, Mcap * 9);
     double* sm = sS + nS;                   // [64] small scratch
     int* sslot = (int*)(sm + 64);           // [Mcap]
     unsigned char* s_trow = (unsigned char*)(sslot + Mcap);   // [tri(n2cap + 1)] packed index -> row lookup
@@ -152,7 +168,8 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
         s_flag[2] = 0;
     }
     for (int i = tid; i < M; i += nth) sslot[i] = slot[i];
-    for (int e = tid; e < tri(n2 + 1); e += nth) s_trow[e] = (unsigned char)tri_row(e);
+    if (!GEO_ONLY)      // (the packed-index lookup serves the assembly of S below)
+        for (int e = tid; e < tri(n2 + 1); e += nth) s_trow[e] = (unsigned char)tri_row(e);
     __syncthreads();
     const int code = s_flag[0];
     if ((code & 0xF) != MSCKF_FEAT_ACCEPTED) {
@@ -189,11 +206,13 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
     }
     __syncthreads();
     if (tid == 0) {
-        double lam[3], V[9];
-        sym3_eig(sm, lam, V);
-        const double lmax = fmax(fabs(lam[0]), fmax(fabs(lam[1]), fabs(lam[2])));
         double p[3] = {0, 0, 0};
-        for (int k = 0; k < 3; ++k) {
+        // comfortably non-singular X: LDL^T solve; otherwise pinv with its singular-value cut-off (as the warp kernels do)
+        const bool solved = fgeom::sym3_solve_spd(sm, sm + 6, p);
+        double lam[3] = {0, 0, 0}, V[9];
+        if (!solved) sym3_eig(sm, lam, V);
+        const double lmax = fmax(fabs(lam[0]), fmax(fabs(lam[1]), fabs(lam[2])));
+        for (int k = 0; k < 3 && !solved; ++k) {
             if (fabs(lam[k]) > 1e-15 * lmax) {   // np.linalg.pinv default rcond
                 const double coef = (V[0 + k] * sm[6] + V[3 + k] * sm[7] + V[6 + k] * sm[8]) / lam[k];
                 p[0] += coef * V[0 + k];
@@ -354,14 +373,20 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
             }
         }
         if (lane == 0) {
-            double G[9], sv[3];
-            for (int k = 0; k < 9; ++k) G[k] = R3[k];
-            svals3(G, sv);
-            const double smax = fmax(sv[0], fmax(sv[1], sv[2]));
-            const double tol = 2.220446049250313e-16 * (double)(n2 > 3 ? n2 : 3) * smax;   // scipy null_space rcond
             int rank = 0;
-            for (int k = 0; k < 3; ++k) rank += (sv[k] > tol) ? 1 : 0;
-            if (rank > n2) rank = n2;
+            // column pivoting bounds s_min >= |r33| / 4 and s_max <= sqrt(6) |r11|, so |r33| > 1e-10 |r11| already proves rank 3
+            // (SciPy's threshold is ~1e-14 s_max); only doubtful factors pay for the Jacobi SVD
+            if (n2 >= 3 && fabs(R3[8]) > 1e-10 * fabs(R3[0])) {
+                rank = 3;
+            } else {
+                double G[9], sv[3];
+                for (int k = 0; k < 9; ++k) G[k] = R3[k];
+                svals3(G, sv);
+                const double smax = fmax(sv[0], fmax(sv[1], sv[2]));
+                const double tol = 2.220446049250313e-16 * (double)(n2 > 3 ? n2 : 3) * smax;   // scipy null_space rcond
+                for (int k = 0; k < 3; ++k) rank += (sv[k] > tol) ? 1 : 0;
+                if (rank > n2) rank = n2;
+            }
             s_flag[1] = rank;
         }
     }
@@ -396,6 +421,27 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(const FrontArgs a)
             a.gamma[fj] = 0.0;
             a.dof[fj] = 0;
             a.fac_rank[fj] = rank;
+        }
+        return;
+    }
+
+    if (GEO_ONLY) {
+        const int fl = (int)blockIdx.y * F + j;
+        double2* Kt = go.Kbuf + (size_t)fl * go.kt_d2;
+        for (int ob = tid; ob < M; ob += nth)
+            ftile::write_appended_obs(Kt, M, ob, srt[2 * ob], srt[2 * ob + 1], sQ[(2 * ob) * 3], sQ[(2 * ob) * 3 + 1], sQ[(2 * ob) * 3 + 2],
+                                      sQ[(2 * ob + 1) * 3], sQ[(2 * ob + 1) * 3 + 1], sQ[(2 * ob + 1) * 3 + 2]);
+        ftile::write_padding_rows(Kt, M, tid, nth);
+        unsigned char* mp = go.slot_map + (size_t)fl * 64;
+        for (int sl = tid; sl < 64; sl += nth) mp[sl] = 0xFF;
+        __syncthreads();
+        for (int ob = tid; ob < M; ob += nth)
+            if (sslot[ob] >= 0 && sslot[ob] < 64) mp[sslot[ob]] = (unsigned char)ob;
+        if (tid == 0) {
+            a.feat_status[fj] = (unsigned char)(MSCKF_FEAT_PENDING | (code & MSCKF_FEAT_LOST_FLAG) | s_flag[2]);
+            a.dof[fj] = dofv;
+            a.fac_rank[fj] = rank;
+            go.pend_list[atomicAdd(go.pend_count, 1)] = fl;
         }
         return;
     }
@@ -525,12 +571,31 @@ cudaError_t launch_front(const FrontArgs& a, cudaStream_t s) {
     const size_t smem = front_smem_bytes(a.dims.M);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     dim3 grid(a.dims.F, a.dims.B);
-    front_kernel<<<grid, FRONT_THREADS, smem, s>>>(a);
+    front_kernel<false><<<grid, FRONT_THREADS, smem, s>>>(a, GeoOut{});
+    msckf_count_launch(1);
+    return cudaGetLastError();
+}
+
+// geometry-only mode for the filters [b0, b0 + nb) (the split front end of tracks longer than 32 observations)
+cudaError_t launch_front_geo_wide(const FrontArgs& a, double2* Kbuf, int kt_d2, unsigned char* slot_map, int* pend_list,
+                                  int* pend_count, int b0, int nb, cudaStream_t s) {
+    const size_t smem = front_smem_bytes(a.dims.M);      // (sized for the full kernel: an upper bound)
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int n2 = 2 * a.dims.M;
+    const size_t geo_smem = ((size_t)n2 * 6 + n2 * 3 + n2 + n2 + n2 * 3 + (size_t)a.dims.M * 9 + 64) * sizeof(double) +
+                            (size_t)a.dims.M * sizeof(int) + (size_t)(n2 + 1) * (n2 + 2) / 2 + 16;
+    dim3 grid(a.dims.F, nb);
+    front_kernel<true><<<grid, FRONT_THREADS, geo_smem, s>>>(a, GeoOut{Kbuf, kt_d2, slot_map, pend_list, pend_count, b0});
     msckf_count_launch(1);
     return cudaGetLastError();
 }

@@ -38,10 +38,13 @@
 #include "msckf_common.cuh"
 #include "dense.cuh"
 #include "front_geom.cuh"
+#include "front_tiles.cuh"
+#include "front_gate.cuh"
 
 namespace {
 
 using namespace fgeom;
+using namespace ftile;
 
 constexpr int FG_THREADS = 256;                // geometry kernel: 8 warps per CTA, 2+ CTAs per SM
 constexpr int FG_WARPS = FG_THREADS / 32;
@@ -52,60 +55,11 @@ constexpr int FC_WARPS = FC_THREADS / 32;
 constexpr int FLAG_KEEP = MSCKF_FEAT_LOST_FLAG | MSCKF_FEAT_TRIANGULATED;   // selection flags carried into the final status
 constexpr int TC = 9;                          // 8x8 tile columns: up to 64 measurement rows (32 observations) + 4 appended rows
 constexpr int NTILE = TC * (TC + 1) / 2;
-constexpr int PB = 38;                         // doubles per staged 6x6 block of P (stride 76 words = 12 mod 32)
-constexpr int AR = 14;                         // doubles per observation's 2x6 block in the warp scratch (28 words)
 constexpr int KT_D2 = NTILE * 32;               // double2 per feature slot in the tile buffer (45 tiles; M = 30 uses 36)
 constexpr int KEY_BINS = 32 * 33 + 1;          // (first slot, length) of a consecutive-slot track; last bin: anything else
 
-__device__ __forceinline__ int tile_index(int I, int J) { return I * (I + 1) / 2 + J; }
-
 // key of a pending feature: bin of the assembly kernel's bucketing, or -1 (not pending)
 __device__ __forceinline__ int make_key(bool affine, int s0, int M) { return affine ? (s0 * 33 + M) : (KEY_BINS - 1); }
-
-// rows [0, n2) measurement rows, [n2, a4) identity (a4 = n2 rounded up to a multiple of 4), [a4, a4 + 4) the appended rows
-// [r~; Q1^T] (they never straddle a tile row and their diagonal block is zero: after the factorisation of the columns < a4
-// it holds minus their Gram matrix), rest zero.  At M = 30 the appended rows fill the four padding rows of the eighth tile row.
-__device__ __forceinline__ void write_appended_rows(double2* Kt, const int M, const int lane, const double rt0, const double rt1,
-                                                    const double (&Hf)[2][3]) {
-    const int n2 = 2 * M, a4 = (n2 + 3) & ~3;
-    const int Tn = (a4 + 4 + 7) >> 3;
-    const int rr = a4 - 8 * (Tn - 1);          // local row of the first appended row in the last tile row: 0 or 4
-    const int ia = a4 >> 1;                     // the appended rows as two observation-sized row pairs ia, ia + 1
-    if (lane < M) {   // columns (2 lane, 2 lane + 1) of the four appended rows
-        double2* Gt = Kt + tile_index(Tn - 1, lane >> 2) * 32 + 4 * rr + (lane & 3);
-        Gt[0] = make_double2(rt0, rt1);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) Gt[4 * (q + 1)] = make_double2(Hf[0][q], Hf[1][q]);
-        if ((lane >> 2) == Tn - 1) {   // measurement rows of the same (diagonal) tile: define the mirrored blocks
-            double2* Tm = Kt + tile_index(Tn - 1, Tn - 1) * 32 + 8 * (lane & 3) + (ia & 3);
-            Tm[0] = Tm[1] = Tm[4] = Tm[5] = make_double2(0.0, 0.0);
-        }
-    }
-}
-
-// the padding row pairs i = M .. Mp-1 (at most 7): identity before the appended rows, zero after; the blocks (appended
-// rows x measurement columns) were written by write_appended_rows
-__device__ __forceinline__ void write_padding_rows(double2* Kt, const int M, const int lane) {
-    const int n2 = 2 * M, a4 = (n2 + 3) & ~3;
-    const int Tn = (a4 + 4 + 7) >> 3, Mp = 4 * Tn;
-    const int ia = a4 >> 1;
-    for (int i = M; i < Mp; ++i) {
-        const bool appended = i >= ia && i < ia + 2;
-        for (int k = (appended ? M : 0) + lane; k <= i; k += 32) {
-            const double dg = (i == k && i < ia) ? 1.0 : 0.0;
-            const int I = i >> 2, J = k >> 2;
-            double2* T = Kt + tile_index(I, J) * 32;
-            const int l0 = 8 * (i & 3) + (k & 3);
-            T[l0] = make_double2(dg, 0.0);
-            T[l0 + 4] = make_double2(0.0, dg);
-            if (I == J && i != k) {
-                const int l1 = 8 * (k & 3) + (i & 3);
-                T[l1] = make_double2(0.0, 0.0);
-                T[l1 + 4] = make_double2(0.0, 0.0);
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // kernel G: geometry, factors, gate bounds, keys
@@ -259,8 +213,8 @@ front_geo_kernel(const FrontArgs a, int* __restrict__ pend_key, unsigned char* _
         }
         // everything of the padded matrix that is not a measurement block: appended rows [r~; Q1^T], identity / zero padding
         double2* Kt = Kbuf + (size_t)fl * KT_D2;
-        write_appended_rows(Kt, M, lane, rt0, rt1, Hf);
-        write_padding_rows(Kt, M, lane);
+        if (live) write_appended_obs(Kt, M, lane, rt0, rt1, Hf[0][0], Hf[0][1], Hf[0][2], Hf[1][0], Hf[1][1], Hf[1][2]);
+        write_padding_rows(Kt, M, lane, 32);
         // window slot -> observation index of this track (0xFF: not observed from that slot)
         unsigned char* mp = slot_map + (size_t)fl * 32;
         mp[lane] = 0xFF;
@@ -280,29 +234,6 @@ struct AsmFeature {
     double2* Kt;      // its tile buffer
     const double* wsA;
 };
-
-__device__ __forceinline__ void store_block(double2* Kt, const int i, const int k, const double o00, const double o01,
-                                            const double o10, const double o11) {
-    // rows 2 i, 2 i + 1 / columns 2 k, 2 k + 1  ->  tile (i / 4, k / 4), lanes 4 (2 (i & 3) + row) + (k & 3)
-    const int I = i >> 2, J = k >> 2;
-    double2* T = Kt + tile_index(I, J) * 32;
-    const int l0 = 8 * (i & 3) + (k & 3);
-    T[l0] = make_double2(o00, o01);
-    T[l0 + 4] = make_double2(o10, o11);
-    if (I == J && i != k) {   // the mirrored block of a diagonal tile is never read as data: keep it defined
-        const int l1 = 8 * (k & 3) + (i & 3);
-        T[l1] = make_double2(0.0, 0.0);
-        T[l1 + 4] = make_double2(0.0, 0.0);
-    }
-}
-
-// pair p = i (i + 1) / 2 + k of the flat lower-triangle list
-__device__ __forceinline__ void pair_of(const int p, int& i, int& k) {
-    i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-    i -= (i * (i + 1) / 2 > p) ? 1 : 0;
-    i += ((i + 1) * (i + 2) / 2 <= p) ? 1 : 0;
-    k = p - i * (i + 1) / 2;
-}
 
 // K = H_x P H_x^T + sigma^2 I of NF features with the SAME consecutive slot pattern (s0, M): one lower 2x2 block per lane
 // per pass and feature; every 16-byte read of a staged block of P feeds the multiply-adds of all NF features.  The
@@ -590,11 +521,17 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int PS_FEAT_BYTES = FW_MAX_OBS * AR * 8 + 32;   // one feature in a batch buffer: Jacobian blocks + slot map
 
-template <int NWARPS>
+// WIDE (tracks of up to 64 observations, windows of up to 64 poses): the block triangle no longer fits one CTA's threads, so
+// gridDim.y CTAs share a filter, CTA y owning the blocks [y NT, (y + 1) NT); every CTA streams all of the filter's pending
+// features (64-observation slots, 64-byte maps) and writes its own blocks of their K.
+template <int NWARPS, bool WIDE>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_map, double2* __restrict__ Kbuf, const int b0,
-                    const int batch) {
+                    const int batch, const int kt_d2) {
     constexpr int NT = NWARPS * 32;
+    constexpr int OBS = WIDE ? 64 : FW_MAX_OBS;          // observation slots per feature in a batch buffer
+    constexpr int MAPB = WIDE ? 64 : 32;                 // bytes of a slot map
+    constexpr int FEATB = OBS * AR * 8 + MAPB;
     const int bl = blockIdx.x, b = b0 + bl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = a.dims.F, Mcap = a.dims.M, Ncap = a.dims.N, ldp = a.dims.ldp;
@@ -602,8 +539,8 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
     const int nblk = nc * (nc + 1) / 2;
 
     extern __shared__ double smem[];
-    unsigned char* sbuf = reinterpret_cast<unsigned char*>(smem);                        // [2][batch][PS_FEAT_BYTES]
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(sbuf + (size_t)2 * batch * PS_FEAT_BYTES);   // [F] pending, in order
+    unsigned char* sbuf = reinterpret_cast<unsigned char*>(smem);                        // [2][batch][FEATB]
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(sbuf + (size_t)2 * batch * FEATB);   // [F] pending, in order
     unsigned char* s_len = reinterpret_cast<unsigned char*>(s_list + ((F + 7) & ~7));    // [F] their lengths
     __shared__ int s_warp_cnt[NWARPS + 1];
 
@@ -630,10 +567,10 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
     if (npend == 0) return;
 
     // ---- teams: ceil(nblk / 32) warps cover the block triangle once; several teams work on different features ----
-    const int team_warps = (nblk + 31) >> 5;
-    const int n_teams = NWARPS / team_warps;           // >= 1 (the launcher guarantees nblk <= NT)
-    const int team = warp / team_warps;
-    const int p = (warp - team * team_warps) * 32 + lane;
+    const int team_warps = WIDE ? NWARPS : (nblk + 31) >> 5;
+    const int n_teams = WIDE ? 1 : NWARPS / team_warps;           // >= 1 (the launcher guarantees nblk <= NT per CTA row)
+    const int team = WIDE ? 0 : warp / team_warps;
+    const int p = WIDE ? (int)blockIdx.y * NT + tid : (warp - team * team_warps) * 32 + lane;
     const bool has_block = team < n_teams && p < nblk;
     int s = 0, t = 0;
     if (has_block) pair_of(p, s, t);
@@ -649,7 +586,7 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
     const int n_batches = (npend + batch - 1) / batch;
 
     auto issue_batch = [&](int bt) {
-        unsigned char* dst = sbuf + (size_t)(bt & 1) * batch * PS_FEAT_BYTES;
+        unsigned char* dst = sbuf + (size_t)(bt & 1) * batch * FEATB;
         const int e_end = min(batch, npend - bt * batch);
         // 16-byte chunks: 6 per observation of Jacobian blocks (AR = 14 doubles per observation in shared memory) + 2 of map
         for (int e = warp; e < e_end; e += NWARPS) {
@@ -657,12 +594,12 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
             const int j = s_list[pos], M = s_len[pos];
             const size_t fj = (size_t)b * F + j;
             const double* gA = a.fac_A + fj * Mcap * 12;
-            unsigned char* d = dst + (size_t)e * PS_FEAT_BYTES;
+            unsigned char* d = dst + (size_t)e * FEATB;
             for (int it = lane; it < 6 * M; it += 32) {
                 const int ob = it / 6, c2 = it - 6 * ob;
                 cp_async16(d + (size_t)(ob * AR + 2 * c2) * 8, gA + (size_t)it * 2);
             }
-            if (lane < 2) cp_async16(d + FW_MAX_OBS * AR * 8 + 16 * lane, slot_map + ((size_t)bl * F + j) * 32 + 16 * lane);
+            if (lane < MAPB / 16) cp_async16(d + OBS * AR * 8 + 16 * lane, slot_map + ((size_t)bl * F + j) * MAPB + 16 * lane);
         }
         cp_async_commit();
     };
@@ -676,22 +613,22 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
             cp_async_wait<0>();
         }
         __syncthreads();
-        const unsigned char* src = sbuf + (size_t)(bt & 1) * batch * PS_FEAT_BYTES;
+        const unsigned char* src = sbuf + (size_t)(bt & 1) * batch * FEATB;
         const int e_end = min(batch, npend - bt * batch);
         if (has_block) {
             // (the slot map of the NEXT feature is read one iteration ahead: its latency is off the dependency chain)
             int i_n = 0xFF, k_n = 0xFF;
             if (team < e_end) {
-                const unsigned char* mp = src + (size_t)team * PS_FEAT_BYTES + FW_MAX_OBS * AR * 8;
+                const unsigned char* mp = src + (size_t)team * FEATB + OBS * AR * 8;
                 i_n = mp[s];
                 k_n = mp[t];
             }
 #pragma unroll 1
             for (int e = team; e < e_end; e += n_teams) {
-                const unsigned char* fb = src + (size_t)e * PS_FEAT_BYTES;
+                const unsigned char* fb = src + (size_t)e * FEATB;
                 const int i = i_n, k = k_n;
                 if (e + n_teams < e_end) {
-                    const unsigned char* mp = fb + (size_t)n_teams * PS_FEAT_BYTES + FW_MAX_OBS * AR * 8;
+                    const unsigned char* mp = fb + (size_t)n_teams * FEATB + OBS * AR * 8;
                     i_n = mp[s];
                     k_n = mp[t];
                 }
@@ -734,7 +671,7 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
                     o[row][0] = q0;
                     o[row][1] = q1;
                 }
-                double2* Kt = Kbuf + ((size_t)bl * F + s_list[bt * batch + e]) * KT_D2;
+                double2* Kt = Kbuf + ((size_t)bl * F + s_list[bt * batch + e]) * (WIDE ? (size_t)kt_d2 : (size_t)KT_D2);
                 if (i == k) { o[0][0] += s2; o[1][1] += s2; }
                 if (i >= k) store_block(Kt, i, k, o[0][0], o[0][1], o[1][0], o[1][1]);
                 else store_block(Kt, k, i, o[0][0], o[1][0], o[0][1], o[1][1]);      // block above the diagonal: its transpose below it
@@ -752,7 +689,7 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
 // update unconditional.  Returns the B fragments of X = L^-T for the panel solve: B[slot t][n = g] = X[2 t + step][g].
 __device__ __forceinline__ void diag_tile_inverse(double D0, double D1, const int g, const int t, double& bf0, double& bf1) {
     double x0 = (g == 2 * t) ? 1.0 : 0.0, x1 = (g == 2 * t + 1) ? 1.0 : 0.0;
-#pragma unroll 1
+#pragma unroll
     for (int tk = 0; tk < 4; ++tk) {
         {
             const int k = 2 * tk;
@@ -790,33 +727,6 @@ __device__ __forceinline__ void diag_tile_inverse(double D0, double D1, const in
     bf1 = (g & 1) ? v11 : v10;
 }
 
-// the first `npass` column pairs of a diagonal tile, no inverse (last tile row: the columns left of the appended rows)
-__device__ __forceinline__ void diag_tile_partial(double& D0, double& D1, const int g, const int t, const int npass) {
-#pragma unroll 1
-    for (int tk = 0; tk < npass; ++tk) {
-        {
-            const int k = 2 * tk;
-            const double rs = fast_rsqrt_spd(shfl_d(D0, k * 4 + tk));
-            const double colv = (g > k) ? D0 * rs : 0.0;
-            const double lg = shfl_d(colv, g * 4 + tk);
-            const double lc0 = shfl_d(colv, (2 * t) * 4 + tk);
-            const double lc1 = shfl_d(colv, (2 * t + 1) * 4 + tk);
-            D0 -= lg * lc0;
-            D1 -= lg * lc1;
-        }
-        {
-            const int k = 2 * tk + 1;
-            const double rs = fast_rsqrt_spd(shfl_d(D1, k * 4 + tk));
-            const double colv = (g > k) ? D1 * rs : 0.0;
-            const double lg = shfl_d(colv, g * 4 + tk);
-            const double lc0 = shfl_d(colv, (2 * t) * 4 + tk);
-            const double lc1 = shfl_d(colv, (2 * t + 1) * 4 + tk);
-            D0 -= lg * lc0;
-            D1 -= lg * lc1;
-        }
-    }
-}
-
 struct CholRegs {
     double L[TC][TC][2];   // finished tiles L[I][c], I > c (statically indexed; live only while later columns need them)
     double Cn[TC][2];      // prefetched tiles of the next block column (rows I >= column)
@@ -846,12 +756,24 @@ __device__ __forceinline__ void chol_block_column(CholRegs& r, const double2* __
 #pragma unroll
     for (int I = BK; I < TC; ++I) { C[I][0] = r.Cn[I][0]; C[I][1] = r.Cn[I][1]; }
     if (BK + 1 < TC) load_column<(BK + 1 < TC) ? BK + 1 : BK, off>(r, Kt);
+    // the diagonal tile first: its in-tile factorisation is a latency chain (shuffles, reciprocal square roots), and the
+    // updates of the tiles below it -- which do not depend on it -- are placed AFTER it in program order so that the
+    // scheduler can issue their tensor instructions into the gaps of that chain
 #pragma unroll
     for (int c = 0; c < BK; ++c) {
         if (c >= off) {   // columns left of the feature's first one were never produced
+            dense::dmma(C[BK][0], C[BK][1], r.L[BK][c][0], -r.L[BK][c][0]);
+            dense::dmma(C[BK][0], C[BK][1], r.L[BK][c][1], -r.L[BK][c][1]);
+        }
+    }
+    double bf0 = 0.0, bf1 = 0.0;
+    if (BK < TC - 1) diag_tile_inverse(C[BK][0], C[BK][1], g, t, bf0, bf1);
+#pragma unroll
+    for (int c = 0; c < BK; ++c) {
+        if (c >= off) {
             const double nb0 = -r.L[BK][c][0], nb1 = -r.L[BK][c][1];
 #pragma unroll
-            for (int I = BK; I < TC; ++I) {
+            for (int I = BK + 1; I < TC; ++I) {
                 dense::dmma(C[I][0], C[I][1], r.L[I][c][0], nb0);
                 dense::dmma(C[I][0], C[I][1], r.L[I][c][1], nb1);
             }
@@ -862,8 +784,6 @@ __device__ __forceinline__ void chol_block_column(CholRegs& r, const double2* __
         D1 = C[BK][1];
         return;
     }
-    double bf0, bf1;
-    diag_tile_inverse(C[BK][0], C[BK][1], g, t, bf0, bf1);
 #pragma unroll
     for (int I = BK + 1; I < TC; ++I) {
         double n0 = 0.0, n1 = 0.0;
@@ -921,33 +841,9 @@ front_chol_kernel(const double2* __restrict__ Kbuf, const int* __restrict__ pend
             case 7: chol_feature<7>(Kt, g, t, D0, D1); break;
             default: chol_feature<8>(Kt, g, t, D0, D1); break;
         }
-        // the measurement columns of the last tile row, then its 4x4 block at (rr, rr) holds MINUS the Gram matrix of
-        // [y; V] = [r~; Q1^T] L^-T:  yy = (0,0), b_q = (q,0), M_qp = (q,p), q >= p (lower triangle of the tile)
-        diag_tile_partial(D0, D1, g, t, rr >> 1);
-        const int l0 = 4 * rr + (rr >> 1);                  // lane of element (rr, rr)
-        const double yy = -shfl_d(D0, l0);
-        double bq[3], Mq[6];
-        bq[0] = -shfl_d(D0, l0 + 4); bq[1] = -shfl_d(D0, l0 + 8); bq[2] = -shfl_d(D0, l0 + 12);
-        Mq[0] = -shfl_d(D1, l0 + 4);                               // (1,1)
-        Mq[1] = -shfl_d(D1, l0 + 8);                               // (2,1)
-        Mq[2] = -shfl_d(D1, l0 + 12);                              // (3,1)
-        Mq[3] = -shfl_d(D0, l0 + 9);                               // (2,2)
-        Mq[4] = -shfl_d(D0, l0 + 13);                              // (3,2)
-        Mq[5] = -shfl_d(D1, l0 + 13);                              // (3,3)
         const int rank = fac_rank[fj], dofv = dof[fj];
         const int st = feat_status[fj];
-        double gam = yy;
-        {   // Cholesky solve on the leading rank x rank block of V V^T (reciprocal square roots: 0 for a non-positive pivot)
-            const double r0 = (rank >= 1) ? fast_rsqrt(Mq[0]) : 0.0;
-            const double z0 = bq[0] * r0;
-            const double l10 = Mq[1] * r0, l20 = Mq[2] * r0;
-            const double r1 = (rank >= 2 && r0 > 0.0) ? fast_rsqrt(Mq[3] - l10 * l10) : 0.0;
-            const double z1 = (bq[1] - l10 * z0) * r1;
-            const double l21 = (Mq[4] - l20 * l10) * r1;
-            const double r2 = (rank >= 3 && r1 > 0.0) ? fast_rsqrt(Mq[5] - l20 * l20 - l21 * l21) : 0.0;
-            const double z2 = (bq[2] - l20 * z0 - l21 * z1) * r2;
-            gam = yy - (z0 * z0 + z1 * z1 + z2 * z2);
-        }
+        const double gam = gamma_from_last_tile(D0, D1, g, t, rr, rank);
         if (lane == 0) {
             const double crit = (dofv < chi2_len) ? chi2_table[dofv] : nan("");
             const bool pass = gam <= crit;
@@ -974,15 +870,25 @@ size_t front_asm_smem(const msckf_dims& d, int warps) {
 
 }  // namespace
 
-bool front_split_supported(const msckf_dims& d) {
-    // (the start-up histogram of the assembly kernel aliases two warps' scratch; the bucketed list holds 16-bit indices)
+static bool front_narrow(const msckf_dims& d) {
+    // (the start-up histogram of the shared-memory assembly kernel aliases two warps' scratch; 16-bit feature indices)
     return d.M <= fgeom::FW_MAX_OBS && d.N <= 32 && d.F <= 65535 && front_asm_warps(d) >= 2;
 }
 
-// filters handled per kernel triple: bounds the tile buffer (20 KB per feature)
+// tracks of up to 64 observations / windows of up to 64 poses: geometry by front.cu's CTA-per-feature kernel, P-stationary
+// assembly over several CTAs per filter, shared-memory factorisation (front_chol_smem.cu)
+static bool front_wide(const msckf_dims& d) { return d.M <= 64 && d.N <= 64 && d.F <= 65535; }
+
+bool front_split_supported(const msckf_dims& d) { return front_narrow(d) || front_wide(d); }
+
+// double2 per feature slot of the tile buffer
+int front_split_kt_d2(const msckf_dims& d) { return front_narrow(d) ? KT_D2 : ftile::tiles_for_capacity(d.M) * 32; }
+int front_split_map_bytes(const msckf_dims& d) { return front_narrow(d) ? 32 : 64; }
+
+// filters handled per kernel triple: bounds the tile buffer (23 KB per feature for short tracks, 78 KB at 64 observations)
 int front_split_sub_filters(const msckf_dims& d) {
     const size_t budget = (size_t)6 << 30;
-    const size_t per_filter = (size_t)(d.F > 0 ? d.F : 1) * KT_D2 * sizeof(double2);
+    const size_t per_filter = (size_t)(d.F > 0 ? d.F : 1) * front_split_kt_d2(d) * sizeof(double2);
     long long sub = (long long)(budget / per_filter);
     if (sub < 1) sub = 1;
     if (sub > d.B) sub = d.B;
@@ -991,7 +897,7 @@ int front_split_sub_filters(const msckf_dims& d) {
 }
 
 size_t front_split_tile_bytes(const msckf_dims& d) {
-    return (size_t)front_split_sub_filters(d) * d.F * KT_D2 * sizeof(double2);
+    return (size_t)front_split_sub_filters(d) * d.F * front_split_kt_d2(d) * sizeof(double2);
 }
 
 // optional per-kernel timing (msckf_set_stage_timing / msckf_front_stage_ms): CUDA events on the launching stream around
@@ -1043,16 +949,75 @@ cudaError_t launch_asm_ps(const FrontArgs& a, const unsigned char* slot_map, dou
                         (((size_t)a.dims.F + 15) & ~(size_t)15);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(front_asm_ps_kernel<NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(front_asm_ps_kernel<NWARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    front_asm_ps_kernel<NWARPS><<<nb, NWARPS * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch);
+    front_asm_ps_kernel<NWARPS, false><<<nb, NWARPS * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch, KT_D2);
     return cudaGetLastError();
+}
+
+cudaError_t launch_front_geo_wide(const FrontArgs& a, double2* Kbuf, int kt_d2, unsigned char* slot_map, int* pend_list,
+                                  int* pend_count, int b0, int nb, cudaStream_t s);
+cudaError_t launch_front_chol_smem(const double2* Kbuf, int kt_d2, const int* pend_list, const int* pend_count, const int* feat_len,
+                                   const int* fac_rank, const int* dof, const double* chi2_table, int chi2_len,
+                                   unsigned char* feat_status, double* gamma, size_t fbase, int Mcap, cudaStream_t s);
+
+static cudaError_t launch_front_wide(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, unsigned char* slot_map,
+                                     cudaStream_t s) {
+    constexpr int NW = 15;
+    constexpr size_t featb = 64 * AR * 8 + 64;
+    const int F = a.dims.F;
+    const int kt_d2 = front_split_kt_d2(a.dims);
+    const size_t lists = (((size_t)F + 7) & ~(size_t)7) * 2 + (((size_t)F + 15) & ~(size_t)15);
+    int batch = (int)(((size_t)227 * 1024 - lists - 1024) / (2 * featb));
+    if (batch > 32) batch = 32;
+    if (batch < 1) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)2 * batch * featb + lists;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(front_asm_ps_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int nblk = a.dims.N * (a.dims.N + 1) / 2;
+    const int parts = (nblk + NW * 32 - 1) / (NW * 32);
+    const int sub = front_split_sub_filters(a.dims);
+    if (g_timing) g_ev_used = 0;
+    for (int b0 = 0; b0 < a.dims.B; b0 += sub) {
+        const int nb = (b0 + sub <= a.dims.B) ? sub : a.dims.B - b0;
+        cudaError_t e = cudaMemsetAsync(pend_count, 0, sizeof(int), s);
+        if (e != cudaSuccess) return e;
+        const bool timed = g_timing && g_ev_used < MAX_SUB;
+        const int slot = g_ev_used;
+        if (timed) {
+            for (; g_ev_created <= slot; ++g_ev_created)
+                for (int q = 0; q < 4; ++q)
+                    if ((e = cudaEventCreate(&g_ev[g_ev_created][q])) != cudaSuccess) return e;
+            cudaEventRecord(g_ev[slot][0], s);
+        }
+        e = launch_front_geo_wide(a, Kbuf, kt_d2, slot_map, pend_list, pend_count, b0, nb, s);
+        if (e != cudaSuccess) return e;
+        if (timed) cudaEventRecord(g_ev[slot][1], s);
+        front_asm_ps_kernel<NW, true><<<dim3(nb, parts), NW * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch, kt_d2);
+        msckf_count_launch(1);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (timed) cudaEventRecord(g_ev[slot][2], s);
+        e = launch_front_chol_smem(Kbuf, kt_d2, pend_list, pend_count, a.feat_len, a.fac_rank, a.dof, a.chi2_table, a.chi2_len,
+                                   a.feat_status, a.gamma, (size_t)b0 * F, a.dims.M, s);
+        if (e != cudaSuccess) return e;
+        if (timed) {
+            cudaEventRecord(g_ev[slot][3], s);
+            ++g_ev_used;
+        }
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_front_split(const FrontArgs& a, double2* Kbuf, int* pend_list, int* pend_count, int* pend_key,
                                unsigned char* slot_map, cudaStream_t s) {
+    if (!front_narrow(a.dims)) return launch_front_wide(a, Kbuf, pend_list, pend_count, slot_map, s);
     // P-stationary assembly when the block triangle of the window fits one CTA's threads and the batch buffers fit its
     // shared memory; P staged in shared memory otherwise
     const int nblk = a.dims.N * (a.dims.N + 1) / 2;

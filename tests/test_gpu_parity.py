@@ -643,8 +643,9 @@ def test_full_size_properties(golden_dir, mode):
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("F,M,N", [(24, 12, 36), (16, 40, 40), (40, 33, 34), (48, 60, 60)])
 def test_large_windows_vs_oracle(mode, F, M, N):
-    """Windows / tracks beyond the warp-per-feature kernel's tile budget (N > 31 or M > 32): CTA-per-feature front end,
-    multi-pass information accumulation (6N > 192), larger update factorisations -- against the oracle on synthetic
+    """Windows / tracks beyond the warp-per-feature kernels' budget (N > 32 or M > 32): the wide front end (CTA-per-feature
+    geometry, P-stationary assembly over several CTAs per filter, shared-memory factorisation), multi-pass information
+    accumulation (6N > 192), larger update factorisations -- against the oracle on synthetic
     cases (the golden fixtures stop at N = 31).  (48, 60, 60) is the per-feature / per-filter shape of BASELINE.json's
     stress config (60-pose window, state 375, 60 observations per track)."""
     from helpers import make_case
@@ -660,6 +661,31 @@ def test_large_windows_vs_oracle(mode, F, M, N):
         compare_update_outputs(flt.case_outputs(b, c), ref, CHI, label=f"synthetic F{F} M{M} N{N} #{b}")
         n_rej += ref["out_n_rejected"]
         assert ref["out_updated"]
+
+
+def test_stress_shape_full_size_vs_oracle():
+    """BASELINE.json configs[4] at its FULL per-filter size -- 1024 features x 60 observations, 60-pose window (state 375) --
+    on sampled filters against the oracle: gate decisions, gamma, delta_x, covariance and poses (the reference's own
+    update() would need a 115 GB matrix here; the oracle's only algebraic change is R_n = sigma^2 Q^T Q).  Ragged track
+    lengths (33..60) ride along in the second filter: geometry by the CTA-per-feature kernel, P-stationary assembly over
+    four CTAs per filter, shared-memory factorisation of up to 16 tile columns, multi-pass information accumulation."""
+    from helpers import make_case
+    cases = [make_case(1024, 60, 60, seed=7), make_case(1024, 60, 60, seed=8)]
+    rng = np.random.default_rng(5)
+    c = cases[1]
+    for j in range(0, 1024, 3):
+        c["feat_len"][j] = int(rng.integers(33, 61))
+        c["tracked_cnt"][j] = c["feat_len"][j]
+    refs = [o.update_case(c) for c in cases]
+    flt = _batch_from_cases(cases, _lib.COMPRESS_GRAM)
+    assert (flt.F, flt.M, flt.N) == (1024, 60, 60)
+    flt.update()
+    torch.cuda.synchronize()
+    for b, (c, ref) in enumerate(zip(cases, refs)):
+        errs = compare_update_outputs(flt.case_outputs(b, c), ref, CHI, label=f"stress 1024x60x60 #{b}")
+        assert ref["out_updated"] and ref["out_n_rejected"] > 10
+        print(f"stress shape filter {b}: {int(ref['out_gate'].sum())} accepted, {ref['out_n_rejected']} gated out, "
+              f"P {errs['out_P']:.1e}, delta_x {errs['delta_x']:.1e}, gamma {errs.get('gamma', 0):.1e}")
 
 
 @pytest.mark.parametrize("F,M,N", [(40, 32, 32), (24, 31, 31), (24, 29, 32), (48, 30, 30)])
