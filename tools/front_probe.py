@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Timing probe of the per-feature front end (geometry / assembly / factorisation kernels) on the benchmark shape:
 B filters x 256 features x 30 observations, 30-pose window, every filter the steady-state snapshot of the golden fixture
-with its own pixel noise.  python tools/front_probe.py [filters] [repeats] [gate: exact|bounds]
+with its own pixel noise.  python tools/front_probe.py [filters] [repeats] [gate: exact|bounds] [front|update]
+("update" runs the whole measurement update, so the compression and correction kernels launch too)
 Short enough to sit under `ncu -k regex:front_asm -c 1`."""
 import ctypes as C
 import os
@@ -27,12 +28,13 @@ for k, v in h.items():
 g = torch.Generator(device="cuda").manual_seed(7)
 flt.obs_uv.add_(0.1 * torch.randn(flt.obs_uv.shape, dtype=torch.float64, device="cuda", generator=g))
 m0, rho0 = flt.idp_m.clone(), flt.idp_rho.clone()
+whole = len(sys.argv) > 4 and sys.argv[4] == "update"
 flt.lib.msckf_set_stage_timing(1)
 best = None
 for _ in range(reps):
     flt.idp_m.copy_(m0)
     flt.idp_rho.copy_(rho0)
-    flt.front()
+    flt.update() if whole else flt.front()
     t = [C.c_double(0) for _ in range(3)]
     n = flt.lib.msckf_front_stage_ms(*[C.byref(x) for x in t])
     v = [x.value for x in t]
