@@ -6,12 +6,16 @@
 // r~_j = (I - Q1 Q1^T) r_j -- the basis-free form of the left-null-space projection (A A^T = I - Q1 Q1^T).  G is what
 // T_H^T T_H of the reference's QR equals, g is T_H^T r_n; the update kernel (update_info.cu) consumes them directly.
 //
-// One 256-thread CTA per filter.  Per panel of PF accepted features:
-//   * cp.async (LDGSTS) prefetches the next panel's compact factors (A_i, Q1 rows, r~_i, slots) into shared memory;
-//   * the 3 PF rows of W (zero where a camera does not observe the feature) are scattered into a shared K-panel;
-//   * every warp folds the panel into its share of the lower-triangular 8 x 8 output tiles of W^T W with FP64 tensor
-//     instructions (DMMA.8x8x4), accumulators resident in registers for the whole filter (<= 40 tiles per warp);
-//   * D and g are accumulated by owner threads in registers in feature order (deterministic, no atomics).
+// One 512-thread CTA per filter, a software pipeline over panels of PF accepted features with ONE CTA barrier per panel:
+//   * cp.async (LDGSTS) prefetches the compact factors (A_i, Q1 rows, r~_i, slots) of panel p + 2 into one of two staging
+//     buffers; the warp that fetched a feature turns its slot list into a slot -> observation map when its copies land;
+//   * the 3 PF rows of W of panel p + 1 (zero where a camera does not observe the feature) are written into one of two
+//     shared K-panels, one (feature, slot, row) unit per thread and round, and D / g of that panel are accumulated on the
+//     tensor pipe straight from the staging buffer (operand A == operand B: the tile [A_i | r~_i | 0] of a window slot);
+//   * every warp folds panel p into its share of the lower-triangular 8 x 8 output tiles of W^T W with FP64 tensor
+//     instructions (DMMA.8x8x4), accumulators resident in registers for the whole filter (20 tiles per warp);
+//   * two of the four warps of every scheduler take the tensor loop first and the scatter second, the other two the other
+//     way round, so the tensor pipe is fed while half of the CTA moves operands.
 // The stacked matrix H_X (22.8 MB per filter at 256 features x 30 poses) is never formed.
 #include "msckf_common.cuh"
 #include "dense.cuh"
@@ -91,7 +95,7 @@ __device__ __forceinline__ void gram_tensor_loop(unsigned wbase, int p0, int J0,
 template <int NMAX, int PF>
 __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a) {
     constexpr int SMAX = NMAX / GW;                     // window slots per warp for the D / g tiles
-    constexpr int LDW = 6 * NMAX + 4, LDX = 8 * NMAX + 4;   // mod 16 == 4 (see ld_pad4)
+    constexpr int LDW = 6 * NMAX + 4;                   // mod 16 == 4 (see below)
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -103,23 +107,20 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a) {
     const int T2 = (T + 1) >> 1;           // 2-row strips
 
     // shared-memory carve-up (offsets, not pointers: a table of generic pointers would pin two dozen registers)
-    //   panelW [3 PF][LDW]   rows of W = Q1^T H_x of the panel's features (k-panel of W^T W)
-    //   panelX [2 PF][LDX]   rows [A_i | r~_i | 0] per window slot, 8 columns per slot (k-panel of D and g)
-    //   stage[2]             prefetched factors of a panel: A [PF][Mcap][12], Q [PF][Mcap][6], r~ [PF][Mcap][2], slot [PF][Mcap]
-    //   Dg [Ncap][48]        D_s (6 x 6, row stride 8; column 6 = g_s)
-    //   acc_list [F], flen [2][PF] (int), seen [PF][Ncap] (bytes: this (feature, slot) pair has an observation)
+    //   panelW[2] [3 PF][LDW]  rows of W = Q1^T H_x of a panel's features (k-panel of W^T W), double-buffered
+    //   stage[2]               prefetched factors of a panel: A [PF][Mcap][12], Q [PF][Mcap][6], r~ [PF][Mcap][2], slot [PF][Mcap]
+    //   Dg [Ncap][48]          D_s (6 x 6, row stride 8; column 6 = g_s)
+    //   acc_list [F] (int), inv[2] [PF][NMAX] (bytes: observation index held by a window slot, 0xFF = none)
     extern __shared__ double smem[];
     const int PM = PF * Mcap;
-    double* const panelW = smem;
-    double* const panelX = smem + 3 * PF * LDW;
-    auto rawA = [&](int st) { return smem + (3 * PF * LDW + 2 * PF * LDX) + (size_t)st * PM * 21; };
+    constexpr int WSZ = 3 * PF * LDW;
+    auto rawA = [&](int st) { return smem + 2 * WSZ + (size_t)st * PM * 21; };
     auto rawQ = [&](int st) { return rawA(st) + PM * 12; };
     auto rawR = [&](int st) { return rawA(st) + PM * 18; };
     auto rawS = [&](int st) { return reinterpret_cast<int*>(rawA(st) + PM * 20); };
     double* const Dg = rawA(2);
     int* const acc_list = reinterpret_cast<int*>(Dg + Ncap * 48);
-    int* const flen = acc_list + F;
-    unsigned char* const seen = reinterpret_cast<unsigned char*>(flen + 2 * PF);
+    unsigned char* const inv = reinterpret_cast<unsigned char*>(acc_list + F);
     __shared__ int s_wcnt[GW];
     __shared__ int s_tot[2];
 
@@ -161,34 +162,52 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a) {
     const int upp = (U + npass - 1) / npass;
     constexpr int KW = 3 * PF, KX = 2 * PF;      // k extents of the two panels (multiples of 4)
 
-    // asynchronous prefetch of one panel's compact factors: warp f fetches feature f
+    // asynchronous prefetch of one panel's compact factors: warp f fetches feature f (and remembers its length)
+    int my_len = 0;
     auto prefetch = [&](int pi, int st) {
-        for (int f = warp; f < PF; f += GW) {
+        if (warp < PF) {
+            const int f = warp;
             const int k = pi * PF + f;
             const int j = (k < nacc) ? acc_list[k] : -1;
             const int M = (j >= 0) ? min(a.feat_len[(size_t)b * F + j], Mcap) : 0;
-            if (lane == 0) flen[st * PF + f] = M;
-            if (M <= 0) continue;
-            const size_t fj = (size_t)b * F + j;
-            const double* gA = a.fac_A + fj * (size_t)Mcap * 12;
-            const double* gQ = a.fac_Q + fj * (size_t)Mcap * 6;
-            const double* gR = a.fac_rt + fj * (size_t)Mcap * 2;
-            const int* gS = a.obs_slot + fj * (size_t)Mcap;
-            double* sA = rawA(st) + (size_t)f * Mcap * 12;
-            double* sQ = rawQ(st) + (size_t)f * Mcap * 6;
-            double* sR = rawR(st) + (size_t)f * Mcap * 2;
-            int* sS = rawS(st) + f * Mcap;
-            for (int it = lane; it < 6 * M; it += 32) cp_async16(sA + 2 * it, gA + 2 * it);
-            for (int it = lane; it < 3 * M; it += 32) cp_async16(sQ + 2 * it, gQ + 2 * it);
-            for (int it = lane; it < M; it += 32) {
-                cp_async16(sR + 2 * it, gR + 2 * it);
-                cp_async4(sS + it, gS + it);
+            my_len = M;
+            if (M > 0) {
+                const size_t fj = (size_t)b * F + j;
+                const double* gA = a.fac_A + fj * (size_t)Mcap * 12;
+                const double* gQ = a.fac_Q + fj * (size_t)Mcap * 6;
+                const double* gR = a.fac_rt + fj * (size_t)Mcap * 2;
+                const int* gS = a.obs_slot + fj * (size_t)Mcap;
+                double* sA = rawA(st) + (size_t)f * Mcap * 12;
+                double* sQ = rawQ(st) + (size_t)f * Mcap * 6;
+                double* sR = rawR(st) + (size_t)f * Mcap * 2;
+                int* sS = rawS(st) + f * Mcap;
+                for (int it = lane; it < 6 * M; it += 32) cp_async16(sA + 2 * it, gA + 2 * it);
+                for (int it = lane; it < 3 * M; it += 32) cp_async16(sQ + 2 * it, gQ + 2 * it);
+                for (int it = lane; it < M; it += 32) {
+                    cp_async16(sR + 2 * it, gR + 2 * it);
+                    cp_async4(sS + it, gS + it);
+                }
             }
         }
         cp_async_commit();
     };
-
-    for (int e = tid; e < PF * Ncap; e += GT) seen[e] = 0;
+    // once its copies have landed, the fetching warp inverts the slot list of its feature: inv[slot] = observation
+    auto land = [&](int st) {
+        cp_async_wait_all();
+        if (warp < PF) {
+            __syncwarp();
+            unsigned char* iv = inv + (st * PF + warp) * NMAX;
+            for (int sl = lane; sl < NMAX; sl += 32) iv[sl] = 0xFF;
+            __syncwarp();
+            const int* sS = rawS(st) + warp * Mcap;
+            for (int i = lane; i < my_len; i += 32) {
+                const int sl = sS[i];
+                if (sl >= 0 && sl < nc) iv[sl] = (unsigned char)i;
+            }
+        }
+    };
+    constexpr int WPF = GW / PF;                 // warps that share a feature in the scatter
+    static_assert(GW % PF == 0, "the scatter assigns whole warps to features");
 
     for (int pass = 0; pass < npass; ++pass) {
         // this warp's contiguous range of units in the linearised (strip, column) order; the per-unit operand offsets
@@ -217,28 +236,21 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a) {
 #pragma unroll
         for (int k = 0; k < SMAX; ++k) accX[k][0] = accX[k][1] = 0.0;
 
-        __syncthreads();
-        prefetch(0, 0);
-        cp_async_wait_all();
-        __syncthreads();
-
-        for (int pi = 0; pi < npanels; ++pi) {
-            const int st = pi & 1;
-            if (pi + 1 < npanels) prefetch(pi + 1, st ^ 1);
-            // ---- scatter: W[3f+q][6 s + e] = Q1[2i][q] A[2i][e] + Q1[2i+1][q] A[2i+1][e];  X[2f+r][8 s + .] = [A[2i+r] | r~ | 0]
-            for (int it = tid; it < PF * Mcap; it += GT) {
-                const int f = it / Mcap, i = it - f * Mcap;
-                if (i >= flen[st * PF + f]) continue;
-                const int s = rawS(st)[f * Mcap + i];
-                if (s < 0 || s >= nc) continue;
-                // (operands are re-read from shared memory per output row: the 80 accumulator registers of the tensor
-                //  loop stay live across this phase, so it must get by with few registers)
-                const double2* A2 = reinterpret_cast<const double2*>(rawA(st) + ((size_t)f * Mcap + i) * 12);
-                const double* Q = rawQ(st) + ((size_t)f * Mcap + i) * 6;
-                seen[f * Ncap + s] = 1;
-#pragma unroll 1
-                for (int q = 0; q < 3; ++q) {
-                    double2* dst = reinterpret_cast<double2*>(panelW + (size_t)(3 * f + q) * LDW + 6 * s);
+        // ---- rows of W of one panel: W[3f+q][6 s + e] = Q1[2i][q] A[2i][e] + Q1[2i+1][q] A[2i+1][e], i = the observation of
+        //      feature f in window slot s (zero row segment when there is none); one (slot, row) unit per thread and round
+        auto scatter = [&](int st) {
+            const int f = warp % PF;
+            const unsigned char* iv = inv + (st * PF + f) * NMAX;
+            double* Wp = smem + (size_t)st * WSZ + (size_t)(3 * f) * LDW;
+            for (int e = (warp / PF) * 32 + lane; e < 3 * nc; e += 32 * WPF) {
+                const int sl = e / 3, q = e - 3 * sl;
+                const int i = iv[sl];
+                double2* dst = reinterpret_cast<double2*>(Wp + (size_t)q * LDW + 6 * sl);
+                if (i == 0xFF) {
+                    dst[0] = dst[1] = dst[2] = make_double2(0.0, 0.0);
+                } else {
+                    const double2* A2 = reinterpret_cast<const double2*>(rawA(st) + ((size_t)f * Mcap + i) * 12);
+                    const double* Q = rawQ(st) + ((size_t)f * Mcap + i) * 6;
                     const double q0 = Q[q], q1 = Q[3 + q];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -246,55 +258,64 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a) {
                         dst[k] = make_double2(q0 * x.x + q1 * y.x, q0 * x.y + q1 * y.y);
                     }
                 }
-                if (doX) {
-                    const double* R = rawR(st) + ((size_t)f * Mcap + i) * 2;
-#pragma unroll 1
-                    for (int r = 0; r < 2; ++r) {
-                        double2* dst = reinterpret_cast<double2*>(panelX + (size_t)(2 * f + r) * LDX + 8 * s);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) dst[k] = A2[3 * r + k];
-                        dst[3] = make_double2(R[r], 0.0);
-                    }
-                }
             }
-            __syncthreads();
-            // ---- (feature, slot) pairs without an observation contribute zero rows ----
-            for (int it = tid; it < PF * nc; it += GT) {
-                const int f = it / nc, s = it - f * nc;
-                if (seen[f * Ncap + s]) { seen[f * Ncap + s] = 0; continue; }
+        };
+        // ---- D_s = sum A_i^T A_i and g_s = sum A_i^T r~_i: one 8 x 8 tile per window slot, operand A == operand B; the
+        //      operand tile [A_i | r~_i | 0] (rows = the 2 PF measurement rows of the panel) is gathered from the stage
+        auto fold_X = [&](int st) {
+            const double* sA = rawA(st);
+            const double* sR = rawR(st);
+            const unsigned char* iv = inv + st * PF * NMAX;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    double2* dst = reinterpret_cast<double2*>(panelW + (size_t)(3 * f + q) * LDW + 6 * s);
-                    dst[0] = dst[1] = dst[2] = make_double2(0.0, 0.0);
-                }
-                if (doX) {
+            for (int kk = 0; kk < KX; kk += 4) {
+                const int f = (kk >> 1) + (t >> 1), r = t & 1;
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        double2* dst = reinterpret_cast<double2*>(panelX + (size_t)(2 * f + r) * LDX + 8 * s);
-                        dst[0] = dst[1] = dst[2] = dst[3] = make_double2(0.0, 0.0);
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- W^T W on the tensor pipe: per k step, the B fragments of a group of units are loaded first, then the
-            //      tensor instructions are issued back to back (no branch per unit; units beyond nu work on dead tiles) ----
-            gram_tensor_loop<KW, LDW>((unsigned)__cvta_generic_to_shared(panelW) + (unsigned)(t * LDW + g) * 8u, p0, J0, nu,
-                                      newstrip, acc);
-            // ---- D_s = sum A_i^T A_i and g_s = sum A_i^T r~_i: one 8 x 8 tile per window slot, operand A == operand B ----
-            if (doX) {
-                const double* xrow = panelX + (size_t)t * LDX + g + 8 * warp;
-#pragma unroll
-                for (int kk = 0; kk < KX; kk += 4) {
-#pragma unroll
-                    for (int k = 0; k < SMAX; ++k) {
-                        if (warp + GW * k < nc) {
-                            const double x = xrow[kk * LDX + 8 * GW * k];
-                            dense::dmma(accX[k][0], accX[k][1], x, x);
+                for (int k = 0; k < SMAX; ++k) {
+                    const int sl = warp + GW * k;
+                    if (sl < nc) {
+                        const int i = iv[f * NMAX + sl];
+                        double x = 0.0;
+                        if (i != 0xFF && g < 7) {
+                            const size_t o = (size_t)f * Mcap + i;
+                            x = (g < 6) ? sA[o * 12 + 6 * r + g] : sR[o * 2 + r];
                         }
+                        dense::dmma(accX[k][0], accX[k][1], x, x);
                     }
                 }
             }
-            cp_async_wait_all();
+        };
+        // ---- W^T W on the tensor pipe: per k step, the B fragments of a group of units are loaded first, then the tensor
+        //      instructions are issued back to back (no branch per unit; units beyond nu work on dead tiles)
+        auto fold_W = [&](int st) {
+            gram_tensor_loop<KW, LDW>((unsigned)__cvta_generic_to_shared(smem + (size_t)st * WSZ) + (unsigned)(t * LDW + g) * 8u,
+                                      p0, J0, nu, newstrip, acc);
+        };
+
+        __syncthreads();                 // (the previous pass is done with every buffer)
+        prefetch(0, 0);
+        land(0);
+        __syncthreads();
+        if (npanels > 1) prefetch(1, 1);
+        scatter(0);
+        if (doX) fold_X(0);
+        land(1);
+        __syncthreads();
+
+        const bool tensor_first = (warp >> 2) & 1;
+        for (int pi = 0; pi < npanels; ++pi) {
+            const int st = pi & 1;
+            // stage st was consumed (scatter, D / g) during the previous iteration: refill it with panel pi + 2
+            if (pi + 2 < npanels) prefetch(pi + 2, st);
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ++ph) {
+                if ((ph == 0) == tensor_first) {
+                    fold_W(st);
+                } else if (pi + 1 < npanels) {
+                    scatter(st ^ 1);
+                    if (doX) fold_X(st ^ 1);
+                }
+            }
+            land(st);
             __syncthreads();
         }
 
@@ -361,10 +382,10 @@ GramPlan gram_plan(const msckf_dims& d) {
     GramPlan best{0, 0, 0};
     if (d.N > 64) return best;
     const int NMAX = d.N <= 32 ? 32 : 64;
-    const int LDW = 6 * NMAX + 4, LDX = 8 * NMAX + 4;
+    const int LDW = 6 * NMAX + 4;
     for (int PF = 8; PF >= 4; PF >>= 1) {
-        size_t doubles = (size_t)3 * PF * LDW + (size_t)2 * PF * LDX + (size_t)2 * PF * d.M * 21 + (size_t)d.N * 48;
-        size_t bytes = doubles * 8 + ((size_t)d.F + 2 * PF) * 4 + (size_t)PF * d.N + 64;
+        size_t doubles = (size_t)2 * 3 * PF * LDW + (size_t)2 * PF * d.M * 21 + (size_t)d.N * 48;
+        size_t bytes = doubles * 8 + (size_t)d.F * 4 + (size_t)2 * PF * NMAX + 64;
         if (bytes <= 227 * 1024) { best = GramPlan{NMAX, PF, bytes}; break; }
     }
     return best;
