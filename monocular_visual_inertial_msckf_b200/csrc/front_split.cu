@@ -689,7 +689,8 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
 // update unconditional.  Returns the B fragments of X = L^-T for the panel solve: B[slot t][n = g] = X[2 t + step][g].
 __device__ __forceinline__ void diag_tile_inverse(double D0, double D1, const int g, const int t, double& bf0, double& bf1) {
     double x0 = (g == 2 * t) ? 1.0 : 0.0, x1 = (g == 2 * t + 1) ? 1.0 : 0.0;
-#pragma unroll
+#pragma unroll 1      // rolled on purpose: 81 instantiations (tile column x tile count) of the unrolled chain overflow the
+                      // instruction cache as soon as the tracks of a launch differ in length (window 31: 11.8 vs 8.9 ms)
     for (int tk = 0; tk < 4; ++tk) {
         {
             const int k = 2 * tk;
@@ -756,24 +757,12 @@ __device__ __forceinline__ void chol_block_column(CholRegs& r, const double2* __
 #pragma unroll
     for (int I = BK; I < TC; ++I) { C[I][0] = r.Cn[I][0]; C[I][1] = r.Cn[I][1]; }
     if (BK + 1 < TC) load_column<(BK + 1 < TC) ? BK + 1 : BK, off>(r, Kt);
-    // the diagonal tile first: its in-tile factorisation is a latency chain (shuffles, reciprocal square roots), and the
-    // updates of the tiles below it -- which do not depend on it -- are placed AFTER it in program order so that the
-    // scheduler can issue their tensor instructions into the gaps of that chain
 #pragma unroll
     for (int c = 0; c < BK; ++c) {
         if (c >= off) {   // columns left of the feature's first one were never produced
-            dense::dmma(C[BK][0], C[BK][1], r.L[BK][c][0], -r.L[BK][c][0]);
-            dense::dmma(C[BK][0], C[BK][1], r.L[BK][c][1], -r.L[BK][c][1]);
-        }
-    }
-    double bf0 = 0.0, bf1 = 0.0;
-    if (BK < TC - 1) diag_tile_inverse(C[BK][0], C[BK][1], g, t, bf0, bf1);
-#pragma unroll
-    for (int c = 0; c < BK; ++c) {
-        if (c >= off) {
             const double nb0 = -r.L[BK][c][0], nb1 = -r.L[BK][c][1];
 #pragma unroll
-            for (int I = BK + 1; I < TC; ++I) {
+            for (int I = BK; I < TC; ++I) {
                 dense::dmma(C[I][0], C[I][1], r.L[I][c][0], nb0);
                 dense::dmma(C[I][0], C[I][1], r.L[I][c][1], nb1);
             }
@@ -784,6 +773,8 @@ __device__ __forceinline__ void chol_block_column(CholRegs& r, const double2* __
         D1 = C[BK][1];
         return;
     }
+    double bf0, bf1;
+    diag_tile_inverse(C[BK][0], C[BK][1], g, t, bf0, bf1);
 #pragma unroll
     for (int I = BK + 1; I < TC; ++I) {
         double n0 = 0.0, n1 = 0.0;

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Where a camera frame of the resident loop spends its time: every BatchedMSCKF call of frame_step_detections timed with
-CUDA events (synchronised per call, so the sum slightly exceeds the un-instrumented frame).  python tools/frame_profile.py [filters]"""
+CUDA events (synchronised per call, so the sum slightly exceeds the un-instrumented frame).  python tools/frame_profile.py [filters] [split]
+("split": every update as its three C-ABI stages front / compress / apply_update, timed separately)"""
 import collections
 import os
 import sys
@@ -41,6 +42,23 @@ def wrap(name):
     setattr(flt, name, f)
 
 
+if len(sys.argv) > 2 and sys.argv[2] == "split":
+    names += ["front", "compress", "apply_update"]
+    names.remove("update")
+    flt.lib.msckf_set_stage_timing(1)
+
+    def split_update():
+        import ctypes as C
+        flt.front()
+        t = [C.c_double(0) for _ in range(3)]
+        flt.lib.msckf_front_stage_ms(*[C.byref(x) for x in t])
+        if active[0]:
+            times.setdefault("  (geo, asm, chol)", []).extend(x.value for x in t)
+        flt.compress()
+        flt.apply_update()
+        if flt.count_feature_updates:
+            pass
+    flt.update = split_update
 for n in names:
     wrap(n)
 for f in range(NW + 4):
