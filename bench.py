@@ -808,7 +808,12 @@ def run_gpu_stream(args):
     if rank == 0:
         sampler.start()
     launches0 = flt.lib.msckf_launch_count()
+    if args.profiler_range:     # `ncu --profile-from-start off`: only the timed region is captured (profiles/*_launches.csv)
+        torch.cuda.cudart().cudaProfilerStart()
     ms_total = timed(lambda k: frame(inputs[k]), K)
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     launches = flt.lib.msckf_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else {}
     fu = int(flt.feature_updates.item())
@@ -1108,6 +1113,8 @@ if __name__ == "__main__":
                          "camera frame; snapshot (config 5, and round 1's benchmark): one steady-state snapshot replicated with "
                          "per-filter noise, a step is 9 propagations + one update")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps of the stream workload (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if "--filters" not in " ".join(sys.argv):
         args.filters = CONFIGS[args.config]["filters"]

@@ -78,7 +78,8 @@ EXPORTS = [
 
 
 def lib_path():
-    return os.path.join(_HERE, "csrc", "libmsckf_b200.so")
+    """The in-tree library; MSCKF_B200_LIB names another build of the same ABI (A/B timing of kernel variants)."""
+    return os.environ.get("MSCKF_B200_LIB") or os.path.join(_HERE, "csrc", "libmsckf_b200.so")
 
 
 def load_library():
