@@ -882,7 +882,11 @@ int front_split_sub_filters(const msckf_dims& d) {
     const size_t per_filter = (size_t)(d.F > 0 ? d.F : 1) * front_split_kt_d2(d) * sizeof(double2);
     long long sub = (long long)(budget / per_filter);
     if (sub < 1) sub = 1;
-    if (sub > d.B) sub = d.B;
+    if (sub >= d.B) return d.B > 0 ? d.B : 1;
+    // the assembly kernel runs one CTA (= filter) per SM: whole waves of the 148 SMs per sub-batch (820 filters = 5.5 waves
+    // cost as much as 6; 888 = 6 waves exactly), the remainder in the last one
+    constexpr int SMS = 148;
+    if (sub >= SMS) return (int)(sub / SMS) * SMS;
     const int n_sub = (int)((d.B + sub - 1) / sub);
     return (d.B + n_sub - 1) / n_sub;
 }
