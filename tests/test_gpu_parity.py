@@ -688,29 +688,43 @@ def test_stress_shape_full_size_vs_oracle():
               f"P {errs['out_P']:.1e}, delta_x {errs['delta_x']:.1e}, gamma {errs.get('gamma', 0):.1e}")
 
 
-@pytest.mark.parametrize("F,M,N", [(40, 32, 32), (24, 31, 31), (24, 29, 32), (48, 30, 30)])
-def test_warp_front_end_capacity_edges(F, M, N):
-    """The warp-per-feature front ends at the edges of their tile budget (M = 32: no padding rows in the last tile row;
-    N = 32: the staged covariance block fills the shared memory), with RAGGED track lengths 1..M in one batch (every
-    tile count of the factorisation kernel) and tracks whose observations are stored newest-first (slots decreasing with
-    the observation index: the transposed-block path of the assembly) -- against the oracle."""
+def _ragged_reversed_gapped(F, M, N, seeds):
+    """Synthetic cases with RAGGED track lengths 1..M (every tile count of the factorisation kernels), tracks stored
+    newest-first (slots decreasing with the observation index: the transposed-block path of the assembly) and tracks with
+    GAPS (a lost track that was matched again later skips window slots: MSCKF.py:400-434 resets lost_for_n_frames)."""
     from helpers import make_case
     cases = []
-    for seed in (3, 4):
+    for seed in seeds:
         c = make_case(F, M, N, seed=seed)
         rng = np.random.default_rng(100 + seed)
         for j in range(F):
             if j % 3 == 1:                                  # ragged: keep the first L observations
                 c["feat_len"][j] = int(rng.integers(1, M + 1))
                 c["tracked_cnt"][j] = c["feat_len"][j]
+            L = int(c["feat_len"][j])
+            if j % 5 == 3 and L >= 6:                       # gaps: drop two observations from the middle of the track
+                for cut in sorted(rng.choice(np.arange(1, L - 1), size=2, replace=False))[::-1]:
+                    for k in ("obs_uv", "obs_dir", "obs_conf", "obs_slot"):
+                        c[k][j, cut:L - 1] = c[k][j, cut + 1:L].copy()
+                    L -= 1
+                c["feat_len"][j] = L
+                c["tracked_cnt"][j] = L
             if j % 4 == 2:                                  # newest-first storage order
-                L = int(c["feat_len"][j])
                 for k in ("obs_uv", "obs_dir", "obs_conf", "obs_slot"):
                     c[k][j, :L] = c[k][j, :L][::-1].copy()
                 c["idp_anchor_slot"][j] = c["obs_slot"][j, 0]
                 c["idp_base"][j] = c["cam_t"][c["obs_slot"][j, 0]]
                 c["idp_m"][j] = c["obs_dir"][j, 0] / np.linalg.norm(c["obs_dir"][j, 0])
         cases.append(c)
+    return cases
+
+
+@pytest.mark.parametrize("F,M,N", [(40, 32, 32), (24, 31, 31), (24, 29, 32), (48, 30, 30)])
+def test_warp_front_end_capacity_edges(F, M, N):
+    """The warp-per-feature front ends at the edges of their tile budget (M = 32: no padding rows in the last tile row;
+    N = 32: the staged covariance block fills the shared memory), with ragged, reversed and gapped tracks in one batch --
+    against the oracle."""
+    cases = _ragged_reversed_gapped(F, M, N, (3, 4))
     refs = [o.update_case(c) for c in cases]
     flt = _batch_from_cases(cases, _lib.COMPRESS_GRAM)
     assert flt.M <= 32 and flt.N <= 32
@@ -718,6 +732,21 @@ def test_warp_front_end_capacity_edges(F, M, N):
     torch.cuda.synchronize()
     for b, (c, ref) in enumerate(zip(cases, refs)):
         compare_update_outputs(flt.case_outputs(b, c), ref, CHI, label=f"edge F{F} M{M} N{N} #{b}")
+        assert ref["out_updated"]
+
+
+@pytest.mark.parametrize("F,M,N", [(40, 48, 50), (32, 64, 64), (36, 33, 61)])
+def test_wide_front_end_ragged_reversed_gapped(F, M, N):
+    """The same irregular tracks through the WIDE front end (tracks of 33..64 observations / windows of 33..64 poses:
+    CTA-per-feature geometry, P-stationary assembly over several CTAs per filter, shared-memory factorisation of 1..17 tile
+    columns), including its capacity corner (64, 64) -- against the oracle."""
+    cases = _ragged_reversed_gapped(F, M, N, (5, 6))
+    refs = [o.update_case(c) for c in cases]
+    flt = _batch_from_cases(cases, _lib.COMPRESS_GRAM)
+    flt.update()
+    torch.cuda.synchronize()
+    for b, (c, ref) in enumerate(zip(cases, refs)):
+        compare_update_outputs(flt.case_outputs(b, c), ref, CHI, label=f"wide F{F} M{M} N{N} #{b}")
         assert ref["out_updated"]
 
 
