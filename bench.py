@@ -78,6 +78,17 @@ def filter_inputs(base, index):
     return uv, samples, qc, t0
 
 
+def captured_traffic(kernel, filters_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed `ncu --set full` capture
+    (profiles/roofline_traffic.json: bytes of one launch over `filters` filters of the benchmark shape), scaled to the
+    number of filters one launch of this run covers.  None when there is no capture of that kernel."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(kernel)
+        return float(t["bytes"]) * filters_per_launch / float(t["filters"])
+    except Exception:
+        return None
+
+
 def algorithmic_bytes_per_filter_step(F, M, N, n):
     """F (52 M + 104) + 2 d^2 8 + 2 (96 N + 168) + 2 15 d 8 + 56 n."""
     d = 15 + 6 * N
@@ -639,11 +650,7 @@ def run_gpu_snapshot(args):
     dom_name, dom_ms, dom_flops = names[dom], stage_ms[dom], stage_flops[dom]
     achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12
     stage_tflops = {names[k]: stage_flops[k] / (stage_ms[k] * 1e-3) / 1e12 for k in stage_flops}
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom_name)
-    except Exception:
-        pass
+    traffic = captured_traffic(dom_name, B / max(1, front_launches) if dom.startswith("front_") else B)
     # shared-memory view of the assembly kernel (what actually binds it, profiles/): every lower 2x2 block of K reads two
     # 2x6 Jacobian blocks (192 B) and HALF a padded 6x6 block of P (288 B shared by the two features a warp pairs up)
     smem_view = None
@@ -986,11 +993,7 @@ def run_gpu_stream(args):
     dom = max(stage_flops, key=lambda k: stage_ms[k])
     dom_ms, dom_flops = stage_ms[dom], stage_flops[dom]
     is_front = dom.startswith("front_")
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(names[dom])
-    except Exception:
-        pass
+    traffic = captured_traffic(names[dom], B / max(1, front_launches) if is_front else B)
     update_flops = sum(stage_flops.values())
     step_bytes = algorithmic_bytes_per_filter_step(L, int(round(Mw)), Nw, N_IMU) * B
     roofline = dict(bound="tensor", pipe="fp64 (DFMA/DMMA share one nominal peak on B200; tcgen05 has no f64 kind)",
