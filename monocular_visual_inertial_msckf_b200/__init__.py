@@ -6,11 +6,11 @@ behind the C ABI of include/msckf_b200.h (csrc/libmsckf_b200.so, built in-tree b
 There is no CPU fallback: every compute entry point raises if the library or a CUDA device is missing.
 """
 from ._lib import LibraryNotBuilt, lib_path, load_library  # noqa: F401
-from .batched import BatchedMSCKF, UpdateParams, pack_cases  # noqa: F401
+from .batched import BatchedMSCKF, FrameGraph, UpdateParams, pack_cases  # noqa: F401
 from .dataset import MetricsAccumulator, project_landmarks, synth_imu  # noqa: F401
 from .msckf import (B200UpdateMixin, Camera, Feature, IMU, IMUMeasurement, InverseDepthPoint, Isometry3D, Line,  # noqa: F401
                     MSCKF, MSCKFParameters, MSCKFState)
 
-__all__ = ["BatchedMSCKF", "UpdateParams", "pack_cases", "synth_imu", "project_landmarks", "MetricsAccumulator", "load_library", "lib_path", "LibraryNotBuilt",
+__all__ = ["BatchedMSCKF", "FrameGraph", "UpdateParams", "pack_cases", "synth_imu", "project_landmarks", "MetricsAccumulator", "load_library", "lib_path", "LibraryNotBuilt",
            "MSCKF", "MSCKFParameters", "MSCKFState", "B200UpdateMixin", "Feature", "Camera", "IMU", "IMUMeasurement",
            "Line", "InverseDepthPoint", "Isometry3D"]

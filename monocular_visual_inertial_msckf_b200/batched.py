@@ -540,6 +540,13 @@ class BatchedMSCKF:
         self.prune_poorest_camera_states(prune_above=max_cameras)
         return action, verdict
 
+    def capture_frame_graph(self, samples, R_I_C, t_I_C, desc_new, kp_new, score_new, n_new, max_cameras, **kwargs):
+        """frame_step_detections captured ONCE into a CUDA graph (a frame is ~60 kernel launches; for one filter or a few
+        dozen the launches, not the kernels, set the frame time).  The arguments give the shapes; the returned FrameGraph
+        copies each frame's inputs into its static buffers and replays the graph.  The filter state is left untouched: the
+        one eager warm-up frame that sizes every lazily allocated buffer runs between snapshot() and restore()."""
+        return FrameGraph(self, (samples, desc_new, kp_new, score_new, n_new), R_I_C, t_I_C, max_cameras, kwargs)
+
     # ------------------------------------------------------------------------------------------------------------
     def snapshot(self):
         """Every state tensor of the batch (filter state, window, tracks, descriptor lists) cloned: restore() brings the
@@ -637,3 +644,40 @@ def pack_cases(cases, F, M, N, ldp):
             h["lost_cnt"][b, :f] = c["lost_cnt"]
             h["tracked_cnt"][b, :f] = c["tracked_cnt"]
     return h
+
+
+class FrameGraph:
+    """One camera frame of a BatchedMSCKF as a replayable CUDA graph (see BatchedMSCKF.capture_frame_graph)."""
+
+    def __init__(self, flt, inputs, R_I_C, t_I_C, max_cameras, kwargs):
+        self.flt = flt
+        self.static = [x.clone() for x in inputs]
+        self.R_I_C, self.t_I_C = np.array(R_I_C, float), np.array(t_I_C, float)     # host values, baked into the graph
+        snap = flt.snapshot()
+        counting, flt.count_feature_updates = flt.count_feature_updates, False
+        side = torch.cuda.Stream(device=flt.device)
+        side.wait_stream(torch.cuda.current_stream(flt.device))
+        with torch.cuda.stream(side):                 # warm-up: lazy allocations, kernel attributes
+            self._run(max_cameras, kwargs)
+        torch.cuda.current_stream(flt.device).wait_stream(side)
+        flt.restore(snap)
+        flt.count_feature_updates = counting
+        torch.cuda.synchronize(flt.device)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = flt.lib.msckf_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.outputs = self._run(max_cameras, kwargs)
+        self.launches_per_replay = int(flt.lib.msckf_launch_count() - n0)     # this library's kernels inside one replay
+        flt.restore(snap)                             # (capture does not execute; restore() is for symmetry with a failed capture)
+
+    def _run(self, max_cameras, kwargs):
+        smp, desc, kp, sc, cnt = self.static
+        return self.flt.frame_step_detections(smp, self.R_I_C, self.t_I_C, desc, kp, sc, cnt, max_cameras, **kwargs)
+
+    def step(self, samples, desc_new, kp_new, score_new, n_new):
+        """Copy one frame's inputs (device or pinned host tensors) into the static buffers and replay.  Returns the
+        (action, verdict) tensors of the captured call (overwritten by the next replay)."""
+        for dst, src in zip(self.static, (samples, desc_new, kp_new, score_new, n_new)):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.outputs

@@ -555,3 +555,42 @@ def test_sixty_four_distinct_filters_vs_their_reference_runs(golden_dir):
     assert sum(gates) > 50 and len(set(tuple(z[f"t{i}.f{nfr - 1}.feat_len"]) for i in range(B))) > 32      # distinct, with rejections
     print(f"64 distinct filters x {nfr} frames as one batch vs their reference runs: worst relative error {worst:.2e}, "
           f"{sum(gates)} gate rejections in the reference runs")
+
+
+@pytest.mark.gpu
+def test_frame_graph_replay_equals_eager_frames():
+    """BatchedMSCKF.capture_frame_graph: 24 camera frames of 6 heterogeneous filters (device-built streams, window cycling
+    through the pruning) replayed from ONE captured CUDA graph leave exactly the bits the eager frame loop leaves -- state,
+    covariance, window, tracks, descriptor lists -- and the capture itself does not touch the filter state."""
+    from monocular_visual_inertial_msckf_b200 import _lib
+    from monocular_visual_inertial_msckf_b200.streams import DeviceStreams
+    B, L, WINDOW, NF = 6, 64, 8, 24
+    st = DeviceStreams(range(B), NF + 1, n_landmarks=L, p_drop=0.05, p_outlier=0.03, desc_dim=32, seed=11)
+    par = UpdateParams(K=st.K, width=st.width, height=st.height, sigma_image=0.1, min_lost=2, min_tracked=3, use_parallax=True,
+                       min_parallax=0.0, compress_mode=_lib.COMPRESS_GRAM)
+
+    def fresh():
+        f = BatchedMSCKF(B, L + 16, WINDOW + 4, WINDOW + 2, par)
+        f.P.zero_(); f.n_cams.zero_(); f.feat_len.zero_()
+        f.Qc_diag.copy_(st.Qc_diag)
+        return f
+
+    kw = dict(min_cosine_similarity=0.82, epipolar_rejection_threshold=1e9, homography_rejection_threshold=1e9)
+    eager, graphed = fresh(), fresh()
+    before = graphed.snapshot()
+    fg = graphed.capture_frame_graph(*st.frame_inputs(0)[:1], st.R_I_C, st.t_I_C, *st.frame_inputs(0)[1:], WINDOW, **kw)
+    after = graphed.snapshot()
+    assert torch.equal(before["P"], after["P"]) and torch.equal(before["small_slab"], after["small_slab"])
+    assert all(torch.equal(before["tracks"][k], after["tracks"][k]) for k in before["tracks"])
+    for f in range(NF):
+        smp, desc, kp, sc, cnt = st.frame_inputs(f)
+        eager.frame_step_detections(smp, st.R_I_C, st.t_I_C, desc, kp, sc, cnt, WINDOW, **kw)
+        fg.step(smp, desc, kp, sc, cnt)
+    torch.cuda.synchronize()
+    eager.check_window_overflow()
+    graphed.check_window_overflow()
+    assert int(eager.n_cams.max()) >= WINDOW                 # the window filled up and was pruned on the way
+    assert torch.equal(eager.n_cams, graphed.n_cams) and torch.equal(eager.feat_len, graphed.feat_len)
+    assert torch.equal(eager.P, graphed.P) and torch.equal(eager.imu_state, graphed.imu_state)
+    assert torch.equal(eager.obs_uv, graphed.obs_uv) and torch.equal(eager.obs_slot, graphed.obs_slot)
+    assert torch.equal(eager.obs_desc, graphed.obs_desc) and torch.equal(eager.lcm_desc, graphed.lcm_desc)
