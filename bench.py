@@ -922,7 +922,7 @@ def run_gpu_stream(args):
     n_tracks = (flt.feat_len > 0).sum(1).to(torch.int32)
     m12, m21, action, new_uv, new_conf, _ = flt.match_descriptors(flt.lcm_desc, desc, 0.82, n_tracks, cnt, kp, sc)
     flt.verify_matches(action, new_uv, 1e9, 1e9)
-    flt.append_descriptors(action, m12, m21, n_tracks, cnt, desc)
+    flt.append_descriptors(action, m12, m21, n_tracks, cnt, desc, new_conf)
     flt.append_observations(action, new_uv, new_conf)
     sub = dict(P=flt.P.clone(), slab=flt.small_slab.clone(), m=flt.idp_m.clone(), rho=flt.idp_rho.clone())
     Nw = int(flt.n_cams.max().item())

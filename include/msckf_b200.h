@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSCKF_B200_ABI_VERSION 9
+#define MSCKF_B200_ABI_VERSION 10
 
 /* error codes (negative); positive return values are cudaError_t */
 #define MSCKF_EINVAL (-1)      /* null pointer / non-positive dimension */
@@ -372,15 +372,24 @@ int msckf_filter_step_host(const msckf_dims* dims, const msckf_update_params* pa
  *   camera's descriptors leave a track's mean one frame after they left its list; a filter that returned early from
  *   add_camera_measurements (no detections / no match, MSCKF.py:286, 320) keeps its old rows: keep_old[B] (may be NULL)
  *   marks those filters.  Rows of deleted tracks follow msckf_compact_descriptors_batched (called with dims->M = 1).
+ * Running sums (optional, NULL = not kept): desc_sum[B][F][D + 2] float64 = (sum_i w_i d_i | sum_i w_i | pad) per track, w_i =
+ *   the observation's score.  msckf_append_descriptors_batched adds the new observation (new_conf[B][F] = its score per track
+ *   slot, the array msckf_append_observations_batched stores as obs_conf), msckf_drop_descriptors_batched subtracts the rows
+ *   that leave (obs_conf = the scores of the lists), the in-place compaction moves the records with their tracks (dims->M = 1,
+ *   D' = 2 (D + 2) floats), msckf_track_descriptors_batched(desc_sum_out) rebuilds them from the lists, and
+ *   msckf_track_descriptors_from_sums_batched produces the same rows as msckf_track_descriptors_batched from D + 2 doubles per
+ *   track instead of its whole list (the two differ by FP64 summation order only, i.e. below the float32 rounding of the rows).
  * ------------------------------------------------------------------------------------------------------------- */
 int msckf_score_filter_batched(int B, int F_new, int D, const int* n_in, const double* scores, const double* kp,
                                const float* desc, double* scores_out, double* kp_out, float* desc_out, int* n_out,
                                void* stream);
 int msckf_append_descriptors_batched(const msckf_dims* dims, int D, int F_new, const unsigned char* action,
                                      const int* match12, const int* match21, const int* n_tracks, const int* n_new,
-                                     const float* desc_new, const int* feat_len, float* obs_desc, void* stream);
+                                     const float* desc_new, const int* feat_len, float* obs_desc, const double* new_conf,
+                                     double* desc_sum, void* stream);
 int msckf_drop_descriptors_batched(const msckf_dims* dims, int D, const unsigned char* remove_mask, const int* feat_len,
-                                   const int* obs_slot, float* obs_desc, void* stream);
+                                   const int* obs_slot, float* obs_desc, const double* obs_conf, double* desc_sum,
+                                   void* stream);
 int msckf_compact_descriptors_batched(const msckf_dims* dims, int D, const int* dest, const int* feat_len_dst,
                                       const float* src, float* dst, void* stream);
 /* in-place variant for msckf_compact_tracks_inplace_batched: desc is compacted where it lies, scratch stages the rows that
@@ -389,7 +398,9 @@ int msckf_compact_descriptors_inplace_batched(const msckf_dims* dims, int D, con
                                               float* desc, float* scratch, int zero_deleted, void* stream);
 int msckf_track_descriptors_batched(const msckf_dims* dims, int D, const int* feat_len, const double* obs_conf,
                                     const float* obs_desc, const unsigned char* keep_old, float* desc_tracks,
-                                    void* stream);
+                                    double* desc_sum_out, void* stream);
+int msckf_track_descriptors_from_sums_batched(const msckf_dims* dims, int D, const int* feat_len, const double* desc_sum,
+                                              const unsigned char* keep_old, float* desc_tracks, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Data synthesis and metrics on the device: a Monte-Carlo run builds its streams and reduces

@@ -11,7 +11,7 @@ COMPRESS_GRAM = 1
 FEAT_SKIPPED, FEAT_ACCEPTED, FEAT_GATED_OUT, FEAT_LOST_DISCARD, FEAT_LOST_FLAG = 0, 1, 2, 3, 0x10
 FEAT_GAMMA_BOUND = 0x20
 FEAT_TRIANGULATED = 0x40
-ABI_VERSION = 9
+ABI_VERSION = 10
 GATE_EXACT, GATE_BOUNDS = 0, 1
 
 
@@ -72,7 +72,7 @@ EXPORTS = [
     "msckf_synth_imu_batched", "msckf_project_landmarks_batched", "msckf_metrics_state_doubles",
     "msckf_metrics_step_batched", "msckf_metrics_finalize_batched",
     "msckf_score_filter_batched", "msckf_append_descriptors_batched", "msckf_drop_descriptors_batched",
-    "msckf_compact_descriptors_batched", "msckf_track_descriptors_batched",
+    "msckf_compact_descriptors_batched", "msckf_track_descriptors_batched", "msckf_track_descriptors_from_sums_batched",
     "msckf_compact_tracks_inplace_batched", "msckf_compact_descriptors_inplace_batched",
 ]
 
@@ -163,15 +163,17 @@ def load_library():
     lib.msckf_score_filter_batched.restype = C.c_int
     lib.msckf_score_filter_batched.argtypes = [C.c_int, C.c_int, C.c_int, ip, dp, dp, dp, dp, dp, dp, ip, vp]
     lib.msckf_append_descriptors_batched.restype = C.c_int
-    lib.msckf_append_descriptors_batched.argtypes = [pd, C.c_int, C.c_int, u8, ip, ip, ip, ip, dp, ip, dp, vp]
+    lib.msckf_append_descriptors_batched.argtypes = [pd, C.c_int, C.c_int, u8, ip, ip, ip, ip, dp, ip, dp, dp, dp, vp]
     lib.msckf_drop_descriptors_batched.restype = C.c_int
-    lib.msckf_drop_descriptors_batched.argtypes = [pd, C.c_int, u8, ip, ip, dp, vp]
+    lib.msckf_drop_descriptors_batched.argtypes = [pd, C.c_int, u8, ip, ip, dp, dp, dp, vp]
     lib.msckf_compact_descriptors_batched.restype = C.c_int
     lib.msckf_compact_descriptors_batched.argtypes = [pd, C.c_int, ip, ip, dp, dp, vp]
     lib.msckf_compact_descriptors_inplace_batched.restype = C.c_int
     lib.msckf_compact_descriptors_inplace_batched.argtypes = [pd, C.c_int, ip, ip, dp, dp, C.c_int, vp]
     lib.msckf_track_descriptors_batched.restype = C.c_int
-    lib.msckf_track_descriptors_batched.argtypes = [pd, C.c_int, ip, dp, dp, u8, dp, vp]
+    lib.msckf_track_descriptors_batched.argtypes = [pd, C.c_int, ip, dp, dp, u8, dp, dp, vp]
+    lib.msckf_track_descriptors_from_sums_batched.restype = C.c_int
+    lib.msckf_track_descriptors_from_sums_batched.argtypes = [pd, C.c_int, ip, dp, u8, dp, vp]
     if lib.msckf_abi_version() != ABI_VERSION:
         raise LibraryNotBuilt("libmsckf_b200.so ABI version mismatch; rebuild with `make`")
     _LIB = lib

@@ -144,7 +144,9 @@ class BatchedMSCKF:
         self.obs_desc = None                     # [B, F, M, D] float32: Feature.descriptors, one row per observation
         self._alt_desc = None
         self.lcm_desc = None                     # [B, F, D] float32: last_camera_measurement.descriptors (the matcher's view)
+        self.desc_sum = None                     # [B, F, D + 2] float64: running (sum_i w_i d_i | sum_i w_i | pad) of every track's list
         self._alt_lcm = None
+        self._alt_sum = None
         self.desc_dim = 0
         self.feature_updates = None              # device int64: features that went through rows 3-8 (set count_feature_updates)
         self.count_feature_updates = False
@@ -393,7 +395,8 @@ class BatchedMSCKF:
         descriptors (if this batch keeps them) lose the same rows (:764-765)."""
         if self.obs_desc is not None:
             rc = self.lib.msckf_drop_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(mask), _ptr(self.feat_len),
-                                                         _ptr(self.obs_slot), _ptr(self.obs_desc), self._stream())
+                                                         _ptr(self.obs_slot), _ptr(self.obs_desc), _ptr(self.obs_conf),
+                                                         _ptr(self.desc_sum), self._stream())
             _lib.check(rc, "msckf_drop_descriptors_batched")
         rc = self.lib.msckf_drop_observations_batched(C.byref(self.dims), _ptr(mask), _ptr(self.n_cams), _ptr(self.cam_t),
                                                       _ptr(self.feat_len), _ptr(self.obs_uv), _ptr(self.obs_dir),
@@ -426,6 +429,7 @@ class BatchedMSCKF:
             if self._alt_desc is None:
                 self._alt_desc = torch.zeros_like(self.obs_desc)
                 self._alt_lcm = torch.zeros_like(self.lcm_desc)
+                self._alt_sum = torch.zeros_like(self.desc_sum)
             rc = self.lib.msckf_compact_descriptors_inplace_batched(C.byref(self.dims), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
                                                                     _ptr(self.obs_desc), _ptr(self._alt_desc), 0, self._stream())
             _lib.check(rc, "msckf_compact_descriptors_inplace_batched")
@@ -433,6 +437,10 @@ class BatchedMSCKF:
             d1 = _lib.Dims(self.B, self.F, 1, self.N, self.ldp)
             rc = self.lib.msckf_compact_descriptors_inplace_batched(C.byref(d1), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
                                                                     _ptr(self.lcm_desc), _ptr(self._alt_lcm), 1, self._stream())
+            _lib.check(rc, "msckf_compact_descriptors_inplace_batched")
+            # ... and so do the running sums (rows of D + 2 doubles = 2 (D + 2) floats)
+            rc = self.lib.msckf_compact_descriptors_inplace_batched(C.byref(d1), 2 * (self.desc_dim + 2), _ptr(dest), _ptr(self.feat_len),
+                                                                    _ptr(self.desc_sum), _ptr(self._alt_sum), 1, self._stream())
             _lib.check(rc, "msckf_compact_descriptors_inplace_batched")
         return (active, dest) if return_map else active
 
@@ -476,7 +484,8 @@ class BatchedMSCKF:
             self.desc_dim = int(D)
             self.obs_desc = torch.zeros((self.B, self.F, self.M, D), dtype=torch.float32, device=self.device)
             self.lcm_desc = torch.zeros((self.B, self.F, D), dtype=torch.float32, device=self.device)
-            self._alt_desc = self._alt_lcm = None
+            self.desc_sum = torch.zeros((self.B, self.F, D + 2), dtype=torch.float64, device=self.device)
+            self._alt_desc = self._alt_lcm = self._alt_sum = None
 
     def score_filter(self, desc_new, kp_new, score_new, n_new=None):
         """The score filter of MSCKF.add_camera_measurements (MSCKF.py:279-284) on the device: detections with
@@ -489,22 +498,37 @@ class BatchedMSCKF:
         _lib.check(rc, "msckf_score_filter_batched")
         return do, ko, so, no
 
-    def track_descriptors(self, out=None, keep_old=None):
+    def track_descriptors(self, out=None, keep_old=None, from_lists=False):
         """[B, F, D] float32: the score-weighted mean descriptor of every track over its current descriptor list
-        (np.average(..., weights=scores), MSCKF.py:436-441).  keep_old [B] uint8: filters whose rows of `out` stay."""
+        (np.average(..., weights=scores), MSCKF.py:436-441).  keep_old [B] uint8: filters whose rows of `out` stay.
+        By default from the running sums the append / drop kernels maintain (D + 2 doubles per track); from_lists=True
+        re-reads every list (the two agree to FP64 summation order, i.e. below the float32 rounding of the rows)."""
         if out is None:
             out = torch.empty((self.B, self.F, self.desc_dim), dtype=torch.float32, device=self.device)
-        rc = self.lib.msckf_track_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(self.feat_len), _ptr(self.obs_conf),
-                                                      _ptr(self.obs_desc), _ptr(keep_old), _ptr(out), self._stream())
-        _lib.check(rc, "msckf_track_descriptors_batched")
+        if from_lists:
+            rc = self.lib.msckf_track_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(self.feat_len), _ptr(self.obs_conf),
+                                                          _ptr(self.obs_desc), _ptr(keep_old), _ptr(out), None, self._stream())
+            _lib.check(rc, "msckf_track_descriptors_batched")
+        else:
+            rc = self.lib.msckf_track_descriptors_from_sums_batched(C.byref(self.dims), self.desc_dim, _ptr(self.feat_len),
+                                                                    _ptr(self.desc_sum), _ptr(keep_old), _ptr(out), self._stream())
+            _lib.check(rc, "msckf_track_descriptors_from_sums_batched")
         return out
 
-    def append_descriptors(self, action, match12, match21, n_tracks, n_new, desc_new):
-        """feature.descriptors.append(...) for the accepted matches and the new tracks (MSCKF.py:407, 425); call with the
-        final actions and before append_observations."""
+    def rebuild_descriptor_sums(self):
+        """The running sums recomputed from the lists (after the lists were written directly, e.g. loaded from a checkpoint)."""
+        rc = self.lib.msckf_track_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(self.feat_len), _ptr(self.obs_conf),
+                                                      _ptr(self.obs_desc), None, None, _ptr(self.desc_sum), self._stream())
+        _lib.check(rc, "msckf_track_descriptors_batched")
+
+    def append_descriptors(self, action, match12, match21, n_tracks, n_new, desc_new, new_conf):
+        """feature.descriptors.append(...) / feature.scores.append(...) for the accepted matches and the new tracks
+        (MSCKF.py:407-408, 425-427); call with the final actions and before append_observations.  new_conf [B, F] = the
+        score of the detection every track slot receives (what append_observations stores as obs_conf)."""
         rc = self.lib.msckf_append_descriptors_batched(C.byref(self.dims), self.desc_dim, int(desc_new.shape[1]), _ptr(action),
                                                        _ptr(match12), _ptr(match21), _ptr(n_tracks), _ptr(n_new), _ptr(desc_new),
-                                                       _ptr(self.feat_len), _ptr(self.obs_desc), self._stream())
+                                                       _ptr(self.feat_len), _ptr(self.obs_desc), _ptr(new_conf), _ptr(self.desc_sum),
+                                                       self._stream())
         _lib.check(rc, "msckf_append_descriptors_batched")
 
     def frame_step_detections(self, samples, R_I_C, t_I_C, desc_new, kp_new, score_new, n_new, max_cameras,
@@ -533,7 +557,7 @@ class BatchedMSCKF:
         skip = (n_new <= 0) | ((n_tracks > 0) & ((m12 >= 0).sum(1) == 0))
         action.masked_fill_(skip[:, None], 0)
         verdict = self.verify_matches(action, new_uv, epipolar_rejection_threshold, homography_rejection_threshold, counters)
-        self.append_descriptors(action, m12, m21, n_tracks, n_new, desc_new)
+        self.append_descriptors(action, m12, m21, n_tracks, n_new, desc_new, new_conf)
         self.append_observations(action, new_uv, new_conf)
         self.track_descriptors(out=self.lcm_desc, keep_old=skip.to(torch.uint8))      # MSCKF.py:436-441
         self.process_features()
@@ -554,7 +578,8 @@ class BatchedMSCKF:
         snap = dict(P=self.P.clone(), small_slab=self.small_slab.clone(), n_cams=self.n_cams.clone(),
                     tracks={n: getattr(self, n).clone() for n in _lib.TRACK_FIELDS},
                     obs_desc=None if self.obs_desc is None else self.obs_desc.clone(),
-                    lcm_desc=None if self.lcm_desc is None else self.lcm_desc.clone())
+                    lcm_desc=None if self.lcm_desc is None else self.lcm_desc.clone(),
+                    desc_sum=None if self.desc_sum is None else self.desc_sum.clone())
         return snap
 
     def restore(self, snap):
@@ -566,6 +591,7 @@ class BatchedMSCKF:
         if snap["obs_desc"] is not None:
             self.obs_desc.copy_(snap["obs_desc"])
             self.lcm_desc.copy_(snap["lcm_desc"])
+            self.desc_sum.copy_(snap["desc_sum"])
 
     def prune_poorest_camera_states(self, max_select=2, prune_above=-1, return_map=False):
         """MSCKF.prune_poorest_camera_states (MSCKF.py:710-737) for every filter, everything resident: select the two

@@ -74,21 +74,34 @@ __global__ void __launch_bounds__(DT) append_descriptors_kernel(msckf_dims dims,
                                                                 const int* __restrict__ match12, const int* __restrict__ match21,
                                                                 const int* __restrict__ n_tracks, const int* __restrict__ n_new,
                                                                 const float* __restrict__ desc_new, const int* __restrict__ feat_len,
-                                                                float* __restrict__ obs_desc) {
+                                                                float* __restrict__ obs_desc, const double* __restrict__ new_conf,
+                                                                double* __restrict__ desc_sum) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = dims.F, M = dims.M;
     const int n1 = n_tracks ? min(max(n_tracks[b], 0), F) : F;
     const int n2 = n_new ? min(max(n_new[b], 0), F2) : F2;
-    const int q4 = D / 4;
-    // matched tracks: warp per track, 16-byte pieces per lane
-    for (int j = warp; j < n1; j += DT / 32) {
-        const size_t fj = (size_t)b * F + j;
-        if (action[fj] != 2) continue;
-        const int src = match12[fj], len = feat_len[fj];
-        if (src < 0 || len >= M) continue;
-        const float4* s = reinterpret_cast<const float4*>(desc_new + ((size_t)b * F2 + src) * D);
-        float4* d = reinterpret_cast<float4*>(obs_desc + ((fj * M) + len) * D);
-        for (int e = lane; e < q4; e += 32) d[e] = s[e];
+    const int q4 = D / 4, DS = D + 2;
+    // matched tracks: q4 = D / 4 lanes per track (16-byte pieces), 32 / q4 tracks per warp at a time; the running sums
+    // sum_i w_i d_i | sum_i w_i follow
+    {
+        const int rpp = (q4 <= 32 && (32 % q4) == 0) ? 32 / q4 : 1;
+        const int piece = lane % q4, sub = lane / q4;
+        const bool lane_on = rpp > 1 || lane < q4;
+        for (int j = warp * rpp + sub; j < n1 && lane_on; j += (DT / 32) * rpp) {
+            const size_t fj = (size_t)b * F + j;
+            if (action[fj] != 2) continue;
+            const int src = match12[fj], len = feat_len[fj];
+            if (src < 0 || len >= M) continue;
+            const float4 v = *reinterpret_cast<const float4*>(desc_new + ((size_t)b * F2 + src) * D + 4 * piece);
+            *reinterpret_cast<float4*>(obs_desc + ((fj * M) + len) * D + 4 * piece) = v;
+            if (desc_sum) {
+                const double w = new_conf[fj];
+                double* a = desc_sum + fj * DS + 4 * piece;
+                if (len == 0) { a[0] = w * (double)v.x; a[1] = w * (double)v.y; a[2] = w * (double)v.z; a[3] = w * (double)v.w; }
+                else { a[0] += w * (double)v.x; a[1] += w * (double)v.y; a[2] += w * (double)v.z; a[3] += w * (double)v.w; }
+                if (piece == 0) desc_sum[fj * DS + D] = (len == 0 ? 0.0 : desc_sum[fj * DS + D]) + w;
+            }
+        }
     }
     // new tracks: the r-th unmatched detection (ascending) went to slot n1 + r (np.setdiff1d order, FeatureExtractor.py:73)
     __shared__ int s_cnt[DT / 32], s_base;
@@ -105,9 +118,19 @@ __global__ void __launch_bounds__(DT) append_descriptors_kernel(msckf_dims dims,
         if (un) {
             const int slot = n1 + off + __popc(bal & ((1u << lane) - 1u));
             if (slot < F && action[(size_t)b * F + slot] == 3) {
+                const size_t fs = (size_t)b * F + slot;
                 const float4* s = reinterpret_cast<const float4*>(desc_new + ((size_t)b * F2 + j) * D);
-                float4* d = reinterpret_cast<float4*>(obs_desc + (((size_t)b * F + slot) * M) * D);
-                for (int e = 0; e < q4; ++e) d[e] = s[e];
+                float4* d = reinterpret_cast<float4*>(obs_desc + (fs * M) * D);
+                const double w = desc_sum ? new_conf[fs] : 0.0;
+                for (int e = 0; e < q4; ++e) {
+                    const float4 v = s[e];
+                    d[e] = v;
+                    if (desc_sum) {
+                        double* a = desc_sum + fs * DS + 4 * e;
+                        a[0] = w * (double)v.x; a[1] = w * (double)v.y; a[2] = w * (double)v.z; a[3] = w * (double)v.w;
+                    }
+                }
+                if (desc_sum) desc_sum[fs * DS + D] = w;
             }
         }
         __syncthreads();
@@ -124,7 +147,8 @@ __global__ void __launch_bounds__(DT) append_descriptors_kernel(msckf_dims dims,
 // Runs BEFORE msckf_drop_observations_batched (same mask; obs_slot / feat_len still describe the window before the deletion).
 __global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, int D, const unsigned char* __restrict__ remove_mask,
                                                               const int* __restrict__ feat_len, const int* __restrict__ obs_slot,
-                                                              float* __restrict__ obs_desc) {
+                                                              float* __restrict__ obs_desc, const double* __restrict__ obs_conf,
+                                                              double* __restrict__ desc_sum) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
     const int F = dims.F, M = dims.M, N = dims.N;
@@ -138,20 +162,57 @@ __global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, i
     const size_t fj = (size_t)b * F + j;
     const int len = min(feat_len[fj], M);
     if (len <= 0) return;
-    const int q4 = D / 4;
-    int w = 0;
-    bool moved = false;
-    for (int i = 0; i < len; ++i) {      // (uniform per warp: the track's observations in order)
-        const int s = obs_slot[fj * M + i];
-        const bool gone = s >= 0 && s < N && remove_mask[(size_t)b * N + s] != 0;
-        if (gone) { moved = true; continue; }
-        if (moved) {
-            const float4* src = reinterpret_cast<const float4*>(obs_desc + (fj * M + i) * D);
-            float4* dst = reinterpret_cast<float4*>(obs_desc + (fj * M + w) * D);
-            for (int e = lane; e < q4; e += 32) dst[e] = src[e];
-            __syncwarp();
+    const int q4 = D / 4, DS = D + 2;
+    // rows move up in parallel: lane l of a pass handles piece l % q4 of row (pass rows) + l / q4; every row of a pass is
+    // loaded before any is stored (a row only ever moves towards the front, so a pass never overwrites a later pass's source)
+    const int rpp = (q4 <= 32 && (32 % q4) == 0) ? 32 / q4 : 1;
+    const int piece = lane % q4, sub = lane / q4;
+    const bool lane_on = rpp > 1 || lane < q4;
+    int kept = 0;
+    double wgone = 0.0;
+    bool any_gone = false;
+    for (int i0 = 0; i0 < len; i0 += 32) {
+        const int i = i0 + lane;
+        const int sl = (i < len) ? obs_slot[fj * M + i] : -1;
+        const bool gone = i < len && sl >= 0 && sl < N && remove_mask[(size_t)b * N + sl] != 0;
+        const unsigned gm = __ballot_sync(0xffffffffu, gone);
+        const unsigned lm = __ballot_sync(0xffffffffu, i < len);
+        const unsigned km = lm & ~gm;
+        if (desc_sum && gm) {          // the rows that leave also leave the running sums
+            for (unsigned m = gm; m; m &= m - 1) {
+                const int r = i0 + __ffs(m) - 1;
+                const double w = obs_conf[fj * M + r];
+                if (lane < q4) {
+                    const float4 v = *reinterpret_cast<const float4*>(obs_desc + (fj * M + r) * D + 4 * lane);
+                    double* a = desc_sum + fj * DS + 4 * lane;
+                    a[0] -= w * (double)v.x; a[1] -= w * (double)v.y; a[2] -= w * (double)v.z; a[3] -= w * (double)v.w;
+                }
+                wgone += w;
+            }
         }
-        ++w;
+        any_gone |= gm != 0;
+        if (any_gone) {
+            const int nrows = 32 - __clz(lm);                      // rows of this chunk (ballot of the live lanes)
+            for (int r0 = 0; r0 < nrows; r0 += rpp) {
+                const int r = r0 + sub;                             // row of the chunk this lane helps to move
+                const bool mv = lane_on && r < nrows && ((km >> r) & 1u);
+                const int dst = kept + __popc(km & ((1u << r) - 1u));
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mv && dst != i0 + r) v = *reinterpret_cast<const float4*>(obs_desc + (fj * M + i0 + r) * D + 4 * piece);
+                __syncwarp();
+                if (mv && dst != i0 + r) *reinterpret_cast<float4*>(obs_desc + (fj * M + dst) * D + 4 * piece) = v;
+                __syncwarp();
+            }
+        }
+        kept += __popc(km);
+    }
+    if (desc_sum && any_gone && lane == 0) {
+        if (kept == 0) desc_sum[fj * DS + D] = 0.0;
+        else desc_sum[fj * DS + D] -= wgone;
+    }
+    if (desc_sum && any_gone && kept == 0 && lane < q4) {          // an emptied track: exact zeros, not rounding residue
+        double* a = desc_sum + fj * DS + 4 * lane;
+        a[0] = a[1] = a[2] = a[3] = 0.0;
     }
 }
 
@@ -221,11 +282,13 @@ __global__ void __launch_bounds__(DT) compact_descriptors_inplace_kernel(msckf_d
 __global__ void __launch_bounds__(DT) track_descriptors_kernel(msckf_dims dims, int D, const int* __restrict__ feat_len,
                                                                const double* __restrict__ obs_conf, const float* __restrict__ obs_desc,
                                                                const unsigned char* __restrict__ keep_old,
-                                                               float* __restrict__ desc_tracks) {
+                                                               float* __restrict__ desc_tracks, double* __restrict__ desc_sum_out) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
     const int F = dims.F, M = dims.M;
-    if (j >= F || (keep_old && keep_old[b])) return;
+    if (j >= F) return;
+    const bool skip_rows = keep_old && keep_old[b];
+    if (skip_rows && !desc_sum_out) return;
     const size_t fj = (size_t)b * F + j;
     const int len = min(feat_len[fj], M);
     // a descriptor row is D / 4 float4 pieces: lane l handles piece l % q4 of the rows l / q4, l / q4 + 32 / q4, ... (D = 32:
@@ -251,17 +314,45 @@ __global__ void __launch_bounds__(DT) track_descriptors_kernel(msckf_dims dims, 
         wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
     }
     if (lane < q4) {
-        const double inv = (len > 0 && wsum != 0.0) ? 1.0 / wsum : 0.0;
-        *reinterpret_cast<float4*>(desc_tracks + fj * D + 4 * lane) =
-            make_float4((float)(a0 * inv), (float)(a1 * inv), (float)(a2 * inv), (float)(a3 * inv));
+        if (desc_sum_out) {                   // (re)build the running sums from the lists
+            double* a = desc_sum_out + fj * (D + 2) + 4 * lane;
+            a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
+            if (lane == 0) desc_sum_out[fj * (D + 2) + D] = wsum;
+        }
+        if (!skip_rows && desc_tracks) {
+            const double inv = (len > 0 && wsum != 0.0) ? 1.0 / wsum : 0.0;
+            *reinterpret_cast<float4*>(desc_tracks + fj * D + 4 * lane) =
+                make_float4((float)(a0 * inv), (float)(a1 * inv), (float)(a2 * inv), (float)(a3 * inv));
+        }
+    }
+}
+
+// the same rows from the running sums (sum_i w_i d_i | sum_i w_i, FP64) the append / drop kernels maintain: D + 2 doubles per
+// track instead of its whole list (128 bytes per observation at D = 32)
+__global__ void __launch_bounds__(DT) track_descriptors_sums_kernel(msckf_dims dims, int D, const int* __restrict__ feat_len,
+                                                                    const double* __restrict__ desc_sum,
+                                                                    const unsigned char* __restrict__ keep_old,
+                                                                    float* __restrict__ desc_tracks) {
+    const int b = blockIdx.y;
+    if (keep_old && keep_old[b]) return;
+    const int q4 = D / 4;
+    const int F = dims.F;
+    for (int e = blockIdx.x * DT + threadIdx.x; e < F * q4; e += gridDim.x * DT) {
+        const int j = e / q4, p = e - j * q4;
+        const size_t fj = (size_t)b * F + j;
+        const double* a = desc_sum + fj * (D + 2);
+        const double wsum = a[D];
+        const double inv = (feat_len[fj] > 0 && wsum != 0.0) ? 1.0 / wsum : 0.0;
+        *reinterpret_cast<float4*>(desc_tracks + fj * D + 4 * p) =
+            make_float4((float)(a[4 * p] * inv), (float)(a[4 * p + 1] * inv), (float)(a[4 * p + 2] * inv), (float)(a[4 * p + 3] * inv));
     }
 }
 
 }  // namespace
 
-static int check_desc(const msckf_dims* d, int D) {
+static int check_desc(const msckf_dims* d, int D, int Dmax = 128) {
     if (!d || d->B <= 0 || d->F <= 0 || d->M <= 0 || d->N <= 0) return MSCKF_EINVAL;
-    if (D <= 0 || D > 128 || (D & 3)) return MSCKF_ECAPACITY;
+    if (D <= 0 || D > Dmax || (D & 3)) return MSCKF_ECAPACITY;
     if (d->B > 65535) return MSCKF_ECAPACITY;
     return 0;
 }
@@ -279,23 +370,26 @@ int msckf_score_filter_batched(int B, int F2, int D, const int* n_in, const doub
 
 int msckf_append_descriptors_batched(const msckf_dims* dims, int D, int F_new, const unsigned char* action, const int* match12,
                                      const int* match21, const int* n_tracks, const int* n_new, const float* desc_new,
-                                     const int* feat_len, float* obs_desc, void* stream) {
+                                     const int* feat_len, float* obs_desc, const double* new_conf, double* desc_sum, void* stream) {
     int rc = check_desc(dims, D);
     if (rc) return rc;
     if (F_new <= 0 || !action || !match12 || !match21 || !desc_new || !feat_len || !obs_desc) return MSCKF_EINVAL;
+    if (desc_sum && !new_conf) return MSCKF_EINVAL;
     append_descriptors_kernel<<<dims->B, DT, 0, (cudaStream_t)stream>>>(*dims, D, F_new, action, match12, match21, n_tracks, n_new,
-                                                                       desc_new, feat_len, obs_desc);
+                                                                       desc_new, feat_len, obs_desc, new_conf, desc_sum);
     msckf_count_launch(1);
     return (int)cudaGetLastError();
 }
 
 int msckf_drop_descriptors_batched(const msckf_dims* dims, int D, const unsigned char* remove_mask, const int* feat_len,
-                                   const int* obs_slot, float* obs_desc, void* stream) {
+                                   const int* obs_slot, float* obs_desc, const double* obs_conf, double* desc_sum, void* stream) {
     int rc = check_desc(dims, D);
     if (rc) return rc;
     if (!remove_mask || !feat_len || !obs_slot || !obs_desc) return MSCKF_EINVAL;
+    if (desc_sum && !obs_conf) return MSCKF_EINVAL;
     dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
-    drop_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, remove_mask, feat_len, obs_slot, obs_desc);
+    drop_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, remove_mask, feat_len, obs_slot, obs_desc, obs_conf,
+                                                                   desc_sum);
     msckf_count_launch(1);
     return (int)cudaGetLastError();
 }
@@ -313,7 +407,7 @@ int msckf_compact_descriptors_batched(const msckf_dims* dims, int D, const int* 
 
 int msckf_compact_descriptors_inplace_batched(const msckf_dims* dims, int D, const int* dest, const int* feat_len_new, float* desc,
                                               float* scratch, int zero_deleted, void* stream) {
-    int rc = check_desc(dims, D);
+    int rc = check_desc(dims, D, 1024);      // (also moves the rows of the running sums: 2 (D + 2) floats each)
     if (rc) return rc;
     if (!dest || !feat_len_new || !desc || !scratch || desc == scratch) return MSCKF_EINVAL;
     compact_descriptors_inplace_kernel<<<dims->B, DT, 0, (cudaStream_t)stream>>>(*dims, D, dest, feat_len_new, desc, scratch, zero_deleted);
@@ -322,12 +416,26 @@ int msckf_compact_descriptors_inplace_batched(const msckf_dims* dims, int D, con
 }
 
 int msckf_track_descriptors_batched(const msckf_dims* dims, int D, const int* feat_len, const double* obs_conf,
-                                    const float* obs_desc, const unsigned char* keep_old, float* desc_tracks, void* stream) {
+                                    const float* obs_desc, const unsigned char* keep_old, float* desc_tracks, double* desc_sum_out,
+                                    void* stream) {
     int rc = check_desc(dims, D);
     if (rc) return rc;
-    if (!feat_len || !obs_conf || !obs_desc || !desc_tracks) return MSCKF_EINVAL;
+    if (!feat_len || !obs_conf || !obs_desc || (!desc_tracks && !desc_sum_out)) return MSCKF_EINVAL;
     dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
-    track_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, feat_len, obs_conf, obs_desc, keep_old, desc_tracks);
+    track_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, feat_len, obs_conf, obs_desc, keep_old, desc_tracks,
+                                                                    desc_sum_out);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+int msckf_track_descriptors_from_sums_batched(const msckf_dims* dims, int D, const int* feat_len, const double* desc_sum,
+                                              const unsigned char* keep_old, float* desc_tracks, void* stream) {
+    int rc = check_desc(dims, D);
+    if (rc) return rc;
+    if (!feat_len || !desc_sum || !desc_tracks) return MSCKF_EINVAL;
+    const int work = dims->F * (D / 4);
+    dim3 grid(min(64, (work + DT - 1) / DT), dims->B);
+    track_descriptors_sums_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, feat_len, desc_sum, keep_old, desc_tracks);
     msckf_count_launch(1);
     return (int)cudaGetLastError();
 }

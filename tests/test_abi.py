@@ -27,7 +27,7 @@ def test_library_loads_and_exports():
     lib = ctypes.CDLL(_lib.lib_path())
     for name in _declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.msckf_abi_version() == _lib.ABI_VERSION == 9
+    assert lib.msckf_abi_version() == _lib.ABI_VERSION == 10
     assert lib.msckf_max_obs_per_feature() >= 61
     assert lib.msckf_max_cameras(0) >= 31 and lib.msckf_max_cameras(1) >= 61
 

@@ -361,14 +361,16 @@ def test_descriptor_kernels_vs_oracle():
     flt.obs_conf.copy_(torch.from_numpy(conf))
     flt.obs_desc.copy_(torch.from_numpy(od))
     flt.n_cams.fill_(N)
+    flt.rebuild_descriptor_sums()          # the lists were written directly: the running sums start from them
 
     def check_means(lens_now, conf_now, od_now):
-        got = flt.track_descriptors().cpu().numpy()
-        for b in range(B):
-            for j in range(F):
-                n = int(lens_now[b, j])
-                want = o.track_mean_descriptor(od_now[b, j, :n], conf_now[b, j, :n]).astype(np.float32) if n else np.zeros(D, np.float32)
-                assert np.max(np.abs(got[b, j] - want)) <= 2e-7 * max(1.0, np.max(np.abs(want))), (b, j)
+        # both routes to the matcher's rows: from the running sums (default) and from the lists
+        for got in (flt.track_descriptors().cpu().numpy(), flt.track_descriptors(from_lists=True).cpu().numpy()):
+            for b in range(B):
+                for j in range(F):
+                    n = int(lens_now[b, j])
+                    want = o.track_mean_descriptor(od_now[b, j, :n], conf_now[b, j, :n]).astype(np.float32) if n else np.zeros(D, np.float32)
+                    assert np.max(np.abs(got[b, j] - want)) <= 2e-7 * max(1.0, np.max(np.abs(want))), (b, j)
 
     check_means(lens, conf, od)
     mask = np.zeros((B, N), np.uint8)
@@ -594,3 +596,7 @@ def test_frame_graph_replay_equals_eager_frames():
     assert torch.equal(eager.P, graphed.P) and torch.equal(eager.imu_state, graphed.imu_state)
     assert torch.equal(eager.obs_uv, graphed.obs_uv) and torch.equal(eager.obs_slot, graphed.obs_slot)
     assert torch.equal(eager.obs_desc, graphed.obs_desc) and torch.equal(eager.lcm_desc, graphed.lcm_desc)
+    # the running descriptor sums (appended to / subtracted from over 24 frames of matches, prunings and track deletions)
+    # still give the rows a fresh pass over the lists gives
+    a, b = eager.track_descriptors(), eager.track_descriptors(from_lists=True)
+    assert float((a - b).abs().max()) <= 1e-6 and float(b.abs().max()) > 0.01
