@@ -348,8 +348,11 @@ int msckf_filter_step_host(const msckf_dims* dims, const msckf_update_params* pa
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Track descriptors of the matching front with the reference's list semantics.
- * obs_desc[B][F][M][D] float32 holds Feature.descriptors (one row per observation, aligned with obs_uv / obs_conf; obs_conf
- * IS Feature.scores: Line.confidence is the same number, MSCKF.py:408-410).  D a multiple of 4, <= 128.
+ * obs_desc[B][F][R][D] float32 holds Feature.descriptors, one row per CAMERA of the window (R >= N rows, <= 64): the descriptor
+ * a track observed from the camera in window slot s sits in row cam_row[B][N][s] -- a camera keeps its row for its whole life
+ * (the "camera ring"), so deleting cameras moves no descriptor (rewriting every list cost 2 ms per pruning frame of 4096
+ * filters); the list of a track is its observations in order, obs_slot[i] -> cam_row -> row.  obs_conf IS Feature.scores
+ * (Line.confidence is the same number, MSCKF.py:408-410).  D a multiple of 4, <= 128.
  *
  * msckf_score_filter_batched  <->  MSCKF.add_camera_measurements' score filter (MSCKF.py:279-284): per filter the detections
  *   with score >= 0.5 mean(score) are kept, in order: (scores, kp[.][2], desc[.][D]) of n_in[b] detections (NULL = F_new) ->
@@ -360,8 +363,9 @@ int msckf_filter_step_host(const msckf_dims* dims, const msckf_update_params* pa
  *   msckf_verify_matches_batched) and BEFORE msckf_append_observations_batched: feat_len must still hold the lengths before
  *   the frame.
  * msckf_drop_descriptors_batched  <->  del feature.descriptors[i] / del feature.scores[i] of MSCKF.remove_cameras
- *   (MSCKF.py:764-765).  Same remove_mask as msckf_drop_observations_batched, called BEFORE it (obs_slot / feat_len still
- *   describe the window before the deletion).
+ *   (MSCKF.py:764-765): the rows of the deleted cameras leave the running sums (they simply stop being referenced in
+ *   obs_desc).  Same remove_mask as msckf_drop_observations_batched, called BEFORE it and before
+ *   msckf_descriptor_rows_remove_batched (obs_slot / feat_len / cam_row still describe the window before the deletion).
  * msckf_compact_descriptors_batched  <->  the track deletions (MSCKF.py:739-741, 768-772) for the descriptor lists: every
  *   track moves to the slot dest[B][F] that msckf_compact_tracks_batched returned (-1: deleted); feat_len_dst = the lengths
  *   AFTER the compaction.  src and dst are two different buffers (the caller swaps them like the track arrays).
@@ -386,10 +390,10 @@ int msckf_score_filter_batched(int B, int F_new, int D, const int* n_in, const d
 int msckf_append_descriptors_batched(const msckf_dims* dims, int D, int F_new, const unsigned char* action,
                                      const int* match12, const int* match21, const int* n_tracks, const int* n_new,
                                      const float* desc_new, const int* feat_len, float* obs_desc, const double* new_conf,
-                                     double* desc_sum, void* stream);
+                                     double* desc_sum, int R, const int* n_cams, const int* cam_row, void* stream);
 int msckf_drop_descriptors_batched(const msckf_dims* dims, int D, const unsigned char* remove_mask, const int* feat_len,
-                                   const int* obs_slot, float* obs_desc, const double* obs_conf, double* desc_sum,
-                                   void* stream);
+                                   const int* obs_slot, const float* obs_desc, const double* obs_conf, double* desc_sum, int R,
+                                   const int* cam_row, void* stream);
 int msckf_compact_descriptors_batched(const msckf_dims* dims, int D, const int* dest, const int* feat_len_dst,
                                       const float* src, float* dst, void* stream);
 /* in-place variant for msckf_compact_tracks_inplace_batched: desc is compacted where it lies, scratch stages the rows that
@@ -398,9 +402,16 @@ int msckf_compact_descriptors_inplace_batched(const msckf_dims* dims, int D, con
                                               float* desc, float* scratch, int zero_deleted, void* stream);
 int msckf_track_descriptors_batched(const msckf_dims* dims, int D, const int* feat_len, const double* obs_conf,
                                     const float* obs_desc, const unsigned char* keep_old, float* desc_tracks,
-                                    double* desc_sum_out, void* stream);
+                                    double* desc_sum_out, int R, const int* obs_slot, const int* cam_row, void* stream);
 int msckf_track_descriptors_from_sums_batched(const msckf_dims* dims, int D, const int* feat_len, const double* desc_sum,
                                               const unsigned char* keep_old, float* desc_tracks, void* stream);
+/* the camera ring: msckf_descriptor_rows_assign_batched gives the camera msckf_augment_batched is ABOUT to append (same
+ * `active`, call it first) the lowest free row; msckf_descriptor_rows_remove_batched compacts cam_row like
+ * msckf_remove_cameras_batched compacts the window (same mask, call it first: n_cams still counts the deleted cameras). */
+int msckf_descriptor_rows_assign_batched(const msckf_dims* dims, int R, const int* n_cams, const unsigned char* active,
+                                         int* cam_row, void* stream);
+int msckf_descriptor_rows_remove_batched(const msckf_dims* dims, const int* n_cams, const unsigned char* remove_mask,
+                                         int* cam_row, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Data synthesis and metrics on the device: a Monte-Carlo run builds its streams and reduces

@@ -73,6 +73,7 @@ EXPORTS = [
     "msckf_metrics_step_batched", "msckf_metrics_finalize_batched",
     "msckf_score_filter_batched", "msckf_append_descriptors_batched", "msckf_drop_descriptors_batched",
     "msckf_compact_descriptors_batched", "msckf_track_descriptors_batched", "msckf_track_descriptors_from_sums_batched",
+    "msckf_descriptor_rows_assign_batched", "msckf_descriptor_rows_remove_batched",
     "msckf_compact_tracks_inplace_batched", "msckf_compact_descriptors_inplace_batched",
 ]
 
@@ -163,15 +164,19 @@ def load_library():
     lib.msckf_score_filter_batched.restype = C.c_int
     lib.msckf_score_filter_batched.argtypes = [C.c_int, C.c_int, C.c_int, ip, dp, dp, dp, dp, dp, dp, ip, vp]
     lib.msckf_append_descriptors_batched.restype = C.c_int
-    lib.msckf_append_descriptors_batched.argtypes = [pd, C.c_int, C.c_int, u8, ip, ip, ip, ip, dp, ip, dp, dp, dp, vp]
+    lib.msckf_append_descriptors_batched.argtypes = [pd, C.c_int, C.c_int, u8, ip, ip, ip, ip, dp, ip, dp, dp, dp, C.c_int, ip, ip, vp]
     lib.msckf_drop_descriptors_batched.restype = C.c_int
-    lib.msckf_drop_descriptors_batched.argtypes = [pd, C.c_int, u8, ip, ip, dp, dp, dp, vp]
+    lib.msckf_drop_descriptors_batched.argtypes = [pd, C.c_int, u8, ip, ip, dp, dp, dp, C.c_int, ip, vp]
     lib.msckf_compact_descriptors_batched.restype = C.c_int
     lib.msckf_compact_descriptors_batched.argtypes = [pd, C.c_int, ip, ip, dp, dp, vp]
     lib.msckf_compact_descriptors_inplace_batched.restype = C.c_int
     lib.msckf_compact_descriptors_inplace_batched.argtypes = [pd, C.c_int, ip, ip, dp, dp, C.c_int, vp]
     lib.msckf_track_descriptors_batched.restype = C.c_int
-    lib.msckf_track_descriptors_batched.argtypes = [pd, C.c_int, ip, dp, dp, u8, dp, dp, vp]
+    lib.msckf_track_descriptors_batched.argtypes = [pd, C.c_int, ip, dp, dp, u8, dp, dp, C.c_int, ip, ip, vp]
+    lib.msckf_descriptor_rows_assign_batched.restype = C.c_int
+    lib.msckf_descriptor_rows_assign_batched.argtypes = [pd, C.c_int, ip, u8, ip, vp]
+    lib.msckf_descriptor_rows_remove_batched.restype = C.c_int
+    lib.msckf_descriptor_rows_remove_batched.argtypes = [pd, ip, u8, ip, vp]
     lib.msckf_track_descriptors_from_sums_batched.restype = C.c_int
     lib.msckf_track_descriptors_from_sums_batched.argtypes = [pd, C.c_int, ip, dp, u8, dp, vp]
     if lib.msckf_abi_version() != ABI_VERSION:

@@ -141,10 +141,12 @@ class BatchedMSCKF:
         self._overflow = None
         self.window_overflow = None
         self._alt_tracks = None
-        self.obs_desc = None                     # [B, F, M, D] float32: Feature.descriptors, one row per observation
+        self.obs_desc = None                     # [B, F, R, D] float32: Feature.descriptors, one row per camera of the window
         self._alt_desc = None
         self.lcm_desc = None                     # [B, F, D] float32: last_camera_measurement.descriptors (the matcher's view)
         self.desc_sum = None                     # [B, F, D + 2] float64: running (sum_i w_i d_i | sum_i w_i | pad) of every track's list
+        self.cam_row = None                      # [B, N] int32: descriptor row of the camera in window slot s (the camera ring)
+        self.desc_rows = max(self.M, self.N)     # R: descriptor rows per track (one per camera of the window)
         self._alt_lcm = None
         self._alt_sum = None
         self.desc_dim = 0
@@ -288,6 +290,10 @@ class BatchedMSCKF:
                               *[float(x) for x in np.asarray(t_I_C, float).flatten()])
         if self.window_overflow is None:
             self.window_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if self.cam_row is not None:             # the new camera's descriptor row (lowest free one), before n_cams grows
+            rc = self.lib.msckf_descriptor_rows_assign_batched(C.byref(self.dims), self.desc_rows, _ptr(self.n_cams), _ptr(active),
+                                                               _ptr(self.cam_row), self._stream())
+            _lib.check(rc, "msckf_descriptor_rows_assign_batched")
         rc = self.lib.msckf_augment_batched(C.byref(self.dims), T, _ptr(self.imu_state), _ptr(self.cam_R),
                                             _ptr(self.cam_t), _ptr(self.P), _ptr(self.n_cams), _ptr(active),
                                             _ptr(self.window_overflow), self._stream())
@@ -307,6 +313,10 @@ class BatchedMSCKF:
         if self._remove_ws is None:
             n = self.lib.msckf_remove_workspace_bytes(C.byref(self.dims))
             self._remove_ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+        if self.cam_row is not None:             # the descriptor rows of the deleted cameras become free again
+            rc = self.lib.msckf_descriptor_rows_remove_batched(C.byref(self.dims), _ptr(self.n_cams), _ptr(mask), _ptr(self.cam_row),
+                                                               self._stream())
+            _lib.check(rc, "msckf_descriptor_rows_remove_batched")
         rc = self.lib.msckf_remove_cameras_batched(C.byref(self.dims), _ptr(mask), _ptr(self.cam_R),
                                                    _ptr(self.cam_t), _ptr(self.P), _ptr(self.n_cams),
                                                    _ptr(self._remove_ws), self._remove_ws.numel(), self._stream())
@@ -396,7 +406,7 @@ class BatchedMSCKF:
         if self.obs_desc is not None:
             rc = self.lib.msckf_drop_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(mask), _ptr(self.feat_len),
                                                          _ptr(self.obs_slot), _ptr(self.obs_desc), _ptr(self.obs_conf),
-                                                         _ptr(self.desc_sum), self._stream())
+                                                         _ptr(self.desc_sum), self.desc_rows, _ptr(self.cam_row), self._stream())
             _lib.check(rc, "msckf_drop_descriptors_batched")
         rc = self.lib.msckf_drop_observations_batched(C.byref(self.dims), _ptr(mask), _ptr(self.n_cams), _ptr(self.cam_t),
                                                       _ptr(self.feat_len), _ptr(self.obs_uv), _ptr(self.obs_dir),
@@ -430,7 +440,9 @@ class BatchedMSCKF:
                 self._alt_desc = torch.zeros_like(self.obs_desc)
                 self._alt_lcm = torch.zeros_like(self.lcm_desc)
                 self._alt_sum = torch.zeros_like(self.desc_sum)
-            rc = self.lib.msckf_compact_descriptors_inplace_batched(C.byref(self.dims), self.desc_dim, _ptr(dest), _ptr(self.feat_len),
+            dr = _lib.Dims(self.B, self.F, self.desc_rows, self.N, self.ldp)
+            rows = (self.feat_len > 0).to(torch.int32) * self.desc_rows          # a live track moves all its camera rows
+            rc = self.lib.msckf_compact_descriptors_inplace_batched(C.byref(dr), self.desc_dim, _ptr(dest), _ptr(rows),
                                                                     _ptr(self.obs_desc), _ptr(self._alt_desc), 0, self._stream())
             _lib.check(rc, "msckf_compact_descriptors_inplace_batched")
             # ... and so do their rows of last_camera_measurement (MSCKF.py:742-747, 774-778): one row per track
@@ -482,7 +494,9 @@ class BatchedMSCKF:
     def _ensure_descriptors(self, D):
         if self.obs_desc is None or self.desc_dim != D:
             self.desc_dim = int(D)
-            self.obs_desc = torch.zeros((self.B, self.F, self.M, D), dtype=torch.float32, device=self.device)
+            self.obs_desc = torch.zeros((self.B, self.F, self.desc_rows, D), dtype=torch.float32, device=self.device)
+            # cameras already in the window get the rows 0 .. n-1 in slot order
+            self.cam_row = torch.arange(self.N, dtype=torch.int32, device=self.device).repeat(self.B, 1).contiguous()
             self.lcm_desc = torch.zeros((self.B, self.F, D), dtype=torch.float32, device=self.device)
             self.desc_sum = torch.zeros((self.B, self.F, D + 2), dtype=torch.float64, device=self.device)
             self._alt_desc = self._alt_lcm = self._alt_sum = None
@@ -507,7 +521,8 @@ class BatchedMSCKF:
             out = torch.empty((self.B, self.F, self.desc_dim), dtype=torch.float32, device=self.device)
         if from_lists:
             rc = self.lib.msckf_track_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(self.feat_len), _ptr(self.obs_conf),
-                                                          _ptr(self.obs_desc), _ptr(keep_old), _ptr(out), None, self._stream())
+                                                          _ptr(self.obs_desc), _ptr(keep_old), _ptr(out), None, self.desc_rows,
+                                                          _ptr(self.obs_slot), _ptr(self.cam_row), self._stream())
             _lib.check(rc, "msckf_track_descriptors_batched")
         else:
             rc = self.lib.msckf_track_descriptors_from_sums_batched(C.byref(self.dims), self.desc_dim, _ptr(self.feat_len),
@@ -518,7 +533,8 @@ class BatchedMSCKF:
     def rebuild_descriptor_sums(self):
         """The running sums recomputed from the lists (after the lists were written directly, e.g. loaded from a checkpoint)."""
         rc = self.lib.msckf_track_descriptors_batched(C.byref(self.dims), self.desc_dim, _ptr(self.feat_len), _ptr(self.obs_conf),
-                                                      _ptr(self.obs_desc), None, None, _ptr(self.desc_sum), self._stream())
+                                                      _ptr(self.obs_desc), None, None, _ptr(self.desc_sum), self.desc_rows,
+                                                      _ptr(self.obs_slot), _ptr(self.cam_row), self._stream())
         _lib.check(rc, "msckf_track_descriptors_batched")
 
     def append_descriptors(self, action, match12, match21, n_tracks, n_new, desc_new, new_conf):
@@ -528,7 +544,7 @@ class BatchedMSCKF:
         rc = self.lib.msckf_append_descriptors_batched(C.byref(self.dims), self.desc_dim, int(desc_new.shape[1]), _ptr(action),
                                                        _ptr(match12), _ptr(match21), _ptr(n_tracks), _ptr(n_new), _ptr(desc_new),
                                                        _ptr(self.feat_len), _ptr(self.obs_desc), _ptr(new_conf), _ptr(self.desc_sum),
-                                                       self._stream())
+                                                       self.desc_rows, _ptr(self.n_cams), _ptr(self.cam_row), self._stream())
         _lib.check(rc, "msckf_append_descriptors_batched")
 
     def frame_step_detections(self, samples, R_I_C, t_I_C, desc_new, kp_new, score_new, n_new, max_cameras,
@@ -579,7 +595,8 @@ class BatchedMSCKF:
                     tracks={n: getattr(self, n).clone() for n in _lib.TRACK_FIELDS},
                     obs_desc=None if self.obs_desc is None else self.obs_desc.clone(),
                     lcm_desc=None if self.lcm_desc is None else self.lcm_desc.clone(),
-                    desc_sum=None if self.desc_sum is None else self.desc_sum.clone())
+                    desc_sum=None if self.desc_sum is None else self.desc_sum.clone(),
+                    cam_row=None if self.cam_row is None else self.cam_row.clone())
         return snap
 
     def restore(self, snap):
@@ -592,6 +609,7 @@ class BatchedMSCKF:
             self.obs_desc.copy_(snap["obs_desc"])
             self.lcm_desc.copy_(snap["lcm_desc"])
             self.desc_sum.copy_(snap["desc_sum"])
+            self.cam_row.copy_(snap["cam_row"])
 
     def prune_poorest_camera_states(self, max_select=2, prune_above=-1, return_map=False):
         """MSCKF.prune_poorest_camera_states (MSCKF.py:710-737) for every filter, everything resident: select the two

@@ -75,12 +75,17 @@ __global__ void __launch_bounds__(DT) append_descriptors_kernel(msckf_dims dims,
                                                                 const int* __restrict__ n_tracks, const int* __restrict__ n_new,
                                                                 const float* __restrict__ desc_new, const int* __restrict__ feat_len,
                                                                 float* __restrict__ obs_desc, const double* __restrict__ new_conf,
-                                                                double* __restrict__ desc_sum) {
+                                                                double* __restrict__ desc_sum, const int R,
+                                                                const int* __restrict__ n_cams, const int* __restrict__ cam_row) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = dims.F, M = dims.M;
     const int n1 = n_tracks ? min(max(n_tracks[b], 0), F) : F;
     const int n2 = n_new ? min(max(n_new[b], 0), F2) : F2;
     const int q4 = D / 4, DS = D + 2;
+    // the frame's observations belong to the newest camera (slot n_cams - 1, msckf_append_observations_batched): its row
+    const int nc = min(n_cams[b], dims.N);
+    const int row = nc > 0 ? cam_row[(size_t)b * dims.N + nc - 1] : -1;
+    const bool row_ok = row >= 0 && row < R;
     // matched tracks: q4 = D / 4 lanes per track (16-byte pieces), 32 / q4 tracks per warp at a time; the running sums
     // sum_i w_i d_i | sum_i w_i follow
     {
@@ -91,9 +96,9 @@ __global__ void __launch_bounds__(DT) append_descriptors_kernel(msckf_dims dims,
             const size_t fj = (size_t)b * F + j;
             if (action[fj] != 2) continue;
             const int src = match12[fj], len = feat_len[fj];
-            if (src < 0 || len >= M) continue;
+            if (src < 0 || len >= M || !row_ok) continue;
             const float4 v = *reinterpret_cast<const float4*>(desc_new + ((size_t)b * F2 + src) * D + 4 * piece);
-            *reinterpret_cast<float4*>(obs_desc + ((fj * M) + len) * D + 4 * piece) = v;
+            *reinterpret_cast<float4*>(obs_desc + ((fj * R) + row) * D + 4 * piece) = v;
             if (desc_sum) {
                 const double w = new_conf[fj];
                 double* a = desc_sum + fj * DS + 4 * piece;
@@ -117,10 +122,10 @@ __global__ void __launch_bounds__(DT) append_descriptors_kernel(msckf_dims dims,
         for (int w = 0; w < warp; ++w) off += s_cnt[w];
         if (un) {
             const int slot = n1 + off + __popc(bal & ((1u << lane) - 1u));
-            if (slot < F && action[(size_t)b * F + slot] == 3) {
+            if (slot < F && action[(size_t)b * F + slot] == 3 && row_ok) {
                 const size_t fs = (size_t)b * F + slot;
                 const float4* s = reinterpret_cast<const float4*>(desc_new + ((size_t)b * F2 + j) * D);
-                float4* d = reinterpret_cast<float4*>(obs_desc + (fs * M) * D);
+                float4* d = reinterpret_cast<float4*>(obs_desc + (fs * R + row) * D);
                 const double w = desc_sum ? new_conf[fs] : 0.0;
                 for (int e = 0; e < q4; ++e) {
                     const float4 v = s[e];
@@ -147,13 +152,14 @@ __global__ void __launch_bounds__(DT) append_descriptors_kernel(msckf_dims dims,
 // Runs BEFORE msckf_drop_observations_batched (same mask; obs_slot / feat_len still describe the window before the deletion).
 __global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, int D, const unsigned char* __restrict__ remove_mask,
                                                               const int* __restrict__ feat_len, const int* __restrict__ obs_slot,
-                                                              float* __restrict__ obs_desc, const double* __restrict__ obs_conf,
-                                                              double* __restrict__ desc_sum) {
+                                                              const float* __restrict__ obs_desc, const double* __restrict__ obs_conf,
+                                                              double* __restrict__ desc_sum, const int R,
+                                                              const int* __restrict__ cam_row) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
     const int F = dims.F, M = dims.M, N = dims.N;
     if (j >= F) return;
-    {   // nothing leaves this filter's window: its lists stay as they are (the usual case)
+    {   // nothing leaves this filter's window: its sums stay as they are (the usual case)
         const unsigned char* mk = remove_mask + (size_t)b * N;
         int any = 0;
         for (int s = lane; s < N; s += 32) any |= mk[s];
@@ -163,11 +169,6 @@ __global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, i
     const int len = min(feat_len[fj], M);
     if (len <= 0) return;
     const int q4 = D / 4, DS = D + 2;
-    // rows move up in parallel: lane l of a pass handles piece l % q4 of row (pass rows) + l / q4; every row of a pass is
-    // loaded before any is stored (a row only ever moves towards the front, so a pass never overwrites a later pass's source)
-    const int rpp = (q4 <= 32 && (32 % q4) == 0) ? 32 / q4 : 1;
-    const int piece = lane % q4, sub = lane / q4;
-    const bool lane_on = rpp > 1 || lane < q4;
     int kept = 0;
     double wgone = 0.0;
     bool any_gone = false;
@@ -175,42 +176,28 @@ __global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, i
         const int i = i0 + lane;
         const int sl = (i < len) ? obs_slot[fj * M + i] : -1;
         const bool gone = i < len && sl >= 0 && sl < N && remove_mask[(size_t)b * N + sl] != 0;
+        const int rw = gone ? cam_row[(size_t)b * N + sl] : -1;
         const unsigned gm = __ballot_sync(0xffffffffu, gone);
         const unsigned lm = __ballot_sync(0xffffffffu, i < len);
-        const unsigned km = lm & ~gm;
-        if (desc_sum && gm) {          // the rows that leave also leave the running sums
-            for (unsigned m = gm; m; m &= m - 1) {
-                const int r = i0 + __ffs(m) - 1;
-                const double w = obs_conf[fj * M + r];
-                if (lane < q4) {
-                    const float4 v = *reinterpret_cast<const float4*>(obs_desc + (fj * M + r) * D + 4 * lane);
-                    double* a = desc_sum + fj * DS + 4 * lane;
-                    a[0] -= w * (double)v.x; a[1] -= w * (double)v.y; a[2] -= w * (double)v.z; a[3] -= w * (double)v.w;
-                }
-                wgone += w;
+        for (unsigned m = gm; m; m &= m - 1) {      // the rows that leave also leave the running sums
+            const int src = __ffs(m) - 1;
+            const int r = __shfl_sync(0xffffffffu, rw, src);
+            const double w = obs_conf[fj * M + i0 + src];
+            if (lane < q4 && r >= 0 && r < R) {
+                const float4 v = *reinterpret_cast<const float4*>(obs_desc + (fj * R + r) * D + 4 * lane);
+                double* a = desc_sum + fj * DS + 4 * lane;
+                a[0] -= w * (double)v.x; a[1] -= w * (double)v.y; a[2] -= w * (double)v.z; a[3] -= w * (double)v.w;
             }
+            wgone += w;
         }
         any_gone |= gm != 0;
-        if (any_gone) {
-            const int nrows = 32 - __clz(lm);                      // rows of this chunk (ballot of the live lanes)
-            for (int r0 = 0; r0 < nrows; r0 += rpp) {
-                const int r = r0 + sub;                             // row of the chunk this lane helps to move
-                const bool mv = lane_on && r < nrows && ((km >> r) & 1u);
-                const int dst = kept + __popc(km & ((1u << r) - 1u));
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (mv && dst != i0 + r) v = *reinterpret_cast<const float4*>(obs_desc + (fj * M + i0 + r) * D + 4 * piece);
-                __syncwarp();
-                if (mv && dst != i0 + r) *reinterpret_cast<float4*>(obs_desc + (fj * M + dst) * D + 4 * piece) = v;
-                __syncwarp();
-            }
-        }
-        kept += __popc(km);
+        kept += __popc(lm & ~gm);
     }
-    if (desc_sum && any_gone && lane == 0) {
+    if (any_gone && lane == 0) {
         if (kept == 0) desc_sum[fj * DS + D] = 0.0;
         else desc_sum[fj * DS + D] -= wgone;
     }
-    if (desc_sum && any_gone && kept == 0 && lane < q4) {          // an emptied track: exact zeros, not rounding residue
+    if (any_gone && kept == 0 && lane < q4) {          // an emptied track: exact zeros, not rounding residue
         double* a = desc_sum + fj * DS + 4 * lane;
         a[0] = a[1] = a[2] = a[3] = 0.0;
     }
@@ -282,7 +269,9 @@ __global__ void __launch_bounds__(DT) compact_descriptors_inplace_kernel(msckf_d
 __global__ void __launch_bounds__(DT) track_descriptors_kernel(msckf_dims dims, int D, const int* __restrict__ feat_len,
                                                                const double* __restrict__ obs_conf, const float* __restrict__ obs_desc,
                                                                const unsigned char* __restrict__ keep_old,
-                                                               float* __restrict__ desc_tracks, double* __restrict__ desc_sum_out) {
+                                                               float* __restrict__ desc_tracks, double* __restrict__ desc_sum_out,
+                                                               const int R, const int* __restrict__ obs_slot,
+                                                               const int* __restrict__ cam_row) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
     const int F = dims.F, M = dims.M;
@@ -300,8 +289,11 @@ __global__ void __launch_bounds__(DT) track_descriptors_kernel(msckf_dims dims, 
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, wsum = 0.0;
     if (lane_on) {
         for (int i = sub; i < len; i += rows_per_pass) {
+            const int sl = obs_slot[fj * M + i];
+            const int r = (sl >= 0 && sl < dims.N) ? cam_row[(size_t)b * dims.N + sl] : -1;
+            if (r < 0 || r >= R) continue;
             const double w = obs_conf[fj * M + i];
-            const float4 v = *reinterpret_cast<const float4*>(obs_desc + (fj * M + i) * D + 4 * piece);
+            const float4 v = *reinterpret_cast<const float4*>(obs_desc + (fj * R + r) * D + 4 * piece);
             wsum += w;
             a0 += w * (double)v.x; a1 += w * (double)v.y; a2 += w * (double)v.z; a3 += w * (double)v.w;
         }
@@ -348,6 +340,33 @@ __global__ void __launch_bounds__(DT) track_descriptors_sums_kernel(msckf_dims d
     }
 }
 
+// ---- the camera ring: cam_row[B][N] = descriptor row (0 .. R-1) of the camera in window slot s.  A camera keeps its row for
+//      its whole life, so the deletion of cameras moves no descriptor; rows of deleted cameras are handed out again. ----
+__global__ void ring_assign_kernel(msckf_dims dims, int R, const int* __restrict__ n_cams, const unsigned char* __restrict__ active,
+                                   int* __restrict__ cam_row) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= dims.B || (active && !active[b])) return;
+    const int n = n_cams[b];
+    if (n < 0 || n >= dims.N) return;                 // (a full window: msckf_augment_batched leaves it untouched as well)
+    unsigned long long used = 0ull;
+    for (int s = 0; s < n; ++s) {
+        const int r = cam_row[(size_t)b * dims.N + s];
+        if (r >= 0 && r < 64) used |= 1ull << r;
+    }
+    const int fr = __ffsll((long long)~used) - 1;     // lowest free row
+    cam_row[(size_t)b * dims.N + n] = (fr >= 0 && fr < R) ? fr : -1;
+}
+
+__global__ void ring_remove_kernel(msckf_dims dims, const int* __restrict__ n_cams, const unsigned char* __restrict__ remove_mask,
+                                   int* __restrict__ cam_row) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= dims.B) return;
+    const int n = min(max(n_cams[b], 0), dims.N);
+    int k = 0;
+    for (int s = 0; s < n; ++s)
+        if (!remove_mask[(size_t)b * dims.N + s]) cam_row[(size_t)b * dims.N + k++] = cam_row[(size_t)b * dims.N + s];
+}
+
 }  // namespace
 
 static int check_desc(const msckf_dims* d, int D, int Dmax = 128) {
@@ -370,26 +389,30 @@ int msckf_score_filter_batched(int B, int F2, int D, const int* n_in, const doub
 
 int msckf_append_descriptors_batched(const msckf_dims* dims, int D, int F_new, const unsigned char* action, const int* match12,
                                      const int* match21, const int* n_tracks, const int* n_new, const float* desc_new,
-                                     const int* feat_len, float* obs_desc, const double* new_conf, double* desc_sum, void* stream) {
+                                     const int* feat_len, float* obs_desc, const double* new_conf, double* desc_sum, int R,
+                                     const int* n_cams, const int* cam_row, void* stream) {
     int rc = check_desc(dims, D);
     if (rc) return rc;
-    if (F_new <= 0 || !action || !match12 || !match21 || !desc_new || !feat_len || !obs_desc) return MSCKF_EINVAL;
+    if (F_new <= 0 || !action || !match12 || !match21 || !desc_new || !feat_len || !obs_desc || !n_cams || !cam_row) return MSCKF_EINVAL;
     if (desc_sum && !new_conf) return MSCKF_EINVAL;
+    if (R <= 0 || R > 64) return MSCKF_ECAPACITY;
     append_descriptors_kernel<<<dims->B, DT, 0, (cudaStream_t)stream>>>(*dims, D, F_new, action, match12, match21, n_tracks, n_new,
-                                                                       desc_new, feat_len, obs_desc, new_conf, desc_sum);
+                                                                       desc_new, feat_len, obs_desc, new_conf, desc_sum, R, n_cams,
+                                                                       cam_row);
     msckf_count_launch(1);
     return (int)cudaGetLastError();
 }
 
 int msckf_drop_descriptors_batched(const msckf_dims* dims, int D, const unsigned char* remove_mask, const int* feat_len,
-                                   const int* obs_slot, float* obs_desc, const double* obs_conf, double* desc_sum, void* stream) {
+                                   const int* obs_slot, const float* obs_desc, const double* obs_conf, double* desc_sum, int R,
+                                   const int* cam_row, void* stream) {
     int rc = check_desc(dims, D);
     if (rc) return rc;
-    if (!remove_mask || !feat_len || !obs_slot || !obs_desc) return MSCKF_EINVAL;
-    if (desc_sum && !obs_conf) return MSCKF_EINVAL;
+    if (!remove_mask || !feat_len || !obs_slot || !obs_desc || !obs_conf || !desc_sum || !cam_row) return MSCKF_EINVAL;
+    if (R <= 0 || R > 64) return MSCKF_ECAPACITY;
     dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
     drop_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, remove_mask, feat_len, obs_slot, obs_desc, obs_conf,
-                                                                   desc_sum);
+                                                                   desc_sum, R, cam_row);
     msckf_count_launch(1);
     return (int)cudaGetLastError();
 }
@@ -417,13 +440,14 @@ int msckf_compact_descriptors_inplace_batched(const msckf_dims* dims, int D, con
 
 int msckf_track_descriptors_batched(const msckf_dims* dims, int D, const int* feat_len, const double* obs_conf,
                                     const float* obs_desc, const unsigned char* keep_old, float* desc_tracks, double* desc_sum_out,
-                                    void* stream) {
+                                    int R, const int* obs_slot, const int* cam_row, void* stream) {
     int rc = check_desc(dims, D);
     if (rc) return rc;
-    if (!feat_len || !obs_conf || !obs_desc || (!desc_tracks && !desc_sum_out)) return MSCKF_EINVAL;
+    if (!feat_len || !obs_conf || !obs_desc || (!desc_tracks && !desc_sum_out) || !obs_slot || !cam_row) return MSCKF_EINVAL;
+    if (R <= 0 || R > 64) return MSCKF_ECAPACITY;
     dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
     track_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, feat_len, obs_conf, obs_desc, keep_old, desc_tracks,
-                                                                    desc_sum_out);
+                                                                    desc_sum_out, R, obs_slot, cam_row);
     msckf_count_launch(1);
     return (int)cudaGetLastError();
 }
@@ -436,6 +460,23 @@ int msckf_track_descriptors_from_sums_batched(const msckf_dims* dims, int D, con
     const int work = dims->F * (D / 4);
     dim3 grid(min(64, (work + DT - 1) / DT), dims->B);
     track_descriptors_sums_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, feat_len, desc_sum, keep_old, desc_tracks);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+int msckf_descriptor_rows_assign_batched(const msckf_dims* dims, int R, const int* n_cams, const unsigned char* active, int* cam_row,
+                                         void* stream) {
+    if (!dims || dims->B <= 0 || dims->N <= 0 || !n_cams || !cam_row) return MSCKF_EINVAL;
+    if (R <= 0 || R > 64 || R < dims->N) return MSCKF_ECAPACITY;
+    ring_assign_kernel<<<(dims->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*dims, R, n_cams, active, cam_row);
+    msckf_count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+int msckf_descriptor_rows_remove_batched(const msckf_dims* dims, const int* n_cams, const unsigned char* remove_mask, int* cam_row,
+                                         void* stream) {
+    if (!dims || dims->B <= 0 || dims->N <= 0 || !n_cams || !remove_mask || !cam_row) return MSCKF_EINVAL;
+    ring_remove_kernel<<<(dims->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*dims, n_cams, remove_mask, cam_row);
     msckf_count_launch(1);
     return (int)cudaGetLastError();
 }

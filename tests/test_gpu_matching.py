@@ -359,9 +359,18 @@ def test_descriptor_kernels_vs_oracle():
     flt.feat_len.copy_(torch.from_numpy(lens))
     flt.obs_slot.copy_(torch.from_numpy(slots))
     flt.obs_conf.copy_(torch.from_numpy(conf))
-    flt.obs_desc.copy_(torch.from_numpy(od))
+    # the descriptor of observation i sits in the row of its camera (the camera ring; here a scrambled slot -> row map)
+    R = flt.desc_rows
+    ring = np.stack([rng.permutation(R)[:N] for _ in range(B)]).astype(np.int32)
+    od_ring = np.zeros((B, F, R, D), np.float32)
+    for b in range(B):
+        for j in range(F):
+            for i in range(lens[b, j]):
+                od_ring[b, j, ring[b, slots[b, j, i]]] = od[b, j, i]
+    flt.cam_row.copy_(torch.from_numpy(ring))
+    flt.obs_desc.copy_(torch.from_numpy(od_ring))
     flt.n_cams.fill_(N)
-    flt.rebuild_descriptor_sums()          # the lists were written directly: the running sums start from them
+    flt.rebuild_descriptor_sums()          # the rows were written directly: the running sums start from them
 
     def check_means(lens_now, conf_now, od_now):
         # both routes to the matcher's rows: from the running sums (default) and from the lists
@@ -376,7 +385,10 @@ def test_descriptor_kernels_vs_oracle():
     mask = np.zeros((B, N), np.uint8)
     mask[:, [1, 4]] = 1
     mask[2, 6] = 1
+    before = flt.obs_desc.clone()
     flt.drop_observations(torch.from_numpy(mask).cuda())
+    flt.remove_cameras(torch.from_numpy(mask).cuda())        # (compacts the slot -> row map like the window)
+    assert torch.equal(before, flt.obs_desc)                 # no descriptor moves when cameras leave
     lens2, conf2, od2 = lens.copy(), conf.copy(), od.copy()
     for b in range(B):
         for j in range(F):
