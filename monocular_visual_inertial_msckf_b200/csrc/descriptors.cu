@@ -156,19 +156,18 @@ __global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, i
                                                               double* __restrict__ desc_sum, const int R,
                                                               const int* __restrict__ cam_row) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
     const int F = dims.F, M = dims.M, N = dims.N;
-    if (j >= F) return;
     {   // nothing leaves this filter's window: its sums stay as they are (the usual case)
         const unsigned char* mk = remove_mask + (size_t)b * N;
         int any = 0;
         for (int s = lane; s < N; s += 32) any |= mk[s];
         if (!__any_sync(0xffffffffu, any != 0)) return;
     }
+    const int q4 = D / 4, DS = D + 2;
+    for (int j = blockIdx.x * (DT / 32) + (threadIdx.x >> 5); j < F; j += gridDim.x * (DT / 32)) {
     const size_t fj = (size_t)b * F + j;
     const int len = min(feat_len[fj], M);
-    if (len <= 0) return;
-    const int q4 = D / 4, DS = D + 2;
+    if (len <= 0) continue;
     int kept = 0;
     double wgone = 0.0;
     bool any_gone = false;
@@ -200,6 +199,7 @@ __global__ void __launch_bounds__(DT) drop_descriptors_kernel(msckf_dims dims, i
     if (any_gone && kept == 0 && lane < q4) {          // an emptied track: exact zeros, not rounding residue
         double* a = desc_sum + fj * DS + 4 * lane;
         a[0] = a[1] = a[2] = a[3] = 0.0;
+    }
     }
 }
 
@@ -410,7 +410,7 @@ int msckf_drop_descriptors_batched(const msckf_dims* dims, int D, const unsigned
     if (rc) return rc;
     if (!remove_mask || !feat_len || !obs_slot || !obs_desc || !obs_conf || !desc_sum || !cam_row) return MSCKF_EINVAL;
     if (R <= 0 || R > 64) return MSCKF_ECAPACITY;
-    dim3 grid((dims->F + DT / 32 - 1) / (DT / 32), dims->B);
+    dim3 grid(min(4, (dims->F + DT / 32 - 1) / (DT / 32)), dims->B);
     drop_descriptors_kernel<<<grid, DT, 0, (cudaStream_t)stream>>>(*dims, D, remove_mask, feat_len, obs_slot, obs_desc, obs_conf,
                                                                    desc_sum, R, cam_row);
     msckf_count_launch(1);
