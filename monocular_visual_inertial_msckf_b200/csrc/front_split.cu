@@ -79,6 +79,22 @@ front_geo_kernel(const FrontArgs a, int* __restrict__ pend_key, unsigned char* _
     const int f_begin = blockIdx.x * feats_per_cta;
     const int f_end = min(F, f_begin + feats_per_cta);
     if (f_begin >= f_end) return;
+    {   // a CTA whose tracks are all empty (an update over a subset of the tracks: the pruning update of a filter that does not
+        // prune this frame) only reports them skipped -- one coalesced pass instead of a walk by eight warps
+        int live = 0;
+        for (int j = f_begin + tid; j < f_end; j += FG_THREADS) live |= a.feat_len[(size_t)b * F + j] > 0;
+        if (!__syncthreads_or(live)) {
+            for (int j = f_begin + tid; j < f_end; j += FG_THREADS) {
+                const size_t fj = (size_t)b * F + j;
+                a.feat_status[fj] = MSCKF_FEAT_SKIPPED;
+                a.gamma[fj] = nan("");
+                a.dof[fj] = 0;
+                a.fac_rank[fj] = 0;
+                pend_key[(size_t)bl * F + j] = -1;
+            }
+            return;
+        }
+    }
     {
         const double* camR = a.cam_R + (size_t)b * Ncap * 9;
         const double* camt = a.cam_t + (size_t)b * Ncap * 3;
