@@ -894,7 +894,10 @@ int front_split_map_bytes(const msckf_dims& d) { return front_narrow(d) ? 32 : 6
 
 // filters handled per kernel triple: bounds the tile buffer (23 KB per feature for short tracks, 78 KB at 64 observations)
 int front_split_sub_filters(const msckf_dims& d) {
-    const size_t budget = (size_t)6 << 30;
+#ifndef MSCKF_TILE_BUDGET_GB
+#define MSCKF_TILE_BUDGET_GB 32
+#endif
+    const size_t budget = (size_t)MSCKF_TILE_BUDGET_GB << 30;
     const size_t per_filter = (size_t)(d.F > 0 ? d.F : 1) * front_split_kt_d2(d) * sizeof(double2);
     long long sub = (long long)(budget / per_filter);
     if (sub < 1) sub = 1;

@@ -54,39 +54,45 @@ __device__ __forceinline__ int strip_len(int p, int T) { return min(2 * p + 2, T
 // 8-byte bank pairs (t * 4 + g); the r01k profile of the previous layout (= 8 mod 16) showed 42% conflicted wavefronts.
 
 // Folds one k-panel (KW rows) into this warp's accumulator tiles.  wbase = shared address of panel element [t][g].
-template <int KW, int LDW, int KK = 0>
+template <int KW, int LDW, int UM = UMAX, int UGR = UG, int KK = 0>
 __device__ __forceinline__ void gram_tensor_loop(unsigned wbase, int p0, int J0, int nu, unsigned newstrip,
-                                                 double (&acc)[UMAX][2][2]) {
+                                                 double (&acc)[UM][2][2]) {
     if constexpr (KK < KW) {
         constexpr int KOFF = KK * LDW * 8;
         unsigned abase = wbase + 128u * p0;
         unsigned offb = 64u * J0;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int u0g = 0; u0g < UMAX; u0g += UG) {
+        for (int u0g = 0; u0g < UM; u0g += UGR) {
             if (u0g < nu) {
-                double bf[UG];
+                double bf[UGR];
 #pragma unroll
-                for (int v = 0; v < UG; ++v) {
+                for (int v = 0; v < UGR; ++v) {
                     const int u = u0g + v;
-                    if (u > 0 && ((newstrip >> u) & 1u)) offb = 0;
-                    bf[v] = lds_f64<KOFF>(wbase + offb);
-                    offb += 64u;
+                    if (u < UM) {                        // (the last group may be short)
+                        if (u > 0 && ((newstrip >> u) & 1u)) offb = 0;
+                        bf[v] = lds_f64<KOFF>(wbase + offb);
+                        offb += 64u;
+                    }
                 }
 #pragma unroll
-                for (int v = 0; v < UG; ++v) {
+                for (int v = 0; v < UGR; ++v) {
                     const int u = u0g + v;
-                    if ((newstrip >> u) & 1u) {
-                        a0 = lds_f64<KOFF>(abase);
-                        a1 = lds_f64<KOFF + 64>(abase);
-                        abase += 128u;
+                    if (u < UM) {
+                        constexpr int UL = UM - 1;
+                        const int uu = u < UM ? u : UL;
+                        if ((newstrip >> u) & 1u) {
+                            a0 = lds_f64<KOFF>(abase);
+                            a1 = lds_f64<KOFF + 64>(abase);
+                            abase += 128u;
+                        }
+                        dense::dmma(acc[uu][0][0], acc[uu][0][1], a0, bf[v]);
+                        dense::dmma(acc[uu][1][0], acc[uu][1][1], a1, bf[v]);
                     }
-                    dense::dmma(acc[u][0][0], acc[u][0][1], a0, bf[v]);
-                    dense::dmma(acc[u][1][0], acc[u][1][1], a1, bf[v]);
                 }
             }
         }
-        gram_tensor_loop<KW, LDW, KK + 4>(wbase, p0, J0, nu, newstrip, acc);
+        gram_tensor_loop<KW, LDW, UM, UGR, KK + 4>(wbase, p0, J0, nu, newstrip, acc);
     }
 }
 
@@ -308,11 +314,14 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a) {
             if (pi + 2 < npanels) prefetch(pi + 2, st);
 #pragma unroll 1
             for (int ph = 0; ph < 2; ++ph) {
+#ifndef GRAM_DIAG
+#define GRAM_DIAG 0
+#endif
                 if ((ph == 0) == tensor_first) {
-                    fold_W(st);
+                    if (GRAM_DIAG != 2) fold_W(st);
                 } else if (pi + 1 < npanels) {
-                    scatter(st ^ 1);
-                    if (doX) fold_X(st ^ 1);
+                    if (GRAM_DIAG != 1 && GRAM_DIAG != 3) scatter(st ^ 1);
+                    if (doX && GRAM_DIAG != 1 && GRAM_DIAG != 4) fold_X(st ^ 1);
                 }
             }
             land(st);
@@ -376,6 +385,318 @@ __global__ void __launch_bounds__(GT, 1) gram_kernel(const CompressArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-specialised flavour for windows of up to 32 poses (the benchmark shape).  The profile of gram_kernel above showed the
+// tensor pipe busy 52 % of the time with the DMMAs only 8 % of the instructions: every warp spent two thirds of its issue
+// slots on the operand movement around them (scatter, D / g gathers, prefetch, addresses re-derived under register
+// pressure) and a sixth of its time at the per-panel CTA barrier.  Here the roles are split:
+//   * warps 0-3 (one warpgroup = one warp per scheduler) are PRODUCERS: cp.async prefetch of the factors two panels ahead,
+//     slot -> observation maps, the rows of W of the next panel into one of two shared K-panels, and D / g of the panel
+//     (8 window slots per warp) on the tensor pipe; they give registers back (setmaxnreg.dec);
+//   * warps 4-15 are CONSUMERS: nothing but the W^T W loop, 13 units = 26 accumulator tiles per warp (setmaxnreg.inc),
+//     resident for the whole filter.
+// The two sides meet at named barriers only (full[2]: producers arrive, consumers wait; empty[2]: the other way round),
+// so a consumer never waits for another consumer and the producers run a panel ahead.
+constexpr int WS_PW = 4;            // producer warps
+constexpr int WS_CW = GW - WS_PW;   // consumer warps
+constexpr int WS_UM = 13;           // units per consumer warp: 12 * 13 = 156 = the units of a 24-tile triangle
+#ifndef WS_UG_N
+#define WS_UG_N 5
+#endif
+constexpr int WS_UG = WS_UG_N;      // units whose B fragments are in flight together
+constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_PROD = 5, BAR_ALL = 6;
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+#ifndef GRAM_WS_REGS
+#define GRAM_WS_REGS 0
+#endif
+#ifndef GRAM_DIAG
+#define GRAM_DIAG 0
+#endif
+
+template <int PF>
+__global__ void __launch_bounds__(GT, 1) gram_ws_kernel(const CompressArgs a) {
+    constexpr int NMAX = 32;
+    constexpr int LDW = 6 * NMAX + 4;
+    constexpr int SMAXP = NMAX / WS_PW;                 // window slots per producer warp for the D / g tiles
+    constexpr int FPW = PF / WS_PW;                     // features fetched / scattered per producer warp
+    static_assert(PF % WS_PW == 0, "whole features per producer warp");
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int F = a.dims.F, Mcap = a.dims.M, Ncap = a.dims.N;
+    const int nc = a.n_cams[b];
+    const int c = 6 * nc;
+    const int ccap = 6 * Ncap;
+    const int T = (c + 7) >> 3;
+    const int T2 = (T + 1) >> 1;
+
+    extern __shared__ double smem[];
+    const int PM = PF * Mcap;
+    constexpr int WSZ = 3 * PF * LDW;
+    auto rawA = [&](int st) { return smem + 2 * WSZ + (size_t)st * PM * 21; };
+    auto rawQ = [&](int st) { return rawA(st) + PM * 12; };
+    auto rawR = [&](int st) { return rawA(st) + PM * 18; };
+    auto rawS = [&](int st) { return reinterpret_cast<int*>(rawA(st) + PM * 20); };
+    double* const Dg = rawA(2);
+    int* const acc_list = reinterpret_cast<int*>(Dg + Ncap * 48);
+    unsigned char* const inv = reinterpret_cast<unsigned char*>(acc_list + F);
+    __shared__ int s_wcnt[GW];
+    __shared__ int s_tot[2];
+    __shared__ int s_len[2][PF];
+
+    // ---- ordered list of the features that passed the gate (stacking order = feature order, MSCKF.py:573-588) ----
+    if (tid < 2) s_tot[tid] = 0;
+    __syncthreads();
+    int nacc = 0, nrej_local = 0;
+    for (int base = 0; base < F; base += GT) {
+        const int j = base + tid;
+        const int st = (j < F) ? (a.feat_status[(size_t)b * F + j] & 0xF) : 0;
+        const bool ok = st == MSCKF_FEAT_ACCEPTED;
+        nrej_local += (st == MSCKF_FEAT_GATED_OUT);
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = nacc;
+        for (int w = 0; w < warp; ++w) off += s_wcnt[w];
+        if (ok) acc_list[off + __popc(bal & ((1u << lane) - 1u))] = j;
+        for (int w = 0; w < GW; ++w) nacc += s_wcnt[w];
+        __syncthreads();
+    }
+    if (nrej_local) atomicAdd(&s_tot[1], nrej_local);
+    // the track length rides along in the list entry (j | len << 20): the producers' prefetch then has no dependent global load
+    for (int k = tid; k < nacc; k += GT) {
+        const int j = acc_list[k];
+        acc_list[k] = j | (min(a.feat_len[(size_t)b * F + j], Mcap) << 20);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        a.n_accepted[b] = nacc;
+        a.n_rejected[b] = s_tot[1];
+    }
+    double* Gout = a.T_H + (size_t)b * ccap * ccap;
+    double* gout = a.r_n + (size_t)b * ccap;
+    if (nacc == 0) {   // nothing survived: the update kernel skips this filter (MSCKF.py:584-585)
+        for (int e = tid; e < ccap; e += GT) gout[e] = 0.0;
+        return;
+    }
+    const int npanels = (nacc + PF - 1) / PF;
+    constexpr int KW = 3 * PF, KX = 2 * PF;
+
+    if (warp < WS_PW) {
+        // =================================================== producers ===================================================
+#if GRAM_WS_REGS
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+#endif
+        const int ptid = tid;                            // 0 .. 127
+        double accX[SMAXP][2];
+#pragma unroll
+        for (int k = 0; k < SMAXP; ++k) accX[k][0] = accX[k][1] = 0.0;
+
+        auto prefetch = [&](int pi, int st) {
+            if (pi < npanels) {
+#pragma unroll
+                for (int h = 0; h < FPW; ++h) {
+                    const int f = warp * FPW + h;
+                    const int k = pi * PF + f;
+                    const int packed = (k < nacc) ? acc_list[k] : 0;
+                    const int j = packed & 0xFFFFF, M = packed >> 20;
+                    if (lane == 0) s_len[st][f] = M;
+                    if (M > 0) {
+                        const size_t fj = (size_t)b * F + j;
+                        const double* gA = a.fac_A + fj * (size_t)Mcap * 12;
+                        const double* gQ = a.fac_Q + fj * (size_t)Mcap * 6;
+                        const double* gR = a.fac_rt + fj * (size_t)Mcap * 2;
+                        const int* gS = a.obs_slot + fj * (size_t)Mcap;
+                        double* sA = rawA(st) + (size_t)f * Mcap * 12;
+                        double* sQ = rawQ(st) + (size_t)f * Mcap * 6;
+                        double* sR = rawR(st) + (size_t)f * Mcap * 2;
+                        int* sS = rawS(st) + f * Mcap;
+                        for (int it = lane; it < 6 * M; it += 32) cp_async16(sA + 2 * it, gA + 2 * it);
+                        for (int it = lane; it < 3 * M; it += 32) cp_async16(sQ + 2 * it, gQ + 2 * it);
+                        for (int it = lane; it < M; it += 32) {
+                            cp_async16(sR + 2 * it, gR + 2 * it);
+                            cp_async4(sS + it, gS + it);
+                        }
+                    }
+                }
+            }
+            cp_async_commit();                           // (an empty group past the last panel keeps the wait count fixed)
+        };
+        prefetch(0, 0);
+        prefetch(1, 1);
+        for (int q = 0; q < npanels; ++q) {
+            const int st = q & 1;
+            cp_async_wait_1();                           // panel q's factors of this warp's features have landed
+            __syncwarp();
+            // slot -> observation maps of this warp's features
+#pragma unroll
+            for (int h = 0; h < FPW; ++h) {
+                const int f = warp * FPW + h;
+                unsigned char* iv = inv + (st * PF + f) * NMAX;
+                iv[lane] = 0xFF;
+                __syncwarp();
+                const int* sS = rawS(st) + f * Mcap;
+                const int len = s_len[st][f];
+                for (int i = lane; i < len; i += 32) {
+                    const int sl = sS[i];
+                    if (sl >= 0 && sl < nc) iv[sl] = (unsigned char)i;
+                }
+            }
+            __syncwarp();
+            if (q >= 2) bar_sync(BAR_EMPTY + st, GT);    // the consumers are done with panel q - 2 in this K-panel
+            // rows of W: W[3f+r][6 s + e] = Q1[2i][r] A[2i][e] + Q1[2i+1][r] A[2i+1][e], i = the observation of feature f in
+            // window slot s (a zero segment when there is none); the three (slot, row) units of a lane are independent chains
+#pragma unroll
+            for (int h = 0; h < (GRAM_DIAG == 1 || GRAM_DIAG == 3 ? 0 : FPW); ++h) {
+                const int f = warp * FPW + h;
+                const unsigned char* iv = inv + (st * PF + f) * NMAX;
+                double* Wp = smem + (size_t)st * WSZ + (size_t)(3 * f) * LDW;
+                const double* fA = rawA(st) + (size_t)f * Mcap * 12;
+                const double* fQ = rawQ(st) + (size_t)f * Mcap * 6;
+#pragma unroll
+                for (int rd = 0; rd < (3 * NMAX) / 32; ++rd) {
+                    const int e = lane + 32 * rd;
+                    const int sl = e / 3, r = e - 3 * sl;
+                    if (e < 3 * nc) {
+                        const int i = iv[sl];
+                        const int ii = (i == 0xFF) ? 0 : i;
+                        const double2* A2 = reinterpret_cast<const double2*>(fA + (size_t)ii * 12);
+                        const double* Q = fQ + (size_t)ii * 6;
+                        const double q0 = (i == 0xFF) ? 0.0 : Q[r], q1 = (i == 0xFF) ? 0.0 : Q[3 + r];
+                        double2* dst = reinterpret_cast<double2*>(Wp + (size_t)r * LDW + 6 * sl);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const double2 x = A2[k], y = A2[3 + k];
+                            dst[k] = make_double2(q0 * x.x + q1 * y.x, q0 * x.y + q1 * y.y);
+                        }
+                    }
+                }
+            }
+            __threadfence_block();
+            bar_arrive(BAR_FULL + st, GT);
+            bar_sync(BAR_PROD, WS_PW * 32);              // every producer's factors and maps of panel q are visible
+            // D_s += A_i^T A_i, g_s += A_i^T r~_i: one 8 x 8 tile per window slot, operand A == operand B = [A_i | r~_i | 0];
+            // the eight gathers of a k step are issued before its tensor instructions (a slot nobody observes adds zeros)
+            if (GRAM_DIAG != 1 && GRAM_DIAG != 4) {
+                const double* sA = rawA(st);
+                const double* sR = rawR(st);
+                const unsigned char* iv = inv + st * PF * NMAX;
+#pragma unroll
+                for (int kk = 0; kk < KX; kk += 4) {
+                    const int f = (kk >> 1) + (t >> 1), r = t & 1;
+                    double x[SMAXP];
+#pragma unroll
+                    for (int k = 0; k < SMAXP; ++k) {
+                        const int i = iv[f * NMAX + warp + WS_PW * k];
+                        const size_t o = (size_t)f * Mcap + (i == 0xFF ? 0 : i);
+                        const double* src = (g < 6) ? sA + o * 12 + 6 * r + g : sR + o * 2 + r;
+                        const double v = *src;
+                        x[k] = (i != 0xFF && g < 7) ? v : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < SMAXP; ++k) dense::dmma(accX[k][0], accX[k][1], x[k], x[k]);
+                }
+            }
+            bar_sync(BAR_PROD, WS_PW * 32);              // every producer is done with stage st: refill it
+            prefetch(q + 2, st);
+        }
+#pragma unroll
+        for (int k = 0; k < SMAXP; ++k) {
+            const int s = warp + WS_PW * k;
+            if (s < nc && g < 6) {   // rows 6, 7 of the tile are by-products (r~^T A, 0)
+                Dg[s * 48 + g * 8 + 2 * t] = accX[k][0];
+                Dg[s * 48 + g * 8 + 2 * t + 1] = accX[k][1];
+            }
+        }
+        bar_sync(BAR_ALL, GT);
+        for (int e = tid; e < ccap; e += GT) {
+            const int s = e / 6, aa = e - 6 * s;
+            gout[e] = (s < nc) ? Dg[s * 48 + aa * 8 + 6] : 0.0;
+        }
+        (void)ptid;
+    } else {
+        // =================================================== consumers ===================================================
+#if GRAM_WS_REGS
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+#endif
+        const int cw = warp - WS_PW;
+        int U = 0;
+        for (int p = 0; p < T2; ++p) U += strip_len(p, T);
+        const int upw = (U + WS_CW - 1) / WS_CW;         // <= WS_UM for T <= 24
+        const int u0 = min(U, cw * upw);
+        const int nu = min(U, u0 + upw) - u0;
+        int p0 = 0, J0 = u0;
+        while (p0 < T2 && J0 >= strip_len(p0, T)) { J0 -= strip_len(p0, T); ++p0; }
+        unsigned newstrip = 0;       // bit u: unit u is the first of a strip (reload the two A fragments, column 0)
+        {
+            int p = p0, J = J0;
+#pragma unroll
+            for (int u = 0; u < WS_UM; ++u) {
+                if (u == 0 || J == 0) newstrip |= 1u << u;
+                if (u < nu && ++J == strip_len(p, T)) { J = 0; ++p; }
+            }
+        }
+        double acc[WS_UM][2][2];
+#pragma unroll
+        for (int u = 0; u < WS_UM; ++u) acc[u][0][0] = acc[u][0][1] = acc[u][1][0] = acc[u][1][1] = 0.0;
+        const unsigned w0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(t * LDW + g) * 8u;
+        for (int pi = 0; pi < npanels; ++pi) {
+            const int st = pi & 1;
+            bar_sync(BAR_FULL + st, GT);
+            if (GRAM_DIAG != 2) gram_tensor_loop<KW, LDW, WS_UM, WS_UG>(w0 + (unsigned)(st * WSZ) * 8u, p0, J0, nu, newstrip, acc);
+            if (pi + 2 < npanels) bar_arrive(BAR_EMPTY + st, GT);
+        }
+        bar_sync(BAR_ALL, GT);
+        for (int e = tid; e < ccap; e += GT) {
+            const int s = e / 6, aa = e - 6 * s;
+            gout[e] = (s < nc) ? Dg[s * 48 + aa * 8 + 6] : 0.0;
+        }
+        // ---- G = D - W^T W: lower tiles written with their mirror image ----
+        int p = p0, J = J0;
+#pragma unroll
+        for (int u = 0; u < WS_UM; ++u) {
+            if (u < nu) {
+                if (u > 0 && ((newstrip >> u) & 1u)) { ++p; J = 0; }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int I = 2 * p + h;
+                    if (I < T && J <= I) {
+                        const int r = 8 * I + g;
+#pragma unroll
+                        for (int x = 0; x < 2; ++x) {
+                            const int col = 8 * J + 2 * t + x;
+                            if (r < c && col <= r) {
+                                double v = -acc[u][h][x];
+                                const int s = r / 6;
+                                if (col >= 6 * s) {
+                                    const int ea = r - 6 * s, eb = col - 6 * s;
+                                    v += Dg[s * 48 + ea * 8 + eb];
+                                }
+                                Gout[(size_t)r * ccap + col] = v;
+                                Gout[(size_t)col * ccap + r] = v;
+                            }
+                        }
+                    }
+                }
+                ++J;
+            }
+        }
+    }
+    // zero padding beyond the live block (capacity > n_cams): the rows below it, then the columns to its right
+    if (c < ccap) {
+        const int pad = ccap - c;
+        for (int e = tid; e < pad * ccap; e += GT) Gout[(size_t)c * ccap + e] = 0.0;
+        for (int e = tid; e < c * pad; e += GT) {
+            const int r = e / pad, cc = e - r * pad;
+            Gout[(size_t)r * ccap + c + cc] = 0.0;
+        }
+    }
+}
+
 struct GramPlan { int NMAX, PF; size_t smem; };
 
 GramPlan gram_plan(const msckf_dims& d) {
@@ -411,6 +732,19 @@ cudaError_t launch_compress_gram(const CompressArgs& a, cudaStream_t s) {
     const GramPlan pl = gram_plan(a.dims);
     if (pl.PF < 4) return cudaErrorInvalidConfiguration;
     msckf_count_launch(1);
+#ifndef GRAM_WS
+#define GRAM_WS 1
+#endif
+    if (GRAM_WS && pl.NMAX == 32 && pl.PF == 8) {
+        static size_t configured = 0;
+        if (pl.smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(gram_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+            if (e != cudaSuccess) return e;
+            configured = pl.smem;
+        }
+        gram_ws_kernel<8><<<a.dims.B, GT, pl.smem, s>>>(a);
+        return cudaGetLastError();
+    }
     if (pl.NMAX == 32) return pl.PF == 8 ? gram_launch<32, 8>(a, pl.smem, s) : gram_launch<32, 4>(a, pl.smem, s);
     return pl.PF == 8 ? gram_launch<64, 8>(a, pl.smem, s) : gram_launch<64, 4>(a, pl.smem, s);
 }
