@@ -645,7 +645,7 @@ def run_gpu_snapshot(args):
         stage_flops["compress"] = algorithmic_gram_flops_per_filter(acc_per_rank / B, N) * B
         stage_flops["apply"] = algorithmic_info_update_flops_per_filter(N) * B
         names = dict(front="front_kernel", front_geo="front_geo_kernel", front_asm="front_asm_kernel", front_chol="front_chol_kernel",
-                     compress="gram_kernel", apply="update_smem_kernel")
+                     compress="gram_ws_kernel", apply="update_smem_kernel")
     dom = max(stage_flops, key=lambda k: stage_ms[k])      # the dominant kernel of the step
     dom_name, dom_ms, dom_flops = names[dom], stage_ms[dom], stage_flops[dom]
     achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12
@@ -1016,7 +1016,7 @@ def run_gpu_stream(args):
                        else algorithmic_qr_flops_per_filter(2.0 * Mw * n_acc1 / B, Nw) * B,
                        apply=(algorithmic_info_update_flops_per_filter(Nw) if mode == _lib.COMPRESS_GRAM else 8.0 * (15 + 6 * Nw) ** 3) * B)
     names = dict(front_geo="front_geo_kernel", front_asm="front_asm_ps_kernel", front_chol="front_chol_kernel",
-                 compress="gram_kernel" if mode == _lib.COMPRESS_GRAM else "tsqr_kernel",
+                 compress=("gram_ws_kernel" if Nw <= 32 else "gram_kernel") if mode == _lib.COMPRESS_GRAM else "tsqr_kernel",
                  apply="update_smem_kernel" if mode == _lib.COMPRESS_GRAM else "apply_kernel")
     if split_front:
         stage_flops.update(front_geo=geo_flops, front_asm=pair_flops, front_chol=chol_flops)
