@@ -12,56 +12,105 @@ constexpr int TT = 256;
 #define TRACKS_KT 2
 #endif
 
-// One CTA per filter.  Observations per window slot are counted with shared-memory atomics together with the slot's first
+// Bit sets of the window slots that observe KS tracks of one filter (tracks j0, j0 + stride, ...): the KS length loads and then
+// the KS slot loads of a round are independent, so a warp has them all in flight (one track at a time left the kernels at the
+// latency of two dependent loads per track).  Lane = observation; the sets come back reduced over the warp.
+template <int KS>
+__device__ __forceinline__ void slot_sets(const int* __restrict__ len, const int* __restrict__ slot, int j0, int stride, int F, int M,
+                                          int nc, int lane, unsigned (&lo)[KS], unsigned (&hi)[KS]) {
+    int n[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        const int j = j0 + k * stride;
+        n[k] = j < F ? min(len[j], M) : 0;
+        lo[k] = hi[k] = 0;
+    }
+    for (int i0 = 0; i0 < M; i0 += 32) {
+        int sl[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) sl[k] = (i0 + lane < n[k]) ? slot[(size_t)(j0 + k * stride) * M + i0 + lane] : -1;
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+            if (sl[k] >= 0 && sl[k] < nc) {
+                if (sl[k] < 32) lo[k] |= 1u << sl[k];
+                else hi[k] |= 1u << (sl[k] - 32);
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        lo[k] = __reduce_or_sync(0xffffffffu, lo[k]);
+        hi[k] = __reduce_or_sync(0xffffffffu, hi[k]);
+    }
+}
+
+// One CTA per filter.  Every track is first reduced to the bit set of the window slots that observe it (warp per track,
+// lane = observation, one OR-reduction); thread s then counts the tracks whose set holds slot s and finds the slot's first
 // appearance in track order (the reference builds a dict while walking the tracks, so cameras enter it in that order, and
-// Python's stable `sorted` keeps it among equal counts); the `max_select` smallest (count, first appearance) pairs win.
+// Python's stable `sorted` keeps it among equal counts); the `max_select` smallest (count, first appearance) pairs win, and
+// a track is touched iff its set meets the selected slots.  (A camera observes a track at most once, so counting sets is
+// counting observations.  The previous version counted with shared-memory atomics -- 9216 of them onto ~30 addresses per
+// filter -- and ran at 12 % of the HBM roofline.)
 __global__ void __launch_bounds__(TT) select_poorest_kernel(msckf_dims dims, int max_select, int prune_above,
                                                             const int* __restrict__ n_cams,
                                                             const int* __restrict__ feat_len, const int* __restrict__ obs_slot,
                                                             unsigned char* __restrict__ remove_mask,
                                                             unsigned char* __restrict__ feat_touch) {
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = dims.F, M = dims.M, N = dims.N;
+    extern __shared__ unsigned long long s_set[];          // [F] slots observing each track
     __shared__ int s_count[MSCKF_MAX_CAMS], s_first[MSCKF_MAX_CAMS];
     __shared__ unsigned char s_sel[MSCKF_MAX_CAMS];
+    __shared__ unsigned long long s_selset;
     const int nc = min(n_cams[b], N);
-    for (int s = tid; s < N; s += TT) { s_count[s] = 0; s_first[s] = 0x7fffffff; s_sel[s] = 0; }
-    __syncthreads();
     const int* len = feat_len + (size_t)b * F;
     const int* slot = obs_slot + (size_t)b * F * M;
-    for (int e = tid; e < F * M; e += TT) {
-        const int j = e / M, i = e - j * M;
-        if (i < len[j]) {
-            const int s = slot[e];
-            if (s >= 0 && s < nc) {
-                atomicAdd(&s_count[s], 1);
-                atomicMin(&s_first[s], e);
-            }
+    constexpr int KS = 4;
+    for (int j0 = warp; j0 < F; j0 += KS * (TT / 32)) {
+        unsigned lo[KS], hi[KS];
+        slot_sets<KS>(len, slot, j0, TT / 32, F, M, nc, lane, lo, hi);
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+            if (lane == 0 && j0 + k * (TT / 32) < F) s_set[j0 + k * (TT / 32)] = ((unsigned long long)hi[k] << 32) | lo[k];
+    }
+    for (int sl = tid; sl < N; sl += TT) s_sel[sl] = 0;
+    __syncthreads();
+    if (tid < nc) {
+        int cnt = 0, jf = -1;
+        for (int j = 0; j < F; ++j) {
+            const int hit = (int)((s_set[j] >> tid) & 1ull);
+            if (hit && jf < 0) jf = j;
+            cnt += hit;
         }
+        int first = 0x7fffffff;
+        if (jf >= 0) {
+            const int n = min(len[jf], M);
+            for (int i = 0; i < n; ++i)
+                if (slot[(size_t)jf * M + i] == tid) { first = jf * M + i; break; }
+        }
+        s_count[tid] = cnt;
+        s_first[tid] = first;
     }
     __syncthreads();
-    if (tid == 0 && nc > prune_above) {      // MSCKF.feature_callback prunes only windows longer than the maximum (MSCKF.py:157-158)
-        for (int pick = 0; pick < max_select; ++pick) {
-            int best = -1;
-            for (int s = 0; s < nc; ++s) {
-                if (s_sel[s] || s_count[s] == 0) continue;
-                if (best < 0 || s_count[s] < s_count[best] || (s_count[s] == s_count[best] && s_first[s] < s_first[best])) best = s;
+    if (tid == 0) {
+        unsigned long long sel = 0;
+        if (nc > prune_above) {      // MSCKF.feature_callback prunes only windows longer than the maximum (MSCKF.py:157-158)
+            for (int pick = 0; pick < max_select; ++pick) {
+                int best = -1;
+                for (int sl = 0; sl < nc; ++sl) {
+                    if (s_sel[sl] || s_count[sl] == 0) continue;
+                    if (best < 0 || s_count[sl] < s_count[best] || (s_count[sl] == s_count[best] && s_first[sl] < s_first[best])) best = sl;
+                }
+                if (best < 0) break;
+                s_sel[best] = 1;
+                sel |= 1ull << best;
             }
-            if (best < 0) break;
-            s_sel[best] = 1;
         }
+        s_selset = sel;
     }
     __syncthreads();
-    for (int s = tid; s < N; s += TT) remove_mask[(size_t)b * N + s] = s_sel[s];
-    for (int j = tid; j < F; j += TT) {
-        unsigned char t = 0;
-        const int n = min(len[j], M);
-        for (int i = 0; i < n; ++i) {
-            const int s = slot[(size_t)j * M + i];
-            if (s >= 0 && s < nc && s_sel[s]) { t = 1; break; }
-        }
-        feat_touch[(size_t)b * F + j] = t;
-    }
+    for (int sl = tid; sl < N; sl += TT) remove_mask[(size_t)b * N + sl] = s_sel[sl];
+    const unsigned long long sel = s_selset;
+    for (int j = tid; j < F; j += TT) feat_touch[(size_t)b * F + j] = (s_set[j] & sel) ? 1 : 0;
 }
 
 // One warp per track, lane = observation (chunks of 32 for longer tracks): observations of removed slots leave the track,
@@ -186,29 +235,37 @@ __global__ void __launch_bounds__(TT) append_observations_kernel(msckf_dims dims
 }
 
 // Window slots of a filter that no track observes any more (MSCKF.get_cameras_without_features, called by remove_features,
-// MSCKF.py:739-749): the same shared-memory histogram as the pruning selection, mask = (count == 0).
+// MSCKF.py:739-749): the union of the tracks' slot sets (warp per track, OR-reductions), mask = slot not in the union.  A
+// filter that is not `active` (no lost track was deleted this frame) does not read its tracks at all.
 __global__ void __launch_bounds__(TT) unobserved_cameras_kernel(msckf_dims dims, const int* __restrict__ n_cams,
                                                                 const int* __restrict__ feat_len, const int* __restrict__ obs_slot,
                                                                 const unsigned char* __restrict__ active,
                                                                 unsigned char* __restrict__ remove_mask) {
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = dims.F, M = dims.M, N = dims.N;
-    __shared__ int s_count[MSCKF_MAX_CAMS];
+    __shared__ unsigned s_lo, s_hi;
+    const bool on = active == nullptr || active[b] != 0;
+    if (!on) {
+        for (int s = tid; s < N; s += TT) remove_mask[(size_t)b * N + s] = 0;
+        return;
+    }
     const int nc = min(n_cams[b], N);
-    for (int s = tid; s < N; s += TT) s_count[s] = 0;
+    if (tid == 0) { s_lo = 0; s_hi = 0; }
     __syncthreads();
     const int* len = feat_len + (size_t)b * F;
     const int* slot = obs_slot + (size_t)b * F * M;
-    for (int e = tid; e < F * M; e += TT) {
-        const int j = e / M, i = e - j * M;
-        if (i < len[j]) {
-            const int s = slot[e];
-            if (s >= 0 && s < nc) atomicAdd(&s_count[s], 1);
-        }
+    unsigned lo = 0, hi = 0;
+    constexpr int KS = 4;
+    for (int j0 = warp; j0 < F; j0 += KS * (TT / 32)) {
+        unsigned l4[KS], h4[KS];
+        slot_sets<KS>(len, slot, j0, TT / 32, F, M, nc, lane, l4, h4);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) { lo |= l4[k]; hi |= h4[k]; }
     }
+    if (lane == 0) { atomicOr(&s_lo, lo); atomicOr(&s_hi, hi); }
     __syncthreads();
-    const bool on = active == nullptr || active[b] != 0;
-    for (int s = tid; s < N; s += TT) remove_mask[(size_t)b * N + s] = (on && s < nc && s_count[s] == 0) ? 1 : 0;
+    const unsigned long long seen = ((unsigned long long)s_hi << 32) | s_lo;
+    for (int s = tid; s < N; s += TT) remove_mask[(size_t)b * N + s] = (s < nc && !((seen >> s) & 1ull)) ? 1 : 0;
 }
 
 // Stable compaction of the track slots of every filter from one set of track arrays into another (the host swaps the two
@@ -475,7 +532,9 @@ cudaError_t launch_append_observations(const msckf_dims& d, const double* Kinv_h
 
 cudaError_t launch_select_poorest(const msckf_dims& d, int max_select, int prune_above, const int* n_cams, const int* feat_len,
                                   const int* obs_slot, unsigned char* remove_mask, unsigned char* feat_touch, cudaStream_t s) {
-    select_poorest_kernel<<<d.B, TT, 0, s>>>(d, max_select, prune_above, n_cams, feat_len, obs_slot, remove_mask, feat_touch);
+    if (d.N > 64) return cudaErrorInvalidValue;      // (slot sets are 64-bit; MSCKF_MAX_CAMS)
+    select_poorest_kernel<<<d.B, TT, (size_t)d.F * sizeof(unsigned long long), s>>>(d, max_select, prune_above, n_cams, feat_len,
+                                                                                    obs_slot, remove_mask, feat_touch);
     msckf_count_launch(1);
     return cudaGetLastError();
 }
