@@ -601,8 +601,8 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
     const double s2 = a.par.sigma_image * a.par.sigma_image;
     const int n_batches = (npend + batch - 1) / batch;
 
-    auto issue_batch = [&](int bt) {
-        unsigned char* dst = sbuf + (size_t)(bt & 1) * batch * FEATB;
+    auto issue_batch = [&](int bt, int buf) {
+        unsigned char* dst = sbuf + (size_t)buf * batch * FEATB;
         const int e_end = min(batch, npend - bt * batch);
         // 16-byte chunks: 6 per observation of Jacobian blocks (AR = 14 doubles per observation in shared memory) + 2 of map
         for (int e = warp; e < e_end; e += NWARPS) {
@@ -620,16 +620,19 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
         cp_async_commit();
     };
 
-    issue_batch(0);
-    for (int bt = 0; bt < n_batches; ++bt) {
-        if (bt + 1 < n_batches) {
-            issue_batch(bt + 1);
+    // gridDim.z CTAs share a filter's pending features batch by batch (z, z + gridDim.z, ...): with fewer filters than SMs
+    // (a single filter: the drop-in's own case) one CTA per filter left the assembly at the latency of 256 features in a row
+    const int zs = (int)gridDim.z, z0 = (int)blockIdx.z;
+    if (z0 < n_batches) issue_batch(z0, 0);
+    for (int bt = z0, it = 0; bt < n_batches; bt += zs, ++it) {
+        if (bt + zs < n_batches) {
+            issue_batch(bt + zs, (it + 1) & 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
-        const unsigned char* src = sbuf + (size_t)(bt & 1) * batch * FEATB;
+        const unsigned char* src = sbuf + (size_t)(it & 1) * batch * FEATB;
         const int e_end = min(batch, npend - bt * batch);
         if (has_block) {
             // (the slot map of the NEXT feature is read one iteration ahead: its latency is off the dependency chain)
@@ -967,7 +970,15 @@ cudaError_t launch_asm_ps(const FrontArgs& a, const unsigned char* slot_map, dou
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    front_asm_ps_kernel<NWARPS, false><<<nb, NWARPS * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch, KT_D2);
+    // few filters: several CTAs per filter, each taking every nz-th batch of its pending features (<= one CTA per SM in all)
+    int nz = 1;
+    if (nb < 148) {
+        const int nbatch = (a.dims.F + batch - 1) / batch;
+        nz = 148 / (nb > 0 ? nb : 1);
+        if (nz > nbatch) nz = nbatch;
+        if (nz < 1) nz = 1;
+    }
+    front_asm_ps_kernel<NWARPS, false><<<dim3(nb, 1, nz), NWARPS * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch, KT_D2);
     return cudaGetLastError();
 }
 
