@@ -540,7 +540,7 @@ constexpr int PS_FEAT_BYTES = FW_MAX_OBS * AR * 8 + 32;   // one feature in a ba
 // WIDE (tracks of up to 64 observations, windows of up to 64 poses): the block triangle no longer fits one CTA's threads, so
 // gridDim.y CTAs share a filter, CTA y owning the blocks [y NT, (y + 1) NT); every CTA streams all of the filter's pending
 // features (64-observation slots, 64-byte maps) and writes its own blocks of their K.
-template <int NWARPS, bool WIDE>
+template <int NWARPS, bool WIDE, bool ZSPLIT = false>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_map, double2* __restrict__ Kbuf, const int b0,
                     const int batch, const int kt_d2) {
@@ -622,7 +622,7 @@ front_asm_ps_kernel(const FrontArgs a, const unsigned char* __restrict__ slot_ma
 
     // gridDim.z CTAs share a filter's pending features batch by batch (z, z + gridDim.z, ...): with fewer filters than SMs
     // (a single filter: the drop-in's own case) one CTA per filter left the assembly at the latency of 256 features in a row
-    const int zs = (int)gridDim.z, z0 = (int)blockIdx.z;
+    const int zs = ZSPLIT ? (int)gridDim.z : 1, z0 = ZSPLIT ? (int)blockIdx.z : 0;      // (compile-time 1 / 0 for full batches)
     if (z0 < n_batches) issue_batch(z0, 0);
     for (int bt = z0, it = 0; bt < n_batches; bt += zs, ++it) {
         if (bt + zs < n_batches) {
@@ -978,7 +978,17 @@ cudaError_t launch_asm_ps(const FrontArgs& a, const unsigned char* slot_map, dou
         if (nz > nbatch) nz = nbatch;
         if (nz < 1) nz = 1;
     }
-    front_asm_ps_kernel<NWARPS, false><<<dim3(nb, 1, nz), NWARPS * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch, KT_D2);
+    if (nz > 1) {
+        static size_t configured_z = 0;
+        if (smem > configured_z) {
+            cudaError_t e = cudaFuncSetAttribute(front_asm_ps_kernel<NWARPS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_z = smem;
+        }
+        front_asm_ps_kernel<NWARPS, false, true><<<dim3(nb, 1, nz), NWARPS * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch, KT_D2);
+    } else {
+        front_asm_ps_kernel<NWARPS, false, false><<<nb, NWARPS * 32, smem, s>>>(a, slot_map, Kbuf, b0, batch, KT_D2);
+    }
     return cudaGetLastError();
 }
 

@@ -417,7 +417,7 @@ __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_
 #define GRAM_DIAG 0
 #endif
 
-template <int PF>
+template <int PF, bool YSPLIT>
 __global__ void __launch_bounds__(GT, 1) gram_ws_kernel(const CompressArgs a) {
     constexpr int NMAX = 32;
     constexpr int LDW = 6 * NMAX + 4;
@@ -473,14 +473,18 @@ __global__ void __launch_bounds__(GT, 1) gram_ws_kernel(const CompressArgs a) {
         acc_list[k] = j | (min(a.feat_len[(size_t)b * F + j], Mcap) << 20);
     }
     __syncthreads();
-    if (tid == 0) {
+    // gridDim.y CTAs may share a filter (fewer filters than SMs): each runs the whole producer side and owns a contiguous
+    // share of the output units; CTA 0 of the filter also writes g, the counters and the padding
+    const int nsplit = YSPLIT ? (int)gridDim.y : 1, split = YSPLIT ? (int)blockIdx.y : 0;      // (compile-time 1 / 0 for full batches)
+    if (tid == 0 && split == 0) {
         a.n_accepted[b] = nacc;
         a.n_rejected[b] = s_tot[1];
     }
     double* Gout = a.T_H + (size_t)b * ccap * ccap;
     double* gout = a.r_n + (size_t)b * ccap;
     if (nacc == 0) {   // nothing survived: the update kernel skips this filter (MSCKF.py:584-585)
-        for (int e = tid; e < ccap; e += GT) gout[e] = 0.0;
+        if (split == 0)
+            for (int e = tid; e < ccap; e += GT) gout[e] = 0.0;
         return;
     }
     const int npanels = (nacc + PF - 1) / PF;
@@ -613,10 +617,11 @@ __global__ void __launch_bounds__(GT, 1) gram_ws_kernel(const CompressArgs a) {
             }
         }
         bar_sync(BAR_ALL, GT);
-        for (int e = tid; e < ccap; e += GT) {
-            const int s = e / 6, aa = e - 6 * s;
-            gout[e] = (s < nc) ? Dg[s * 48 + aa * 8 + 6] : 0.0;
-        }
+        if (split == 0)
+            for (int e = tid; e < ccap; e += GT) {
+                const int s = e / 6, aa = e - 6 * s;
+                gout[e] = (s < nc) ? Dg[s * 48 + aa * 8 + 6] : 0.0;
+            }
         (void)ptid;
     } else {
         // =================================================== consumers ===================================================
@@ -626,9 +631,10 @@ __global__ void __launch_bounds__(GT, 1) gram_ws_kernel(const CompressArgs a) {
         const int cw = warp - WS_PW;
         int U = 0;
         for (int p = 0; p < T2; ++p) U += strip_len(p, T);
-        const int upw = (U + WS_CW - 1) / WS_CW;         // <= WS_UM for T <= 24
-        const int u0 = min(U, cw * upw);
-        const int nu = min(U, u0 + upw) - u0;
+        const int ub = (int)(((long long)U * split) / nsplit), ue = (int)(((long long)U * (split + 1)) / nsplit);
+        const int upw = (ue - ub + WS_CW - 1) / WS_CW;   // <= WS_UM for T <= 24
+        const int u0 = min(ue, ub + cw * upw);
+        const int nu = min(ue, u0 + upw) - u0;
         int p0 = 0, J0 = u0;
         while (p0 < T2 && J0 >= strip_len(p0, T)) { J0 -= strip_len(p0, T); ++p0; }
         unsigned newstrip = 0;       // bit u: unit u is the first of a strip (reload the two A fragments, column 0)
@@ -651,10 +657,11 @@ __global__ void __launch_bounds__(GT, 1) gram_ws_kernel(const CompressArgs a) {
             if (pi + 2 < npanels) bar_arrive(BAR_EMPTY + st, GT);
         }
         bar_sync(BAR_ALL, GT);
-        for (int e = tid; e < ccap; e += GT) {
-            const int s = e / 6, aa = e - 6 * s;
-            gout[e] = (s < nc) ? Dg[s * 48 + aa * 8 + 6] : 0.0;
-        }
+        if (split == 0)
+            for (int e = tid; e < ccap; e += GT) {
+                const int s = e / 6, aa = e - 6 * s;
+                gout[e] = (s < nc) ? Dg[s * 48 + aa * 8 + 6] : 0.0;
+            }
         // ---- G = D - W^T W: lower tiles written with their mirror image ----
         int p = p0, J = J0;
 #pragma unroll
@@ -687,7 +694,7 @@ __global__ void __launch_bounds__(GT, 1) gram_ws_kernel(const CompressArgs a) {
         }
     }
     // zero padding beyond the live block (capacity > n_cams): the rows below it, then the columns to its right
-    if (c < ccap) {
+    if (c < ccap && split == 0) {
         const int pad = ccap - c;
         for (int e = tid; e < pad * ccap; e += GT) Gout[(size_t)c * ccap + e] = 0.0;
         for (int e = tid; e < c * pad; e += GT) {
@@ -738,11 +745,15 @@ cudaError_t launch_compress_gram(const CompressArgs& a, cudaStream_t s) {
     if (GRAM_WS && pl.NMAX == 32 && pl.PF == 8) {
         static size_t configured = 0;
         if (pl.smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(gram_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+            cudaError_t e = cudaFuncSetAttribute(gram_ws_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gram_ws_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
             if (e != cudaSuccess) return e;
             configured = pl.smem;
         }
-        gram_ws_kernel<8><<<a.dims.B, GT, pl.smem, s>>>(a);
+        int ny = a.dims.B > 0 ? 148 / a.dims.B : 1;      // few filters: several CTAs per filter, each a share of the output tiles
+        if (ny > 6) ny = 6;
+        if (ny > 1) gram_ws_kernel<8, true><<<dim3(a.dims.B, ny), GT, pl.smem, s>>>(a);
+        else gram_ws_kernel<8, false><<<a.dims.B, GT, pl.smem, s>>>(a);
         return cudaGetLastError();
     }
     if (pl.NMAX == 32) return pl.PF == 8 ? gram_launch<32, 8>(a, pl.smem, s) : gram_launch<32, 4>(a, pl.smem, s);
