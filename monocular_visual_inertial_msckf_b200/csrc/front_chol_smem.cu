@@ -212,15 +212,191 @@ front_chol_smem_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LEFT-looking variant: four warps per feature, five features per SM.  The right-looking kernel above keeps the whole lower
+// triangle of a feature in shared memory (70 KB at 60 observations: three features per SM) and its profile is the sixteen
+// serial in-tile factorisations of a feature (1400 clocks each, seven warps waiting): 0.23 of the FP64 peak.  Left-looking,
+// block column k needs the finished tiles L[I][j] with j < k <= I only -- at most max_k k (T - k) = 64 tiles = 32 KB, in slots
+// assigned by interval colouring (a tile is live from the column that creates it to the column of its row) -- plus the current
+// column (8 KB), so five CTAs fit an SM and their serial phases interleave.  Column k of K is read from the tile buffer when
+// it is needed (and only then: the trailing matrix is never held).
+constexpr int LT = 128;           // threads per CTA
+constexpr int LWARPS = LT / 32;
+constexpr int LMAXT = 17;         // tile rows at 64 observations
+
+__host__ __device__ inline int ll_slots(int T) {
+    int m = 0;
+    for (int k = 0; k < T; ++k) m = (k * (T - k) > m) ? k * (T - k) : m;
+    return m;
+}
+
+__global__ void __launch_bounds__(LT, 5)
+front_chol_ll_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const int* __restrict__ pend_list,
+                     const int* __restrict__ pend_count, const int* __restrict__ feat_len, const int* __restrict__ fac_rank,
+                     const int* __restrict__ dof, const double* __restrict__ chi2_table, const int chi2_len,
+                     unsigned char* __restrict__ feat_status, double* __restrict__ gamma, const size_t fbase, const int Tcap) {
+    extern __shared__ double sm[];
+    const int nslots = ll_slots(Tcap);
+    double* Ls = sm;                                   // [nslots][64] finished tiles
+    double* Cc = Ls + (size_t)nslots * TILE;           // [Tcap][64]   current block column (tile row k first)
+    double* Xs = Cc + (size_t)Tcap * TILE;             // [64]
+    __shared__ unsigned char s_slot[LMAXT][LMAXT];     // slot of tile (I, j), I > j, for THIS feature's tile count
+    __shared__ int s_T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int count = *pend_count;
+    if (tid == 0) s_T = -1;
+    __syncthreads();
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int fl = pend_list[q];
+        const size_t fj = fbase + (size_t)fl;
+        const int n2 = 2 * feat_len[fj];
+        const int a4 = (n2 + 3) & ~3;
+        const int Tn = (a4 + 4 + 7) >> 3;
+        const int rr = a4 - 8 * (Tn - 1);
+        const double2* Kt = Kbuf + (size_t)fl * kt_d2;
+        if (s_T != Tn) {                               // (interval colouring of the tiles of a Tn-row triangle; CTA-uniform test)
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long fr[2] = {~0ull, ~0ull};             // free slots (bit set = free), <= 128
+                for (int c = 0; c < Tn; ++c) {
+                    for (int j = 0; j < c; ++j) { const int sl = s_slot[c][j]; fr[sl >> 6] |= 1ull << (sl & 63); }
+                    for (int I = c + 1; I < Tn; ++I) {
+                        const int w = fr[0] ? 0 : 1;
+                        const int b = __ffsll((long long)fr[w]) - 1;
+                        fr[w] &= ~(1ull << b);
+                        s_slot[I][c] = (unsigned char)(64 * w + b);
+                    }
+                }
+                s_T = Tn;
+            }
+            __syncthreads();
+        }
+        // column k of K: tiles (I, k), I = k .. Tn - 1 (row-major inside the tile: double2 number 4 g + t), kept in registers
+        // from the moment they are requested (during column k - 1's work) until column k starts: the read of the tile buffer is
+        // off the critical path of every column but the first
+        constexpr int LPRE = (LMAXT * 32 + LT - 1) / LT;      // double2 per thread of one column
+        double2 pre[LPRE];
+        auto fetch_column = [&](int k) {
+            const int nt = Tn - k;
+#pragma unroll
+            for (int u = 0; u < LPRE; ++u) {
+                const int e = tid + u * LT;
+                if (e < nt * 32) pre[u] = __ldcs(Kt + (size_t)(tri(k + (e >> 5)) + k) * 32 + (e & 31));
+            }
+        };
+        fetch_column(0);
+        for (int k = 0; k < Tn; ++k) {
+            {
+                const int nt = Tn - k;
+#pragma unroll
+                for (int u = 0; u < LPRE; ++u) {
+                    const int e = tid + u * LT;
+                    if (e < nt * 32) {
+                        const int l = e & 31;
+                        st2(Cc + (size_t)(e >> 5) * TILE + swz(l >> 2, 2 * (l & 3)), pre[u].x, pre[u].y);
+                    }
+                }
+            }
+            __syncthreads();
+            if (k + 1 < Tn) fetch_column(k + 1);
+            // C[I] -= sum_{j < k} L[I][j] L[k][j]^T, one tile row per warp and round (keeping a warp's tile rows in registers to
+            // share the B fragments of L[k][j] across them was measured: 13.3 vs 9.05 ms, the per-row slot look-ups and
+            // predicates in the inner loop cost more than the re-reads)
+            for (int I = k + warp; I < Tn; I += LWARPS) {
+                double* p = Cc + (size_t)(I - k) * TILE + swz(g, 2 * t);
+                double2 c = ld2(p);
+                double2 c2 = make_double2(0.0, 0.0);           // second accumulator: two independent DMMA chains
+                int j = 0;
+                for (; j + 1 < k; j += 2) {
+                    const double* Aa = Ls + (size_t)s_slot[I][j] * TILE;
+                    const double* Ba = Ls + (size_t)s_slot[k][j] * TILE;
+                    const double* Ab = Ls + (size_t)s_slot[I][j + 1] * TILE;
+                    const double* Bb = Ls + (size_t)s_slot[k][j + 1] * TILE;
+#pragma unroll
+                    for (int sx = 0; sx < 2; ++sx) {
+                        const int fo = swz(g, 4 * sx + t);
+                        dmma(c.x, c.y, -Aa[fo], Ba[fo]);
+                        dmma(c2.x, c2.y, -Ab[fo], Bb[fo]);
+                    }
+                }
+                if (j < k) {
+                    const double* Aa = Ls + (size_t)s_slot[I][j] * TILE;
+                    const double* Ba = Ls + (size_t)s_slot[k][j] * TILE;
+#pragma unroll
+                    for (int sx = 0; sx < 2; ++sx) {
+                        const int fo = swz(g, 4 * sx + t);
+                        dmma(c.x, c.y, -Aa[fo], Ba[fo]);
+                    }
+                }
+                st2(p, c.x + c2.x, c.y + c2.y);
+            }
+            __syncthreads();
+            if (k == Tn - 1) break;
+            if (warp == 0) {
+                const double2 v = ld2(Cc + swz(g, 2 * t));
+                diag_factor(v.x, v.y, Cc, Xs, g, t);
+            }
+            __syncthreads();
+            {   // panel: L[I][k] = C[I] X into its slot
+                const double bf0 = Xs[swz(2 * t, g)], bf1 = Xs[swz(2 * t + 1, g)];
+                for (int I = k + 1 + warp; I < Tn; I += LWARPS) {
+                    const double2 v = ld2(Cc + (size_t)(I - k) * TILE + swz(g, 2 * t));
+                    double n0 = 0.0, n1 = 0.0;
+                    dmma(n0, n1, v.x, bf0);
+                    dmma(n0, n1, v.y, bf1);
+                    st2(Ls + (size_t)s_slot[I][k] * TILE + swz(g, 2 * t), n0, n1);
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            const double2 v = ld2(Cc + swz(g, 2 * t));
+            const int rank = fac_rank[fj], dofv = dof[fj];
+            const int st = feat_status[fj];
+            const double gam = gamma_from_last_tile(v.x, v.y, g, t, rr, rank);
+            if (lane == 0) {
+                const double crit = (dofv < chi2_len) ? chi2_table[dofv] : nan("");
+                const bool pass = gam <= crit;
+                feat_status[fj] = (unsigned char)((pass ? MSCKF_FEAT_ACCEPTED : MSCKF_FEAT_GATED_OUT) | (st & FLAG_KEEP));
+                gamma[fj] = gam;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 size_t front_chol_smem_bytes(int Mcap) {
     return ((size_t)ftile::tiles_for_capacity(Mcap) * TILE + TILE) * sizeof(double);
 }
 
+#ifndef CHOL_LL
+#define CHOL_LL 1
+#endif
+
 cudaError_t launch_front_chol_smem(const double2* Kbuf, int kt_d2, const int* pend_list, const int* pend_count, const int* feat_len,
                                    const int* fac_rank, const int* dof, const double* chi2_table, int chi2_len,
                                    unsigned char* feat_status, double* gamma, size_t fbase, int Mcap, cudaStream_t s) {
+    if (CHOL_LL) {
+        const int Tcap = ftile::tile_rows(Mcap);
+        const size_t smem = ((size_t)ll_slots(Tcap) * TILE + (size_t)Tcap * TILE + TILE) * sizeof(double);
+        static size_t configured_ll = 0;
+        if (smem > configured_ll) {
+            cudaError_t e = cudaFuncSetAttribute(front_chol_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_ll = smem;
+        }
+        int per_sm = (int)((227 * 1024) / (smem + 1024 + 512));
+        if (per_sm > 5) per_sm = 5;
+        if (per_sm < 1) per_sm = 1;
+        front_chol_ll_kernel<<<148 * per_sm, LT, smem, s>>>(Kbuf, kt_d2, pend_list, pend_count, feat_len, fac_rank, dof, chi2_table,
+                                                           chi2_len, feat_status, gamma, fbase, Tcap);
+        msckf_count_launch(1);
+        return cudaGetLastError();
+    }
     const size_t smem = front_chol_smem_bytes(Mcap);
     static size_t configured = 0;
     if (smem > configured) {
