@@ -239,8 +239,8 @@ front_chol_ll_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const in
     extern __shared__ double sm[];
     const int nslots = ll_slots(Tcap);
     double* Ls = sm;                                   // [nslots][64] finished tiles
-    double* Cc = Ls + (size_t)nslots * TILE;           // [Tcap][64]   current block column (tile row k first)
-    double* Xs = Cc + (size_t)Tcap * TILE;             // [64]
+    double* const Cbase = Ls + (size_t)nslots * TILE;  // [2][Tcap][64] block columns k and k + 1 (tile row k first)
+    double* Xs = Cbase + (size_t)2 * Tcap * TILE;      // [64]
     __shared__ unsigned char s_slot[LMAXT][LMAXT];     // slot of tile (I, j), I > j, for THIS feature's tile count
     __shared__ int s_T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -256,6 +256,7 @@ front_chol_ll_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const in
         const int Tn = (a4 + 4 + 7) >> 3;
         const int rr = a4 - 8 * (Tn - 1);
         const double2* Kt = Kbuf + (size_t)fl * kt_d2;
+        double* Cc = Cbase;
         if (s_T != Tn) {                               // (interval colouring of the tiles of a Tn-row triangle; CTA-uniform test)
             __syncthreads();
             if (tid == 0) {
@@ -273,9 +274,8 @@ front_chol_ll_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const in
             }
             __syncthreads();
         }
-        // column k of K: tiles (I, k), I = k .. Tn - 1 (row-major inside the tile: double2 number 4 g + t), kept in registers
-        // from the moment they are requested (during column k - 1's work) until column k starts: the read of the tile buffer is
-        // off the critical path of every column but the first
+        // column k of K: tiles (I, k), I = k .. Tn - 1 (row-major inside the tile: double2 number 4 g + t), requested two
+        // columns ahead and parked in registers: the read of the tile buffer is off the critical path
         constexpr int LPRE = (LMAXT * 32 + LT - 1) / LT;      // double2 per thread of one column
         double2 pre[LPRE];
         auto fetch_column = [&](int k) {
@@ -286,34 +286,29 @@ front_chol_ll_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const in
                 if (e < nt * 32) pre[u] = __ldcs(Kt + (size_t)(tri(k + (e >> 5)) + k) * 32 + (e & 31));
             }
         };
-        fetch_column(0);
-        for (int k = 0; k < Tn; ++k) {
-            {
-                const int nt = Tn - k;
+        auto park_column = [&](double* C, int k) {
+            const int nt = Tn - k;
 #pragma unroll
-                for (int u = 0; u < LPRE; ++u) {
-                    const int e = tid + u * LT;
-                    if (e < nt * 32) {
-                        const int l = e & 31;
-                        st2(Cc + (size_t)(e >> 5) * TILE + swz(l >> 2, 2 * (l & 3)), pre[u].x, pre[u].y);
-                    }
+            for (int u = 0; u < LPRE; ++u) {
+                const int e = tid + u * LT;
+                if (e < nt * 32) {
+                    const int l = e & 31;
+                    st2(C + (size_t)(e >> 5) * TILE + swz(l >> 2, 2 * (l & 3)), pre[u].x, pre[u].y);
                 }
             }
-            __syncthreads();
-            if (k + 1 < Tn) fetch_column(k + 1);
-            // C[I] -= sum_{j < k} L[I][j] L[k][j]^T, one tile row per warp and round (keeping a warp's tile rows in registers to
-            // share the B fragments of L[k][j] across them was measured: 13.3 vs 9.05 ms, the per-row slot look-ups and
-            // predicates in the inner loop cost more than the re-reads)
-            for (int I = k + warp; I < Tn; I += LWARPS) {
-                double* p = Cc + (size_t)(I - k) * TILE + swz(g, 2 * t);
+        };
+        // C[I - kk] -= sum_{jlo <= j < jhi} L[I][j] L[kk][j]^T for the tile rows I = kk + w, kk + w + nw, ... of column kk
+        auto update_tiles = [&](double* C, int kk, int jlo, int jhi, int w, int nw) {
+            for (int I = kk + w; I < Tn; I += nw) {
+                double* p = C + (size_t)(I - kk) * TILE + swz(g, 2 * t);
                 double2 c = ld2(p);
                 double2 c2 = make_double2(0.0, 0.0);           // second accumulator: two independent DMMA chains
-                int j = 0;
-                for (; j + 1 < k; j += 2) {
+                int j = jlo;
+                for (; j + 1 < jhi; j += 2) {
                     const double* Aa = Ls + (size_t)s_slot[I][j] * TILE;
-                    const double* Ba = Ls + (size_t)s_slot[k][j] * TILE;
+                    const double* Ba = Ls + (size_t)s_slot[kk][j] * TILE;
                     const double* Ab = Ls + (size_t)s_slot[I][j + 1] * TILE;
-                    const double* Bb = Ls + (size_t)s_slot[k][j + 1] * TILE;
+                    const double* Bb = Ls + (size_t)s_slot[kk][j + 1] * TILE;
 #pragma unroll
                     for (int sx = 0; sx < 2; ++sx) {
                         const int fo = swz(g, 4 * sx + t);
@@ -321,9 +316,9 @@ front_chol_ll_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const in
                         dmma(c2.x, c2.y, -Ab[fo], Bb[fo]);
                     }
                 }
-                if (j < k) {
+                if (j < jhi) {
                     const double* Aa = Ls + (size_t)s_slot[I][j] * TILE;
-                    const double* Ba = Ls + (size_t)s_slot[k][j] * TILE;
+                    const double* Ba = Ls + (size_t)s_slot[kk][j] * TILE;
 #pragma unroll
                     for (int sx = 0; sx < 2; ++sx) {
                         const int fo = swz(g, 4 * sx + t);
@@ -332,17 +327,34 @@ front_chol_ll_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const in
                 }
                 st2(p, c.x + c2.x, c.y + c2.y);
             }
+        };
+        // Look-ahead: while one warp factors the diagonal tile of column k (a chain of ~1400 clocks, longer under the other
+        // CTAs' tensor work), the other three already subtract the finished columns j < k from column k + 1; column k's own
+        // contribution follows when its panel exists.  (Without it 40 % of the warp time was the three warps waiting.)
+        fetch_column(0);
+        park_column(Cc, 0);
+        if (Tn > 1) fetch_column(1);
+        __syncthreads();
+        for (int k = 0; k < Tn; ++k) {
+            double* cur = Cc + (size_t)(k & 1) * Tcap * TILE;
+            double* nxt = Cc + (size_t)((k + 1) & 1) * Tcap * TILE;
+            if (k >= 1) update_tiles(cur, k, k - 1, k, warp, LWARPS);        // column k - 1's share of column k
+            if (k + 1 < Tn) park_column(nxt, k + 1);
             __syncthreads();
+            if (k + 2 < Tn) fetch_column(k + 2);
             if (k == Tn - 1) break;
-            if (warp == 0) {
-                const double2 v = ld2(Cc + swz(g, 2 * t));
-                diag_factor(v.x, v.y, Cc, Xs, g, t);
+            const int dw = k & (LWARPS - 1);
+            if (warp == dw) {
+                const double2 v = ld2(cur + swz(g, 2 * t));
+                diag_factor(v.x, v.y, cur, Xs, g, t);
+            } else if (k >= 1) {
+                update_tiles(nxt, k + 1, 0, k, (warp - dw - 1) & (LWARPS - 1), LWARPS - 1);
             }
             __syncthreads();
             {   // panel: L[I][k] = C[I] X into its slot
                 const double bf0 = Xs[swz(2 * t, g)], bf1 = Xs[swz(2 * t + 1, g)];
                 for (int I = k + 1 + warp; I < Tn; I += LWARPS) {
-                    const double2 v = ld2(Cc + (size_t)(I - k) * TILE + swz(g, 2 * t));
+                    const double2 v = ld2(cur + (size_t)(I - k) * TILE + swz(g, 2 * t));
                     double n0 = 0.0, n1 = 0.0;
                     dmma(n0, n1, v.x, bf0);
                     dmma(n0, n1, v.y, bf1);
@@ -351,6 +363,7 @@ front_chol_ll_kernel(const double2* __restrict__ Kbuf, const int kt_d2, const in
             }
             __syncthreads();
         }
+        Cc = Cc + (size_t)((Tn - 1) & 1) * Tcap * TILE;       // (the last column's buffer holds the appended rows' tile)
         if (warp == 0) {
             const double2 v = ld2(Cc + swz(g, 2 * t));
             const int rank = fac_rank[fj], dofv = dof[fj];
@@ -382,7 +395,7 @@ cudaError_t launch_front_chol_smem(const double2* Kbuf, int kt_d2, const int* pe
                                    unsigned char* feat_status, double* gamma, size_t fbase, int Mcap, cudaStream_t s) {
     if (CHOL_LL) {
         const int Tcap = ftile::tile_rows(Mcap);
-        const size_t smem = ((size_t)ll_slots(Tcap) * TILE + (size_t)Tcap * TILE + TILE) * sizeof(double);
+        const size_t smem = ((size_t)ll_slots(Tcap) * TILE + (size_t)2 * Tcap * TILE + TILE) * sizeof(double);
         static size_t configured_ll = 0;
         if (smem > configured_ll) {
             cudaError_t e = cudaFuncSetAttribute(front_chol_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
