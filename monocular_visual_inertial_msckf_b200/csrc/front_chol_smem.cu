@@ -7,6 +7,8 @@
 // diagonal tiles factored by one warp with shuffles (the routine of update_smem.cu, here for 8 warps).  The appended rows
 // [r~; Q1^T] ride along as ordinary rows of the last tile row; after the measurement columns are factored, the block
 // under them holds minus the Gram matrix of [y; V], from which gamma follows (front_gate.cuh).
+// The kernel that runs is the LEFT-looking one further down (front_chol_ll_kernel: four warps per feature, four features per
+// SM, look-ahead); the right-looking one stays as the reference variant (CHOL_LL=0).
 #include "msckf_common.cuh"
 #include "dense.cuh"
 #include "front_tiles.cuh"
