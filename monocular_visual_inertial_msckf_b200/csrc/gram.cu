@@ -410,6 +410,9 @@ __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
+// Build switches of the measurements in profiles/r02_summary.md section 5 (tools/build_variant.sh): GRAM_WS_REGS = 1 moves
+// registers from the producers to the consumers with setmaxnreg (3 % slower, off); GRAM_DIAG != 0 SKIPS a stage (1: scatter and
+// D / g, 2: the tensor loop, 3: scatter, 4: D / g) to time the rest -- wrong results, never shipped.
 #ifndef GRAM_WS_REGS
 #define GRAM_WS_REGS 0
 #endif
